@@ -1,0 +1,214 @@
+/*
+ * rm_b200.h -- C ABI of the B200-native render hot path of rusty-marcher.
+ *
+ * This is the drop-in boundary.  In the reference the whole hot path sits inside
+ *     Renderer::render(&self, frame: &mut FrameBuffer, scene: &Scene) -> String
+ * (engine/src/renderer.rs:36-126): a Rayon `into_par_iter` over 32x32 pixel patches
+ * (renderer.rs:63-89) followed by a single-threaded reassembly copy (renderer.rs:92-108).
+ * A maintainer replaces exactly those lines with one call to rm_render(); everything the
+ * kernels need is passed as plain f64 PODs that mirror the reference's own structs field
+ * by field (the reference computes in f64, engine/src/geometry.rs:4-8).  No torch, CUDA or
+ * C++ types appear in any signature.  INTEGRATION.md shows the Rust `extern "C"` block,
+ * build.rs and the `Shape::flatten` glue.
+ *
+ * Error convention: every int-returning call yields RM_OK (0) or a negative RmStatus;
+ * rm_last_error() returns the message of the last failure on the calling thread.  There
+ * is NO CPU fallback: without a usable sm_100 device rm_init() fails with RM_ERR_NO_DEVICE
+ * and every other entry point with RM_ERR_NOT_INITIALISED.
+ */
+#ifndef RM_B200_H
+#define RM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RM_ABI_VERSION 1
+
+typedef enum RmStatus {
+    RM_OK = 0,
+    RM_ERR_NO_DEVICE = -1,        /* no CUDA device / not an sm_100 part / driver error at init      */
+    RM_ERR_NOT_INITIALISED = -2,
+    RM_ERR_INVALID_ARGUMENT = -3, /* null pointer, bad handle, negative count ...                     */
+    RM_ERR_DIMENSIONS = -4,       /* width not a multiple of the patch size (renderer.rs:107 panics)  */
+    RM_ERR_SCENE = -5,            /* malformed flat scene (index out of range, polygon with <3 verts) */
+    RM_ERR_CUDA = -6,             /* a CUDA runtime call failed; see rm_last_error()                  */
+    RM_ERR_OUT_OF_MEMORY = -7
+} RmStatus;
+
+/* ---- scene PODs: field-for-field mirrors of the reference structs (all f64) ------------------ */
+
+/* engine/src/shapes.rs:21-32  struct Reflectance */
+typedef struct RmReflectance {
+    double  diffusion;
+    double  diffuse_color[3];
+    double  specular;
+    double  specular_exponent;
+    int32_t is_glass_like;
+    double  reflection;
+    double  refractive_index;
+} RmReflectance;
+
+/* engine/src/sphere.rs:6-11  struct Sphere (bounding_box is dead on the hot path) */
+typedef struct RmSphere {
+    double        center[3];
+    double        radius_square;
+    RmReflectance reflectance;
+} RmSphere;
+
+/* engine/src/polygon.rs:6-12  struct ConvexPolygon; vertices live in RmFlatScene.polygon_vertices */
+typedef struct RmPolygon {
+    int32_t       first_vertex;
+    int32_t       n_vertices;
+    double        plane_normal[3];
+    double        plane_point[3];
+    RmReflectance reflectance;
+} RmPolygon;
+
+/* engine/src/triangle.rs:6-10  struct Triangle (vertices, precomputed normal and center) */
+typedef struct RmTriangle {
+    double vertices[9];
+    double normal[3];
+    double center[3];
+} RmTriangle;
+
+/* engine/src/obj.rs:14-20  struct Obj: a run of triangles + their per-triangle reflectances */
+typedef struct RmObj {
+    int32_t first_triangle;
+    int32_t n_triangles;
+} RmObj;
+
+/* engine/src/lights.rs:4-8  struct Light (color already L-inf normalised by create_light) */
+typedef struct RmLight {
+    double position[3];
+    double color[3];
+    double intensity;
+} RmLight;
+
+typedef enum RmShapeKind { RM_SHAPE_SPHERE = 0, RM_SHAPE_POLYGON = 1, RM_SHAPE_OBJ = 2 } RmShapeKind;
+
+/* one entry of Scene.shapes (engine/src/scene.rs:11), in scene order */
+typedef struct RmShapeRef {
+    int32_t kind;    /* RmShapeKind */
+    int32_t index;   /* into spheres / polygons / objs */
+} RmShapeRef;
+
+/* engine/src/scene.rs:9-13  struct Scene, flattened.  All arrays are host memory owned by the
+ * caller and are copied by rm_scene_upload().  The primitive id reported by rm_render is the index
+ * in the list obtained by walking `shapes` in order, an Obj counting once per triangle. */
+typedef struct RmFlatScene {
+    int32_t              n_shapes;
+    const RmShapeRef*    shapes;
+    int32_t              n_spheres;
+    const RmSphere*      spheres;
+    int32_t              n_polygons;
+    const RmPolygon*     polygons;
+    int32_t              n_polygon_vertices;
+    const double*        polygon_vertices;        /* xyz triples */
+    int32_t              n_objs;
+    const RmObj*         objs;
+    int32_t              n_triangles;
+    const RmTriangle*    triangles;
+    const RmReflectance* triangle_reflectances;   /* n_triangles entries (obj.rs:17) */
+    int32_t              n_lights;
+    const RmLight*       lights;
+} RmFlatScene;
+
+typedef enum RmPrecision {
+    RM_FP32 = 0,   /* production kernels: FP32 CUDA cores                                          */
+    RM_FP64 = 1    /* validation kernels: the reference's f64 arithmetic, operation for operation */
+} RmPrecision;
+
+/* Per-frame parameters.  rm_params_default() fills in the constants the reference hard-codes. */
+typedef struct RmParams {
+    int32_t width;            /* FrameBuffer.width  (framebuffer.rs:7); multiple of patch_size      */
+    int32_t height;           /* FrameBuffer.height (framebuffer.rs:8)                              */
+    double  fov;              /* create_renderer(fov, ..) radians (renderer.rs:25, main.rs:368: 1.5)*/
+    double  camera[3];        /* Scene.camera (scene.rs:12)                                         */
+    int32_t max_depth;        /* cast_ray depth cap, renderer.rs:262: 3                             */
+    double  background;       /* renderer.rs:40-44: 0.1                                             */
+    int32_t patch_size;       /* renderer.rs:47: 32 (only 32 is supported)                          */
+    int32_t precision;        /* RmPrecision                                                        */
+    int32_t patch_row_begin;  /* row tile of this call, in patch rows; [0, -1) = every rendered row */
+    int32_t patch_row_end;
+    int32_t cull_backfacing;  /* drop planar primitives that can never pass the reference's z-only
+                                 inside test (projected winding not CCW); 0 = keep all             */
+} RmParams;
+
+/* Event counters (same definitions as SURVEY.md 8d) + timings of one call. */
+typedef struct RmStats {
+    uint64_t pixels, closest_segments, anyhit_segments;
+    uint64_t sphere_tests, sphere_disc, sphere_hits;
+    uint64_t plane_tests, plane_dist, plane_point, edge_tests;
+    uint64_t cand_dist, hits, light_evals, lit_lights;
+    uint64_t glass_hits, reflections, refractions;
+    double   max_value;       /* FrameBuffer::normalize's max (framebuffer.rs:59-69) over rendered rows */
+    double   ms_render;       /* device time of the render kernel(s), CUDA events                       */
+    double   ms_total;        /* device time of the whole call incl. copies                             */
+    int32_t  kernel_launches; /* kernels launched by this call                                          */
+    int32_t  resident_prims;  /* primitives actually traced (after culling)                             */
+} RmStats;
+
+typedef int64_t RmScene;   /* opaque handle, > 0 */
+
+/* ---- lifecycle --------------------------------------------------------------------------------- */
+int         rm_abi_version(void);
+int         rm_init(int device);            /* binds the calling process to CUDA device `device` */
+void        rm_shutdown(void);
+const char* rm_last_error(void);
+int         rm_device_info(char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz);
+void        rm_params_default(RmParams* p, int width, int height);
+void        rm_reflectance_default(RmReflectance* r);     /* shapes.rs:50-60 */
+
+/* ---- scene ------------------------------------------------------------------------------------- */
+int rm_scene_upload(const RmFlatScene* scene, RmScene* out_handle);
+int rm_scene_free(RmScene handle);
+int rm_scene_num_prims(RmScene handle);
+
+/* ---- the hot path, host buffers (what Renderer::render binds) -------------------------------- *
+ * Renders patch rows [patch_row_begin, patch_row_end) and copies the results to HOST memory.
+ *   out_rgb     H*W*3 floats (RM_FP32) row-major RGB, or NULL.  Only rendered rows are written;
+ *               the rest of the buffer is left untouched like frame.buffer in the reference.
+ *   out_prim_id H*W int32: primitive hit by the primary ray, -1 = miss; or NULL.
+ *   out_rgb8    H*W*3 bytes: normalize() + to_vec() of the rendered tile (framebuffer.rs:40-82),
+ *               normalised by this call's own max; or NULL.
+ *   stats       optional; counters are only collected when stats->pixels is set to 1 on entry
+ *               (instrumented kernel, slower), timings always.
+ * Host buffers may be pageable; pinned ones (rm_host_alloc / rm_host_register) copy faster. */
+int rm_render(RmScene scene, const RmParams* params, float* out_rgb, int32_t* out_prim_id,
+              uint8_t* out_rgb8, RmStats* stats);
+/* Same with RM_FP64 arithmetic and a double framebuffer (validation mode). */
+int rm_render_f64(RmScene scene, const RmParams* params, double* out_rgb, int32_t* out_prim_id,
+                  uint8_t* out_rgb8, RmStats* stats);
+
+/* ---- the hot path, device buffers (no copies; for callers that keep frames in HBM) ----------- *
+ * d_rgb: device float (RM_FP32) or double (RM_FP64) H*W*3; d_prim_id optional; d_max: device
+ * scalar of the same type as d_rgb that receives max(previous value, tile max) -- zero it first.
+ * `stream` is a cudaStream_t (NULL = default stream).  Asynchronous. */
+int rm_render_device(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id,
+                     void* d_max, void* stream);
+/* Instrumented variant of rm_render_device: also accumulates the event counters (synchronous). */
+int rm_render_device_stats(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id,
+                           void* d_max, void* stream, RmStats* stats);
+/* FrameBuffer::normalize + to_vec on device (framebuffer.rs:40-82) for rows of this tile:
+ * d_rgb8[y][x][c] = (u8)(255*clamp(d_rgb*(1/max),0,1)); d_rgb8 may be a peer-mapped pointer of
+ * another GPU (fused gather).  normalise=0 gives the un-normalised display path (main.rs:337). */
+int rm_tonemap_device(const RmParams* params, const void* d_rgb, const void* d_max, int normalise,
+                      uint8_t* d_rgb8, void* stream);
+
+/* ---- pinned host memory helpers ---------------------------------------------------------------- */
+void* rm_host_alloc(size_t bytes);
+void  rm_host_free(void* p);
+int   rm_host_register(void* p, size_t bytes);
+int   rm_host_unregister(void* p);
+
+/* ---- FP32 peak probe: a pure-FFMA kernel, returns measured TFLOP/s (roofline denominator) ----- */
+int rm_measure_fp32_peak(double* out_tflops, double* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RM_B200_H */

@@ -91,6 +91,7 @@ def lib():
     L.orc_reflect_ray.argtypes = [d3, d3, d3, C.c_double, d3, d3]
     L.orc_refract_ray.argtypes = [d3, d3, d3, C.c_double, d3, d3]
     L.orc_triangle_intersect.argtypes = [d3, d3, d3, d3, d3]
+    L.orc_last_degenerate_hits.restype = C.c_uint64
     L.orc_sphere_intersect.argtypes = [d3, C.c_double, d3, d3, d3, d3]
     _lib = L
     return L
@@ -207,7 +208,8 @@ def render(scene, width, height, fov=1.5, max_depth=3, threads=None, patch_rows=
                           C.byref(cnt) if want_counters else None)
     if rc != 0:
         raise ValueError("oracle: width must be a positive multiple of 32 (renderer.rs:107)")
-    return {"rgb": rgb, "prim_id": ids, "fragile": frag, "counters": cnt.as_dict() if want_counters else None}
+    return {"rgb": rgb, "prim_id": ids, "fragile": frag, "counters": cnt.as_dict() if want_counters else None,
+            "degenerate_hits": int(lib().orc_last_degenerate_hits())}
 
 
 def normalize(rgb):

@@ -109,6 +109,8 @@ int    orc_triangle_intersect(const double verts[9], const double orig[3], const
                               double out_point[3], double out_normal[3]);   /* triangle.rs:33-83 */
 int    orc_sphere_intersect(const double center[3], double radius, const double orig[3],
                             const double dir[3], double out_point[3], double out_normal[3]); /* sphere.rs:27-61 */
+/* hits on degenerate-projection planar primitives during the last instrumented orc_render (see rm_oracle.cpp) */
+uint64_t orc_last_degenerate_hits(void);
 int    orc_hardware_threads(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,433 @@
+// rm_api.cu -- implementation of the C ABI declared in include/rm_b200.h.
+//
+// One process drives one GPU (rm_init(device)).  Scenes are packed on the host (rm_scene.cpp),
+// uploaded once and stay resident in HBM; per-frame scratch (float framebuffer, primitive ids,
+// RGB8, the max scalar, counters) is cached across calls so the steady-state path allocates
+// nothing.  There is no CPU fallback anywhere in this file: every entry point either runs the
+// CUDA kernels or returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rm_b200.h"
+#include "rm_kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return (e == cudaErrorMemoryAllocation) ? RM_ERR_OUT_OF_MEMORY : RM_ERR_CUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call);      \
+    } while (0)
+
+template <typename R> struct DevicePack {
+    bool ready = false;
+    void* blob = nullptr;
+    void* mat_a = nullptr;
+    void* mat_b = nullptr;
+    int* mat_f = nullptr;
+    int* order[2] = {nullptr, nullptr};
+    int* order_shape[2] = {nullptr, nullptr};
+    rm::DeviceScene<R> ds;
+    void release() {
+        cudaFree(blob); cudaFree(mat_a); cudaFree(mat_b); cudaFree(mat_f);
+        for (int i = 0; i < 2; i++) { cudaFree(order[i]); cudaFree(order_shape[i]); }
+        *this = DevicePack<R>();
+    }
+};
+
+struct SceneEntry {
+    rm::OwnedFlatScene flat;
+    int n_prims = 0;
+    DevicePack<float> f32;
+    DevicePack<double> f64;
+};
+
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return RM_OK;
+        cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        CK(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return RM_OK;
+    }
+    void release() { cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    cudaDeviceProp prop{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::map<RmScene, SceneEntry> scenes;
+    RmScene next_handle = 1;
+    Scratch rgb, prim, rgb8, small;   // small: [0,8) max scalar, [64, 64+17*8) counters
+    std::mutex mu;
+};
+Context g;
+
+template <typename T> int upload_vec(const std::vector<T>& v, void** out) {
+    *out = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    CK(cudaMalloc(out, bytes));
+    if (!v.empty()) CK(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return RM_OK;
+}
+
+template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
+    if (dp.ready) return RM_OK;
+    rm::PackedScene<R> ps;
+    std::string err;
+    RmFlatScene fs = se.flat.view();
+    int rc = rm::pack_scene<R>(fs, ps, err);
+    if (rc != RM_OK) return fail(rc, err);
+    if ((rc = upload_vec(ps.blob, &dp.blob)) != RM_OK) return rc;   // BlobChunk = 32 bytes each
+    if ((rc = upload_vec(ps.mat_a, &dp.mat_a)) != RM_OK) return rc;
+    if ((rc = upload_vec(ps.mat_b, &dp.mat_b)) != RM_OK) return rc;
+    if ((rc = upload_vec(ps.mat_f, (void**)&dp.mat_f)) != RM_OK) return rc;
+    for (int i = 0; i < 2; i++) {
+        if ((rc = upload_vec(ps.order[i], (void**)&dp.order[i])) != RM_OK) return rc;
+        if ((rc = upload_vec(ps.order_shape[i], (void**)&dp.order_shape[i])) != RM_OK) return rc;
+        dp.ds.order[i] = dp.order[i];
+        dp.ds.order_shape[i] = dp.order_shape[i];
+        dp.ds.n_order[i] = (int)ps.order[i].size();
+    }
+    dp.ds.blob = static_cast<const unsigned char*>(dp.blob);
+    dp.ds.lay = ps.lay;
+    dp.ds.mat_a = static_cast<const rm::R4<R>*>(dp.mat_a);
+    dp.ds.mat_b = static_cast<const rm::R4<R>*>(dp.mat_b);
+    dp.ds.mat_f = dp.mat_f;
+    se.n_prims = ps.n_prims;
+    dp.ready = true;
+    return RM_OK;
+}
+
+template <typename R> DevicePack<R>& pack_of(SceneEntry& se);
+template <> DevicePack<float>& pack_of<float>(SceneEntry& se) { return se.f32; }
+template <> DevicePack<double>& pack_of<double>(SceneEntry& se) { return se.f64; }
+
+int check_params(const RmParams* p) {
+    if (!p) return fail(RM_ERR_INVALID_ARGUMENT, "params is null");
+    if (p->width <= 0 || p->height <= 0) return fail(RM_ERR_INVALID_ARGUMENT, "width and height must be positive");
+    if (p->patch_size != 32) return fail(RM_ERR_INVALID_ARGUMENT, "only patch_size 32 is supported (renderer.rs:47)");
+    if (p->width % p->patch_size != 0)
+        return fail(RM_ERR_DIMENSIONS, "Dimensions mismatch: width must be a multiple of 32 (renderer.rs:49-51,107)");
+    if (p->max_depth < 0 || p->max_depth > rm::kMaxDepth) return fail(RM_ERR_INVALID_ARGUMENT, "max_depth must be in [0, 8]");
+    return RM_OK;
+}
+
+void fill_counters(RmStats* st, const unsigned long long* c) {
+    uint64_t* dst = &st->pixels;
+    for (int i = 0; i < rm::C_COUNT; i++) dst[i] = c[i];
+}
+
+template <typename R>
+int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_prim, R* d_max, cudaStream_t stream,
+                       int buf_row0_is_tile, unsigned long long* d_counters, rm::FrameParams<R>* out_fp, int* resident) {
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
+    int rc = check_params(params);
+    if (rc != RM_OK) return rc;
+    auto it = g.scenes.find(scene);
+    if (it == g.scenes.end()) return fail(RM_ERR_INVALID_ARGUMENT, "unknown scene handle");
+    DevicePack<R>& dp = pack_of<R>(it->second);
+    if ((rc = ensure_pack<R>(it->second, dp)) != RM_OK) return rc;
+    rm::FrameParams<R> fp = rm::make_frame_params<R>(*params);
+    fp.buf_row0 = buf_row0_is_tile ? fp.row_begin : 0;
+    if (out_fp) *out_fp = fp;
+    const bool cull = params->cull_backfacing != 0;
+    if (resident) *resident = dp.ds.lay.n_sph + rm::plane_count<R>(dp.ds.lay, cull);
+    CK(rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, stream));
+    return RM_OK;
+}
+
+template <typename R>
+int render_host_impl(RmScene scene, const RmParams* params, R* out_rgb, int32_t* out_prim, uint8_t* out_rgb8, RmStats* stats) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
+    int rc = check_params(params);
+    if (rc != RM_OK) return rc;
+    const bool want_counters = stats && stats->pixels == 1;
+    rm::FrameParams<R> fp = rm::make_frame_params<R>(*params);
+    const size_t rows = (size_t)(fp.row_end - fp.row_begin);
+    const size_t n_px = rows * (size_t)fp.width;
+    if ((rc = g.rgb.ensure(std::max<size_t>(n_px * 3 * sizeof(R), 16))) != RM_OK) return rc;
+    if (out_prim && (rc = g.prim.ensure(std::max<size_t>(n_px * sizeof(int), 16))) != RM_OK) return rc;
+    if (out_rgb8 && (rc = g.rgb8.ensure(std::max<size_t>(n_px * 3, 16))) != RM_OK) return rc;
+    if ((rc = g.small.ensure(1024)) != RM_OK) return rc;
+    R* d_max = static_cast<R*>(g.small.p);
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(static_cast<char*>(g.small.p) + 64);
+    cudaStream_t s = g.stream;
+
+    CK(cudaEventRecord(g.ev[0], s));
+    CK(cudaMemsetAsync(g.small.p, 0, 1024, s));
+    CK(cudaEventRecord(g.ev[1], s));
+    int resident = 0;
+    rc = render_device_impl<R>(scene, params, static_cast<R*>(g.rgb.p), out_prim ? static_cast<int*>(g.prim.p) : nullptr,
+                               d_max, s, 1, want_counters ? d_cnt : nullptr, &fp, &resident);
+    if (rc != RM_OK) return rc;
+    CK(cudaEventRecord(g.ev[2], s));
+    int launches = rows ? 1 : 0;
+    const size_t first_px = (size_t)fp.row_begin * fp.width;
+    if (out_rgb8 && rows) {
+        CK(rm::launch_tonemap<R>(fp, static_cast<const R*>(g.rgb.p), d_max, true, static_cast<unsigned char*>(g.rgb8.p), s));
+        launches++;
+    }
+    if (out_rgb && rows) CK(cudaMemcpyAsync(out_rgb + first_px * 3, g.rgb.p, n_px * 3 * sizeof(R), cudaMemcpyDeviceToHost, s));
+    if (out_prim && rows) CK(cudaMemcpyAsync(out_prim + first_px, g.prim.p, n_px * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (out_rgb8 && rows) CK(cudaMemcpyAsync(out_rgb8 + first_px * 3, g.rgb8.p, n_px * 3, cudaMemcpyDeviceToHost, s));
+    unsigned char small_host[1024];
+    if (stats) CK(cudaMemcpyAsync(small_host, g.small.p, 64 + rm::C_COUNT * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(g.ev[3], s));
+    CK(cudaStreamSynchronize(s));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        if (want_counters) fill_counters(stats, reinterpret_cast<const unsigned long long*>(small_host + 64));
+        R mx;
+        std::memcpy(&mx, small_host, sizeof(R));
+        stats->max_value = (double)mx;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]));
+        stats->ms_render = ms;
+        CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[3]));
+        stats->ms_total = ms;
+        stats->kernel_launches = launches;
+        stats->resident_prims = resident;
+    }
+    return RM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rm_abi_version(void) { return RM_ABI_VERSION; }
+
+const char* rm_last_error(void) { return g_err.c_str(); }
+
+int rm_init(int device) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (g.ready && g.device == device) return RM_OK;
+    if (g.ready) return fail(RM_ERR_INVALID_ARGUMENT, "already initialised on another device; call rm_shutdown() first");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_err = std::string("no CUDA device available: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                " -- this library has no CPU fallback";
+        return RM_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) return fail(RM_ERR_NO_DEVICE, "device ordinal out of range");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail_cuda(e, "cudaSetDevice"), RM_ERR_NO_DEVICE;
+    if ((e = cudaGetDeviceProperties(&g.prop, device)) != cudaSuccess) return fail_cuda(e, "cudaGetDeviceProperties"), RM_ERR_NO_DEVICE;
+    if (g.prop.major != 10) {
+        char buf[256];
+        std::snprintf(buf, sizeof buf, "device %d (%s) is sm_%d%d; the kernels are built for sm_100a only", device, g.prop.name,
+                      g.prop.major, g.prop.minor);
+        return fail(RM_ERR_NO_DEVICE, buf);
+    }
+    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    for (auto& ev : g.ev) CK(cudaEventCreate(&ev));
+    g.device = device;
+    g.ready = true;
+    return RM_OK;
+}
+
+void rm_shutdown(void) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return;
+    cudaSetDevice(g.device);
+    cudaDeviceSynchronize();
+    for (auto& kv : g.scenes) { kv.second.f32.release(); kv.second.f64.release(); }
+    g.scenes.clear();
+    g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release();
+    for (auto& ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    if (g.stream) cudaStreamDestroy(g.stream);
+    g.stream = nullptr;
+    g.ready = false;
+    g.device = -1;
+}
+
+int rm_device_info(char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz) {
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    if (name && name_len > 0) { std::strncpy(name, g.prop.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = g.prop.multiProcessorCount;
+    if (cc_major) *cc_major = g.prop.major;
+    if (cc_minor) *cc_minor = g.prop.minor;
+    if (clock_khz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g.device);
+        *clock_khz = khz;
+    }
+    return RM_OK;
+}
+
+void rm_params_default(RmParams* p, int width, int height) {
+    std::memset(p, 0, sizeof(*p));
+    p->width = width;
+    p->height = height;
+    p->fov = 1.5;            // main.rs:368
+    p->max_depth = 3;        // renderer.rs:262
+    p->background = 0.1;     // renderer.rs:40-44
+    p->patch_size = 32;      // renderer.rs:47
+    p->precision = RM_FP32;
+    p->patch_row_begin = 0;
+    p->patch_row_end = -1;
+    p->cull_backfacing = 1;
+}
+
+int rm_scene_upload(const RmFlatScene* scene, RmScene* out_handle) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
+    if (!scene || !out_handle) return fail(RM_ERR_INVALID_ARGUMENT, "scene or out_handle is null");
+    std::string err;
+    int rc = rm::validate_scene(*scene, err);
+    if (rc != RM_OK) return fail(rc, err);
+    SceneEntry se;
+    se.flat.assign(*scene);
+    if ((rc = ensure_pack<float>(se, se.f32)) != RM_OK) { se.f32.release(); return rc; }
+    RmScene h = g.next_handle++;
+    g.scenes.emplace(h, std::move(se));
+    *out_handle = h;
+    return RM_OK;
+}
+
+int rm_scene_free(RmScene handle) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    auto it = g.scenes.find(handle);
+    if (it == g.scenes.end()) return fail(RM_ERR_INVALID_ARGUMENT, "unknown scene handle");
+    cudaDeviceSynchronize();
+    it->second.f32.release();
+    it->second.f64.release();
+    g.scenes.erase(it);
+    return RM_OK;
+}
+
+int rm_scene_num_prims(RmScene handle) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    auto it = g.scenes.find(handle);
+    if (it == g.scenes.end()) return fail(RM_ERR_INVALID_ARGUMENT, "unknown scene handle");
+    return it->second.n_prims;
+}
+
+int rm_render(RmScene scene, const RmParams* params, float* out_rgb, int32_t* out_prim_id, uint8_t* out_rgb8, RmStats* stats) {
+    if (params && params->precision != RM_FP32) return fail(RM_ERR_INVALID_ARGUMENT, "rm_render computes in RM_FP32; use rm_render_f64 for RM_FP64");
+    return render_host_impl<float>(scene, params, out_rgb, out_prim_id, out_rgb8, stats);
+}
+
+int rm_render_f64(RmScene scene, const RmParams* params, double* out_rgb, int32_t* out_prim_id, uint8_t* out_rgb8, RmStats* stats) {
+    return render_host_impl<double>(scene, params, out_rgb, out_prim_id, out_rgb8, stats);
+}
+
+int rm_render_device(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id, void* d_max, void* stream) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!d_rgb || !d_max) return fail(RM_ERR_INVALID_ARGUMENT, "d_rgb and d_max must be device pointers");
+    if (params && params->precision == RM_FP64)
+        return render_device_impl<double>(scene, params, static_cast<double*>(d_rgb), d_prim_id, static_cast<double*>(d_max),
+                                          static_cast<cudaStream_t>(stream), 0, nullptr, nullptr, nullptr);
+    return render_device_impl<float>(scene, params, static_cast<float*>(d_rgb), d_prim_id, static_cast<float*>(d_max),
+                                     static_cast<cudaStream_t>(stream), 0, nullptr, nullptr, nullptr);
+}
+
+int rm_render_device_stats(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id, void* d_max, void* stream,
+                           RmStats* stats) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!d_rgb || !d_max || !stats) return fail(RM_ERR_INVALID_ARGUMENT, "d_rgb, d_max and stats are required");
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    int rc;
+    if ((rc = g.small.ensure(1024)) != RM_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(static_cast<char*>(g.small.p) + 64);
+    CK(cudaMemsetAsync(d_cnt, 0, rm::C_COUNT * 8, s));
+    int resident = 0;
+    if (params && params->precision == RM_FP64)
+        rc = render_device_impl<double>(scene, params, static_cast<double*>(d_rgb), d_prim_id, static_cast<double*>(d_max), s, 0,
+                                        d_cnt, nullptr, &resident);
+    else
+        rc = render_device_impl<float>(scene, params, static_cast<float*>(d_rgb), d_prim_id, static_cast<float*>(d_max), s, 0,
+                                       d_cnt, nullptr, &resident);
+    if (rc != RM_OK) return rc;
+    unsigned long long host[rm::C_COUNT];
+    CK(cudaMemcpyAsync(host, d_cnt, sizeof host, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::memset(stats, 0, sizeof(*stats));
+    fill_counters(stats, host);
+    stats->kernel_launches = 1;
+    stats->resident_prims = resident;
+    return RM_OK;
+}
+
+int rm_tonemap_device(const RmParams* params, const void* d_rgb, const void* d_max, int normalise, uint8_t* d_rgb8, void* stream) {
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    int rc = check_params(params);
+    if (rc != RM_OK) return rc;
+    if (!d_rgb || !d_rgb8 || (normalise && !d_max)) return fail(RM_ERR_INVALID_ARGUMENT, "null device pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (params->precision == RM_FP64) {
+        auto fp = rm::make_frame_params<double>(*params);
+        CK(rm::launch_tonemap<double>(fp, static_cast<const double*>(d_rgb), static_cast<const double*>(d_max), normalise != 0, d_rgb8, s));
+    } else {
+        auto fp = rm::make_frame_params<float>(*params);
+        CK(rm::launch_tonemap<float>(fp, static_cast<const float*>(d_rgb), static_cast<const float*>(d_max), normalise != 0, d_rgb8, s));
+    }
+    return RM_OK;
+}
+
+void* rm_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void rm_host_free(void* p) { if (p) cudaFreeHost(p); }
+int rm_host_register(void* p, size_t bytes) {
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return RM_OK;
+}
+int rm_host_unregister(void* p) {
+    CK(cudaHostUnregister(p));
+    return RM_OK;
+}
+
+int rm_measure_fp32_peak(double* out_tflops, double* out_ms) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    const int blocks = g.prop.multiProcessorCount * 8;
+    const int iters = 1 << 15;
+    int rc;
+    if ((rc = g.rgb.ensure((size_t)blocks * 256 * sizeof(float))) != RM_OK) return rc;
+    double flops = 0;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {          // first repetition warms up
+        CK(cudaEventRecord(g.ev[0], g.stream));
+        CK(rm::launch_ffma_probe(static_cast<float*>(g.rgb.p), iters, blocks, g.stream, &flops));
+        CK(cudaEventRecord(g.ev[1], g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    if (out_ms) *out_ms = best;
+    if (out_tflops) *out_tflops = flops / (best * 1e-3) / 1e12;
+    return RM_OK;
+}
+
+}  // extern "C"

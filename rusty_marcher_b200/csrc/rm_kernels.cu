@@ -1,0 +1,226 @@
+// rm_kernels.cu -- hand-written sm_100a kernels of the render hot path.
+//
+// K1 render_kernel   replaces the Rayon loop over 32x32 patches and everything under it:
+//                    engine/src/renderer.rs:63-89,128-309, shapes.rs:92-143, sphere.rs:27-61,
+//                    triangle.rs:49-83, polygon.rs:60-98, obj.rs:186-216, optics.rs:4-89.
+//                    One thread per pixel, a warp owns an 8x4 pixel tile, a CTA a 32x8 tile (so a
+//                    reference patch is four CTAs and tile edges coincide with patch edges).  The
+//                    scene's hot blob is staged once per CTA into shared memory with 128-bit
+//                    copies and every lane of a warp reads the same primitive (broadcast, no bank
+//                    conflicts).  The per-CTA channel maximum needed by FrameBuffer::normalize
+//                    (framebuffer.rs:58-69) is fused in: warp shuffle -> shared -> one atomicMax.
+// K4 tonemap_kernel  FrameBuffer::normalize + to_vec + quantize (framebuffer.rs:40-82): 16 values
+//                    per thread, 128-bit loads, one 128-bit store of packed RGB8.
+// ffma_probe         measures the FP32 FMA issue peak that the roofline fraction is quoted against.
+//
+// No tensor cores: the work is ray/primitive predicates and shading, not a dense contraction.
+// Compiled with -fmad=false: FP32 code states its FMAs explicitly (rm_math.cuh), FP64 code must not
+// fuse at all to stay bit-faithful to the reference.
+#include "rm_kernels.h"
+
+namespace rm {
+
+namespace {
+
+constexpr int kBlock = 256;          // 8 warps: 4 across x 2 down, each an 8x4 pixel tile
+constexpr int kTileW = 32, kTileH = 8;
+constexpr int kSmemLimit = 200 * 1024;
+
+template <typename R>
+__device__ __forceinline__ SceneView<R> make_view(const DeviceScene<R>& ds, const unsigned char* base, int cull) {
+    SceneView<R> sc;
+    const BlobLayout& L = ds.lay;
+    sc.sph = reinterpret_cast<const R4<R>*>(base + L.off_sph);
+    sc.sph_id = reinterpret_cast<const int*>(base + L.off_sph_id);
+    sc.n_sph = L.n_sph;
+    sc.pln_n = reinterpret_cast<const R4<R>*>(base + L.off_pln_n);
+    sc.pln_c = reinterpret_cast<const R4<R>*>(base + L.off_pln_c);
+    sc.pln_v = reinterpret_cast<const I2*>(base + L.off_pln_v);
+    sc.pln_id = reinterpret_cast<const int*>(base + L.off_pln_id);
+    sc.n_pln = plane_count<R>(L, cull != 0);
+    sc.vert = reinterpret_cast<const VertT<R>*>(base + L.off_vert);
+    sc.mat_a = ds.mat_a;
+    sc.mat_b = ds.mat_b;
+    sc.mat_f = ds.mat_f;
+    sc.lgt_p = reinterpret_cast<const R4<R>*>(base + L.off_lgt_p);
+    sc.lgt_c = reinterpret_cast<const R4<R>*>(base + L.off_lgt_c);
+    sc.n_lgt = L.n_lgt;
+    sc.order = ds.order[cull];
+    sc.order_shape = ds.order_shape[cull];
+    sc.n_order = ds.n_order[cull];
+    return sc;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));            // v >= 0: int order == float order
+}
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+template <typename R, bool S>
+__global__ void __launch_bounds__(kBlock)
+render_kernel(const DeviceScene<R> ds, const FrameParams<R> fp, const int cull, const int use_smem,
+              R* __restrict__ rgb, int* __restrict__ prim_id, R* __restrict__ dmax,
+              unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    __shared__ R warp_max[kBlock / 32];
+
+    const unsigned char* base = ds.blob;
+    if (use_smem) {
+        const uint4* src = reinterpret_cast<const uint4*>(ds.blob);
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+        for (int i = threadIdx.x; i < ds.lay.bytes / 16; i += kBlock) dst[i] = __ldg(src + i);
+        __syncthreads();
+        base = smem_raw;
+    }
+    const SceneView<R> sc = make_view<R>(ds, base, cull);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = blockIdx.x * kTileW + (warp & 3) * 8 + (lane & 7);
+    const int y = fp.row_begin + blockIdx.y * kTileH + (warp >> 2) * 4 + (lane >> 3);
+
+    Counters<S> st;
+    st.clear();
+
+    R m = R(0);
+    if (x < fp.width && y < fp.row_end) {
+        st.add(C_PIXELS);
+        int pid;
+        const Vec3<R> dir = backproject<R>(fp, x, y);
+        const Vec3<R> c = cast_ray<R, S>(sc, fp.camera, dir, fp.background, fp.max_depth, pid, st);
+        const size_t px = (size_t)(y - fp.buf_row0) * fp.width + x;
+        rgb[3 * px] = c.x;
+        rgb[3 * px + 1] = c.y;
+        rgb[3 * px + 2] = c.z;
+        if (prim_id) prim_id[px] = pid;
+        m = Num<R>::max_(Num<R>::max_(Num<R>::max_(c.x, c.y), c.z), R(0));
+    }
+
+    // fused K3: channel maximum of the tile (framebuffer.rs:58-69)
+    for (int off = 16; off > 0; off >>= 1) m = Num<R>::max_(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) warp_max[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kBlock / 32; w++) m = Num<R>::max_(m, warp_max[w]);
+        if (m > R(0)) atomic_max_nonneg(dmax, m);
+    }
+
+    if (S) {
+        const unsigned* c = reinterpret_cast<const unsigned*>(&st);
+        for (int i = 0; i < C_COUNT; i++) {
+            unsigned v = c[i];
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0 && v) atomicAdd(counters + i, (unsigned long long)v);
+        }
+    }
+}
+
+template <typename R> struct Tone;
+template <> struct Tone<float> {
+    static __device__ __forceinline__ unsigned q(float v, float inv) {
+        return (unsigned)(unsigned char)(255.f * fminf(fmaxf(v * inv, 0.f), 1.f));     // framebuffer.rs:80-82
+    }
+};
+template <> struct Tone<double> {
+    static __device__ __forceinline__ unsigned q(double v, double inv) {
+        return (unsigned)(unsigned char)(255. * fmin(fmax(v * inv, 0.), 1.));
+    }
+};
+
+// 16 consecutive channel values per thread -> one 16-byte store.  Rows are W*3 values with W a
+// multiple of 32, so every thread's span is 16-byte aligned on both sides.
+template <typename R>
+__global__ void __launch_bounds__(256)
+tonemap_kernel(const R* __restrict__ rgb, const R* __restrict__ dmax, const int normalise, const size_t first,
+               const size_t count16, unsigned char* __restrict__ rgb8) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count16) return;
+    R inv = R(1);
+    if (normalise) {
+        const R mx = *dmax;
+        if (mx > R(0)) inv = R(1) / mx;                         // framebuffer.rs:71-76: scale(1. / max_val)
+    }
+    const R* src = rgb + i * 16;
+    unsigned w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        R v0, v1, v2, v3;
+        if (sizeof(R) == 4) {
+            const float4 f = __ldcs(reinterpret_cast<const float4*>(src) + k);
+            v0 = f.x; v1 = f.y; v2 = f.z; v3 = f.w;
+        } else {
+            const double2 a = __ldcs(reinterpret_cast<const double2*>(src) + 2 * k);
+            const double2 b = __ldcs(reinterpret_cast<const double2*>(src) + 2 * k + 1);
+            v0 = a.x; v1 = a.y; v2 = b.x; v3 = b.y;
+        }
+        w[k] = Tone<R>::q(v0, inv) | (Tone<R>::q(v1, inv) << 8) | (Tone<R>::q(v2, inv) << 16) | (Tone<R>::q(v3, inv) << 24);
+    }
+    reinterpret_cast<uint4*>(rgb8 + first)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(256) ffma_probe_kernel(float* __restrict__ sink, const int iters) {
+    const float b = 0.9999999f, c = 1e-7f;
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = (float)(threadIdx.x + k) * 1e-3f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = fmaf(a[k], b, c);
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = fmaf(a[k], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k];
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+template <typename R>
+cudaError_t launch_render(const DeviceScene<R>& ds, const FrameParams<R>& fp, bool cull, R* rgb, int* prim_id, R* dmax,
+                          unsigned long long* counters, cudaStream_t stream) {
+    const int rows = fp.row_end - fp.row_begin;
+    if (rows <= 0 || fp.width <= 0) return cudaSuccess;
+    const dim3 grid((fp.width + kTileW - 1) / kTileW, (rows + kTileH - 1) / kTileH);
+    const int use_smem = ds.lay.bytes <= kSmemLimit;
+    const size_t smem = use_smem ? (size_t)ds.lay.bytes : 0;
+    cudaError_t e;
+    if (counters) {
+        auto k = render_kernel<R, true>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, use_smem, rgb, prim_id, dmax, counters);
+    } else {
+        auto k = render_kernel<R, false>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, use_smem, rgb, prim_id, dmax, nullptr);
+    }
+    return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t launch_tonemap(const FrameParams<R>& fp, const R* rgb, const R* dmax, bool normalise, unsigned char* rgb8,
+                           cudaStream_t stream) {
+    const int rows = fp.row_end - fp.row_begin;
+    if (rows <= 0) return cudaSuccess;
+    // both buffers are indexed from pixel row fp.buf_row0
+    const size_t first = (size_t)(fp.row_begin - fp.buf_row0) * fp.width * 3;
+    const size_t count16 = (size_t)rows * fp.width * 3 / 16;
+    const int blocks = (int)((count16 + 255) / 256);
+    tonemap_kernel<R><<<blocks, 256, 0, stream>>>(rgb + first, dmax, normalise ? 1 : 0, first, count16, rgb8);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ffma_probe(float* sink, int iters, int blocks, cudaStream_t stream, double* flops) {
+    ffma_probe_kernel<<<blocks, 256, 0, stream>>>(sink, iters);
+    if (flops) *flops = (double)blocks * 256.0 * (double)iters * 16.0 * 2.0;
+    return cudaGetLastError();
+}
+
+template cudaError_t launch_render<float>(const DeviceScene<float>&, const FrameParams<float>&, bool, float*, int*, float*, unsigned long long*, cudaStream_t);
+template cudaError_t launch_render<double>(const DeviceScene<double>&, const FrameParams<double>&, bool, double*, int*, double*, unsigned long long*, cudaStream_t);
+template cudaError_t launch_tonemap<float>(const FrameParams<float>&, const float*, const float*, bool, unsigned char*, cudaStream_t);
+template cudaError_t launch_tonemap<double>(const FrameParams<double>&, const double*, const double*, bool, unsigned char*, cudaStream_t);
+
+}  // namespace rm

@@ -1,0 +1,36 @@
+// rm_kernels.h -- launchers of the sm_100a kernels (rm_kernels.cu), used by the C ABI (rm_api.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "rm_scene.h"
+
+namespace rm {
+
+// The packed scene in HBM (see rm_scene.h for the blob layout).
+template <typename R> struct DeviceScene {
+    const unsigned char* blob = nullptr;
+    BlobLayout lay;
+    const R4<R>* mat_a = nullptr;
+    const R4<R>* mat_b = nullptr;
+    const int* mat_f = nullptr;
+    const int* order[2] = {nullptr, nullptr};        // [0] every primitive, [1] after culling
+    const int* order_shape[2] = {nullptr, nullptr};
+    int n_order[2] = {0, 0};
+};
+
+// K1: render rows [fp.row_begin, fp.row_end).  rgb: H*W*3 of R; prim_id optional; dmax: scalar R that
+// receives max(old, tile max); counters: 17 x u64 (instrumented kernel) or null (production kernel).
+template <typename R>
+cudaError_t launch_render(const DeviceScene<R>& ds, const FrameParams<R>& fp, bool cull, R* rgb, int* prim_id, R* dmax,
+                          unsigned long long* counters, cudaStream_t stream);
+
+// K4: FrameBuffer::normalize + to_vec (framebuffer.rs:40-82) over rows [fp.row_begin, fp.row_end).
+template <typename R>
+cudaError_t launch_tonemap(const FrameParams<R>& fp, const R* rgb, const R* dmax, bool normalise, unsigned char* rgb8,
+                           cudaStream_t stream);
+
+// Pure-FFMA probe: `iters` x 16 dependent-chain FFMAs per thread on every SM; returns flop count.
+cudaError_t launch_ffma_probe(float* sink, int iters, int blocks, cudaStream_t stream, double* flops);
+
+}  // namespace rm

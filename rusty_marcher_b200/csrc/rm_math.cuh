@@ -1,0 +1,90 @@
+// rm_math.cuh -- scalar/vector helpers of the render kernels.
+//
+// Two numeric policies share one code base (template parameter R):
+//   R = double : the reference's f64 arithmetic restated operation for operation
+//                (engine/src/geometry.rs:18-182): left-to-right dot products, NO fused
+//                multiply-add (the translation unit is compiled with -fmad=false), IEEE sqrt
+//                and division.  This is the validation mode (RM_FP64).
+//   R = float  : production mode.  Every multiply-add is an explicit fmaf() so the FP32
+//                pipe issues one FFMA where the reference spends a mul and an add; nothing is
+//                left to the compiler's contraction heuristics (-fmad=false).
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RM_HD __host__ __device__ __forceinline__
+#define RM_D __device__ __forceinline__
+#else
+#define RM_HD inline
+#define RM_D inline
+#endif
+
+namespace rm {
+
+template <typename R> struct alignas(4 * sizeof(R)) R4 { R x, y, z, w; };
+template <typename R> struct alignas(2 * sizeof(R)) R2 { R x, y; };
+struct alignas(8) I2 { int x, y; };
+
+template <typename R> struct Vec3 { R x, y, z; };
+
+template <typename R> struct Num;
+
+template <> struct Num<double> {
+    static RM_HD double madd(double a, double b, double c) { return a * b + c; }     // unfused (-fmad=false)
+    static RM_HD double msub(double a, double b, double c) { return a * b - c; }
+    static RM_HD double nmadd(double a, double b, double c) { return c - a * b; }
+    static RM_HD double sqrt_(double a) { return sqrt(a); }
+    static RM_HD double abs_(double a) { return fabs(a); }
+    static RM_HD double max_(double a, double b) { return fmax(a, b); }
+    static RM_HD double pow_(double a, double b) { return pow(a, b); }
+    static RM_HD double div_(double a, double b) { return a / b; }
+    static RM_HD double rcp_(double a) { return 1. / a; }
+};
+
+template <> struct Num<float> {
+    static RM_HD float madd(float a, float b, float c) { return fmaf(a, b, c); }
+    static RM_HD float msub(float a, float b, float c) { return fmaf(a, b, -c); }
+    static RM_HD float nmadd(float a, float b, float c) { return fmaf(-a, b, c); }
+    static RM_HD float sqrt_(float a) { return sqrtf(a); }
+    static RM_HD float abs_(float a) { return fabsf(a); }
+    static RM_HD float max_(float a, float b) { return fmaxf(a, b); }
+    static RM_HD float pow_(float a, float b) { return powf(a, b); }
+    static RM_HD float div_(float a, float b) { return a / b; }
+    static RM_HD float rcp_(float a) { return 1.f / a; }
+};
+
+template <typename R> RM_HD Vec3<R> operator+(Vec3<R> a, Vec3<R> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename R> RM_HD Vec3<R> operator-(Vec3<R> a, Vec3<R> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename R> RM_HD Vec3<R> operator*(Vec3<R> a, Vec3<R> b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+template <typename R> RM_HD Vec3<R> operator-(Vec3<R> a) { return {-a.x, -a.y, -a.z}; }
+template <typename R> RM_HD Vec3<R> scaled(Vec3<R> a, R s) { return {a.x * s, a.y * s, a.z * s}; }
+
+// geometry.rs:180-182: v1.x*v2.x + v1.y*v2.y + v1.z*v2.z, left to right
+template <typename R> RM_HD R dot(Vec3<R> a, Vec3<R> b) {
+    return Num<R>::madd(a.z, b.z, Num<R>::madd(a.y, b.y, a.x * b.x));
+}
+template <> RM_HD double dot<double>(Vec3<double> a, Vec3<double> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+template <typename R> RM_HD R squared_norm(Vec3<R> a) { return dot(a, a); }
+
+// a + b*s  (e.g. orig + dir.scaled(t), sphere.rs:54)
+template <typename R> RM_HD Vec3<R> axpy(Vec3<R> a, Vec3<R> b, R s) {
+    return {Num<R>::madd(b.x, s, a.x), Num<R>::madd(b.y, s, a.y), Num<R>::madd(b.z, s, a.z)};
+}
+// a - b*s
+template <typename R> RM_HD Vec3<R> axmy(Vec3<R> a, Vec3<R> b, R s) {
+    return {Num<R>::nmadd(b.x, s, a.x), Num<R>::nmadd(b.y, s, a.y), Num<R>::nmadd(b.z, s, a.z)};
+}
+
+// geometry.rs:104-109: norm = sqrt(dot); if norm > 0 { scale(1/norm) }
+template <typename R> RM_HD Vec3<R> normalized(Vec3<R> a) {
+    R norm = Num<R>::sqrt_(dot(a, a));
+    if (norm > R(0)) a = scaled(a, Num<R>::rcp_(norm));
+    return a;
+}
+
+template <typename R> RM_HD Vec3<R> xyz(const R4<R>& v) { return {v.x, v.y, v.z}; }
+
+}  // namespace rm

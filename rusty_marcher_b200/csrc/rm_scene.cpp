@@ -1,0 +1,321 @@
+// rm_scene.cpp -- see rm_scene.h.
+#include "rm_scene.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace rm {
+
+RmFlatScene OwnedFlatScene::view() const {
+    RmFlatScene fs{};
+    fs.n_shapes = (int32_t)shapes.size();
+    fs.shapes = shapes.data();
+    fs.n_spheres = (int32_t)spheres.size();
+    fs.spheres = spheres.data();
+    fs.n_polygons = (int32_t)polygons.size();
+    fs.polygons = polygons.data();
+    fs.n_polygon_vertices = (int32_t)(polygon_vertices.size() / 3);
+    fs.polygon_vertices = polygon_vertices.data();
+    fs.n_objs = (int32_t)objs.size();
+    fs.objs = objs.data();
+    fs.n_triangles = (int32_t)triangles.size();
+    fs.triangles = triangles.data();
+    fs.triangle_reflectances = triangle_reflectances.data();
+    fs.n_lights = (int32_t)lights.size();
+    fs.lights = lights.data();
+    return fs;
+}
+
+void OwnedFlatScene::assign(const RmFlatScene& fs) {
+    shapes.assign(fs.shapes, fs.shapes + fs.n_shapes);
+    spheres.assign(fs.spheres, fs.spheres + fs.n_spheres);
+    polygons.assign(fs.polygons, fs.polygons + fs.n_polygons);
+    polygon_vertices.assign(fs.polygon_vertices, fs.polygon_vertices + 3 * (size_t)fs.n_polygon_vertices);
+    objs.assign(fs.objs, fs.objs + fs.n_objs);
+    triangles.assign(fs.triangles, fs.triangles + fs.n_triangles);
+    triangle_reflectances.assign(fs.triangle_reflectances, fs.triangle_reflectances + fs.n_triangles);
+    lights.assign(fs.lights, fs.lights + fs.n_lights);
+}
+
+int validate_scene(const RmFlatScene& fs, std::string& err) {
+    auto bad = [&](const char* m) { err = m; return (int)RM_ERR_SCENE; };
+    if (fs.n_shapes < 0 || fs.n_spheres < 0 || fs.n_polygons < 0 || fs.n_polygon_vertices < 0 || fs.n_objs < 0 ||
+        fs.n_triangles < 0 || fs.n_lights < 0)
+        return bad("negative count in RmFlatScene");
+    if ((fs.n_shapes && !fs.shapes) || (fs.n_spheres && !fs.spheres) || (fs.n_polygons && !fs.polygons) ||
+        (fs.n_polygon_vertices && !fs.polygon_vertices) || (fs.n_objs && !fs.objs) ||
+        (fs.n_triangles && (!fs.triangles || !fs.triangle_reflectances)) || (fs.n_lights && !fs.lights)) {
+        err = "null array with non-zero count in RmFlatScene";
+        return RM_ERR_INVALID_ARGUMENT;
+    }
+    for (int s = 0; s < fs.n_shapes; s++) {
+        const RmShapeRef& r = fs.shapes[s];
+        switch (r.kind) {
+            case RM_SHAPE_SPHERE:
+                if (r.index < 0 || r.index >= fs.n_spheres) return bad("shape refers to a sphere out of range");
+                break;
+            case RM_SHAPE_POLYGON: {
+                if (r.index < 0 || r.index >= fs.n_polygons) return bad("shape refers to a polygon out of range");
+                const RmPolygon& p = fs.polygons[r.index];
+                if (p.n_vertices < 3) return bad("polygon with fewer than 3 vertices (polygon.rs:18)");
+                if (p.first_vertex < 0 || p.first_vertex + p.n_vertices > fs.n_polygon_vertices)
+                    return bad("polygon vertex range out of bounds");
+                break;
+            }
+            case RM_SHAPE_OBJ: {
+                if (r.index < 0 || r.index >= fs.n_objs) return bad("shape refers to an obj out of range");
+                const RmObj& o = fs.objs[r.index];
+                if (o.n_triangles < 0 || o.first_triangle < 0 || o.first_triangle + o.n_triangles > fs.n_triangles)
+                    return bad("obj triangle range out of bounds");
+                break;
+            }
+            default:
+                return bad("unknown shape kind");
+        }
+    }
+    return RM_OK;
+}
+
+namespace {
+
+template <typename R> R pred_1e6();
+template <> double pred_1e6<double>() { return std::nextafter(1e-6, 0.); }
+template <> float pred_1e6<float>() { return std::nextafterf(1e-6f, 0.f); }
+
+int align32(int x) { return (x + 31) & ~31; }
+
+struct PlaneTmp {
+    double n[3], c[3];
+    double thr_is_triangle;
+    std::vector<double> vxy;   // x,y pairs
+    int id, shape;
+    int cls;   // 0 hittable, 1 back-facing (projected winding clockwise), 2 degenerate projection
+};
+
+// A planar primitive is hit only if every edge term ((v_i-p) x (v_i+1-p)).z is > 0
+// (triangle.rs:13-15,72-76).  Their sum over the closed polygon equals 2*signed area of the
+// XY-projected polygon for ANY p, so in exact arithmetic
+//   class 1: clockwise projected winding (area < 0)  -> some term is < 0 -> never hit;
+//   class 2: degenerate projection (normal.z == 0, area == 0) -> every term is exactly 0 for a point of
+//            the plane -> `> 0` fails -> never hit.  The reference's f64 evaluation of such a primitive
+//            is pure rounding noise with a common-mode error that keeps the three terms from being
+//            positive together (0 hits on every test scene, checked against the oracle in tests/).
+// "Degenerate" is judged at the resolution of the arithmetic that will evaluate the edge terms: for
+// f64 only an (almost) exactly zero area; for f32 also slivers whose projected area is below 1e-6 of
+// their squared perimeter (e.g. the dodecahedron faces whose normal.z is 5e-9 because tobj rounds
+// vertices to f32): their edge terms are smaller than FP32 rounding noise, and no pixel ray of any
+// test scene passes through such a sliver in the reference either.
+int classify_plane(const std::vector<double>& vxy, bool single_precision) {
+    size_t n = vxy.size() / 2;
+    double area2 = 0., scale = 0., perimeter = 0.;
+    for (size_t i = 0; i < n; i++) {
+        size_t j = (i + 1) % n;
+        area2 += vxy[2 * i] * vxy[2 * j + 1] - vxy[2 * i + 1] * vxy[2 * j];
+        scale = std::fmax(scale, std::fmax(std::fabs(vxy[2 * i]), std::fabs(vxy[2 * i + 1])));
+        perimeter += std::hypot(vxy[2 * j] - vxy[2 * i], vxy[2 * j + 1] - vxy[2 * i + 1]);
+    }
+    double tol = 1e-9 * scale * scale;
+    if (single_precision) tol = std::fmax(tol, 1e-6 * perimeter * perimeter);
+    if (area2 > tol) return 0;
+    return (area2 < -tol) ? 1 : 2;
+}
+
+template <typename R> R4<R> mk4(double x, double y, double z, double w) { return {(R)x, (R)y, (R)z, (R)w}; }
+
+// f64 layout: the reference's own operands -- plane point and the x,y of every vertex.
+void write_plane(const PlaneTmp& p, R4<double>& c4, R2<double>* vert) {
+    c4 = {p.c[0], p.c[1], p.c[2], 0.};
+    for (size_t v = 0; v < p.vxy.size() / 2; v++) vert[v] = {p.vxy[2 * v], p.vxy[2 * v + 1]};
+}
+// f32 layout: n.C and the affine edge functions about vertex 0, all folded in f64 and then rounded
+// once (see plane_intersect<float> in rm_trace.cuh).
+void write_plane(const PlaneTmp& p, R4<float>& k4, R4<float>* edge) {
+    const size_t nv = p.vxy.size() / 2;
+    const double x0 = p.vxy[0], y0 = p.vxy[1];
+    const double dn = p.c[0] * p.n[0] + p.c[1] * p.n[1] + p.c[2] * p.n[2];
+    k4 = {(float)dn, (float)x0, (float)y0, 0.f};
+    for (size_t i = 0; i < nv; i++) {
+        const size_t j = (i + 1) % nv;
+        const double ax = p.vxy[2 * i] - x0, ay = p.vxy[2 * i + 1] - y0;
+        const double bx = p.vxy[2 * j] - x0, by = p.vxy[2 * j + 1] - y0;
+        edge[i] = {(float)(ay - by), (float)(bx - ax), (float)(ax * by - ay * bx), 0.f};
+    }
+}
+
+template <typename R> void push_material(PackedScene<R>& out, const RmReflectance& r) {
+    out.mat_a.push_back(mk4<R>(r.diffuse_color[0], r.diffuse_color[1], r.diffuse_color[2], r.diffusion));
+    out.mat_b.push_back(mk4<R>(r.specular, r.specular_exponent, r.reflection, r.refractive_index));
+    out.mat_f.push_back(r.is_glass_like ? 1 : 0);
+}
+
+}  // namespace
+
+template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out, std::string& err) {
+    int rc = validate_scene(fs, err);
+    if (rc != RM_OK) return rc;
+    out = PackedScene<R>();
+
+    struct SphTmp { const RmSphere* s; int id, shape; };
+    std::vector<SphTmp> sph;
+    std::vector<PlaneTmp> pln;
+    int id = 0;
+    for (int s = 0; s < fs.n_shapes; s++) {
+        const RmShapeRef& ref = fs.shapes[s];
+        if (ref.kind == RM_SHAPE_SPHERE) {
+            const RmSphere& sp = fs.spheres[ref.index];
+            sph.push_back({&sp, id++, s});
+            push_material(out, sp.reflectance);
+        } else if (ref.kind == RM_SHAPE_POLYGON) {
+            const RmPolygon& p = fs.polygons[ref.index];
+            PlaneTmp t;
+            std::memcpy(t.n, p.plane_normal, sizeof t.n);
+            std::memcpy(t.c, p.plane_point, sizeof t.c);
+            t.thr_is_triangle = 0.;
+            for (int v = 0; v < p.n_vertices; v++) {
+                t.vxy.push_back(fs.polygon_vertices[3 * (p.first_vertex + v)]);
+                t.vxy.push_back(fs.polygon_vertices[3 * (p.first_vertex + v) + 1]);
+            }
+            t.id = id++;
+            t.shape = s;
+            t.cls = classify_plane(t.vxy, sizeof(R) == 4);
+            pln.push_back(std::move(t));
+            push_material(out, p.reflectance);
+        } else {
+            const RmObj& o = fs.objs[ref.index];
+            for (int k = 0; k < o.n_triangles; k++) {
+                const RmTriangle& tr = fs.triangles[o.first_triangle + k];
+                PlaneTmp t;
+                std::memcpy(t.n, tr.normal, sizeof t.n);
+                std::memcpy(t.c, tr.center, sizeof t.c);
+                t.thr_is_triangle = 1.;
+                for (int v = 0; v < 3; v++) {
+                    t.vxy.push_back(tr.vertices[3 * v]);
+                    t.vxy.push_back(tr.vertices[3 * v + 1]);
+                }
+                t.id = id++;
+                t.shape = s | (1 << 30);
+                t.cls = classify_plane(t.vxy, sizeof(R) == 4);
+                pln.push_back(std::move(t));
+                push_material(out, fs.triangle_reflectances[o.first_triangle + k]);
+            }
+        }
+    }
+    out.n_prims = id;
+
+    // hittable planes first, then back-facing, then degenerate (stable: scene order inside each class)
+    std::stable_sort(pln.begin(), pln.end(), [](const PlaneTmp& a, const PlaneTmp& b) { return a.cls < b.cls; });
+
+    BlobLayout& L = out.lay;
+    L.n_sph = (int)sph.size();
+    L.n_pln = (int)pln.size();
+    L.n_pln_live = 0;
+    L.n_pln_nondegenerate = 0;
+    L.n_vert = 0;
+    for (auto& p : pln) {
+        L.n_pln_live += p.cls == 0 ? 1 : 0;
+        L.n_pln_nondegenerate += p.cls != 2 ? 1 : 0;
+        L.n_vert += (int)p.vxy.size() / 2;
+    }
+    L.n_lgt = fs.n_lights;
+    int off = 0;
+    L.off_sph = off;    off = align32(off + L.n_sph * (int)sizeof(R4<R>));
+    L.off_pln_n = off;  off = align32(off + L.n_pln * (int)sizeof(R4<R>));
+    L.off_pln_c = off;  off = align32(off + L.n_pln * (int)sizeof(R4<R>));
+    L.off_vert = off;   off = align32(off + L.n_vert * (int)sizeof(VertT<R>));
+    L.off_lgt_p = off;  off = align32(off + L.n_lgt * (int)sizeof(R4<R>));
+    L.off_lgt_c = off;  off = align32(off + L.n_lgt * (int)sizeof(R4<R>));
+    L.off_pln_v = off;  off = align32(off + L.n_pln * (int)sizeof(I2));
+    L.off_sph_id = off; off = align32(off + L.n_sph * (int)sizeof(int));
+    L.off_pln_id = off; off = align32(off + L.n_pln * (int)sizeof(int));
+    L.bytes = std::max(off, 32);
+    out.blob.assign(L.bytes / 32, BlobChunk{});
+    unsigned char* b = reinterpret_cast<unsigned char*>(out.blob.data());
+    auto* b_sph = reinterpret_cast<R4<R>*>(b + L.off_sph);
+    auto* b_pn = reinterpret_cast<R4<R>*>(b + L.off_pln_n);
+    auto* b_pc = reinterpret_cast<R4<R>*>(b + L.off_pln_c);
+    auto* b_v = reinterpret_cast<VertT<R>*>(b + L.off_vert);
+    auto* b_lp = reinterpret_cast<R4<R>*>(b + L.off_lgt_p);
+    auto* b_lc = reinterpret_cast<R4<R>*>(b + L.off_lgt_c);
+    auto* b_pv = reinterpret_cast<I2*>(b + L.off_pln_v);
+    auto* b_sid = reinterpret_cast<int*>(b + L.off_sph_id);
+    auto* b_pid = reinterpret_cast<int*>(b + L.off_pln_id);
+
+    for (int i = 0; i < L.n_sph; i++) {
+        const RmSphere& s = *sph[i].s;
+        b_sph[i] = mk4<R>(s.center[0], s.center[1], s.center[2], s.radius_square);
+        b_sid[i] = sph[i].id;
+    }
+    int v0 = 0;
+    for (int i = 0; i < L.n_pln; i++) {
+        const PlaneTmp& p = pln[i];
+        R thr = (p.thr_is_triangle != 0.) ? pred_1e6<R>() : R(0);
+        b_pn[i] = {(R)p.n[0], (R)p.n[1], (R)p.n[2], thr};
+        int nv = (int)p.vxy.size() / 2;
+        b_pv[i] = {v0, nv};
+        write_plane(p, b_pc[i], b_v + v0);
+        v0 += nv;
+        b_pid[i] = p.id;
+    }
+    for (int l = 0; l < L.n_lgt; l++) {
+        const RmLight& lg = fs.lights[l];
+        b_lp[l] = mk4<R>(lg.position[0], lg.position[1], lg.position[2], lg.intensity);
+        b_lc[l] = mk4<R>(lg.color[0], lg.color[1], lg.color[2], 0.);
+    }
+
+    // scene-order lists for the instrumented kernel: sort slots by primitive id
+    std::vector<std::pair<int, std::pair<int, int>>> all;   // id -> (slot, shape)
+    for (int i = 0; i < L.n_sph; i++) all.push_back({sph[i].id, {i, sph[i].shape}});
+    for (int i = 0; i < L.n_pln; i++) all.push_back({pln[i].id, {L.n_sph + i, pln[i].shape}});
+    std::sort(all.begin(), all.end());
+    const int keep0 = plane_count<R>(L, false), keep1 = plane_count<R>(L, true);
+    for (auto& e : all) {
+        int slot = e.second.first;
+        if (slot < L.n_sph || (slot - L.n_sph) < keep0) {
+            out.order[0].push_back(slot);
+            out.order_shape[0].push_back(e.second.second);
+        }
+        if (slot < L.n_sph || (slot - L.n_sph) < keep1) {
+            out.order[1].push_back(slot);
+            out.order_shape[1].push_back(e.second.second);
+        }
+    }
+    return RM_OK;
+}
+
+template int pack_scene<float>(const RmFlatScene&, PackedScene<float>&, std::string&);
+template int pack_scene<double>(const RmFlatScene&, PackedScene<double>&, std::string&);
+
+template <typename R> FrameParams<R> make_frame_params(const RmParams& p) {
+    FrameParams<R> fp{};
+    fp.width = p.width;
+    fp.height = p.height;
+    const int patch = 32;
+    int n_rows = p.height / patch;                          // renderer.rs:53: rows >= floor(H/32)*32 are never rendered
+    int r0 = p.patch_row_begin < 0 ? 0 : p.patch_row_begin;
+    int r1 = (p.patch_row_end < 0 || p.patch_row_end > n_rows) ? n_rows : p.patch_row_end;
+    if (r0 > r1) r0 = r1;
+    fp.row_begin = r0 * patch;
+    fp.row_end = r1 * patch;
+    // renderer.rs:25-33
+    const double half_fov = std::tan(p.fov / 2.);
+    const double width = (double)p.width, height = (double)p.height;
+    const double ratio = width / height;
+    fp.width_r = (R)width;
+    fp.height_r = (R)height;
+    fp.half_fov = (R)half_fov;
+    fp.ratio = (R)ratio;
+    fp.half_w = (R)(width / 2.);
+    fp.half_h = (R)(height / 2.);
+    fp.sx = (R)(2. * half_fov * ratio / width);
+    fp.sy = (R)(-2. * half_fov / height);
+    fp.camera = {(R)p.camera[0], (R)p.camera[1], (R)p.camera[2]};
+    fp.background = (R)p.background;
+    fp.max_depth = p.max_depth < 0 ? 0 : (p.max_depth > kMaxDepth ? kMaxDepth : p.max_depth);
+    return fp;
+}
+
+template FrameParams<float> make_frame_params<float>(const RmParams&);
+template FrameParams<double> make_frame_params<double>(const RmParams&);
+
+}  // namespace rm

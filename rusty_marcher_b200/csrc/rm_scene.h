@@ -1,0 +1,71 @@
+// rm_scene.h -- host-side packing of an RmFlatScene (f64 mirrors of the reference structs)
+// into the layout the kernels read.  Pure C++ (no CUDA) so the same packer feeds the device
+// upload and the dev-time CPU emulation of the kernel code.
+//
+// HBM layout.  Everything the inner loops touch is one contiguous "hot blob" of 32-byte aligned
+// SoA arrays (so a CTA can stage it into shared memory with 128-bit copies):
+//   [sph R4 x n_sph][pln_n R4 x n_pln][pln_c R4 x n_pln][vert R2 x n_vert][lgt_p R4 x n_lgt]
+//   [lgt_c R4 x n_lgt][pln_v I2 x n_pln][sph_id int x n_sph][pln_id int x n_pln]
+// Planar primitives that can never pass the reference's z-only inside test are sorted to the end
+// (hittable | back-facing | degenerate projection) so culling is just a shorter loop.  Materials (touched once per hit) and
+// the scene-order lists of the instrumented kernel stay in plain global arrays.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "../../include/rm_b200.h"
+#include "rm_trace.cuh"
+
+namespace rm {
+
+struct BlobLayout {
+    int n_sph = 0, n_pln = 0, n_pln_live = 0, n_pln_nondegenerate = 0, n_vert = 0, n_lgt = 0;
+    int off_sph = 0, off_pln_n = 0, off_pln_c = 0, off_vert = 0, off_lgt_p = 0, off_lgt_c = 0;
+    int off_pln_v = 0, off_sph_id = 0, off_pln_id = 0;
+    int bytes = 0;
+};
+
+struct alignas(32) BlobChunk { unsigned char b[32]; };
+
+// Planar primitives traced: culling keeps the hittable class only.  Without culling the f64 kernels
+// trace everything like the reference; the f32 kernels still skip the degenerate-projection class,
+// whose edge terms are rounding noise that single precision cannot reproduce.
+template <typename R> RM_HD int plane_count(const BlobLayout& L, bool cull) {
+    return cull ? L.n_pln_live : (sizeof(R) == 4 ? L.n_pln_nondegenerate : L.n_pln);
+}
+
+template <typename R> struct PackedScene {
+    BlobLayout lay;
+    std::vector<BlobChunk> blob;      // lay.bytes bytes, 32-byte aligned
+    const unsigned char* blob_data() const { return reinterpret_cast<const unsigned char*>(blob.data()); }
+    size_t blob_bytes() const { return blob.size() * sizeof(BlobChunk); }
+    std::vector<R4<R>> mat_a, mat_b;
+    std::vector<int> mat_f;
+    // scene-order traversal lists: [0] = every primitive, [1] = after culling
+    std::vector<int> order[2], order_shape[2];
+    int n_prims = 0;
+};
+
+// Validates `fs` and packs it.  Returns RM_OK or RM_ERR_SCENE / RM_ERR_INVALID_ARGUMENT with `err` set.
+template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out, std::string& err);
+
+// Deep copy of a flat scene (the caller's arrays may go away after rm_scene_upload).
+struct OwnedFlatScene {
+    std::vector<RmShapeRef> shapes;
+    std::vector<RmSphere> spheres;
+    std::vector<RmPolygon> polygons;
+    std::vector<double> polygon_vertices;
+    std::vector<RmObj> objs;
+    std::vector<RmTriangle> triangles;
+    std::vector<RmReflectance> triangle_reflectances;
+    std::vector<RmLight> lights;
+    RmFlatScene view() const;
+    void assign(const RmFlatScene& fs);
+};
+
+int validate_scene(const RmFlatScene& fs, std::string& err);
+
+template <typename R> FrameParams<R> make_frame_params(const RmParams& p);
+
+}  // namespace rm

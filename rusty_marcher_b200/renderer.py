@@ -1,0 +1,72 @@
+"""Renderer (engine/src/renderer.rs:17-135): the drop-in for the reference's render driver.
+
+`Renderer.render(frame, scene)` keeps the reference's signature and return value (the status
+string of renderer.rs:116-121) but runs the hot path on the GPU through the C ABI (rm_render)."""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _abi
+from .geometry import Vec3f
+
+
+class Renderer:
+    def __init__(self, fov, height, width):                     # renderer.rs:25-33
+        self.fov = float(fov)
+        self.height = float(height)
+        self.width = float(width)
+        self.max_depth = 3                                      # renderer.rs:262
+        self.background = 0.1                                   # renderer.rs:40-44
+        self.cull_backfacing = True
+        self.precision = _abi.RM_FP32
+        self.last_stats = None
+
+    def params(self, frame, scene, patch_rows=(0, -1)):
+        p = _abi.RmParams()
+        _abi.load().rm_params_default(C.byref(p), frame.width, frame.height)
+        p.fov = self.fov
+        p.camera[:] = list(Vec3f.of(scene.camera))
+        p.max_depth = self.max_depth
+        p.background = self.background
+        p.precision = self.precision
+        p.patch_row_begin, p.patch_row_end = patch_rows
+        p.cull_backfacing = int(self.cull_backfacing)
+        return p
+
+    def render(self, frame, scene, prim_id=None, rgb8=None, counters=False, patch_rows=(0, -1)):
+        """Renderer::render (renderer.rs:36-126).  Fills frame.buffer rows [0, floor(H/32)*32) and
+        returns the reference's status message.  Optional outputs: prim_id (H, W) int32 array,
+        rgb8 (H, W, 3) uint8 array (normalize + to_vec done on device)."""
+        L = _abi.load()
+        _abi.init(_abi._initialised_device if _abi._initialised_device is not None else 0)
+        now = time.perf_counter()
+        patch_size = 32
+        if frame.height % patch_size != 0 or frame.width % patch_size != 0:
+            print("Dimensions mismatch")                        # renderer.rs:49-51
+        n_patches = (frame.height // patch_size) * (frame.width // patch_size)
+        print("Rendering using patches of size %d, using %d patches overall" % (patch_size, n_patches))
+        p = self.params(frame, scene, patch_rows)
+        handle = scene.device_handle()
+        stats = _abi.RmStats()
+        stats.pixels = 1 if counters else 0
+        want64 = self.precision == _abi.RM_FP64
+        want_dtype = np.float64 if want64 else np.float32
+        if frame.buffer.dtype != want_dtype or not frame.buffer.flags.c_contiguous:
+            frame.buffer = np.zeros((frame.height, frame.width, 3), dtype=want_dtype)
+        fn = L.rm_render_f64 if want64 else L.rm_render
+        _abi.check(fn(handle, C.byref(p), frame.buffer.ctypes.data,
+                      prim_id.ctypes.data if prim_id is not None else None,
+                      rgb8.ctypes.data if rgb8 is not None else None, C.byref(stats)))
+        self.last_stats = stats
+        ms_render_time = int((time.perf_counter() - now) * 1000)
+        fps = 1000. / ms_render_time if ms_render_time > 0 else float("inf")
+        pix_scale = frame.height * frame.width / 1e6
+        message = "Scene rendered in %d ms (%d fps, %.2f MP/s)" % (
+            ms_render_time, int(min(fps, 2**32 - 1)), fps * pix_scale)   # renderer.rs:116-121
+        print(message)
+        return message
+
+
+def create_renderer(fov, height, width):
+    return Renderer(fov, height, width)

@@ -1,0 +1,171 @@
+"""Scene (engine/src/scene.rs:9-211): lights, shapes and the camera position, plus the flattening
+of the shape list into the RmFlatScene PODs the C ABI consumes."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, lights, polygon, sphere
+from .geometry import Vec3f
+from .obj import REFL_DTYPE, Obj
+from .shapes import Reflectance
+
+
+class _Flat:
+    """Accumulates the arrays of an RmFlatScene and keeps them alive."""
+
+    def __init__(self):
+        self.shapes, self.spheres, self.polygons, self.polygon_vertices, self.objs = [], [], [], [], []
+        self.triangle_chunks, self.reflectance_chunks = [], []
+        self.n_triangles = 0
+        self.n_prims = 0
+        self.lights = []
+
+    def finish(self):
+        def arr(ctype, items):
+            a = (ctype * max(len(items), 1))()
+            for i, it in enumerate(items):
+                a[i] = it
+            return a
+
+        self._shapes = arr(_abi.RmShapeRef, [_abi.RmShapeRef(k, i) for k, i in self.shapes])
+        self._spheres = arr(_abi.RmSphere, self.spheres)
+        self._polygons = arr(_abi.RmPolygon, self.polygons)
+        self._pv = np.ascontiguousarray(self.polygon_vertices if self.polygon_vertices else [0.], dtype=np.float64)
+        self._objs = arr(_abi.RmObj, [_abi.RmObj(f, n) for f, n in self.objs])
+        self._tris = np.ascontiguousarray(np.concatenate(self.triangle_chunks) if self.triangle_chunks else np.zeros((1, 15)))
+        self._refl = np.ascontiguousarray(np.concatenate(self.reflectance_chunks) if self.reflectance_chunks
+                                          else np.zeros(1, dtype=REFL_DTYPE))
+        self._lights = arr(_abi.RmLight, self.lights)
+        fs = _abi.RmFlatScene()
+        fs.n_shapes, fs.shapes = len(self.shapes), self._shapes
+        fs.n_spheres, fs.spheres = len(self.spheres), self._spheres
+        fs.n_polygons, fs.polygons = len(self.polygons), self._polygons
+        fs.n_polygon_vertices = len(self.polygon_vertices) // 3
+        fs.polygon_vertices = self._pv.ctypes.data_as(C.POINTER(C.c_double))
+        fs.n_objs, fs.objs = len(self.objs), self._objs
+        fs.n_triangles = self.n_triangles
+        fs.triangles = C.cast(self._tris.ctypes.data, C.POINTER(_abi.RmTriangle))
+        fs.triangle_reflectances = C.cast(self._refl.ctypes.data, C.POINTER(_abi.RmReflectance))
+        fs.n_lights, fs.lights = len(self.lights), self._lights
+        self.c = fs
+        return self
+
+
+class Scene:
+    def __init__(self):                                         # Scene::new, scene.rs:16-23
+        self.lights = []
+        self.shapes = []
+        self.camera = Vec3f.zero()
+        self._handle = None
+        self._fingerprint = None
+
+    @staticmethod
+    def new():
+        return Scene()
+
+    def offset_camera(self, offset):                            # scene.rs:25-27
+        self.camera = self.camera + Vec3f.of(offset)
+
+    @staticmethod
+    def create_default():
+        """Scene::create_default (scene.rs:28-211).  The reference mutates one Reflectance value
+        between shapes, so fields carry over; the same mutation sequence is kept here."""
+        r = Reflectance.create_default()
+        r.diffuse_color = Vec3f(0.8, 0., 0.)
+        r.specular_exponent = 100.
+        sphere_red = sphere.create(Vec3f(-5., 0., -16.), 4., r)
+        r.diffuse_color = Vec3f(0.6, 0., 0.7)
+        triangle = polygon.ConvexPolygon.create([Vec3f(7., -4., -8.), Vec3f(15., 0., -9.), Vec3f(6., 3., -8.)], r)
+        r.diffusion = 1.0
+        r.specular = 1.
+        r.is_glass_like = True
+        r.refractive_index = 1.5
+        r.reflection = 0.5
+        r.diffuse_color = Vec3f(0.3, 0.9, 0.9)
+        square = polygon.ConvexPolygon.create(
+            [Vec3f(20., -3., -50.), Vec3f(-20., -3., -50.), Vec3f(-15., -6., -3.), Vec3f(15., -6., -3.)], r)
+        r.specular = 1.0
+        r.diffusion = 0.1
+        r.diffuse_color = Vec3f(0., 0., 0.2)
+        r.is_glass_like = True
+        r.refractive_index = 1.5
+        r.reflection = 0.2
+        sphere_blue = sphere.create(Vec3f(-0.5, -1.5, -5.), 2., r)
+        r.diffusion = 1.
+        r.reflection = 1.
+        r.is_glass_like = False
+        r.specular = 0.8
+        r.diffuse_color = Vec3f(0., 1., 0.)
+        sphere_green = sphere.create(Vec3f(6., -0.5, -18.), 3., r)
+        r.diffuse_color = Vec3f(0.9, 0.9, 0.9)
+        sphere_white = sphere.create(Vec3f(-10., 6., -14.), 4., r)
+        s = Scene()
+        s.lights = [lights.create_light(Vec3f(0., 0., 0.), Vec3f.ones(), 1.),
+                    lights.create_light(Vec3f(20., 20., 20.), Vec3f(1., 0.5, 0.5), 0.8)]
+        s.shapes = [sphere_blue, sphere_green, sphere_red, sphere_white, triangle, square]   # scene.rs:201-208
+        return s
+
+    @staticmethod
+    def from_obj(path, offset=(0., 0., -500.)):
+        """Win::open_obj (main.rs:261-315): load, move every model by `offset`, add the two lights."""
+        from . import obj
+        objects = obj.load(path)
+        s = Scene()
+        if objects is not None:
+            for o in objects:
+                o.offset(offset)
+                s.shapes.append(o)
+        s.lights.append(lights.create_light(Vec3f(0., 0., 0.), Vec3f.ones(), 1.))
+        s.lights.append(lights.create_light(Vec3f(20., 20., 20.), Vec3f(1., 0.5, 0.5), 0.8))
+        return s
+
+    # ---- flattening / device residency -------------------------------------------------------
+    def flatten(self):
+        flat = _Flat()
+        for sh in self.shapes:
+            sh.flatten(flat)
+        for lg in self.lights:
+            c = _abi.RmLight()
+            c.position[:] = list(lg.position)
+            c.color[:] = list(lg.color)
+            c.intensity = lg.intensity
+            flat.lights.append(c)
+        return flat.finish()
+
+    def _fp(self):
+        def key(s):
+            if isinstance(s, Obj):
+                return (id(s), s.triangles.shape[0], float(s.triangles[:, 12:15].sum()) if s.triangles.size else 0.)
+            if isinstance(s, sphere.Sphere):
+                return (id(s), tuple(s.center), s.radius_square, repr(s.reflectance))
+            return (id(s), tuple(tuple(v) for v in s.vertices), repr(s.reflectance))
+        return (tuple(key(s) for s in self.shapes),
+                tuple((tuple(l.position), tuple(l.color), l.intensity) for l in self.lights))
+
+    def device_handle(self):
+        """Uploads the scene (once; again only after it changed) and returns the RmScene handle."""
+        L = _abi.load()
+        fp = self._fp()
+        if self._handle is not None and fp == self._fingerprint:
+            return self._handle
+        self.release()
+        flat = self.flatten()
+        h = C.c_int64(0)
+        _abi.check(L.rm_scene_upload(C.byref(flat.c), C.byref(h)))
+        self._handle, self._fingerprint = h.value, fp
+        return self._handle
+
+    @property
+    def num_prims(self):
+        return sum(s.triangles.shape[0] if isinstance(s, Obj) else 1 for s in self.shapes)
+
+    def release(self):
+        if self._handle is not None and _abi._lib is not None:
+            _abi._lib.rm_scene_free(self._handle)
+        self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass

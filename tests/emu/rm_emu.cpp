@@ -1,0 +1,109 @@
+// rm_emu.cpp -- DEV/TEST TOOL, not part of the product and never loaded by it.
+//
+// Compiles the product's own kernel code (rusty_marcher_b200/csrc/rm_trace.cuh, the same
+// templates the CUDA kernels instantiate) for the host, so that logic and FP32-vs-FP64 parity
+// can be studied in this GPU-less container before spending GPU minutes.  It is NOT a fallback:
+// librm_b200.so does not contain it and fails loudly without a GPU.  Differences to the device:
+// powf/sqrtf/division come from glibc instead of the CUDA math library.
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../rusty_marcher_b200/csrc/rm_scene.cpp"
+#include "../../rusty_marcher_b200/csrc/rm_host.cpp"
+
+// rm_host.cpp's rm_builder_upload needs this symbol; the emulator has no device.
+extern "C" int rm_scene_upload(const RmFlatScene*, RmScene*) { return RM_ERR_NO_DEVICE; }
+
+namespace {
+
+template <typename R>
+rm::SceneView<R> view_of(const rm::PackedScene<R>& ps, bool cull) {
+    rm::SceneView<R> sc;
+    const rm::BlobLayout& L = ps.lay;
+    const unsigned char* base = ps.blob_data();
+    sc.sph = reinterpret_cast<const rm::R4<R>*>(base + L.off_sph);
+    sc.sph_id = reinterpret_cast<const int*>(base + L.off_sph_id);
+    sc.n_sph = L.n_sph;
+    sc.pln_n = reinterpret_cast<const rm::R4<R>*>(base + L.off_pln_n);
+    sc.pln_c = reinterpret_cast<const rm::R4<R>*>(base + L.off_pln_c);
+    sc.pln_v = reinterpret_cast<const rm::I2*>(base + L.off_pln_v);
+    sc.pln_id = reinterpret_cast<const int*>(base + L.off_pln_id);
+    sc.n_pln = rm::plane_count<R>(L, cull);
+    sc.vert = reinterpret_cast<const rm::VertT<R>*>(base + L.off_vert);
+    sc.mat_a = ps.mat_a.data();
+    sc.mat_b = ps.mat_b.data();
+    sc.mat_f = ps.mat_f.data();
+    sc.lgt_p = reinterpret_cast<const rm::R4<R>*>(base + L.off_lgt_p);
+    sc.lgt_c = reinterpret_cast<const rm::R4<R>*>(base + L.off_lgt_c);
+    sc.n_lgt = L.n_lgt;
+    sc.order = ps.order[cull].data();
+    sc.order_shape = ps.order_shape[cull].data();
+    sc.n_order = (int)ps.order[cull].size();
+    return sc;
+}
+
+template <typename R>
+int emu_render_impl(const RmFlatScene* fs, const RmParams* p, R* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
+    rm::PackedScene<R> ps;
+    std::string err;
+    int rc = rm::pack_scene<R>(*fs, ps, err);
+    if (rc != RM_OK) return rc;
+    if (p->width % 32) return RM_ERR_DIMENSIONS;
+    const bool cull = p->cull_backfacing != 0;
+    const rm::SceneView<R> sc = view_of(ps, cull);
+    const rm::FrameParams<R> fp = rm::make_frame_params<R>(*p);
+    std::atomic<int> next{fp.row_begin};
+    std::vector<rm::Counters<true>> tc(n_threads);
+    std::vector<R> tmax(n_threads, R(0));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++) {
+        pool.emplace_back([&, t] {
+            rm::Counters<true>& st = tc[t];
+            st.clear();
+            for (;;) {
+                int y = next.fetch_add(1);
+                if (y >= fp.row_end) break;
+                for (int x = 0; x < fp.width; x++) {
+                    st.add(rm::C_PIXELS);
+                    int pid;
+                    rm::Vec3<R> dir = rm::backproject<R>(fp, x, y);
+                    rm::Vec3<R> c = rm::cast_ray<R, true>(sc, fp.camera, dir, fp.background, fp.max_depth, pid, st);
+                    size_t px = (size_t)y * fp.width + x;
+                    out_rgb[3 * px] = c.x; out_rgb[3 * px + 1] = c.y; out_rgb[3 * px + 2] = c.z;
+                    if (prim) prim[px] = pid;
+                    R m = rm::Num<R>::max_(rm::Num<R>::max_(c.x, c.y), c.z);
+                    if (m > tmax[t]) tmax[t] = m;
+                }
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        uint64_t* dst = &stats->pixels;
+        for (auto& c : tc) for (int i = 0; i < rm::C_COUNT; i++) dst[i] += c.c[i];
+        R m = 0;
+        for (R v : tmax) m = v > m ? v : m;
+        stats->max_value = (double)m;
+        stats->resident_prims = sc.n_sph + sc.n_pln;
+    }
+    return RM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+int emu_render_f32(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
+    return emu_render_impl<float>(fs, p, out_rgb, prim, stats, n_threads);
+}
+int emu_render_f64(const RmFlatScene* fs, const RmParams* p, double* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
+    return emu_render_impl<double>(fs, p, out_rgb, prim, stats, n_threads);
+}
+void rm_params_default(RmParams* p, int width, int height) {
+    std::memset(p, 0, sizeof(*p));
+    p->width = width; p->height = height; p->fov = 1.5; p->max_depth = 3; p->background = 0.1;
+    p->patch_size = 32; p->precision = RM_FP32; p->patch_row_begin = 0; p->patch_row_end = -1; p->cull_backfacing = 1;
+}
+}
