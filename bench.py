@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- ray segments/s and ms/frame of the render hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workload (config.workload): the cornell_box mesh at 3840x2160, fov 1.5, camera origin, depth cap 3
+-- the configuration BASELINE.json's metric and north_star target are quoted on (configs[2]; the
+cornell_box2.obj it names does not exist in the reference).  A step is one frame:
+K1 render (float framebuffer + fused channel max) and K4 normalise+quantise to RGB8; with N > 1 GPUs
+the frame's 67 patch rows are split into contiguous row tiles, one process per GPU, with a one-float
+max all-reduce and an RGB8 gather to rank 0 over NCCL (scaling "strong": the frame is fixed).
+
+`--impl reference` times the reference's own CPU algorithm (the f64 oracle restatement of the Rayon
+patch loop -- the Rust original cannot be built here) on the host cores, same workload and metric.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ray_segments_per_s"
+UNIT = "segments/s"
+WORKLOADS = {
+    # name: (scene, width, height, max_depth, scene kwargs)
+    "cornell_4k": ("cornell_box", 3840, 2160, 3, {}),
+    "cornell_1080p": ("cornell_box", 1920, 1080, 3, {}),
+    "demo": ("demo", 1600, 1280, 3, {}),
+    "dodecahedron_4k": ("dodecahedron", 3840, 2160, 3, {}),
+    "stress_small": ("stress", 1920, 1080, 6, dict(n_spheres=512, grid=32)),
+}
+
+
+def config_of(args, extra=None):
+    scene, w, h, depth, _kw = WORKLOADS[args.workload]
+    cfg = {"workload": "%s %dx%d fov 1.5 camera origin depth-cap %d (reference semantics: rows >= floor(H/32)*32 not rendered)"
+                       % (scene, w, h, depth),
+           "width": w, "height": h, "max_depth": depth, "scene": scene}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        out = self.proc.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower() == "active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_frame_time(desc, w, h, depth, budget_s, reps):
+    """Times the oracle's Rayon-analogue patch loop (all host threads, uninstrumented).  Returns
+    (seconds for a FULL frame, threads, sample description); strided patch sampling keeps it bounded."""
+    from oracle import oracle as O
+    from tests.oracle_scenes import build_oracle_scene
+    import numpy as np
+    osc = build_oracle_scene(desc)
+    threads = O.hardware_threads()
+    out = np.zeros((h, w, 3), dtype=np.float64)
+    n_patches = (h // 32) * (w // 32)
+    # calibrate on every 16th patch
+    t0 = time.perf_counter()
+    O.render(osc, w, h, max_depth=depth, threads=threads, patch_stride=16, want_ids=False, want_fragile=False, want_counters=False, out=out)
+    full_est = (time.perf_counter() - t0) * 16
+    stride = 1
+    while full_est / stride * reps > budget_s and stride < 64:
+        stride *= 2
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.render(osc, w, h, max_depth=depth, threads=threads, patch_stride=stride, want_ids=False, want_fragile=False, want_counters=False, out=out)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    n_sampled = len(range(0, n_patches, stride))
+    full = best * n_patches / n_sampled
+    sample = "best of %d passes over %d of %d 32x32 patches (every %d%s), %d threads, f64 restatement of the Rayon loop" % (
+        reps, n_sampled, n_patches, stride, "th, extrapolated" if stride > 1 else "", threads)
+    return full, threads, sample
+
+
+def oracle_segments(desc, w, h, depth):
+    """Segments of one frame from the oracle's counters (reference arm only)."""
+    from oracle import oracle as O
+    from tests.oracle_scenes import build_oracle_scene
+    r = O.render(build_oracle_scene(desc), w, h, max_depth=depth, want_ids=False, want_fragile=False, want_counters=True)
+    c = r["counters"]
+    return c["closest_segments"] + c["anyhit_segments"]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from rusty_marcher_b200 import workloads
+    scene, w, h, depth, kw = WORKLOADS[args.workload]
+    desc = workloads.describe(scene, **kw)
+    segs = oracle_segments(desc, w, h, depth)
+    # one "step" = one (possibly patch-sampled) frame; keep the whole run within a few minutes
+    total_steps = args.steps + args.warmup
+    full, threads, sample = cpu_reference_frame_time(desc, w, h, depth, budget_s=150.0 / max(total_steps, 1) * 3, reps=3)
+    from oracle import oracle as O
+    from tests.oracle_scenes import build_oracle_scene
+    import numpy as np
+    osc = build_oracle_scene(desc)
+    out = np.zeros((h, w, 3), dtype=np.float64)
+    n_patches = (h // 32) * (w // 32)
+    stride = 1
+    while full / stride * total_steps > 150.0 and stride < 64:
+        stride *= 2
+    n_sampled = len(range(0, n_patches, stride))
+    times = []
+    for i in range(total_steps):
+        t0 = time.perf_counter()
+        O.render(osc, w, h, max_depth=depth, threads=threads, patch_stride=stride, want_ids=False, want_fragile=False, want_counters=False, out=out)
+        if i >= args.warmup:
+            times.append((time.perf_counter() - t0) * n_patches / n_sampled)
+    ms = 1e3 * sum(times) / len(times)
+    value = segs / (ms * 1e-3)
+    sample = "each step renders %d of %d 32x32 patches (every %d%s) with %d host threads; f64 C++ restatement of the reference's Rayon loop (Rust toolchain absent)" % (
+        n_sampled, n_patches, stride, "th, time extrapolated to the frame" if stride > 1 else "", threads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_of(args, {"segments_per_frame": segs}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import rusty_marcher_b200 as rm
+    from rusty_marcher_b200 import _abi, tiled, work, workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rm.init(local_rank)
+    L = _abi.load()
+
+    scene_name, w, h, depth, kw = WORKLOADS[args.workload]
+    desc = workloads.describe(scene_name, **kw)
+    scene = workloads.build_scene(desc)
+    renderer = rm.create_renderer(1.5, h, w)
+    renderer.max_depth = depth
+    renderer.cull_backfacing = not args.no_cull
+    backend = tiled.CudaBackend(scene, renderer, w, h, dev)
+    tr = tiled.TiledRenderer(backend, w, h, dev)
+    rows = (h // 32) * 32
+
+    # ---- algorithmic work of one frame: instrumented kernel, outside the timed region (whole frame, rank 0's GPU)
+    fb = rm.FrameBuffer.__new__(rm.FrameBuffer)
+    fb.width, fb.height = w, h
+    p_all = renderer.params(fb, scene, (0, -1))
+    st = _abi.RmStats()
+    scratch = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+    smax = torch.zeros(1, dtype=torch.float32, device=dev)
+    _abi.check(L.rm_render_device_stats(backend.handle, C.byref(p_all), scratch.data_ptr(), None, smax.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream, C.byref(st)))
+    counters = st.counters()
+    segs = work.segments(counters)
+    flops, slots = work.algorithmic_work(counters)
+    del scratch
+
+    # ---- FP32 FMA peak, measured live (roofline denominator)
+    peak_t, peak_ms = C.c_double(0), C.c_double(0)
+    _abi.check(L.rm_measure_fp32_peak(C.byref(peak_t), C.byref(peak_ms)))
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        tr.render()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    barrier()
+    for a, k1_done, b in ev:
+        flush.fill_(0)                       # L2 flush between timed iterations, outside the step's events
+        a.record()
+        tr.dmax.zero_()
+        backend.render_rows(tr.rows, tr.rgb, tr.dmax)
+        k1_done.record()
+        if world > 1:
+            dist.all_reduce(tr.dmax, op=dist.ReduceOp.MAX)
+        backend.tonemap_rows(tr.rows, tr.rgb, tr.dmax, tr.rgb8)
+        if world > 1:
+            n = (tr.rows[1] - tr.rows[0]) * 32
+            tr.slot[:n].copy_(tr.rgb8[tr.rows[0] * 32:tr.rows[1] * 32])
+            dist.gather(tr.slot, tr.gathered, dst=0)
+        b.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, _k, b in ev]
+    k1_ms = [a.elapsed_time(k) for a, k, _b in ev]
+    total = torch.tensor([sum(step_ms), sum(k1_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    total_ms, k1_total_ms = float(total[0]), float(total[1])
+    ms_per_step = total_ms / args.steps
+    value = segs / (ms_per_step * 1e-3)
+
+    # ---- e2e: the public call a user makes -- Renderer.render(frame, scene) with HOST buffers: scene (re)upload H2D and the
+    # float framebuffer D2H inside the timed region.  With N > 1 every rank delivers its own row tile to its pinned host buffer.
+    frame = rm.create_frame_buffer(w, h)
+    nbytes = frame.buffer.nbytes
+    pinned = L.rm_host_alloc(nbytes)
+    if pinned:
+        frame.buffer = np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_float)), shape=(h, w, 3))
+    devnull = open(os.devnull, "w")
+    stdout = sys.stdout
+    e2e_times = []
+    flat_bytes = 0
+    try:
+        sys.stdout = devnull                   # Renderer.render prints the reference's status lines
+        for i in range(args.warmup + args.steps):
+            flush.fill_(0)
+            barrier()
+            t0 = time.perf_counter()
+            scene.release()                    # force the H2D re-upload of the scene every step
+            renderer.render(frame, scene, patch_rows=tr.rows)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                e2e_times.append(dt)
+    finally:
+        sys.stdout = stdout
+    flat = scene.flatten()
+    flat_bytes = (C.sizeof(_abi.RmSphere) * flat.c.n_spheres + C.sizeof(_abi.RmPolygon) * flat.c.n_polygons
+                  + 24 * flat.c.n_polygon_vertices + (C.sizeof(_abi.RmTriangle) + C.sizeof(_abi.RmReflectance)) * flat.c.n_triangles
+                  + C.sizeof(_abi.RmLight) * flat.c.n_lights + C.sizeof(_abi.RmParams))
+    e2e_t = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_t[0]) * 1e3 / args.steps
+    tile_rows = (tr.rows[1] - tr.rows[0]) * 32
+    d2h = tile_rows * w * 12
+
+    line = None
+    if rank == 0:
+        k1_ms_avg = k1_total_ms / args.steps
+        # K1 of rank 0's share: with N ranks each kernel processes ~1/N of the frame's work
+        ach_tflops = flops / world / (k1_ms_avg * 1e-3) / 1e12
+        issue_frac = (slots / world / (k1_ms_avg * 1e-3)) / (peak_t.value * 1e12 / 2.0)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            full_s, threads, sample = cpu_reference_frame_time(desc, w, h, depth, budget_s=25.0, reps=3)
+            cpu = {"value": segs / full_s, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                   "ms_per_frame": full_s * 1e3}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": config_of(args, {
+                "segments_per_frame": segs, "pixels_per_frame": rows * w, "resident_prims": st.resident_prims,
+                "cull_backfacing": bool(renderer.cull_backfacing),
+                "step": "K1 render + fused max, K4 normalise+quantise RGB8" + (", max all-reduce + RGB8 gather to rank 0 (NCCL)" if world > 1 else ""),
+                "parallelism": "row tiles x%d" % world,
+                "l2": "flushed between steps (256 MiB fill, outside each step's CUDA events)"}),
+            "ms_per_frame": ms_per_step,
+            "clocks": clocks,
+            "e2e": {"value": segs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_frame": e2e_ms,
+                    "h2d_bytes_per_step": flat_bytes, "d2h_bytes_per_step": d2h,
+                    "path": "Renderer.render(frame, scene) -> rm_scene_upload + rm_render, float32 framebuffer into pinned host memory"
+                            + ("; each rank delivers its own row tile" if world > 1 else "")},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak_t.value, "unit": "TFLOP/s",
+                         "frac": ach_tflops / peak_t.value, "traffic": None,
+                         "kernel": "render_kernel<float,false>", "kernel_ms": k1_ms_avg,
+                         "algorithmic_flops_per_frame": flops, "algorithmic_issue_slots_per_frame": slots,
+                         "issue_slot_frac": issue_frac,
+                         "peak_source": "measured live: ffma_probe_kernel (pure dependent-chain FFMA, all SMs); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                         "hbm_gbs_achieved": (rows * w * 12 / world) / (k1_ms_avg * 1e-3) / 1e9},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if pinned:
+        frame.buffer = None
+        L.rm_host_free(pinned)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cornell_4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cull", action="store_true", help="trace every primitive like the reference's brute force")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -102,11 +102,15 @@ RM_HD bool sphere_intersect(const R4<double> s, const Vec3<double> o, const Vec3
     c.key = squared_norm(c.p - o);                             // shapes.rs:128
     return true;
 }
+// f32: the reference's d2 = line.line - tca^2 cancels catastrophically in single precision for a small
+// far sphere (error 2^-24*|line|^2 against r^2), so the squared distance of the centre to the ray is
+// taken from the perpendicular component itself: perp = line - tca*d, d2 = perp.perp.
 template <bool S>
 RM_HD bool sphere_intersect(const R4<float> s, const Vec3<float> o, const Vec3<float> d, Cand<float>& c, Counters<S>& st) {
     Vec3<float> line = {s.x - o.x, s.y - o.y, s.z - o.z};
     float tca = dot(line, d);
-    float d2 = fmaf(-tca, tca, dot(line, line));
+    Vec3<float> perp = axmy(line, d, tca);
+    float d2 = dot(perp, perp);
     st.add(C_SPH_TEST);
     if (d2 > s.w) return false;
     st.add(C_SPH_DISC);
@@ -117,6 +121,26 @@ RM_HD bool sphere_intersect(const R4<float> s, const Vec3<float> o, const Vec3<f
     st.add(C_SPH_HIT);
     c.key = t0;
     return true;
+}
+
+// Hit point and unit normal of the winning sphere hit (sphere.rs:54-60).
+RM_HD void sphere_point_normal(const R4<double> s, const Vec3<double>, const Vec3<double>, const Vec3<double> p_in,
+                               Vec3<double>& p, Vec3<double>& n) {
+    p = p_in;
+    n = normalized(p_in - xyz(s));
+}
+// f32: p - c = (t - tca)*d - perp = -+thc*d - perp, formed from the two short vectors instead of the
+// difference of two long ones (o + t*d) - c.
+RM_HD void sphere_point_normal(const R4<float> s, const Vec3<float> o, const Vec3<float> d, const Vec3<float>,
+                               Vec3<float>& p, Vec3<float>& n) {
+    Vec3<float> line = {s.x - o.x, s.y - o.y, s.z - o.z};
+    float tca = dot(line, d);
+    Vec3<float> perp = axmy(line, d, tca);
+    float thc = sqrtf(fmaxf(s.w - dot(perp, perp), 0.f));
+    float w = (tca - thc < 0.f) ? thc : -thc;                  // same root as sphere_intersect chose
+    Vec3<float> pc = {fmaf(w, d.x, -perp.x), fmaf(w, d.y, -perp.y), fmaf(w, d.z, -perp.z)};
+    p = xyz(s) + pc;
+    n = normalized(pc);
 }
 
 // ---------------------------------------------------------------- triangle.rs:49-83, polygon.rs:60-98
@@ -363,10 +387,13 @@ RM_HD Vec3<R> cast_ray(const SceneView<R>& sc, Vec3<R> o, Vec3<R> d, R backgroun
                 v = (level > 1) ? bg : Vec3<R>{R(0), R(0), R(0)};       // renderer.rs:300-306
             } else {
                 st.add(C_HITS);
-                if (sizeof(R) == 4) h.p = axpy(o, d, h.dist);   // f32: the point of the winner only
                 Vec3<R> normal;
-                if (h.slot < sc.n_sph) normal = normalized(h.p - xyz(sc.sph[h.slot]));   // sphere.rs:58
-                else normal = xyz(sc.pln_n[h.slot - sc.n_sph]);
+                if (h.slot < sc.n_sph) {
+                    sphere_point_normal(sc.sph[h.slot], o, d, h.p, h.p, normal);         // sphere.rs:54-58
+                } else {
+                    if (sizeof(R) == 4) h.p = axpy(o, d, h.dist);                        // f32: point of the winner only
+                    normal = xyz(sc.pln_n[h.slot - sc.n_sph]);
+                }
                 const R4<R> ma = sc.mat_a[h.id];
                 const R4<R> mb = sc.mat_b[h.id];
                 Vec3<R> c = bg + direct_lighting<R, S>(sc, o, h.p, normal, ma, mb, st);   // renderer.rs:272-275

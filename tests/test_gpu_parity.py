@@ -1,0 +1,217 @@
+"""Parity of the CUDA path against the oracle, through the C ABI, on a real B200 (-m gpu).
+
+  * RM_FP64 validation kernels: primitive ids and event counters bit-exact, colours bit-exact up to
+    the ulps by which CUDA's pow differs from glibc's (1e-13 relative);
+  * RM_FP32 production kernels: the north_star criteria of tests/parity.py;
+  * at BASELINE.json's full sizes: size-independent properties (tiles == whole frame, idempotence,
+    culling on == off, FP32 agrees with FP64 on device, counters consistent).
+"""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from rusty_marcher_b200 import _abi, workloads
+from tests import parity
+from tests.oracle_scenes import build_oracle_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_render(rm, scene, w, h, precision="f32", depth=3, cull=True, counters=False, rows=(0, -1), want_rgb8=True):
+    r = rm.create_renderer(1.5, h, w)
+    r.max_depth, r.cull_backfacing = depth, cull
+    r.precision = rm.RM_FP64 if precision == "f64" else rm.RM_FP32
+    fb = rm.create_frame_buffer(w, h, dtype=np.float64 if precision == "f64" else np.float32)
+    ids = np.full((h, w), -1, dtype=np.int32)
+    rgb8 = np.zeros((h, w, 3), dtype=np.uint8) if want_rgb8 else None
+    msg = r.render(fb, scene, prim_id=ids, rgb8=rgb8, counters=counters, patch_rows=rows)
+    assert msg.startswith("Scene rendered in ")
+    st = r.last_stats
+    return {"rgb": fb.buffer, "prim_id": ids, "rgb8": rgb8, "counters": st.counters() if counters else None,
+            "max": st.max_value, "stats": st}
+
+
+CASES = [("demo", 800, 600, 3, {}), ("cornell_box", 640, 480, 3, {}), ("dodecahedron", 640, 480, 3, {}),
+         ("stress", 160, 128, 6, dict(n_spheres=64, grid=7))]
+
+
+@pytest.fixture(scope="module", params=CASES, ids=[c[0] for c in CASES])
+def case(request, rm_gpu):
+    name, w, h, depth, kw = request.param
+    desc = workloads.describe(name, **kw)
+    ref = O.render(build_oracle_scene(desc), w, h, max_depth=depth)
+    return name, w, h, depth, workloads.build_scene(desc), ref
+
+
+@pytest.mark.parametrize("cull", [False, True])
+def test_fp64_kernels_match_the_oracle(rm_gpu, case, cull):
+    name, w, h, depth, scene, ref = case
+    got = gpu_render(rm_gpu, scene, w, h, "f64", depth, cull, counters=True)
+    parity.check_exact(got, ref, rel=1e-13)
+    assert abs(got["max"] - ref["rgb"].max()) <= 1e-13 * ref["rgb"].max()
+    if not cull:
+        assert got["counters"] == ref["counters"]
+    else:
+        for k in ("pixels", "closest_segments", "anyhit_segments", "hits", "light_evals", "lit_lights", "glass_hits",
+                  "reflections", "refractions", "sphere_tests", "sphere_hits"):
+            assert got["counters"][k] == ref["counters"][k], k
+    rows = (h // 32) * 32
+    d = np.abs(got["rgb8"][:rows].astype(np.int16) - parity.oracle_rgb8(ref["rgb"])[:rows].astype(np.int16))
+    assert (d > 0).mean() < 1e-4 and d.max() <= 1              # only pow-ulp flips at a quantisation boundary
+
+
+@pytest.mark.parametrize("cull", [False, True])
+def test_fp32_kernels_meet_the_north_star_tolerance(rm_gpu, case, cull):
+    name, w, h, depth, scene, ref = case
+    got = gpu_render(rm_gpu, scene, w, h, "f32", depth, cull)
+    rep = parity.check_fp32(got, ref, (h // 32) * 32, got["rgb8"])
+    print(name, "cull", cull, rep)
+    assert np.all(got["rgb"][(h // 32) * 32:] == 0)            # renderer.rs:47-55: rows never rendered stay untouched
+
+
+def test_demo_golden_image_on_gpu(rm_gpu):
+    """The GPU's FP64 render of the demo scene against the reference's golden engine/out.ppm."""
+    scene = workloads.scene("demo")
+    got = gpu_render(rm_gpu, scene, 800, 600, "f64", cull=False)
+    rgb = got["rgb"].copy()
+    O.normalize(rgb)
+    ppm = O.ppm_bytes(rgb)
+    golden = hashlib.sha256(ppm).hexdigest() == "82d51afaaf4a644547728dde89478e484c245d2e3eb1e40da8b928ebd7584797"
+    if not golden:      # a pow ulp at a quantisation boundary may flip single bytes; nothing more
+        ref = O.render(O.Scene.create_default(), 800, 600, want_ids=False, want_fragile=False, want_counters=False)
+        a = np.frombuffer(ppm[15:], dtype=np.uint8).astype(np.int16)
+        b = parity.oracle_rgb8(ref["rgb"]).ravel().astype(np.int16)
+        assert np.abs(a - b).max() <= 1 and (a != b).mean() < 1e-5
+    # and the device-side normalize + to_vec (K4) reproduces the same bytes from the device max
+    assert np.abs(got["rgb8"].ravel().astype(np.int16) - np.frombuffer(ppm[15:], dtype=np.uint8).astype(np.int16)).max() <= 1
+
+
+def test_cornell_1080p_config2(rm_gpu):
+    """BASELINE.json config 2 at full size against the oracle (the oracle needs about a second)."""
+    desc = workloads.describe("cornell_box")
+    ref = O.render(build_oracle_scene(desc), 1920, 1080)
+    scene = workloads.build_scene(desc)
+    got = gpu_render(rm_gpu, scene, 1920, 1080, "f32")
+    rep = parity.check_fp32(got, ref, 1056, got["rgb8"])
+    assert rep["id_mismatch"] == 0
+    hit = got["prim_id"] >= 0
+    assert hit.sum() == (ref["prim_id"] >= 0).sum() == 279591
+    assert got["prim_id"][hit].min() >= 18 and got["prim_id"][hit].max() < 28     # only short_block is visible
+    g64 = gpu_render(rm_gpu, scene, 1920, 1080, "f64", counters=True, cull=False)
+    parity.check_exact(g64, ref, rel=1e-13)
+    assert g64["counters"] == ref["counters"]
+
+
+@pytest.mark.parametrize("name,w,h", [("cornell_box", 3840, 2160), ("dodecahedron", 3840, 2160), ("demo", 1600, 1280)])
+def test_full_size_properties(rm_gpu, name, w, h):
+    """Configs 1, 3, 4 at full size: properties that need no oracle pass."""
+    scene = workloads.scene(name)
+    whole = gpu_render(rm_gpu, scene, w, h, "f32", counters=True)
+    rows = (h // 32) * 32
+    n_patch = h // 32
+    # idempotence
+    again = gpu_render(rm_gpu, scene, w, h, "f32")
+    assert np.array_equal(whole["rgb"], again["rgb"]) and np.array_equal(whole["prim_id"], again["prim_id"])
+    # row tiles of 2, 4, 8 ranks reassemble to the whole frame, and the tile maxima combine to the frame max
+    for g in (2, 8):
+        acc = np.zeros_like(whole["rgb"])
+        ids = np.full_like(whole["prim_id"], -1)
+        mx = 0.
+        for k in range(g):
+            a, b = (k * n_patch) // g, ((k + 1) * n_patch) // g
+            t = gpu_render(rm_gpu, scene, w, h, "f32", rows=(a, b), want_rgb8=False)
+            acc[a * 32:b * 32] = t["rgb"][a * 32:b * 32]
+            ids[a * 32:b * 32] = t["prim_id"][a * 32:b * 32]
+            assert np.all(t["rgb"][:a * 32] == 0) and np.all(t["rgb"][b * 32:] == 0)
+            mx = max(mx, t["max"])
+        assert np.array_equal(acc, whole["rgb"]) and np.array_equal(ids, whole["prim_id"])
+        assert mx == whole["max"] == float(whole["rgb"].max())
+    # culling never changes a pixel
+    nocull = gpu_render(rm_gpu, scene, w, h, "f32", cull=False)
+    assert np.array_equal(nocull["prim_id"], whole["prim_id"])
+    assert np.array_equal(nocull["rgb"], whole["rgb"])
+    # FP32 against the device's own FP64 validation kernels (which the other tests pin to the oracle)
+    g64 = gpu_render(rm_gpu, scene, w, h, "f64", counters=True)
+    mism = whole["prim_id"] != g64["prim_id"]
+    assert mism.mean() < 2e-4
+    rel = (np.abs(whole["rgb"][:rows].astype(np.float64) - g64["rgb"][:rows]) / np.maximum(np.abs(g64["rgb"][:rows]), 1e-12)).max(axis=2)
+    assert (rel <= parity.REL_TOL).mean() >= parity.GOOD_FRACTION
+    d = np.abs(whole["rgb8"][:rows].astype(np.int16) - g64["rgb8"][:rows].astype(np.int16)).max(axis=2)
+    assert (d <= 1).mean() >= parity.GOOD_FRACTION
+    # counters: one closest segment per pixel at least, shadow rays only from hits, same control flow in both precisions
+    c32, c64 = whole["counters"], g64["counters"]
+    assert c32["pixels"] == rows * w == c64["pixels"]
+    assert c32["closest_segments"] >= c32["pixels"] and c32["anyhit_segments"] == c32["light_evals"] == 2 * c32["hits"]
+    for k in ("closest_segments", "hits", "glass_hits"):
+        assert abs(c32[k] - c64[k]) <= 2e-4 * max(c64[k], 1), k
+    # rows below the last patch row are untouched, rgb8 there is zero
+    assert np.all(whole["rgb"][rows:] == 0) and np.all(whole["rgb8"][rows:] == 0)
+
+
+def test_error_behaviour(rm_gpu):
+    rm = rm_gpu
+    L = _abi.load()
+    scene = workloads.scene("demo")
+    fb = rm.create_frame_buffer(100, 64)                        # width not a multiple of 32: renderer.rs:107 panics
+    with pytest.raises(rm.RmError) as e:
+        rm.create_renderer(1.5, 64, 100).render(fb, scene)
+    assert e.value.code == -4 and "Dimensions mismatch" in str(e.value)
+    p = _abi.RmParams()
+    L.rm_params_default(C.byref(p), 64, 64)
+    assert L.rm_render(987654, C.byref(p), None, None, None, None) == -3       # unknown handle
+    assert b"unknown scene handle" in L.rm_last_error()
+    p.max_depth = 99
+    assert L.rm_render(scene.device_handle(), C.byref(p), None, None, None, None) == -3
+    # malformed flat scene
+    flat = scene.flatten()
+    flat.c.shapes[0].index = 77
+    h = C.c_int64(0)
+    assert L.rm_scene_upload(C.byref(flat.c), C.byref(h)) == -5
+    # empty scene renders black, misses everywhere
+    empty = rm.Scene.new()
+    got = gpu_render(rm, empty, 64, 64, "f32")
+    assert np.all(got["rgb"] == 0) and np.all(got["prim_id"] == -1) and np.all(got["rgb8"] == 0)
+    # height not a multiple of 32 only prints (renderer.rs:49-51) and renders floor(H/32) patch rows
+    got = gpu_render(rm, scene, 64, 70, "f32")
+    assert np.any(got["rgb"][:64] > 0) and np.all(got["rgb"][64:] == 0)
+
+
+def test_depth_and_camera(rm_gpu):
+    scene = workloads.scene("demo")
+    osc = O.Scene.create_default()
+    for depth in (0, 1, 2, 5):
+        parity.check_exact(gpu_render(rm_gpu, scene, 96, 64, "f64", depth=depth, cull=False),
+                           O.render(osc, 96, 64, max_depth=depth), rel=1e-13)
+    scene.offset_camera((5., 0., -5.))                          # main.rs:124-171
+    osc.offset_camera((5., 0., -5.))
+    ref = O.render(osc, 256, 160)
+    parity.check_exact(gpu_render(rm_gpu, scene, 256, 160, "f64"), ref, rel=1e-13)
+    parity.check_fp32(gpu_render(rm_gpu, scene, 256, 160, "f32"), ref, 160)
+
+
+def test_device_api_with_torch_buffers(rm_gpu):
+    """rm_render_device / rm_tonemap_device on caller-owned device memory and stream."""
+    import torch
+    from rusty_marcher_b200 import tiled
+    w, h = 640, 480
+    scene = workloads.scene("cornell_box")
+    dev = torch.device("cuda:0")
+    r = rm_gpu.create_renderer(1.5, h, w)
+    tr = tiled.TiledRenderer(tiled.CudaBackend(scene, r, w, h, dev), w, h, dev)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        frame = tr.render()
+    s.synchronize()
+    host = gpu_render(rm_gpu, scene, w, h, "f32")
+    assert np.array_equal(tr.rgb.cpu().numpy(), host["rgb"])
+    assert np.array_equal(frame.cpu().numpy(), host["rgb8"])
+    assert float(tr.dmax.item()) == host["max"]
+
+
+def test_fp32_peak_probe(rm_gpu):
+    t, ms = C.c_double(0), C.c_double(0)
+    _abi.check(_abi.load().rm_measure_fp32_peak(C.byref(t), C.byref(ms)))
+    assert 20. < t.value < 90., t.value                        # 148 SMs x 128 lanes x 2 x ~1.9 GHz = 72 TFLOP/s nominal

@@ -1,0 +1,81 @@
+"""The product's kernel code (csrc/rm_trace.cuh -- the very templates the CUDA kernels instantiate)
+compiled for the host by tests/emu and checked against the oracle.  Keeps the kernel LOGIC under
+test in the GPU-less container; the real parity tests (through the C ABI, on a B200) are in
+test_gpu_parity.py.  The emulation is a test tool, not a fallback: the product cannot reach it."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from rusty_marcher_b200 import workloads
+from tests import parity
+from tests.emu import emu
+from tests.oracle_scenes import build_oracle_scene
+
+CASES = [("demo", 256, 160, 3, {}), ("cornell_box", 160, 128, 3, {}), ("dodecahedron", 160, 128, 3, {}),
+         ("stress", 160, 128, 6, dict(n_spheres=64, grid=7))]
+
+
+@pytest.fixture(scope="module", params=CASES, ids=[c[0] for c in CASES])
+def case(request):
+    name, w, h, depth, kw = request.param
+    desc = workloads.describe(name, **kw)
+    ref = O.render(build_oracle_scene(desc), w, h, max_depth=depth)
+    return name, w, h, depth, workloads.build_scene(desc), ref
+
+
+@pytest.mark.parametrize("cull", [False, True])
+def test_fp64_kernel_code_is_bit_exact(case, cull):
+    name, w, h, depth, scene, ref = case
+    got = emu.render(scene, w, h, "f64", max_depth=depth, cull=cull)
+    parity.check_exact(got, ref)
+    if not cull:
+        assert got["counters"] == ref["counters"]
+        assert got["max"] == ref["rgb"].max()
+    else:
+        # culling removes primitives that can never be hit: same control flow, fewer tests
+        for k in ("pixels", "closest_segments", "anyhit_segments", "hits", "light_evals", "lit_lights", "glass_hits",
+                  "reflections", "refractions", "sphere_tests", "sphere_hits"):
+            assert got["counters"][k] == ref["counters"][k], k
+        assert got["counters"]["plane_tests"] <= ref["counters"]["plane_tests"]
+
+
+@pytest.mark.parametrize("cull", [False, True])
+def test_fp32_kernel_code_within_tolerance(case, cull):
+    name, w, h, depth, scene, ref = case
+    got = emu.render(scene, w, h, "f32", max_depth=depth, cull=cull)
+    m = np.float32(got["rgb"].max())
+    rgb8 = (np.float32(255) * np.clip(got["rgb"] * (np.float32(1) / m), 0, 1)).astype(np.uint8)
+    parity.check_fp32(got, ref, (h // 32) * 32, rgb8)
+
+
+def test_row_tiles_reassemble_to_the_full_frame():
+    scene = workloads.scene("demo")
+    full = emu.render(scene, 128, 160, "f32")
+    parts = [emu.render(scene, 128, 160, "f32", patch_rows=r) for r in ((0, 2), (2, 3), (3, 5))]
+    acc = np.zeros_like(full["rgb"])
+    for p, (a, b) in zip(parts, ((0, 2), (2, 3), (3, 5))):
+        assert np.all(p["rgb"][:a * 32] == 0) and np.all(p["rgb"][b * 32:] == 0)
+        acc += p["rgb"]
+    assert np.array_equal(acc, full["rgb"])
+
+
+def test_depth_cap_semantics():
+    """renderer.rs:262-264: max_depth 0 returns the background for every pixel, deeper caps add light."""
+    scene = workloads.scene("demo")
+    d0 = emu.render(scene, 64, 64, "f64", max_depth=0)
+    assert np.all(d0["rgb"] == 0.1) and np.all(d0["prim_id"] == -1)
+    osc = O.Scene.create_default()
+    for depth in (1, 2, 5):
+        parity.check_exact(emu.render(scene, 64, 64, "f64", max_depth=depth), O.render(osc, 64, 64, max_depth=depth))
+
+
+def test_empty_scene_and_camera_offset():
+    import rusty_marcher_b200 as rm
+    empty = rm.Scene.new()
+    r = emu.render(empty, 64, 32, "f32")
+    assert np.all(r["rgb"] == 0) and np.all(r["prim_id"] == -1)
+    scene = workloads.scene("demo")
+    scene.offset_camera((5., 0., -5.))                          # main.rs:124-171 moves by +-5
+    osc = O.Scene.create_default()
+    osc.offset_camera((5., 0., -5.))
+    parity.check_exact(emu.render(scene, 96, 64, "f64"), O.render(osc, 96, 64))
