@@ -97,7 +97,27 @@ struct Probe {
     void begin_segment() { ncand = 0; counting = true; }
     void end_closest() { if (ncand > 1 && (second - best) < 2. * kF32 * best) mark(); }
 };
-#define CNT(field) do { if (T && pr->counting) pr->c.field++; } while (0)
+#define CNT(field) do { if (T && pr->counting && trail.alive) pr->c.field++; } while (0)
+#define CNT0(field) do { if (T && pr->counting) pr->c.field++; } while (0)
+
+// The decisions of one ray/primitive test.  Untracked, a failed decision ends the test (the
+// reference's early return).  Tracked, a failed decision whose margin is within FP32 resolution
+// lets the evaluation continue in "what-if" mode (nothing is counted any more): if every later
+// decision passes or is itself marginal, the primitive's hit/miss outcome hinges on a near-tie
+// and the pixel is marked fragile.  A robust failure anywhere makes the primitive a robust miss.
+template <bool T> struct Trail {
+    Probe* pr;
+    bool alive = true, frag = false;
+    explicit Trail(Probe* p) : pr(p) {}
+    bool step(bool pass, double margin, double tol) {
+        if (!T) return pass;
+        const bool fr = std::fabs(margin) < (pr->primary ? tol : 0.25 * tol);
+        if (fr) frag = true;
+        if (!pass) { alive = false; if (!fr) return false; }
+        return true;
+    }
+    bool finish() { if (T && frag) pr->mark(); return alive; }
+};
 
 struct Shape {
     int prim_base = 0;
@@ -118,25 +138,32 @@ struct Sphere : Shape {
     Reflectance reflectance;
     template <bool T>
     bool isect(const V3& o, const V3& d, Hit& h, Probe* pr) const {
+        Trail<T> trail(pr);
         V3 line = center - o;                                  // sphere.rs:28
         double tca = dot(line, d);                             // sphere.rs:33
         double d2 = dot(line, line) - tca * tca;               // sphere.rs:34
         CNT(sphere_tests);
-        if (T) pr->near(d2 - radius_square, kF32 * std::fmax(radius_square, dot(line, line)));
-        if (d2 > radius_square) return false;                  // sphere.rs:36-38
+        if (!trail.step(!(d2 > radius_square), d2 - radius_square, kF32 * std::fmax(radius_square, dot(line, line))))
+            return false;                                      // sphere.rs:36-38
         CNT(sphere_disc);
-        double thc = std::sqrt(radius_square - d2);            // sphere.rs:40
+        double thc = std::sqrt(std::fmax(radius_square - d2, 0.));   // sphere.rs:40 (the clamp only matters in what-if mode)
+        if (!T) thc = std::sqrt(radius_square - d2);
         double t0 = tca - thc;                                 // sphere.rs:42
         double t1 = tca + thc;                                 // sphere.rs:43
-        if (T) { double tol = kF32 * std::sqrt(dot(line, line)); pr->near(t0, tol); if (t0 < 0.) pr->near(t1, tol); }
-        if (t0 < 0.) t0 = t1;                                  // sphere.rs:45-47
-        if (t0 < 0.) return false;                             // sphere.rs:49-51
+        const double ttol = kF32 * std::sqrt(dot(line, line));
+        if (t0 < 0.) {                                         // sphere.rs:45-47
+            if (T && std::fabs(t0) < (pr->primary ? ttol : 0.25 * ttol)) trail.frag = true;   // which root is taken is marginal
+            t0 = t1;
+        }
+        if (!trail.step(!(t0 < 0.), t0, ttol)) return false;   // sphere.rs:49-51
+        if (T && !trail.alive) { trail.finish(); return false; }
         CNT(sphere_hits);
         V3 p = o + scaled(d, t0);                              // sphere.rs:54
         h.point = p;
         h.normal = normalized(p - center);                     // sphere.rs:58
         h.refl = reflectance;
         h.prim = prim_base;
+        trail.finish();
         return true;
     }
     bool intersect(const V3& o, const V3& d, Hit& h) const override { return isect<false>(o, d, h, nullptr); }
@@ -161,15 +188,16 @@ inline bool degenerate_projection(const V3* v, size_t n) {
 
 // shared by triangle.rs:13-15 and polygon.rs:54-56: only the z component of the cross product
 template <bool T>
-inline bool inside(const V3& a, const V3& p1, const V3& p2, Probe* pr) {
+inline bool inside(const V3& a, const V3& p1, const V3& p2, Probe* pr, Trail<T>& trail) {
     V3 u = p1 - a, v = p2 - a;
     double cz = cross(u, v).z;
     CNT(edge_tests);
+    double tol = 0.;
     if (T) {
         double nu = std::sqrt(squared_norm(u)), nv = std::sqrt(squared_norm(v));
-        pr->near(cz, kF32 * (nu * nv + (max_abs3(a) + max_abs3(p1)) * (nu + nv)));
+        tol = kF32 * (nu * nv + (max_abs3(a) + max_abs3(p1)) * (nu + nv));
     }
-    return cz > 0.;
+    return trail.step(cz > 0., cz, tol);
 }
 
 // ---------------------------------------------------------------- triangle.rs:6-83
@@ -200,20 +228,20 @@ struct Triangle {
     }
     template <bool T>
     bool isect_impl(const V3& o, const V3& d, V3& point, Probe* pr) const {
+        Trail<T> trail(pr);
         double dot_product = dot(d, normal);                   // triangle.rs:56
         CNT(plane_tests);
-        if (T) pr->near(std::fabs(dot_product) - 1e-6, kF32);
-        if (std::fabs(dot_product) < 1e-6) return false;       // triangle.rs:57-59
+        if (!trail.step(!(std::fabs(dot_product) < 1e-6), std::fabs(dot_product) - 1e-6, kF32)) return false;   // triangle.rs:57-59
         double dist = dot(center - o, normal) / dot_product;   // triangle.rs:62
         CNT(plane_dist);
-        if (T) pr->near(dist, kF32 * (max_abs3(center) + max_abs3(o)) / std::fabs(dot_product));
-        if (dist < 0.) return false;                           // triangle.rs:65-67
+        if (!trail.step(!(dist < 0.), dist, kF32 * (max_abs3(center) + max_abs3(o)) / std::fabs(dot_product)))
+            return false;                                      // triangle.rs:65-67
         V3 p = o + scaled(d, dist);                            // triangle.rs:69
         CNT(plane_point);
         for (int i = 0; i < 3; i++)                            // triangle.rs:72-76
-            if (!inside<T>(p, v[i], v[(i + 1) % 3], pr)) return false;
+            if (!inside<T>(p, v[i], v[(i + 1) % 3], pr, trail)) return false;
         point = p;
-        return true;
+        return trail.finish();
     }
 };
 
@@ -246,19 +274,20 @@ struct ConvexPolygon : Shape {
     }
     template <bool T>
     bool isect_impl(const V3& o, const V3& d, Hit& h, Probe* pr) const {
+        Trail<T> trail(pr);
         double dotprod = dot(d, plane_normal);                 // polygon.rs:65
         CNT(plane_tests);
-        if (T) pr->near(dotprod, kF32);
-        if (dotprod == 0.) return false;                       // polygon.rs:66-68
+        if (!trail.step(!(dotprod == 0.), dotprod, kF32)) return false;     // polygon.rs:66-68
         double dist = dot(plane_point - o, plane_normal) / dotprod;   // polygon.rs:71
         CNT(plane_dist);
-        if (T) pr->near(dist, kF32 * (max_abs3(plane_point) + max_abs3(o)) / std::fabs(dotprod));
-        if (dist < 0.) return false;                           // polygon.rs:74-76
+        if (!trail.step(!(dist < 0.), dist, kF32 * (max_abs3(plane_point) + max_abs3(o)) / std::fmax(std::fabs(dotprod), 1e-300)))
+            return false;                                      // polygon.rs:74-76
         V3 p = o + scaled(d, dist);                            // polygon.rs:78
         CNT(plane_point);
         size_t n = vertices.size();
         for (size_t i = 0; i < n; i++)                         // polygon.rs:83-91
-            if (!inside<T>(p, vertices[i], vertices[(i + 1) % n], pr)) return false;
+            if (!inside<T>(p, vertices[i], vertices[(i + 1) % n], pr, trail)) return false;
+        if (!trail.finish()) return false;
         h.point = p;
         h.normal = plane_normal;
         h.refl = reflectance;
@@ -298,7 +327,7 @@ struct Obj : Shape {
             V3 p;
             if (triangles[i].isect<T>(o, d, p, pr)) {
                 double dist_hit = squared_norm(p - o);         // obj.rs:197
-                CNT(cand_dist);
+                CNT0(cand_dist);
                 if (T && !anyhit) pr->cand(dist_hit);
                 if (!hit_triangle || dist_hit < dist_closest) {   // obj.rs:198
                     h.point = p;
@@ -375,7 +404,7 @@ bool find_closest_intersect(const V3& o, const V3& d, const OrcScene& sc, Hit& o
         bool got = T ? shape->intersect_probe(o, d, test, pr, false) : shape->intersect(o, d, test);
         if (got) {
             double dist_hit = squared_norm(test.point - o);    // shapes.rs:128
-            CNT(cand_dist);
+            CNT0(cand_dist);
             if (T && !shape->is_obj()) pr->cand(dist_hit);
             if (!hit || dist_hit < dist_closest) {             // shapes.rs:130
                 out = test;

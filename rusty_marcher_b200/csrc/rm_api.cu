@@ -44,9 +44,11 @@ template <typename R> struct DevicePack {
     int* mat_f = nullptr;
     int* order[2] = {nullptr, nullptr};
     int* order_shape[2] = {nullptr, nullptr};
+    void* tri_src = nullptr;
+    void* tri_r = nullptr;
     rm::DeviceScene<R> ds;
     void release() {
-        cudaFree(blob); cudaFree(mat_a); cudaFree(mat_b); cudaFree(mat_f);
+        cudaFree(blob); cudaFree(mat_a); cudaFree(mat_b); cudaFree(mat_f); cudaFree(tri_src); cudaFree(tri_r);
         for (int i = 0; i < 2; i++) { cudaFree(order[i]); cudaFree(order_shape[i]); }
         *this = DevicePack<R>();
     }
@@ -113,6 +115,15 @@ template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
         dp.ds.order_shape[i] = dp.order_shape[i];
         dp.ds.n_order[i] = (int)ps.order[i].size();
     }
+    if (sizeof(R) == 4 && ps.lay.n_tri > 0) {
+        if ((rc = upload_vec(ps.tri_src, &dp.tri_src)) != RM_OK) return rc;
+        CK(cudaMalloc(&dp.tri_r, (size_t)ps.lay.n_tri * 64));
+        dp.ds.tri_src = static_cast<const double*>(dp.tri_src);
+        dp.ds.tri_r = static_cast<rm::R4<float>*>(dp.tri_r);
+    } else if (sizeof(R) == 4) {
+        CK(cudaMalloc(&dp.tri_r, 64));                          // no triangles: the fast path still runs (spheres / n-gons)
+        dp.ds.tri_r = static_cast<rm::R4<float>*>(dp.tri_r);
+    }
     dp.ds.blob = static_cast<const unsigned char*>(dp.blob);
     dp.ds.lay = ps.lay;
     dp.ds.mat_a = static_cast<const rm::R4<R>*>(dp.mat_a);
@@ -144,7 +155,8 @@ void fill_counters(RmStats* st, const unsigned long long* c) {
 
 template <typename R>
 int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_prim, R* d_max, cudaStream_t stream,
-                       int buf_row0_is_tile, unsigned long long* d_counters, rm::FrameParams<R>* out_fp, int* resident) {
+                       int buf_row0_is_tile, unsigned long long* d_counters, rm::FrameParams<R>* out_fp, int* resident,
+                       int* launches = nullptr) {
     if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
     int rc = check_params(params);
     if (rc != RM_OK) return rc;
@@ -157,7 +169,7 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
     if (out_fp) *out_fp = fp;
     const bool cull = params->cull_backfacing != 0;
     if (resident) *resident = dp.ds.lay.n_sph + rm::plane_count<R>(dp.ds.lay, cull);
-    CK(rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, stream));
+    CK(rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, stream, params->camera, launches));
     return RM_OK;
 }
 
@@ -183,11 +195,11 @@ int render_host_impl(RmScene scene, const RmParams* params, R* out_rgb, int32_t*
     CK(cudaMemsetAsync(g.small.p, 0, 1024, s));
     CK(cudaEventRecord(g.ev[1], s));
     int resident = 0;
+    int launches = 0;
     rc = render_device_impl<R>(scene, params, static_cast<R*>(g.rgb.p), out_prim ? static_cast<int*>(g.prim.p) : nullptr,
-                               d_max, s, 1, want_counters ? d_cnt : nullptr, &fp, &resident);
+                               d_max, s, 1, want_counters ? d_cnt : nullptr, &fp, &resident, &launches);
     if (rc != RM_OK) return rc;
     CK(cudaEventRecord(g.ev[2], s));
-    int launches = rows ? 1 : 0;
     const size_t first_px = (size_t)fp.row_begin * fp.width;
     if (out_rgb8 && rows) {
         CK(rm::launch_tonemap<R>(fp, static_cast<const R*>(g.rgb.p), d_max, true, static_cast<unsigned char*>(g.rgb8.p), s));

@@ -88,7 +88,7 @@ render_kernel(const DeviceScene<R> ds, const FrameParams<R> fp, const int cull, 
         st.add(C_PIXELS);
         int pid;
         const Vec3<R> dir = backproject<R>(fp, x, y);
-        const Vec3<R> c = cast_ray<R, S>(sc, fp.camera, dir, fp.background, fp.max_depth, pid, st);
+        const Vec3<R> c = cast_ray<R, S, SceneView<R>>(sc, fp.camera, dir, fp.background, fp.max_depth, pid, st);
         const size_t px = (size_t)(y - fp.buf_row0) * fp.width + x;
         rgb[3 * px] = c.x;
         rgb[3 * px + 1] = c.y;
@@ -113,6 +113,87 @@ render_kernel(const DeviceScene<R> ds, const FrameParams<R> fp, const int cull, 
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
             if (lane == 0 && v) atomicAdd(counters + i, (unsigned long long)v);
         }
+    }
+}
+
+// K0: camera-specialised raster records of every fast-path triangle, in FP64, once per frame.
+__global__ void __launch_bounds__(128)
+prepare_raster_kernel(const double* __restrict__ tri_src, const int n_tri, const double cx, const double cy, const double cz,
+                      R4<float>* __restrict__ tri_r) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_tri) return;
+    const double cam[3] = {cx, cy, cz};
+    R4<float> out[4];
+    prepare_raster(tri_src + (size_t)j * kTriSrcDoubles, cam, out);
+#pragma unroll
+    for (int k = 0; k < 4; k++) tri_r[4 * j + k] = out[k];
+}
+
+// K1, FP32 production kernel (rm_fast.cuh).  Same pixel mapping and fused max as render_kernel.
+template <bool kSmem>
+__global__ void __launch_bounds__(kBlock)
+render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull,
+                   float* __restrict__ rgb, int* __restrict__ prim_id, float* __restrict__ dmax) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    __shared__ float warp_max[kBlock / 32];
+    const BlobLayout& L = ds.lay;
+    const int n_tri = tri_count(L, cull != 0);
+
+    const unsigned char* base = ds.blob;
+    const R4<float>* tri_r = ds.tri_r;
+    if (kSmem) {
+        const uint4* src = reinterpret_cast<const uint4*>(ds.blob);
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+        const int n16 = L.bytes / 16;
+        for (int i = threadIdx.x; i < n16; i += kBlock) dst[i] = __ldg(src + i);
+        const uint4* rsrc = reinterpret_cast<const uint4*>(ds.tri_r);
+        for (int i = threadIdx.x; i < n_tri * 4; i += kBlock) dst[n16 + i] = rsrc[i];
+        __syncthreads();
+        base = smem_raw;
+        tri_r = reinterpret_cast<const R4<float>*>(smem_raw + L.bytes);
+    }
+    FastView fv;
+    fv.sph = reinterpret_cast<const R4<float>*>(base + L.off_sph);
+    fv.sph_id = reinterpret_cast<const int*>(base + L.off_sph_id);
+    fv.n_sph = L.n_sph;
+    fv.tri_g = reinterpret_cast<const R4<float>*>(base + L.off_tri_g);
+    fv.tri_r = tri_r;
+    fv.n_tri = n_tri;
+    fv.poly_slot = reinterpret_cast<const int*>(base + L.off_poly_slot);
+    fv.n_poly = poly_count(L, cull != 0);
+    fv.pln_n = reinterpret_cast<const R4<float>*>(base + L.off_pln_n);
+    fv.pln_c = reinterpret_cast<const R4<float>*>(base + L.off_pln_c);
+    fv.pln_v = reinterpret_cast<const I2*>(base + L.off_pln_v);
+    fv.pln_id = reinterpret_cast<const int*>(base + L.off_pln_id);
+    fv.vert = reinterpret_cast<const R4<float>*>(base + L.off_vert);
+    fv.mat_a = ds.mat_a;
+    fv.mat_b = ds.mat_b;
+    fv.mat_f = ds.mat_f;
+    fv.lgt_p = reinterpret_cast<const R4<float>*>(base + L.off_lgt_p);
+    fv.lgt_c = reinterpret_cast<const R4<float>*>(base + L.off_lgt_c);
+    fv.n_lgt = L.n_lgt;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = blockIdx.x * kTileW + (warp & 3) * 8 + (lane & 7);
+    const int y = fp.row_begin + blockIdx.y * kTileH + (warp >> 2) * 4 + (lane >> 3);
+
+    float m = 0.f;
+    if (x < fp.width && y < fp.row_end) {
+        int pid;
+        const Vec3<float> c = fast_pixel(fv, fp, x, y, pid);
+        const size_t px = (size_t)(y - fp.buf_row0) * fp.width + x;
+        rgb[3 * px] = c.x;
+        rgb[3 * px + 1] = c.y;
+        rgb[3 * px + 2] = c.z;
+        if (prim_id) prim_id[px] = pid;
+        m = fmaxf(fmaxf(fmaxf(c.x, c.y), c.z), 0.f);
+    }
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) warp_max[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kBlock / 32; w++) m = fmaxf(m, warp_max[w]);
+        if (m > 0.f) atomic_max_nonneg(dmax, m);
     }
 }
 
@@ -178,12 +259,38 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(float* __restrict__ sin
 
 }  // namespace
 
+namespace {
+cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& fp, bool cull, float* rgb, int* prim_id,
+                        float* dmax, cudaStream_t stream, const double camera[3], int* launches, dim3 grid) {
+    const int n_tri = tri_count(ds.lay, cull);
+    if (n_tri > 0) {
+        prepare_raster_kernel<<<(n_tri + 127) / 128, 128, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r);
+        if (launches) (*launches)++;
+    }
+    const size_t smem = (size_t)ds.lay.bytes + (size_t)n_tri * 64;
+    cudaError_t e;
+    if (smem <= (size_t)kSmemLimit) {
+        auto k = render_fast_kernel<true>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<grid, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, rgb, prim_id, dmax);
+    } else {
+        render_fast_kernel<false><<<grid, kBlock, 0, stream>>>(ds, fp, cull ? 1 : 0, rgb, prim_id, dmax);
+    }
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+cudaError_t launch_fast(const DeviceScene<double>&, const FrameParams<double>&, bool, double*, int*, double*, cudaStream_t,
+                        const double*, int*, dim3) { return cudaErrorInvalidValue; }
+}  // namespace
+
 template <typename R>
 cudaError_t launch_render(const DeviceScene<R>& ds, const FrameParams<R>& fp, bool cull, R* rgb, int* prim_id, R* dmax,
-                          unsigned long long* counters, cudaStream_t stream) {
+                          unsigned long long* counters, cudaStream_t stream, const double camera[3], int* launches) {
     const int rows = fp.row_end - fp.row_begin;
     if (rows <= 0 || fp.width <= 0) return cudaSuccess;
     const dim3 grid((fp.width + kTileW - 1) / kTileW, (rows + kTileH - 1) / kTileH);
+    if (sizeof(R) == 4 && !counters && camera && ds.tri_r) return launch_fast(ds, fp, cull, rgb, prim_id, dmax, stream, camera, launches, grid);
+    if (launches) (*launches)++;
     const int use_smem = ds.lay.bytes <= kSmemLimit;
     const size_t smem = use_smem ? (size_t)ds.lay.bytes : 0;
     cudaError_t e;
@@ -218,8 +325,8 @@ cudaError_t launch_ffma_probe(float* sink, int iters, int blocks, cudaStream_t s
     return cudaGetLastError();
 }
 
-template cudaError_t launch_render<float>(const DeviceScene<float>&, const FrameParams<float>&, bool, float*, int*, float*, unsigned long long*, cudaStream_t);
-template cudaError_t launch_render<double>(const DeviceScene<double>&, const FrameParams<double>&, bool, double*, int*, double*, unsigned long long*, cudaStream_t);
+template cudaError_t launch_render<float>(const DeviceScene<float>&, const FrameParams<float>&, bool, float*, int*, float*, unsigned long long*, cudaStream_t, const double*, int*);
+template cudaError_t launch_render<double>(const DeviceScene<double>&, const FrameParams<double>&, bool, double*, int*, double*, unsigned long long*, cudaStream_t, const double*, int*);
 template cudaError_t launch_tonemap<float>(const FrameParams<float>&, const float*, const float*, bool, unsigned char*, cudaStream_t);
 template cudaError_t launch_tonemap<double>(const FrameParams<double>&, const double*, const double*, bool, unsigned char*, cudaStream_t);
 

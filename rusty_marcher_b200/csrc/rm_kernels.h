@@ -17,13 +17,20 @@ template <typename R> struct DeviceScene {
     const int* order[2] = {nullptr, nullptr};        // [0] every primitive, [1] after culling
     const int* order_shape[2] = {nullptr, nullptr};
     int n_order[2] = {0, 0};
+    // FP32 fast path: FP64 triangle sources (input of the per-frame prepare kernel) and the
+    // camera-specialised raster records it writes (4 x R4<float> per triangle, rebuilt every frame)
+    const double* tri_src = nullptr;
+    R4<float>* tri_r = nullptr;
 };
 
+// K0 + K1.  With counters == null and R = float this is the production path: prepare_raster_kernel
+// (one thread per triangle, FP64) followed by render_fast_kernel; otherwise the generic kernel.
 // K1: render rows [fp.row_begin, fp.row_end).  rgb: H*W*3 of R; prim_id optional; dmax: scalar R that
 // receives max(old, tile max); counters: 17 x u64 (instrumented kernel) or null (production kernel).
 template <typename R>
 cudaError_t launch_render(const DeviceScene<R>& ds, const FrameParams<R>& fp, bool cull, R* rgb, int* prim_id, R* dmax,
-                          unsigned long long* counters, cudaStream_t stream);
+                          unsigned long long* counters, cudaStream_t stream, const double camera[3] = nullptr,
+                          int* launches = nullptr);
 
 // K4: FrameBuffer::normalize + to_vec (framebuffer.rs:40-82) over rows [fp.row_begin, fp.row_end).
 template <typename R>

@@ -12,6 +12,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define RM_HD __host__ __device__ __forceinline__

@@ -130,16 +130,57 @@ void write_plane(const PlaneTmp& p, R4<double>& c4, R2<double>* vert) {
 }
 // f32 layout: n.C and the affine edge functions about vertex 0, all folded in f64 and then rounded
 // once (see plane_intersect<float> in rm_trace.cuh).
-void write_plane(const PlaneTmp& p, R4<float>& k4, R4<float>* edge) {
-    const size_t nv = p.vxy.size() / 2;
+// edge function i of a plane about its vertex 0, in f64: e_i(q) = A*q.x + B*q.y + C, q = p - v0
+void edge_about_v0(const PlaneTmp& p, size_t i, double& A, double& B, double& C) {
+    const size_t nv = p.vxy.size() / 2, j = (i + 1) % nv;
     const double x0 = p.vxy[0], y0 = p.vxy[1];
-    const double dn = p.c[0] * p.n[0] + p.c[1] * p.n[1] + p.c[2] * p.n[2];
-    k4 = {(float)dn, (float)x0, (float)y0, 0.f};
-    for (size_t i = 0; i < nv; i++) {
-        const size_t j = (i + 1) % nv;
-        const double ax = p.vxy[2 * i] - x0, ay = p.vxy[2 * i + 1] - y0;
-        const double bx = p.vxy[2 * j] - x0, by = p.vxy[2 * j + 1] - y0;
-        edge[i] = {(float)(ay - by), (float)(bx - ax), (float)(ax * by - ay * bx), 0.f};
+    const double ax = p.vxy[2 * i] - x0, ay = p.vxy[2 * i + 1] - y0;
+    const double bx = p.vxy[2 * j] - x0, by = p.vxy[2 * j + 1] - y0;
+    A = ay - by;
+    B = bx - ax;
+    C = ax * by - ay * bx;
+}
+double plane_dn(const PlaneTmp& p) { return p.c[0] * p.n[0] + p.c[1] * p.n[1] + p.c[2] * p.n[2]; }
+
+void write_plane(const PlaneTmp& p, R4<float>& k4, R4<float>* edge) {
+    k4 = {(float)plane_dn(p), (float)p.vxy[0], (float)p.vxy[1], 0.f};
+    for (size_t i = 0; i < p.vxy.size() / 2; i++) {
+        double A, B, C;
+        edge_about_v0(p, i, A, B, C);
+        edge[i] = {(float)A, (float)B, (float)C, 0.f};
+    }
+}
+
+// fast-path records of a 3-vertex plane: FP64 source for prepare_raster and the FP32 general-ray record
+void write_triangle(const PlaneTmp& p, double* src, R4<float>* g) {
+    double A[3], B[3], C[3];
+    for (size_t i = 0; i < 3; i++) edge_about_v0(p, i, A[i], B[i], C[i]);   // C[0] == C[2] == 0: both edges touch vertex 0
+    const double dn = plane_dn(p);
+    const float thr = (p.thr_is_triangle != 0.) ? std::nextafterf(1e-6f, 0.f) : 0.f;
+    const double s[kTriSrcDoubles] = {p.n[0], p.n[1], p.n[2], dn, p.vxy[0], p.vxy[1], A[0], B[0], A[1], B[1], C[1],
+                                      A[2], B[2], (double)thr, (double)p.id, 0.};
+    std::memcpy(src, s, sizeof s);
+    float idf;
+    std::memcpy(&idf, &p.id, 4);
+    g[0] = {(float)p.n[0], (float)p.n[1], (float)p.n[2], (float)dn};
+    g[1] = {(float)p.vxy[0], (float)p.vxy[1], (float)A[0], (float)B[0]};
+    g[2] = {(float)A[1], (float)B[1], (float)C[1], (float)A[2]};
+    g[3] = {(float)B[2], thr, idf, 0.f};
+}
+template <typename R> void write_fast(const std::vector<PlaneTmp>&, BlobLayout&, unsigned char*, PackedScene<R>&) {}
+template <> void write_fast<float>(const std::vector<PlaneTmp>& pln, BlobLayout& L, unsigned char* b, PackedScene<float>& out) {
+    auto* g = reinterpret_cast<R4<float>*>(b + L.off_tri_g);
+    auto* slot = reinterpret_cast<int*>(b + L.off_poly_slot);
+    out.tri_src.assign((size_t)L.n_tri * kTriSrcDoubles + kTriSrcDoubles, 0.);
+    int t = 0, k = 0;
+    for (size_t i = 0; i < pln.size(); i++) {
+        if (pln[i].cls == 2) continue;
+        if (pln[i].vxy.size() == 6) {
+            write_triangle(pln[i], out.tri_src.data() + (size_t)t * kTriSrcDoubles, g + 4 * t);
+            t++;
+        } else {
+            slot[k++] = (int)i;
+        }
     }
 }
 
@@ -218,6 +259,14 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
         L.n_vert += (int)p.vxy.size() / 2;
     }
     L.n_lgt = fs.n_lights;
+    if (sizeof(R) == 4) {
+        for (auto& p : pln) {
+            if (p.cls == 2) continue;
+            const bool tri = p.vxy.size() == 6;
+            (tri ? L.n_tri : L.n_poly)++;
+            if (p.cls == 0) (tri ? L.n_tri_live : L.n_poly_live)++;
+        }
+    }
     int off = 0;
     L.off_sph = off;    off = align32(off + L.n_sph * (int)sizeof(R4<R>));
     L.off_pln_n = off;  off = align32(off + L.n_pln * (int)sizeof(R4<R>));
@@ -228,6 +277,8 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
     L.off_pln_v = off;  off = align32(off + L.n_pln * (int)sizeof(I2));
     L.off_sph_id = off; off = align32(off + L.n_sph * (int)sizeof(int));
     L.off_pln_id = off; off = align32(off + L.n_pln * (int)sizeof(int));
+    L.off_tri_g = off;  off = align32(off + L.n_tri * 4 * (int)sizeof(R4<float>));
+    L.off_poly_slot = off; off = align32(off + L.n_poly * (int)sizeof(int));
     L.bytes = std::max(off, 32);
     out.blob.assign(L.bytes / 32, BlobChunk{});
     unsigned char* b = reinterpret_cast<unsigned char*>(out.blob.data());
@@ -257,6 +308,7 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
         v0 += nv;
         b_pid[i] = p.id;
     }
+    write_fast<R>(pln, L, b, out);
     for (int l = 0; l < L.n_lgt; l++) {
         const RmLight& lg = fs.lights[l];
         b_lp[l] = mk4<R>(lg.position[0], lg.position[1], lg.position[2], lg.intensity);

@@ -6,6 +6,7 @@
 // SoA arrays (so a CTA can stage it into shared memory with 128-bit copies):
 //   [sph R4 x n_sph][pln_n R4 x n_pln][pln_c R4 x n_pln][vert R2 x n_vert][lgt_p R4 x n_lgt]
 //   [lgt_c R4 x n_lgt][pln_v I2 x n_pln][sph_id int x n_sph][pln_id int x n_pln]
+//   FP32 only: [tri_g 4 x R4 x n_tri][poly_slot int x n_poly]
 // Planar primitives that can never pass the reference's z-only inside test are sorted to the end
 // (hittable | back-facing | degenerate projection) so culling is just a shorter loop.  Materials (touched once per hit) and
 // the scene-order lists of the instrumented kernel stay in plain global arrays.
@@ -15,7 +16,7 @@
 #include <vector>
 
 #include "../../include/rm_b200.h"
-#include "rm_trace.cuh"
+#include "rm_fast.cuh"
 
 namespace rm {
 
@@ -23,6 +24,10 @@ struct BlobLayout {
     int n_sph = 0, n_pln = 0, n_pln_live = 0, n_pln_nondegenerate = 0, n_vert = 0, n_lgt = 0;
     int off_sph = 0, off_pln_n = 0, off_pln_c = 0, off_vert = 0, off_lgt_p = 0, off_lgt_c = 0;
     int off_pln_v = 0, off_sph_id = 0, off_pln_id = 0;
+    // FP32 fast path (rm_fast.cuh): non-degenerate 3-vertex planes as fixed records, the other
+    // non-degenerate planes as indices into the generic arrays; hittable ones first in both lists
+    int n_tri = 0, n_tri_live = 0, n_poly = 0, n_poly_live = 0;
+    int off_tri_g = 0, off_poly_slot = 0;
     int bytes = 0;
 };
 
@@ -35,11 +40,15 @@ template <typename R> RM_HD int plane_count(const BlobLayout& L, bool cull) {
     return cull ? L.n_pln_live : (sizeof(R) == 4 ? L.n_pln_nondegenerate : L.n_pln);
 }
 
+RM_HD int tri_count(const BlobLayout& L, bool cull) { return cull ? L.n_tri_live : L.n_tri; }
+RM_HD int poly_count(const BlobLayout& L, bool cull) { return cull ? L.n_poly_live : L.n_poly; }
+
 template <typename R> struct PackedScene {
     BlobLayout lay;
     std::vector<BlobChunk> blob;      // lay.bytes bytes, 32-byte aligned
     const unsigned char* blob_data() const { return reinterpret_cast<const unsigned char*>(blob.data()); }
     size_t blob_bytes() const { return blob.size() * sizeof(BlobChunk); }
+    std::vector<double> tri_src;      // FP32 pack only: kTriSrcDoubles per fast-path triangle (prepare_raster input)
     std::vector<R4<R>> mat_a, mat_b;
     std::vector<int> mat_f;
     // scene-order traversal lists: [0] = every primitive, [1] = after culling

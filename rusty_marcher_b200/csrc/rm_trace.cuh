@@ -48,7 +48,24 @@ template <typename R> struct VertOf { typedef R2<R> type; };
 template <> struct VertOf<float> { typedef R4<float> type; };
 template <typename R> using VertT = typename VertOf<R>::type;
 
+template <typename R> struct HitRec;
+template <typename R> struct SceneView;
+template <typename R, bool S>
+RM_HD bool find_closest_intersect(const SceneView<R>& sc, const Vec3<R> o, const Vec3<R> d, HitRec<R>& best, Counters<S>& st);
+template <typename R, bool S>
+RM_HD bool intersect_shape_set(const SceneView<R>& sc, const Vec3<R> o, const Vec3<R> d, Counters<S>& st);
+template <typename R> RM_HD void surface_of(const SceneView<R>& sc, HitRec<R>& h, const Vec3<R> o, const Vec3<R> d, Vec3<R>& normal);
+
 template <typename R> struct SceneView {
+    // the query interface cast_ray / direct_lighting are written against (rm_fast.cuh has a second implementation)
+    template <bool S> RM_HD bool closest(const Vec3<R> o, const Vec3<R> d, int /*level*/, HitRec<R>& h, Counters<S>& st) const {
+        return find_closest_intersect<R, S>(*this, o, d, h, st);
+    }
+    template <bool S> RM_HD bool anyhit(const Vec3<R> o, const Vec3<R> d, Counters<S>& st) const {
+        return intersect_shape_set<R, S>(*this, o, d, st);
+    }
+    RM_HD void surface(HitRec<R>& h, const Vec3<R> o, const Vec3<R> d, Vec3<R>& normal) const { surface_of(*this, h, o, d, normal); }
+
     const R4<R>* sph;
     const int* sph_id;
     int n_sph;
@@ -330,9 +347,19 @@ RM_HD bool refract_ray(Vec3<R> incident, Vec3<R> point, Vec3<R> hit_normal, R re
     return true;
 }
 
+// point + unit normal of the winning hit (sphere.rs:54-58; planes carry their precomputed normal)
+template <typename R> RM_HD void surface_of(const SceneView<R>& sc, HitRec<R>& h, const Vec3<R> o, const Vec3<R> d, Vec3<R>& normal) {
+    if (h.slot < sc.n_sph) {
+        sphere_point_normal(sc.sph[h.slot], o, d, h.p, h.p, normal);
+    } else {
+        if (sizeof(R) == 4) h.p = axpy(o, d, h.dist);          // f32: point of the winner only
+        normal = xyz(sc.pln_n[h.slot - sc.n_sph]);
+    }
+}
+
 // ---------------------------------------------------------------- renderer.rs:138-193
-template <typename R, bool S>
-RM_HD Vec3<R> direct_lighting(const SceneView<R>& sc, const Vec3<R> origin, const Vec3<R> point, const Vec3<R> normal,
+template <typename R, bool S, typename SC>
+RM_HD Vec3<R> direct_lighting(const SC& sc, const Vec3<R> origin, const Vec3<R> point, const Vec3<R> normal,
                               const R4<R> ma, const R4<R> mb, Counters<S>& st) {
     Vec3<R> acc = {R(0), R(0), R(0)};
     for (int l = 0; l < sc.n_lgt; l++) {
@@ -343,7 +370,7 @@ RM_HD Vec3<R> direct_lighting(const SceneView<R>& sc, const Vec3<R> origin, cons
         R side = dot(light_dir, normal);
         st.add(C_LIGHT_EVAL);
         Vec3<R> so = (side < R(0)) ? axmy(point, normal, R(1e-3)) : axpy(point, normal, R(1e-3)); // renderer.rs:168-172
-        if (intersect_shape_set<R, S>(sc, so, light_dir, st)) continue;                           // renderer.rs:174-177
+        if (sc.template anyhit<S>(so, light_dir, st)) continue;                                   // renderer.rs:174-177
         st.add(C_LIT);
         R diffusion = Num<R>::max_(side, R(0));                                                   // renderer.rs:138-140
         Vec3<R> kd = {ma.x, ma.y, ma.z};
@@ -362,8 +389,8 @@ RM_HD Vec3<R> direct_lighting(const SceneView<R>& sc, const Vec3<R> origin, cons
 // pushed for a glass hit that spawned at least one secondary ray; it keeps the partial sum and the
 // pending refracted ray so that the additions happen in the reference's order:
 //   c = bg + direct;  c += cast(reflected) * k;  c += cast(refracted) * (1 - k).
-template <typename R, bool S>
-RM_HD Vec3<R> cast_ray(const SceneView<R>& sc, Vec3<R> o, Vec3<R> d, R background, int max_depth, int& primary_id,
+template <typename R, bool S, typename SC>
+RM_HD Vec3<R> cast_ray(const SC& sc, Vec3<R> o, Vec3<R> d, R background, int max_depth, int& primary_id,
                        Counters<S>& st) {
     struct Frame {
         Vec3<R> c, ro, rd;
@@ -381,22 +408,17 @@ RM_HD Vec3<R> cast_ray(const SceneView<R>& sc, Vec3<R> o, Vec3<R> d, R backgroun
             v = bg;                                             // renderer.rs:262-264
         } else {
             HitRec<R> h;
-            bool got = find_closest_intersect<R, S>(sc, o, d, h, st);   // renderer.rs:266
+            bool got = sc.template closest<S>(o, d, level, h, st);      // renderer.rs:266
             if (level == 1 && got) primary_id = h.id;
             if (!got) {
                 v = (level > 1) ? bg : Vec3<R>{R(0), R(0), R(0)};       // renderer.rs:300-306
             } else {
                 st.add(C_HITS);
                 Vec3<R> normal;
-                if (h.slot < sc.n_sph) {
-                    sphere_point_normal(sc.sph[h.slot], o, d, h.p, h.p, normal);         // sphere.rs:54-58
-                } else {
-                    if (sizeof(R) == 4) h.p = axpy(o, d, h.dist);                        // f32: point of the winner only
-                    normal = xyz(sc.pln_n[h.slot - sc.n_sph]);
-                }
+                sc.surface(h, o, d, normal);
                 const R4<R> ma = sc.mat_a[h.id];
                 const R4<R> mb = sc.mat_b[h.id];
-                Vec3<R> c = bg + direct_lighting<R, S>(sc, o, h.p, normal, ma, mb, st);   // renderer.rs:272-275
+                Vec3<R> c = bg + direct_lighting<R, S, SC>(sc, o, h.p, normal, ma, mb, st);   // renderer.rs:272-275
                 bool pushed = false;
                 if (sc.mat_f[h.id] & 1) {                       // renderer.rs:277
                     st.add(C_GLASS);

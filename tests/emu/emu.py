@@ -15,7 +15,7 @@ _lib = None
 
 def build(force=False):
     srcs = [os.path.join(HERE, "rm_emu.cpp")] + [os.path.join(ROOT, "rusty_marcher_b200", "csrc", f) for f in
-                                                 ("rm_trace.cuh", "rm_math.cuh", "rm_scene.cpp", "rm_scene.h", "rm_host.cpp")]
+                                                 ("rm_trace.cuh", "rm_fast.cuh", "rm_math.cuh", "rm_scene.cpp", "rm_scene.h", "rm_host.cpp")]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(s) for s in srcs):
         return LIB
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-pthread",
@@ -28,7 +28,7 @@ def lib():
     if _lib is None:
         build()
         _lib = C.CDLL(LIB)
-        for name in ("emu_render_f32", "emu_render_f64"):
+        for name in ("emu_render_f32", "emu_render_f64", "emu_render_fast"):
             fn = getattr(_lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(_abi.RmFlatScene), C.POINTER(_abi.RmParams), C.c_void_p, C.c_void_p,
@@ -44,11 +44,11 @@ def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=Tru
     p.max_depth, p.background, p.patch_size = max_depth, 0.1, 32
     p.patch_row_begin, p.patch_row_end = patch_rows
     p.cull_backfacing = int(cull)
-    dt = np.float32 if precision == "f32" else np.float64
+    dt = np.float32 if precision in ("f32", "fast") else np.float64
     rgb = np.zeros((height, width, 3), dtype=dt)
     ids = np.full((height, width), -1, dtype=np.int32)
     st = _abi.RmStats()
-    fn = lib().emu_render_f32 if precision == "f32" else lib().emu_render_f64
+    fn = {"f32": lib().emu_render_f32, "f64": lib().emu_render_f64, "fast": lib().emu_render_fast}[precision]
     rc = fn(C.byref(flat.c), C.byref(p), rgb.ctypes.data, ids.ctypes.data, C.byref(st), threads)
     if rc != 0:
         raise RuntimeError("emu rc %d" % rc)

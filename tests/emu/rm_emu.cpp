@@ -69,7 +69,7 @@ int emu_render_impl(const RmFlatScene* fs, const RmParams* p, R* out_rgb, int32_
                     st.add(rm::C_PIXELS);
                     int pid;
                     rm::Vec3<R> dir = rm::backproject<R>(fp, x, y);
-                    rm::Vec3<R> c = rm::cast_ray<R, true>(sc, fp.camera, dir, fp.background, fp.max_depth, pid, st);
+                    rm::Vec3<R> c = rm::cast_ray<R, true, rm::SceneView<R>>(sc, fp.camera, dir, fp.background, fp.max_depth, pid, st);
                     size_t px = (size_t)y * fp.width + x;
                     out_rgb[3 * px] = c.x; out_rgb[3 * px + 1] = c.y; out_rgb[3 * px + 2] = c.z;
                     if (prim) prim[px] = pid;
@@ -94,7 +94,76 @@ int emu_render_impl(const RmFlatScene* fs, const RmParams* p, R* out_rgb, int32_
 
 }  // namespace
 
+// the FP32 production path (rm_fast.cuh): prepare_raster + fast_pixel, as the CUDA kernels run them
+int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
+    rm::PackedScene<float> ps;
+    std::string err;
+    int rc = rm::pack_scene<float>(*fs, ps, err);
+    if (rc != RM_OK) return rc;
+    if (p->width % 32) return RM_ERR_DIMENSIONS;
+    const bool cull = p->cull_backfacing != 0;
+    const rm::BlobLayout& L = ps.lay;
+    const unsigned char* base = ps.blob_data();
+    const int n_tri = rm::tri_count(L, cull);
+    std::vector<rm::R4<float>> tri_r((size_t)n_tri * 4 + 4);
+    for (int j = 0; j < n_tri; j++) rm::prepare_raster(ps.tri_src.data() + (size_t)j * rm::kTriSrcDoubles, p->camera, tri_r.data() + 4 * j);
+    rm::FastView fv0;
+    fv0.sph = reinterpret_cast<const rm::R4<float>*>(base + L.off_sph);
+    fv0.sph_id = reinterpret_cast<const int*>(base + L.off_sph_id);
+    fv0.n_sph = L.n_sph;
+    fv0.tri_g = reinterpret_cast<const rm::R4<float>*>(base + L.off_tri_g);
+    fv0.tri_r = tri_r.data();
+    fv0.n_tri = n_tri;
+    fv0.poly_slot = reinterpret_cast<const int*>(base + L.off_poly_slot);
+    fv0.n_poly = rm::poly_count(L, cull);
+    fv0.pln_n = reinterpret_cast<const rm::R4<float>*>(base + L.off_pln_n);
+    fv0.pln_c = reinterpret_cast<const rm::R4<float>*>(base + L.off_pln_c);
+    fv0.pln_v = reinterpret_cast<const rm::I2*>(base + L.off_pln_v);
+    fv0.pln_id = reinterpret_cast<const int*>(base + L.off_pln_id);
+    fv0.vert = reinterpret_cast<const rm::R4<float>*>(base + L.off_vert);
+    fv0.mat_a = ps.mat_a.data();
+    fv0.mat_b = ps.mat_b.data();
+    fv0.mat_f = ps.mat_f.data();
+    fv0.lgt_p = reinterpret_cast<const rm::R4<float>*>(base + L.off_lgt_p);
+    fv0.lgt_c = reinterpret_cast<const rm::R4<float>*>(base + L.off_lgt_c);
+    fv0.n_lgt = L.n_lgt;
+    const rm::FrameParams<float> fp = rm::make_frame_params<float>(*p);
+    std::atomic<int> next{fp.row_begin};
+    std::vector<float> tmax(n_threads, 0.f);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++) {
+        pool.emplace_back([&, t] {
+            rm::FastView fv = fv0;
+            for (;;) {
+                int y = next.fetch_add(1);
+                if (y >= fp.row_end) break;
+                for (int x = 0; x < fp.width; x++) {
+                    int pid;
+                    rm::Vec3<float> c = rm::fast_pixel(fv, fp, x, y, pid);
+                    size_t px = (size_t)y * fp.width + x;
+                    out_rgb[3 * px] = c.x; out_rgb[3 * px + 1] = c.y; out_rgb[3 * px + 2] = c.z;
+                    if (prim) prim[px] = pid;
+                    float m = fmaxf(fmaxf(c.x, c.y), c.z);
+                    if (m > tmax[t]) tmax[t] = m;
+                }
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        float m = 0;
+        for (float v : tmax) m = v > m ? v : m;
+        stats->max_value = (double)m;
+        stats->resident_prims = L.n_sph + n_tri + fv0.n_poly;
+    }
+    return RM_OK;
+}
+
 extern "C" {
+int emu_render_fast(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
+    return emu_render_fast_impl(fs, p, out_rgb, prim, stats, n_threads);
+}
 int emu_render_f32(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
     return emu_render_impl<float>(fs, p, out_rgb, prim, stats, n_threads);
 }

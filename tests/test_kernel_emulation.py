@@ -39,10 +39,11 @@ def test_fp64_kernel_code_is_bit_exact(case, cull):
         assert got["counters"]["plane_tests"] <= ref["counters"]["plane_tests"]
 
 
+@pytest.mark.parametrize("path", ["f32", "fast"])   # generic FP32 kernel code / production fast path (rm_fast.cuh)
 @pytest.mark.parametrize("cull", [False, True])
-def test_fp32_kernel_code_within_tolerance(case, cull):
+def test_fp32_kernel_code_within_tolerance(case, cull, path):
     name, w, h, depth, scene, ref = case
-    got = emu.render(scene, w, h, "f32", max_depth=depth, cull=cull)
+    got = emu.render(scene, w, h, path, max_depth=depth, cull=cull)
     m = np.float32(got["rgb"].max())
     rgb8 = (np.float32(255) * np.clip(got["rgb"] * (np.float32(1) / m), 0, 1)).astype(np.uint8)
     parity.check_fp32(got, ref, (h // 32) * 32, rgb8)
@@ -50,8 +51,8 @@ def test_fp32_kernel_code_within_tolerance(case, cull):
 
 def test_row_tiles_reassemble_to_the_full_frame():
     scene = workloads.scene("demo")
-    full = emu.render(scene, 128, 160, "f32")
-    parts = [emu.render(scene, 128, 160, "f32", patch_rows=r) for r in ((0, 2), (2, 3), (3, 5))]
+    full = emu.render(scene, 128, 160, "fast")
+    parts = [emu.render(scene, 128, 160, "fast", patch_rows=r) for r in ((0, 2), (2, 3), (3, 5))]
     acc = np.zeros_like(full["rgb"])
     for p, (a, b) in zip(parts, ((0, 2), (2, 3), (3, 5))):
         assert np.all(p["rgb"][:a * 32] == 0) and np.all(p["rgb"][b * 32:] == 0)
@@ -72,7 +73,7 @@ def test_depth_cap_semantics():
 def test_empty_scene_and_camera_offset():
     import rusty_marcher_b200 as rm
     empty = rm.Scene.new()
-    r = emu.render(empty, 64, 32, "f32")
+    r = emu.render(empty, 64, 32, "fast")
     assert np.all(r["rgb"] == 0) and np.all(r["prim_id"] == -1)
     scene = workloads.scene("demo")
     scene.offset_camera((5., 0., -5.))                          # main.rs:124-171 moves by +-5
