@@ -115,14 +115,13 @@ template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
         dp.ds.order_shape[i] = dp.order_shape[i];
         dp.ds.n_order[i] = (int)ps.order[i].size();
     }
-    if (sizeof(R) == 4 && ps.lay.n_tri > 0) {
+    if (sizeof(R) == 4) {
         if ((rc = upload_vec(ps.tri_src, &dp.tri_src)) != RM_OK) return rc;
-        CK(cudaMalloc(&dp.tri_r, (size_t)ps.lay.n_tri * 64));
+        CK(cudaMalloc(&dp.tri_r, (size_t)ps.lay.n_tri * 64 + 64 + 64));   // raster records + the tile counter behind them
+        CK(cudaMemset(dp.tri_r, 0, (size_t)ps.lay.n_tri * 64 + 64 + 64));
         dp.ds.tri_src = static_cast<const double*>(dp.tri_src);
         dp.ds.tri_r = static_cast<rm::R4<float>*>(dp.tri_r);
-    } else if (sizeof(R) == 4) {
-        CK(cudaMalloc(&dp.tri_r, 64));                          // no triangles: the fast path still runs (spheres / n-gons)
-        dp.ds.tri_r = static_cast<rm::R4<float>*>(dp.tri_r);
+        dp.ds.tile_counter = reinterpret_cast<int*>(static_cast<char*>(dp.tri_r) + (size_t)ps.lay.n_tri * 64 + 64);
     }
     dp.ds.blob = static_cast<const unsigned char*>(dp.blob);
     dp.ds.lay = ps.lay;

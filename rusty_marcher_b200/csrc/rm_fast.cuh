@@ -25,9 +25,21 @@ namespace rm {
 constexpr int kTriSrcDoubles = 16;   // n[3], dn, v0x, v0y, A0, B0, A1, B1, C1, A2, B2, thr, id, pad
 
 #if defined(__CUDA_ARCH__)
+#define RM_PIN(v) asm volatile("" : "+f"(v))
+#else
+#define RM_PIN(v) (void)(v)
+#endif
+
+#if defined(__CUDA_ARCH__)
 RM_HD float fast_div(float a, float b) { return __fdividef(a, b); }
+// MUFU.RSQ (2 ulp) + one Newton step: 1/sqrt(a) to ~1 ulp in 4 instructions instead of IEEE sqrt + IEEE divide
+RM_HD float fast_rsqrt(float a) {
+    const float r = rsqrtf(a);
+    return r * fmaf(-0.5f * a * r, r, 1.5f);
+}
 #else
 RM_HD float fast_div(float a, float b) { return a / b; }
+RM_HD float fast_rsqrt(float a) { return 1.f / sqrtf(a); }
 #endif
 
 // Camera-specialised record of one triangle (4 x R4<float>), from its FP64 source record.
@@ -118,34 +130,6 @@ struct FastView {
         }
     }
 
-    // closest hit of the primary ray of pixel direction D = (X, Y, -1), |D| = lenD, d = D / lenD
-    RM_HD void primary(const Vec3<float> cam, const float X, const float Y, const float lenD, const Vec3<float> d) {
-        bool hit = false;
-        HitRec<float> best;
-        Counters<false> st;
-        for (int i = 0; i < n_sph; i++) {
-            Cand<float> c;
-            if (sphere_intersect<false>(sph[i], cam, d, c, st)) keep(best, hit, c.key, i, sph_id[i]);
-        }
-        for (int j = 0; j < n_tri; j++) {
-            const R4<float> r0 = tri_r[4 * j], r1 = tri_r[4 * j + 1], r2 = tri_r[4 * j + 2], r3 = tri_r[4 * j + 3];
-            const float dpD = fmaf(r0.x, X, fmaf(r0.y, Y, r0.z));
-            const float s0 = fmaf(r1.x, X, fmaf(r1.y, Y, r1.z));
-            const float s1 = fmaf(r2.x, X, fmaf(r2.y, Y, r2.z));
-            const float s2 = fmaf(r3.x, X, fmaf(r3.y, Y, r3.z));
-            if (fminf(fminf(s0, s1), s2) > 0.f && dpD > r1.w * lenD)
-                keep(best, hit, fast_div(r0.w * lenD, dpD), n_sph + j, as_int(r2.w));
-        }
-        for (int k = 0; k < n_poly; k++) {
-            const int i = poly_slot[k];
-            Cand<float> c;
-            if (plane_intersect<false>(pln_n[i], pln_c[i], pln_v[i], vert, cam, d, c, st))
-                keep(best, hit, c.key, n_sph + n_tri + i, pln_id[i]);
-        }
-        prim_got = hit;
-        prim_hit = best;
-    }
-
     template <bool S> RM_HD bool closest(const Vec3<float> o, const Vec3<float> d, int level, HitRec<float>& h, Counters<S>& st) const {
         if (level == 1) {
             h = prim_hit;
@@ -193,16 +177,101 @@ struct FastView {
     }
 };
 
-// One pixel of the FP32 production kernel.
-RM_HD Vec3<float> fast_pixel(FastView& fv, const FrameParams<float>& fp, int x, int y, int& primary_id) {
+// Primary visibility of kPx horizontally adjacent pixels of one thread (the CUDA kernel uses 4; they
+// share Y, so each affine function of a triangle costs one FFMA for the row part plus one FFMA per
+// pixel, and the four 128-bit record loads are amortised over kPx pixels; the independent chains give
+// the FP32 pipe its ILP).  Results: ray parameter, slot and primitive id of the closest hit (slot < 0: miss).
+template <int kPx>
+RM_HD void fast_primary(const FastView& fv, const FrameParams<float>& fp, const int x0, const int y, float* best_t,
+                        int* best_slot, int* best_id) {
+    float Y = (float(y) - fp.half_h) * fp.sy;
+    float X[kPx];
+    RM_PIN(Y);      // keep the pixel coordinates in registers: ptxas otherwise rematerialises them (int->float,
+                    // sub, mul per pixel) inside the triangle loop when registers are tight
+#pragma unroll
+    for (int k = 0; k < kPx; k++) {
+        X[k] = (float(x0 + k) - fp.half_w) * fp.sx;
+        RM_PIN(X[k]);
+        best_slot[k] = -1;
+        best_id[k] = -1;
+        best_t[k] = 0.f;
+    }
+    // triangles: no normalisation, no division unless a pixel is inside the triangle.  The four pixels'
+    // predicates are folded into one branch so the common (all miss) iteration is straight-line code.
+#pragma unroll 2
+    for (int j = 0; j < fv.n_tri; j++) {
+        const R4<float> r0 = fv.tri_r[4 * j], r1 = fv.tri_r[4 * j + 1], r2 = fv.tri_r[4 * j + 2], r3 = fv.tri_r[4 * j + 3];
+        const float bd = fmaf(r0.y, Y, r0.z), b0 = fmaf(r1.y, Y, r1.z), b1 = fmaf(r2.y, Y, r2.z), b2 = fmaf(r3.y, Y, r3.z);
+        float mk[kPx], dpD[kPx];
+        float any = 0.f;
+#pragma unroll
+        for (int k = 0; k < kPx; k++) {
+            dpD[k] = fmaf(r0.x, X[k], bd);
+            const float s0 = fmaf(r1.x, X[k], b0), s1 = fmaf(r2.x, X[k], b1), s2 = fmaf(r3.x, X[k], b2);
+            mk[k] = fminf(fminf(fminf(s0, s1), s2), dpD[k]);   // > 0 <=> inside all three edges and in front
+            any = fmaxf(any, mk[k]);
+        }
+        if (any > 0.f) {
+#pragma unroll
+            for (int k = 0; k < kPx; k++) {
+                if (mk[k] > 0.f) {
+                    const float lenD = sqrtf(fmaf(X[k], X[k], fmaf(Y, Y, 1.f)));
+                    if (dpD[k] > r1.w * lenD) {                  // |d.n| >= 1e-6 (triangle.rs:57) on the unit direction
+                        const float t = fast_div(r0.w * lenD, dpD[k]);   // triangle.rs:62
+                        const int id = FastView::as_int(r2.w);
+                        if (best_slot[k] < 0 || t < best_t[k] || (t == best_t[k] && id < best_id[k])) {
+                            best_t[k] = t;
+                            best_slot[k] = fv.n_sph + j;
+                            best_id[k] = id;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (fv.n_sph + fv.n_poly == 0) return;
+    // spheres / n-gons: the general routines from the camera
+#pragma unroll 1
+    for (int k = 0; k < kPx; k++) {
+        const float inv = fast_rsqrt(fmaf(X[k], X[k], fmaf(Y, Y, 1.f)));
+        const Vec3<float> d = {X[k] * inv, Y * inv, -inv};
+        bool hit = best_slot[k] >= 0;
+        HitRec<float> best;
+        best.dist = best_t[k];
+        best.slot = best_slot[k];
+        best.id = best_id[k];
+        Counters<false> st;
+        for (int i = 0; i < fv.n_sph; i++) {
+            Cand<float> c;
+            if (sphere_intersect<false>(fv.sph[i], fp.camera, d, c, st)) FastView::keep(best, hit, c.key, i, fv.sph_id[i]);
+        }
+        for (int q = 0; q < fv.n_poly; q++) {
+            const int i = fv.poly_slot[q];
+            Cand<float> c;
+            if (plane_intersect<false>(fv.pln_n[i], fv.pln_c[i], fv.pln_v[i], fv.vert, fp.camera, d, c, st))
+                FastView::keep(best, hit, c.key, fv.n_sph + fv.n_tri + i, fv.pln_id[i]);
+        }
+        if (hit) {
+            best_t[k] = best.dist;
+            best_slot[k] = best.slot;
+            best_id[k] = best.id;
+        }
+    }
+}
+
+// Shading + recursion of one pixel whose primary ray hit (t, slot, id): renderer.rs:254-309 from level 1.
+RM_HD Vec3<float> fast_shade(FastView& fv, const FrameParams<float>& fp, const int x, const int y, const float t, const int slot,
+                             const int id) {
     const float X = (float(x) - fp.half_w) * fp.sx, Y = (float(y) - fp.half_h) * fp.sy;
-    const float len2 = fmaf(X, X, fmaf(Y, Y, 1.f));
-    const float lenD = sqrtf(len2);
-    const float inv = 1.f / lenD;                              // geometry.rs:104-109: scale(1/norm)
+    const float inv = fast_rsqrt(fmaf(X, X, fmaf(Y, Y, 1.f)));     // geometry.rs:104-109: scale(1/norm)
     const Vec3<float> d = {X * inv, Y * inv, -inv};
-    fv.primary(fp.camera, X, Y, lenD, d);
+    fv.prim_got = true;
+    fv.prim_hit.dist = t;
+    fv.prim_hit.slot = slot;
+    fv.prim_hit.id = id;
     Counters<false> st;
-    return cast_ray<float, false, FastView>(fv, fp.camera, d, fp.background, fp.max_depth, primary_id, st);
+    int pid;
+    return cast_ray<float, false, FastView>(fv, fp.camera, d, fp.background, fp.max_depth, pid, st);
 }
 
 }  // namespace rm

@@ -18,6 +18,8 @@
 // fuse at all to stay bit-faithful to the reference.
 #include "rm_kernels.h"
 
+#include <algorithm>
+
 namespace rm {
 
 namespace {
@@ -119,8 +121,9 @@ render_kernel(const DeviceScene<R> ds, const FrameParams<R> fp, const int cull, 
 // K0: camera-specialised raster records of every fast-path triangle, in FP64, once per frame.
 __global__ void __launch_bounds__(128)
 prepare_raster_kernel(const double* __restrict__ tri_src, const int n_tri, const double cx, const double cy, const double cz,
-                      R4<float>* __restrict__ tri_r) {
+                      R4<float>* __restrict__ tri_r, int* __restrict__ tile_counter) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) *tile_counter = 0;                              // work counter of the render kernel that follows
     if (j >= n_tri) return;
     const double cam[3] = {cx, cy, cz};
     R4<float> out[4];
@@ -129,18 +132,40 @@ prepare_raster_kernel(const double* __restrict__ tri_src, const int n_tri, const
     for (int k = 0; k < 4; k++) tri_r[4 * j + k] = out[k];
 }
 
-// K1, FP32 production kernel (rm_fast.cuh).  Same pixel mapping and fused max as render_kernel.
+// K1, FP32 production kernel (rm_fast.cuh).  Persistent: the grid is (SMs x resident CTAs), every
+// CTA stages the scene into shared memory ONCE and then pulls 32x32-pixel tiles -- exactly the
+// reference's patches (renderer.rs:46-89) -- from an atomic counter, the GPU analogue of Rayon's
+// work stealing.  Each tile is processed as a two-stage wavefront:
+//   A  primary visibility, divergence-free: a thread owns 4 horizontally adjacent pixels
+//      (fast_primary<4>), a warp a 32x4 strip.  Misses are final (black) and are written at once with
+//      128-bit stores; hits are appended to a shared-memory queue, compacted with ballot/popc so that
+//   B  shading + shadow rays + the reflect/refract recursion (the divergent part) runs on warps that
+//      are fully populated with hit pixels: one queue entry per thread.
+// The channel maximum (framebuffer.rs:58-69) is kept per thread across all its tiles and reduced once:
+// REDUX over the warp, shared atomic, one global atomic per CTA.
+constexpr int kFastTile = 32;
 template <bool kSmem>
-__global__ void __launch_bounds__(kBlock)
-render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull,
-                   float* __restrict__ rgb, int* __restrict__ prim_id, float* __restrict__ dmax) {
+__global__ void __launch_bounds__(kBlock, 3)
+render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
+                   const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
+                   float* __restrict__ dmax, int* __restrict__ tile_counter) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    __shared__ float warp_max[kBlock / 32];
+    __shared__ int cta_max, next_tile, q_count;
+    constexpr int kQueue = kFastTile * kFastTile + kBlock;     // one tile of hits on top of a partial round
+    __shared__ float q_t[kQueue];
+    __shared__ int q_slot[kQueue];
+    __shared__ int q_id[kQueue];
+    __shared__ unsigned q_xy[kQueue];                           // x | y << 16
     const BlobLayout& L = ds.lay;
     const int n_tri = tri_count(L, cull != 0);
 
     const unsigned char* base = ds.blob;
     const R4<float>* tri_r = ds.tri_r;
+    if (threadIdx.x == 0) {
+        cta_max = 0;
+        q_count = 0;
+        next_tile = atomicAdd(tile_counter, 1);
+    }
     if (kSmem) {
         const uint4* src = reinterpret_cast<const uint4*>(ds.blob);
         uint4* dst = reinterpret_cast<uint4*>(smem_raw);
@@ -148,10 +173,10 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         for (int i = threadIdx.x; i < n16; i += kBlock) dst[i] = __ldg(src + i);
         const uint4* rsrc = reinterpret_cast<const uint4*>(ds.tri_r);
         for (int i = threadIdx.x; i < n_tri * 4; i += kBlock) dst[n16 + i] = rsrc[i];
-        __syncthreads();
         base = smem_raw;
         tri_r = reinterpret_cast<const R4<float>*>(smem_raw + L.bytes);
     }
+    __syncthreads();
     FastView fv;
     fv.sph = reinterpret_cast<const R4<float>*>(base + L.off_sph);
     fv.sph_id = reinterpret_cast<const int*>(base + L.off_sph_id);
@@ -174,27 +199,91 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     fv.n_lgt = L.n_lgt;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = blockIdx.x * kTileW + (warp & 3) * 8 + (lane & 7);
-    const int y = fp.row_begin + blockIdx.y * kTileH + (warp >> 2) * 4 + (lane >> 3);
-
+    const int lx = (lane & 7) * 4, ly = warp * 4 + (lane >> 3);
+    const unsigned lane_lt = (1u << lane) - 1u;
     float m = 0.f;
-    if (x < fp.width && y < fp.row_end) {
-        int pid;
-        const Vec3<float> c = fast_pixel(fv, fp, x, y, pid);
-        const size_t px = (size_t)(y - fp.buf_row0) * fp.width + x;
-        rgb[3 * px] = c.x;
-        rgb[3 * px + 1] = c.y;
-        rgb[3 * px + 2] = c.z;
-        if (prim_id) prim_id[px] = pid;
-        m = fmaxf(fmaxf(fmaxf(c.x, c.y), c.z), 0.f);
+    for (;;) {
+        const int tile = next_tile;
+        const bool last = tile >= n_tiles;                      // no tile left: only flush the queue
+        if (!last) {
+            const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);      // exact for tile < 2^22
+            const int tx = tile - ty * tiles_x;
+            const int x0 = tx * kFastTile, y0 = fp.row_begin + ty * kFastTile;
+            // ---- stage A: primary visibility of this thread's 4 pixels
+            float bt[4];
+            int bslot[4], bid[4];
+            fast_primary<4>(fv, fp, x0 + lx, y0 + ly, bt, bslot, bid);
+            {
+                const size_t px = (size_t)(y0 + ly - fp.buf_row0) * fp.width + x0 + lx;
+                float4* dst = reinterpret_cast<float4*>(rgb + 3 * px);      // 48 contiguous bytes, 16-byte aligned (x % 4 == 0)
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);          // renderer.rs:300-306: a primary miss is black
+                __stcs(dst, z);
+                __stcs(dst + 1, z);
+                __stcs(dst + 2, z);
+                if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + px), make_int4(bid[0], bid[1], bid[2], bid[3]));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool hit = bslot[k] >= 0;
+                const unsigned mask = __ballot_sync(0xffffffffu, hit);
+                if (mask) {
+                    const int leader = __ffs(mask) - 1;
+                    int qbase = 0;
+                    if (lane == leader) qbase = atomicAdd(&q_count, __popc(mask));
+                    qbase = __shfl_sync(0xffffffffu, qbase, leader);
+                    if (hit) {
+                        const int q = qbase + __popc(mask & lane_lt);
+                        q_t[q] = bt[k];
+                        q_slot[q] = bslot[k];
+                        q_id[q] = bid[k];
+                        q_xy[q] = (unsigned)(x0 + lx + k) | ((unsigned)(y0 + ly) << 16);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                        // queue complete; everyone has read next_tile
+        // ---- stage B: full rounds only (every warp fully populated); the remainder waits for the next
+        //      tile's hits, and is flushed after the last tile
+        const int n_hit = q_count;
+        const int n_full = last ? n_hit : (n_hit & ~(kBlock - 1));
+        for (int q = threadIdx.x; q < n_full; q += kBlock) {
+            const unsigned xy = q_xy[q];
+            const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+            const Vec3<float> c = fast_shade(fv, fp, x, y, q_t[q], q_slot[q], q_id[q]);
+            float* dst = rgb + 3 * ((size_t)(y - fp.buf_row0) * fp.width + x);
+            dst[0] = c.x;
+            dst[1] = c.y;
+            dst[2] = c.z;
+            m = fmaxf(m, fmaxf(fmaxf(c.x, c.y), c.z));
+        }
+        if (last) break;
+        __syncthreads();                                        // full rounds consumed
+        const int rest = n_hit - n_full;                        // < kBlock; source [n_full, n_hit) and target [0, rest) are disjoint
+        float mv_t = 0.f;
+        int mv_slot = 0, mv_id = 0;
+        unsigned mv_xy = 0;
+        const bool mv = n_full > 0 && (int)threadIdx.x < rest;
+        if (mv) {
+            mv_t = q_t[n_full + threadIdx.x];
+            mv_slot = q_slot[n_full + threadIdx.x];
+            mv_id = q_id[n_full + threadIdx.x];
+            mv_xy = q_xy[n_full + threadIdx.x];
+            q_t[threadIdx.x] = mv_t;
+            q_slot[threadIdx.x] = mv_slot;
+            q_id[threadIdx.x] = mv_id;
+            q_xy[threadIdx.x] = mv_xy;
+        }
+        if (threadIdx.x == 0) {
+            q_count = rest;
+            next_tile = atomicAdd(tile_counter, 1);
+        }
+        __syncthreads();
     }
-    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if (lane == 0) warp_max[warp] = m;
+    // values are >= 0, so the integer order of the bit patterns is the float order
+    const int wm = __reduce_max_sync(0xffffffffu, __float_as_int(m));
+    if (lane == 0 && wm > 0) atomicMax(&cta_max, wm);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < kBlock / 32; w++) m = fmaxf(m, warp_max[w]);
-        if (m > 0.f) atomic_max_nonneg(dmax, m);
-    }
+    if (threadIdx.x == 0 && cta_max > 0) atomicMax(reinterpret_cast<int*>(dmax), cta_max);
 }
 
 template <typename R> struct Tone;
@@ -263,18 +352,33 @@ namespace {
 cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& fp, bool cull, float* rgb, int* prim_id,
                         float* dmax, cudaStream_t stream, const double camera[3], int* launches, dim3 grid) {
     const int n_tri = tri_count(ds.lay, cull);
-    if (n_tri > 0) {
-        prepare_raster_kernel<<<(n_tri + 127) / 128, 128, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r);
-        if (launches) (*launches)++;
-    }
+    prepare_raster_kernel<<<(std::max(n_tri, 1) + 127) / 128, 128, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2],
+                                                                                ds.tri_r, ds.tile_counter);
+    if (launches) (*launches)++;
     const size_t smem = (size_t)ds.lay.bytes + (size_t)n_tri * 64;
+    const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * ((fp.row_end - fp.row_begin) / kFastTile);
+    (void)grid;
+    const float inv_tiles_x = 1.0f / (float)tiles_x;
+    static int sm_count = 0;
     cudaError_t e;
+    if (!sm_count) {
+        int dev = 0;
+        if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    }
     if (smem <= (size_t)kSmemLimit) {
         auto k = render_fast_kernel<true>;
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<grid, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, rgb, prim_id, dmax);
+        int occ = 1;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, smem)) != cudaSuccess) return e;
+        const int ctas = std::min(n_tiles, sm_count * std::max(occ, 1));
+        k<<<ctas, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.tile_counter);
     } else {
-        render_fast_kernel<false><<<grid, kBlock, 0, stream>>>(ds, fp, cull ? 1 : 0, rgb, prim_id, dmax);
+        auto k = render_fast_kernel<false>;
+        int occ = 1;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, 0)) != cudaSuccess) return e;
+        const int ctas = std::min(n_tiles, sm_count * std::max(occ, 1));
+        k<<<ctas, kBlock, 0, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.tile_counter);
     }
     if (launches) (*launches)++;
     return cudaGetLastError();

@@ -21,6 +21,7 @@ template <typename R> struct DeviceScene {
     // camera-specialised raster records it writes (4 x R4<float> per triangle, rebuilt every frame)
     const double* tri_src = nullptr;
     R4<float>* tri_r = nullptr;
+    int* tile_counter = nullptr;   // work counter of the persistent render kernel (reset by the prepare kernel)
 };
 
 // K0 + K1.  With counters == null and R = float this is the production path: prepare_raster_kernel

@@ -137,14 +137,20 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
             for (;;) {
                 int y = next.fetch_add(1);
                 if (y >= fp.row_end) break;
-                for (int x = 0; x < fp.width; x++) {
-                    int pid;
-                    rm::Vec3<float> c = rm::fast_pixel(fv, fp, x, y, pid);
-                    size_t px = (size_t)y * fp.width + x;
-                    out_rgb[3 * px] = c.x; out_rgb[3 * px + 1] = c.y; out_rgb[3 * px + 2] = c.z;
-                    if (prim) prim[px] = pid;
-                    float m = fmaxf(fmaxf(c.x, c.y), c.z);
-                    if (m > tmax[t]) tmax[t] = m;
+                for (int x = 0; x < fp.width; x += 4) {
+                    int pid[4], slot[4];
+                    float bt[4];
+                    rm::Vec3<float> c[4];
+                    rm::fast_primary<4>(fv, fp, x, y, bt, slot, pid);
+                    for (int k = 0; k < 4; k++)
+                        c[k] = slot[k] >= 0 ? rm::fast_shade(fv, fp, x + k, y, bt[k], slot[k], pid[k]) : rm::Vec3<float>{0.f, 0.f, 0.f};
+                    for (int k = 0; k < 4; k++) {
+                        size_t px = (size_t)y * fp.width + x + k;
+                        out_rgb[3 * px] = c[k].x; out_rgb[3 * px + 1] = c[k].y; out_rgb[3 * px + 2] = c[k].z;
+                        if (prim) prim[px] = pid[k];
+                        float m = fmaxf(fmaxf(c[k].x, c[k].y), c[k].z);
+                        if (m > tmax[t]) tmax[t] = m;
+                    }
                 }
             }
         });
