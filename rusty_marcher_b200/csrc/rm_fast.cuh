@@ -30,18 +30,6 @@ constexpr int kTriSrcDoubles = 16;   // n[3], dn, v0x, v0y, A0, B0, A1, B1, C1, 
 #define RM_PIN(v) (void)(v)
 #endif
 
-#if defined(__CUDA_ARCH__)
-RM_HD float fast_div(float a, float b) { return __fdividef(a, b); }
-// MUFU.RSQ (2 ulp) + one Newton step: 1/sqrt(a) to ~1 ulp in 4 instructions instead of IEEE sqrt + IEEE divide
-RM_HD float fast_rsqrt(float a) {
-    const float r = rsqrtf(a);
-    return r * fmaf(-0.5f * a * r, r, 1.5f);
-}
-#else
-RM_HD float fast_div(float a, float b) { return a / b; }
-RM_HD float fast_rsqrt(float a) { return 1.f / sqrtf(a); }
-#endif
-
 // Camera-specialised record of one triangle (4 x R4<float>), from its FP64 source record.
 //   r0 = {n'x, n'y, -n'z, |K|}   r1 = {G0x, G0y, -G0z, thr}   r2 = {G1x, G1y, -G1z, id}   r3 = {G2x, G2y, -G2z, 0}
 // with everything multiplied by sign(K) so that a hit needs dpD > 0 and s_i > 0.
@@ -108,9 +96,12 @@ struct FastView {
         const R4<float> a = tri_g[4 * j], l = tri_g[4 * j + 3];
         const Vec3<float> n = xyz(a);
         const float dp = dot(d, n);
-        if (!(fabsf(dp) > l.y)) return false;                  // triangle.rs:57
-        const float t = fast_div(a.w - dot(o, n), dp);         // triangle.rs:62
-        if (t < 0.f) return false;                             // triangle.rs:65
+        const float num = a.w - dot(o, n);
+        // triangle.rs:57 (parallel) and triangle.rs:65 (t < 0 <=> numerator and denominator of triangle.rs:62
+        // have strictly opposite signs): both rejections before the division
+        if (!(fabsf(dp) > l.y) || num * dp < 0.f) return false;
+        const float t = fast_div(num, dp);                     // triangle.rs:62
+        if (t < 0.f) return false;
         const R4<float> b = tri_g[4 * j + 1], c = tri_g[4 * j + 2];
         const float qx = fmaf(t, d.x, o.x - b.x), qy = fmaf(t, d.y, o.y - b.y);   // hit point relative to vertex 0
         const float e0 = fmaf(b.z, qx, b.w * qy);
@@ -177,69 +168,96 @@ struct FastView {
     }
 };
 
-// Primary visibility of kPx horizontally adjacent pixels of one thread (the CUDA kernel uses 4; they
-// share Y, so each affine function of a triangle costs one FFMA for the row part plus one FFMA per
-// pixel, and the four 128-bit record loads are amortised over kPx pixels; the independent chains give
-// the FP32 pipe its ILP).  Results: ray parameter, slot and primitive id of the closest hit (slot < 0: miss).
-template <int kPx>
-RM_HD void fast_primary(const FastView& fv, const FrameParams<float>& fp, const int x0, const int y, float* best_t,
-                        int* best_slot, int* best_id) {
-    float Y = (float(y) - fp.half_h) * fp.sy;
-    float X[kPx];
-    RM_PIN(Y);      // keep the pixel coordinates in registers: ptxas otherwise rematerialises them (int->float,
+// ---- primary visibility (stage A of the render kernel) ------------------------------------------
+// kPx horizontally adjacent pixels of one thread (the CUDA kernel uses 4; they share Y, so each affine
+// function of a triangle costs one FFMA for the row part plus one FFMA per pixel, and the four 128-bit
+// record loads are amortised over kPx pixels; the independent chains give the FP32 pipe its ILP).
+// best_*: ray parameter, slot and primitive id of the closest hit so far (slot < 0: none).
+template <int kPx> struct PrimaryState {
+    float X[kPx], Y;
+    float t[kPx];
+    int slot[kPx], id[kPx];
+};
+
+RM_HD float pixel_X(const FrameParams<float>& fp, int x) { return (float(x) - fp.half_w) * fp.sx; }
+RM_HD float pixel_Y(const FrameParams<float>& fp, int y) { return (float(y) - fp.half_h) * fp.sy; }
+
+template <int kPx> RM_HD void primary_begin(PrimaryState<kPx>& ps, const FrameParams<float>& fp, const int x0, const int y) {
+    ps.Y = pixel_Y(fp, y);
+    RM_PIN(ps.Y);   // keep the pixel coordinates in registers: ptxas otherwise rematerialises them (int->float,
                     // sub, mul per pixel) inside the triangle loop when registers are tight
 #pragma unroll
     for (int k = 0; k < kPx; k++) {
-        X[k] = (float(x0 + k) - fp.half_w) * fp.sx;
-        RM_PIN(X[k]);
-        best_slot[k] = -1;
-        best_id[k] = -1;
-        best_t[k] = 0.f;
+        ps.X[k] = pixel_X(fp, x0 + k);
+        RM_PIN(ps.X[k]);
+        ps.slot[k] = -1;
+        ps.id[k] = -1;
+        ps.t[k] = 0.f;
     }
-    // triangles: no normalisation, no division unless a pixel is inside the triangle.  The four pixels'
-    // predicates are folded into one branch so the common (all miss) iteration is straight-line code.
-#pragma unroll 2
-    for (int j = 0; j < fv.n_tri; j++) {
-        const R4<float> r0 = fv.tri_r[4 * j], r1 = fv.tri_r[4 * j + 1], r2 = fv.tri_r[4 * j + 2], r3 = fv.tri_r[4 * j + 3];
-        const float bd = fmaf(r0.y, Y, r0.z), b0 = fmaf(r1.y, Y, r1.z), b1 = fmaf(r2.y, Y, r2.z), b2 = fmaf(r3.y, Y, r3.z);
-        float mk[kPx], dpD[kPx];
-        float any = 0.f;
+}
+
+// Exact rectangle bound of a raster record.  Each of the four functions f(X, Y) = fmaf(r.x, X, fmaf(r.y, Y, r.z))
+// -- evaluated with the very operations primary_tri uses per pixel -- is monotone in X and in Y because fmaf is
+// correctly rounded, so its maximum over the pixels of a rectangle [Xa, Xb] x [Ya, Yb] is attained at a corner,
+// bit for bit.  A triangle can only be hit inside the rectangle if all four maxima are positive; dropping the
+// others changes no pixel.  (pixel_X / pixel_Y are monotone in the pixel index for the same reason.)
+RM_HD float rect_max(const R4<float> r, const float Xa, const float Xb, const float Ya, const float Yb) {
+    const float ba = fmaf(r.y, Ya, r.z), bb = fmaf(r.y, Yb, r.z);
+    return fmaxf(fmaxf(fmaf(r.x, Xa, ba), fmaf(r.x, Xb, ba)), fmaxf(fmaf(r.x, Xa, bb), fmaf(r.x, Xb, bb)));
+}
+RM_HD bool tri_may_touch(const R4<float> r0, const R4<float> r1, const R4<float> r2, const R4<float> r3, const float Xa,
+                         const float Xb, const float Ya, const float Yb) {
+    return fminf(fminf(rect_max(r0, Xa, Xb, Ya, Yb), rect_max(r1, Xa, Xb, Ya, Yb)),
+                 fminf(rect_max(r2, Xa, Xb, Ya, Yb), rect_max(r3, Xa, Xb, Ya, Yb))) > 0.f;
+}
+
+// One triangle (raster records r0..r3, slot) against the kPx pixels: no normalisation, no division unless a
+// pixel is inside the triangle.  The pixels' predicates are folded into one branch so the common (all miss)
+// case is straight-line code.
+template <int kPx>
+RM_HD void primary_tri(PrimaryState<kPx>& ps, const R4<float> r0, const R4<float> r1, const R4<float> r2, const R4<float> r3,
+                       const int slot) {
+    const float Y = ps.Y;
+    const float bd = fmaf(r0.y, Y, r0.z), b0 = fmaf(r1.y, Y, r1.z), b1 = fmaf(r2.y, Y, r2.z), b2 = fmaf(r3.y, Y, r3.z);
+    float mk[kPx], dpD[kPx];
+    float any = 0.f;
+#pragma unroll
+    for (int k = 0; k < kPx; k++) {
+        dpD[k] = fmaf(r0.x, ps.X[k], bd);
+        const float s0 = fmaf(r1.x, ps.X[k], b0), s1 = fmaf(r2.x, ps.X[k], b1), s2 = fmaf(r3.x, ps.X[k], b2);
+        mk[k] = fminf(fminf(fminf(s0, s1), s2), dpD[k]);       // > 0 <=> inside all three edges and in front
+        any = fmaxf(any, mk[k]);
+    }
+    if (any > 0.f) {
 #pragma unroll
         for (int k = 0; k < kPx; k++) {
-            dpD[k] = fmaf(r0.x, X[k], bd);
-            const float s0 = fmaf(r1.x, X[k], b0), s1 = fmaf(r2.x, X[k], b1), s2 = fmaf(r3.x, X[k], b2);
-            mk[k] = fminf(fminf(fminf(s0, s1), s2), dpD[k]);   // > 0 <=> inside all three edges and in front
-            any = fmaxf(any, mk[k]);
-        }
-        if (any > 0.f) {
-#pragma unroll
-            for (int k = 0; k < kPx; k++) {
-                if (mk[k] > 0.f) {
-                    const float lenD = sqrtf(fmaf(X[k], X[k], fmaf(Y, Y, 1.f)));
-                    if (dpD[k] > r1.w * lenD) {                  // |d.n| >= 1e-6 (triangle.rs:57) on the unit direction
-                        const float t = fast_div(r0.w * lenD, dpD[k]);   // triangle.rs:62
-                        const int id = FastView::as_int(r2.w);
-                        if (best_slot[k] < 0 || t < best_t[k] || (t == best_t[k] && id < best_id[k])) {
-                            best_t[k] = t;
-                            best_slot[k] = fv.n_sph + j;
-                            best_id[k] = id;
-                        }
+            if (mk[k] > 0.f) {
+                const float lenD = sqrtf(fmaf(ps.X[k], ps.X[k], fmaf(Y, Y, 1.f)));
+                if (dpD[k] > r1.w * lenD) {                    // |d.n| >= 1e-6 (triangle.rs:57) on the unit direction
+                    const float t = fast_div(r0.w * lenD, dpD[k]);   // triangle.rs:62
+                    const int id = FastView::as_int(r2.w);
+                    if (ps.slot[k] < 0 || t < ps.t[k] || (t == ps.t[k] && id < ps.id[k])) {
+                        ps.t[k] = t;
+                        ps.slot[k] = slot;
+                        ps.id[k] = id;
                     }
                 }
             }
         }
     }
-    if (fv.n_sph + fv.n_poly == 0) return;
-    // spheres / n-gons: the general routines from the camera
-#pragma unroll 1
+}
+
+// spheres / n-gons: the general routines from the camera
+template <int kPx> RM_HD void primary_rest(PrimaryState<kPx>& ps, const FastView& fv, const FrameParams<float>& fp) {
+#pragma unroll
     for (int k = 0; k < kPx; k++) {
-        const float inv = fast_rsqrt(fmaf(X[k], X[k], fmaf(Y, Y, 1.f)));
-        const Vec3<float> d = {X[k] * inv, Y * inv, -inv};
-        bool hit = best_slot[k] >= 0;
+        const float inv = fast_rsqrt(fmaf(ps.X[k], ps.X[k], fmaf(ps.Y, ps.Y, 1.f)));
+        const Vec3<float> d = {ps.X[k] * inv, ps.Y * inv, -inv};
+        bool hit = ps.slot[k] >= 0;
         HitRec<float> best;
-        best.dist = best_t[k];
-        best.slot = best_slot[k];
-        best.id = best_id[k];
+        best.dist = ps.t[k];
+        best.slot = ps.slot[k];
+        best.id = ps.id[k];
         Counters<false> st;
         for (int i = 0; i < fv.n_sph; i++) {
             Cand<float> c;
@@ -251,11 +269,9 @@ RM_HD void fast_primary(const FastView& fv, const FrameParams<float>& fp, const 
             if (plane_intersect<false>(fv.pln_n[i], fv.pln_c[i], fv.pln_v[i], fv.vert, fp.camera, d, c, st))
                 FastView::keep(best, hit, c.key, fv.n_sph + fv.n_tri + i, fv.pln_id[i]);
         }
-        if (hit) {
-            best_t[k] = best.dist;
-            best_slot[k] = best.slot;
-            best_id[k] = best.id;
-        }
+        ps.t[k] = best.dist;
+        ps.slot[k] = hit ? best.slot : -1;
+        ps.id[k] = hit ? best.id : -1;
     }
 }
 

@@ -136,9 +136,11 @@ prepare_raster_kernel(const double* __restrict__ tri_src, const int n_tri, const
 // CTA stages the scene into shared memory ONCE and then pulls 32x32-pixel tiles -- exactly the
 // reference's patches (renderer.rs:46-89) -- from an atomic counter, the GPU analogue of Rayon's
 // work stealing.  Each tile is processed as a two-stage wavefront:
-//   A  primary visibility, divergence-free: a thread owns 4 horizontally adjacent pixels
-//      (fast_primary<4>), a warp a 32x4 strip.  Misses are final (black) and are written at once with
-//      128-bit stores; hits are appended to a shared-memory queue, compacted with ballot/popc so that
+//   A  primary visibility, divergence-free: a warp owns a 32x4 strip, a thread 4 horizontally adjacent
+//      pixels.  First the warp bounds every triangle against its strip (one triangle per lane, exact
+//      corner test tri_may_touch, ballot), then all lanes walk the surviving triangles together
+//      (primary_tri<4>).  Misses are final (black) and are written at once with 128-bit stores; hits
+//      are appended to a shared-memory queue, compacted with ballot/popc, so that
 //   B  shading + shadow rays + the reflect/refract recursion (the divergent part) runs on warps that
 //      are fully populated with hit pixels: one queue entry per thread.
 // The channel maximum (framebuffer.rs:58-69) is kept per thread across all its tiles and reduced once:
@@ -152,10 +154,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     extern __shared__ __align__(32) unsigned char smem_raw[];
     __shared__ int cta_max, next_tile, q_count;
     constexpr int kQueue = kFastTile * kFastTile + kBlock;     // one tile of hits on top of a partial round
-    __shared__ float q_t[kQueue];
-    __shared__ int q_slot[kQueue];
-    __shared__ int q_id[kQueue];
-    __shared__ unsigned q_xy[kQueue];                           // x | y << 16
+    __shared__ float4 queue[kQueue];                            // {t, slot, id, x | y << 16}
     const BlobLayout& L = ds.lay;
     const int n_tri = tri_count(L, cull != 0);
 
@@ -201,6 +200,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lx = (lane & 7) * 4, ly = warp * 4 + (lane >> 3);
     const unsigned lane_lt = (1u << lane) - 1u;
+    const bool rest = fv.n_sph + fv.n_poly > 0;
     float m = 0.f;
     for (;;) {
         const int tile = next_tile;
@@ -210,35 +210,50 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
             const int tx = tile - ty * tiles_x;
             const int x0 = tx * kFastTile, y0 = fp.row_begin + ty * kFastTile;
             // ---- stage A: primary visibility of this thread's 4 pixels
-            float bt[4];
-            int bslot[4], bid[4];
-            fast_primary<4>(fv, fp, x0 + lx, y0 + ly, bt, bslot, bid);
+            PrimaryState<4> ps;
+            primary_begin<4>(ps, fp, x0 + lx, y0 + ly);
             {
-                const size_t px = (size_t)(y0 + ly - fp.buf_row0) * fp.width + x0 + lx;
+                // the warp's strip: pixels [x0, x0 + 31] x [y0 + 4 warp, y0 + 4 warp + 3]
+                const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + kFastTile - 1);
+                const float Ya = pixel_Y(fp, y0 + warp * 4), Yb = pixel_Y(fp, y0 + warp * 4 + 3);
+                for (int jb = 0; jb < n_tri; jb += 32) {
+                    const int j = jb + lane;
+                    bool cand = false;
+                    if (j < n_tri) cand = tri_may_touch(tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], Xa, Xb, Ya, Yb);
+                    unsigned cm = __ballot_sync(0xffffffffu, cand);
+                    while (cm) {                                // uniform across the warp
+                        const int jj = jb + __ffs(cm) - 1;
+                        cm &= cm - 1;
+                        primary_tri<4>(ps, tri_r[4 * jj], tri_r[4 * jj + 1], tri_r[4 * jj + 2], tri_r[4 * jj + 3], fv.n_sph + jj);
+                    }
+                }
+                if (rest) primary_rest<4>(ps, fv, fp);
+            }
+            const size_t px = (size_t)(y0 + ly - fp.buf_row0) * fp.width + x0 + lx;
+            {
                 float4* dst = reinterpret_cast<float4*>(rgb + 3 * px);      // 48 contiguous bytes, 16-byte aligned (x % 4 == 0)
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);          // renderer.rs:300-306: a primary miss is black
                 __stcs(dst, z);
                 __stcs(dst + 1, z);
                 __stcs(dst + 2, z);
-                if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + px), make_int4(bid[0], bid[1], bid[2], bid[3]));
+                if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + px), make_int4(ps.id[0], ps.id[1], ps.id[2], ps.id[3]));
             }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const bool hit = bslot[k] >= 0;
-                const unsigned mask = __ballot_sync(0xffffffffu, hit);
-                if (mask) {
-                    const int leader = __ffs(mask) - 1;
-                    int qbase = 0;
-                    if (lane == leader) qbase = atomicAdd(&q_count, __popc(mask));
-                    qbase = __shfl_sync(0xffffffffu, qbase, leader);
-                    if (hit) {
-                        const int q = qbase + __popc(mask & lane_lt);
-                        q_t[q] = bt[k];
-                        q_slot[q] = bslot[k];
-                        q_id[q] = bid[k];
-                        q_xy[q] = (unsigned)(x0 + lx + k) | ((unsigned)(y0 + ly) << 16);
-                    }
-                }
+            // ---- hits -> queue: one shared atomic per warp
+            const unsigned m0 = __ballot_sync(0xffffffffu, ps.slot[0] >= 0), m1 = __ballot_sync(0xffffffffu, ps.slot[1] >= 0);
+            const unsigned m2 = __ballot_sync(0xffffffffu, ps.slot[2] >= 0), m3 = __ballot_sync(0xffffffffu, ps.slot[3] >= 0);
+            if (m0 | m1 | m2 | m3) {
+                const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
+                int qb = 0;
+                if (lane == 0) qb = atomicAdd(&q_count, c0 + c1 + c2 + c3);
+                qb = __shfl_sync(0xffffffffu, qb, 0);
+                const unsigned xy = (unsigned)(x0 + lx) | ((unsigned)(y0 + ly) << 16);
+                if (ps.slot[0] >= 0) queue[qb + __popc(m0 & lane_lt)] = make_float4(ps.t[0], __int_as_float(ps.slot[0]), __int_as_float(ps.id[0]), __uint_as_float(xy));
+                qb += c0;
+                if (ps.slot[1] >= 0) queue[qb + __popc(m1 & lane_lt)] = make_float4(ps.t[1], __int_as_float(ps.slot[1]), __int_as_float(ps.id[1]), __uint_as_float(xy + 1));
+                qb += c1;
+                if (ps.slot[2] >= 0) queue[qb + __popc(m2 & lane_lt)] = make_float4(ps.t[2], __int_as_float(ps.slot[2]), __int_as_float(ps.id[2]), __uint_as_float(xy + 2));
+                qb += c2;
+                if (ps.slot[3] >= 0) queue[qb + __popc(m3 & lane_lt)] = make_float4(ps.t[3], __int_as_float(ps.slot[3]), __int_as_float(ps.id[3]), __uint_as_float(xy + 3));
             }
         }
         __syncthreads();                                        // queue complete; everyone has read next_tile
@@ -247,9 +262,10 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         const int n_hit = q_count;
         const int n_full = last ? n_hit : (n_hit & ~(kBlock - 1));
         for (int q = threadIdx.x; q < n_full; q += kBlock) {
-            const unsigned xy = q_xy[q];
+            const float4 e = queue[q];
+            const unsigned xy = __float_as_uint(e.w);
             const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
-            const Vec3<float> c = fast_shade(fv, fp, x, y, q_t[q], q_slot[q], q_id[q]);
+            const Vec3<float> c = fast_shade(fv, fp, x, y, e.x, __float_as_int(e.y), __float_as_int(e.z));
             float* dst = rgb + 3 * ((size_t)(y - fp.buf_row0) * fp.width + x);
             dst[0] = c.x;
             dst[1] = c.y;
@@ -258,23 +274,10 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         }
         if (last) break;
         __syncthreads();                                        // full rounds consumed
-        const int rest = n_hit - n_full;                        // < kBlock; source [n_full, n_hit) and target [0, rest) are disjoint
-        float mv_t = 0.f;
-        int mv_slot = 0, mv_id = 0;
-        unsigned mv_xy = 0;
-        const bool mv = n_full > 0 && (int)threadIdx.x < rest;
-        if (mv) {
-            mv_t = q_t[n_full + threadIdx.x];
-            mv_slot = q_slot[n_full + threadIdx.x];
-            mv_id = q_id[n_full + threadIdx.x];
-            mv_xy = q_xy[n_full + threadIdx.x];
-            q_t[threadIdx.x] = mv_t;
-            q_slot[threadIdx.x] = mv_slot;
-            q_id[threadIdx.x] = mv_id;
-            q_xy[threadIdx.x] = mv_xy;
-        }
+        const int left = n_hit - n_full;                        // < kBlock; source [n_full, n_hit) and target [0, left) are disjoint
+        if (n_full > 0 && (int)threadIdx.x < left) queue[threadIdx.x] = queue[n_full + threadIdx.x];
         if (threadIdx.x == 0) {
-            q_count = rest;
+            q_count = left;
             next_tile = atomicAdd(tile_counter, 1);
         }
         __syncthreads();

@@ -44,6 +44,41 @@ template <> struct Num<double> {
     static RM_HD double rcp_(double a) { return 1. / a; }
 };
 
+// FP32 fast-math primitives of the production path (device: MUFU-based, host emulation: libm).
+#if defined(__CUDA_ARCH__)
+// a/b as a * rcp(b) without the denormal rescue sequence; callers guarantee |b| is a normal number
+RM_HD float fast_div(float a, float b) {
+    float r;
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+// MUFU.RSQ (2 ulp) + one Newton step: 1/sqrt(a) to ~1 ulp in a handful of instructions instead of IEEE sqrt + IEEE divide
+RM_HD float fast_rsqrt(float a) {
+    const float r = rsqrtf(a);
+    return r * fmaf(-0.5f * a * r, r, 1.5f);
+}
+#else
+RM_HD float fast_div(float a, float b) { return a / b; }
+RM_HD float fast_rsqrt(float a) { return 1.f / sqrtf(a); }
+#endif
+
+// x^e for x >= 0.  The specular exponents of the reference are small integers (30 in
+// Reflectance::create_default, shapes.rs:55; 10..100 in scene.rs), for which square-and-multiply is both
+// cheaper (about 15 FMULs) and more accurate (<= e * 2^-24 relative) than a generic powf; anything else
+// takes the library routine.
+RM_HD float pow_nonneg(float x, float e) {
+    const int n = (int)e;
+    if ((float)n == e && n >= 0 && n <= 1024) {
+        float r = 1.f;
+        for (int k = n; k; k >>= 1) {
+            if (k & 1) r *= x;
+            x *= x;
+        }
+        return r;
+    }
+    return powf(x, e);
+}
+
 template <> struct Num<float> {
     static RM_HD float madd(float a, float b, float c) { return fmaf(a, b, c); }
     static RM_HD float msub(float a, float b, float c) { return fmaf(a, b, -c); }
@@ -51,7 +86,7 @@ template <> struct Num<float> {
     static RM_HD float sqrt_(float a) { return sqrtf(a); }
     static RM_HD float abs_(float a) { return fabsf(a); }
     static RM_HD float max_(float a, float b) { return fmaxf(a, b); }
-    static RM_HD float pow_(float a, float b) { return powf(a, b); }
+    static RM_HD float pow_(float a, float b) { return pow_nonneg(a, b); }
     static RM_HD float div_(float a, float b) { return a / b; }
     static RM_HD float rcp_(float a) { return 1.f / a; }
 };
@@ -83,6 +118,13 @@ template <typename R> RM_HD Vec3<R> axmy(Vec3<R> a, Vec3<R> b, R s) {
 template <typename R> RM_HD Vec3<R> normalized(Vec3<R> a) {
     R norm = Num<R>::sqrt_(dot(a, a));
     if (norm > R(0)) a = scaled(a, Num<R>::rcp_(norm));
+    return a;
+}
+
+// f32: scale by rsqrt(|a|^2) -- one MUFU + Newton step instead of IEEE sqrt and reciprocal
+template <> RM_HD Vec3<float> normalized<float>(Vec3<float> a) {
+    const float s = dot(a, a);
+    if (s > 0.f) a = scaled(a, fast_rsqrt(s));
     return a;
 }
 

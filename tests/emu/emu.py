@@ -36,7 +36,8 @@ def lib():
     return _lib
 
 
-def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=True, threads=8, patch_rows=(0, -1)):
+def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=True, threads=8, patch_rows=(0, -1), strip_bound=True):
+    lib().emu_set_strip_bound(int(strip_bound))
     flat = scene.flatten()
     p = _abi.RmParams()
     p.width, p.height, p.fov = width, height, fov

@@ -94,6 +94,8 @@ int emu_render_impl(const RmFlatScene* fs, const RmParams* p, R* out_rgb, int32_
 
 }  // namespace
 
+static std::atomic<int> g_strip_bound{1};   // 0: walk every triangle in every strip (to prove the bound changes no pixel)
+
 // the FP32 production path (rm_fast.cuh): prepare_raster + fast_pixel, as the CUDA kernels run them
 int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
     rm::PackedScene<float> ps;
@@ -134,22 +136,33 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
     for (int t = 0; t < n_threads; t++) {
         pool.emplace_back([&, t] {
             rm::FastView fv = fv0;
+            std::vector<int> cand;
             for (;;) {
-                int y = next.fetch_add(1);
-                if (y >= fp.row_end) break;
-                for (int x = 0; x < fp.width; x += 4) {
-                    int pid[4], slot[4];
-                    float bt[4];
-                    rm::Vec3<float> c[4];
-                    rm::fast_primary<4>(fv, fp, x, y, bt, slot, pid);
-                    for (int k = 0; k < 4; k++)
-                        c[k] = slot[k] >= 0 ? rm::fast_shade(fv, fp, x + k, y, bt[k], slot[k], pid[k]) : rm::Vec3<float>{0.f, 0.f, 0.f};
-                    for (int k = 0; k < 4; k++) {
-                        size_t px = (size_t)y * fp.width + x + k;
-                        out_rgb[3 * px] = c[k].x; out_rgb[3 * px + 1] = c[k].y; out_rgb[3 * px + 2] = c[k].z;
-                        if (prim) prim[px] = pid[k];
-                        float m = fmaxf(fmaxf(c[k].x, c[k].y), c[k].z);
-                        if (m > tmax[t]) tmax[t] = m;
+                // one 4-row band per grab; inside it the kernel's 32x4 warp strips, each with its own exact
+                // triangle bound (tri_may_touch) followed by the per-thread walk over the survivors
+                int y0 = next.fetch_add(4);
+                if (y0 >= fp.row_end) break;
+                for (int xs = 0; xs < fp.width; xs += 32) {
+                    const float Xa = rm::pixel_X(fp, xs), Xb = rm::pixel_X(fp, xs + 31);
+                    const float Ya = rm::pixel_Y(fp, y0), Yb = rm::pixel_Y(fp, y0 + 3);
+                    cand.clear();
+                    for (int j = 0; j < n_tri; j++)
+                        if (!g_strip_bound.load() || rm::tri_may_touch(tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], Xa, Xb, Ya, Yb)) cand.push_back(j);
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int x = xs + (lane & 7) * 4, y = y0 + (lane >> 3);
+                        rm::PrimaryState<4> ps;
+                        rm::primary_begin<4>(ps, fp, x, y);
+                        for (int j : cand) rm::primary_tri<4>(ps, tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], fv.n_sph + j);
+                        if (fv.n_sph + fv.n_poly > 0) rm::primary_rest<4>(ps, fv, fp);
+                        for (int k = 0; k < 4; k++) {
+                            rm::Vec3<float> c = ps.slot[k] >= 0 ? rm::fast_shade(fv, fp, x + k, y, ps.t[k], ps.slot[k], ps.id[k])
+                                                                : rm::Vec3<float>{0.f, 0.f, 0.f};
+                            size_t px = (size_t)y * fp.width + x + k;
+                            out_rgb[3 * px] = c.x; out_rgb[3 * px + 1] = c.y; out_rgb[3 * px + 2] = c.z;
+                            if (prim) prim[px] = ps.id[k];
+                            float m = fmaxf(fmaxf(c.x, c.y), c.z);
+                            if (m > tmax[t]) tmax[t] = m;
+                        }
                     }
                 }
             }
@@ -167,6 +180,7 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
 }
 
 extern "C" {
+void emu_set_strip_bound(int on) { g_strip_bound.store(on); }
 int emu_render_fast(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
     return emu_render_fast_impl(fs, p, out_rgb, prim, stats, n_threads);
 }

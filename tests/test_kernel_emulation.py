@@ -49,6 +49,25 @@ def test_fp32_kernel_code_within_tolerance(case, cull, path):
     parity.check_fp32(got, ref, (h // 32) * 32, rgb8)
 
 
+@pytest.mark.parametrize("cull", [False, True])
+def test_strip_bound_changes_no_pixel(case, cull):
+    """Stage A drops, per 32x4 strip, the triangles whose raster functions cannot be positive anywhere in the strip
+    (exact corner bound, rm_fast.cuh tri_may_touch): the frame must be bit-identical to walking every triangle."""
+    name, w, h, depth, scene, ref = case
+    a = emu.render(scene, w, h, "fast", max_depth=depth, cull=cull, strip_bound=True)
+    b = emu.render(scene, w, h, "fast", max_depth=depth, cull=cull, strip_bound=False)
+    assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["rgb"], b["rgb"])
+
+
+def test_strip_bound_off_centre_camera():
+    scene = workloads.scene("cornell_box")
+    scene.offset_camera((35., -20., 15.))
+    a = emu.render(scene, 416, 224, "fast", cull=False, strip_bound=True)
+    b = emu.render(scene, 416, 224, "fast", cull=False, strip_bound=False)
+    assert (a["prim_id"] >= 0).any()
+    assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["rgb"], b["rgb"])
+
+
 def test_row_tiles_reassemble_to_the_full_frame():
     scene = workloads.scene("demo")
     full = emu.render(scene, 128, 160, "fast")
