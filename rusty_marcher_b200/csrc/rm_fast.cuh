@@ -31,7 +31,7 @@ constexpr int kTriSrcDoubles = 16;   // n[3], dn, v0x, v0y, A0, B0, A1, B1, C1, 
 #endif
 
 // Camera-specialised record of one triangle (4 x R4<float>), from its FP64 source record.
-//   r0 = {n'x, n'y, -n'z, |K|}   r1 = {G0x, G0y, -G0z, thr}   r2 = {G1x, G1y, -G1z, id}   r3 = {G2x, G2y, -G2z, 0}
+//   r0 = {n'x, n'y, -n'z, |K|}   r1 = {G0x, G0y, -G0z, thr^2}   r2 = {G1x, G1y, -G1z, id}   r3 = {G2x, G2y, -G2z, 0}
 // with everything multiplied by sign(K) so that a hit needs dpD > 0 and s_i > 0.
 RM_HD void prepare_raster(const double* __restrict__ src, const double cam[3], R4<float>* __restrict__ out) {
     const double nx = src[0], ny = src[1], nz = src[2], dn = src[3];
@@ -40,7 +40,7 @@ RM_HD void prepare_raster(const double* __restrict__ src, const double cam[3], R
     const double A[3] = {src[6], src[8], src[11]}, B[3] = {src[7], src[9], src[12]}, Cc[3] = {0., src[10], 0.};
     const double s = (K < 0.) ? -1. : 1.;
     out[0] = {(float)(s * nx), (float)(s * ny), (float)(-s * nz), (float)fabs(K)};
-    float last[3] = {(float)src[13], 0.f, 0.f};
+    float last[3] = {(float)(src[13] * src[13]), 0.f, 0.f};    // thr^2: the test runs on squared quantities
     int id = (int)src[14];
 #if defined(__CUDA_ARCH__)
     last[1] = __int_as_float(id);
@@ -91,18 +91,18 @@ struct FastView {
 #endif
     }
 
-    // general ray against triangle j
-    RM_HD bool tri_hit(int j, const Vec3<float> o, const Vec3<float> d, float& t_out) const {
-        const R4<float> a = tri_g[4 * j], l = tri_g[4 * j + 3];
-        const Vec3<float> n = xyz(a);
-        const float dp = dot(d, n);
-        const float num = a.w - dot(o, n);
-        // triangle.rs:57 (parallel) and triangle.rs:65 (t < 0 <=> numerator and denominator of triangle.rs:62
-        // have strictly opposite signs): both rejections before the division
-        if (!(fabsf(dp) > l.y) || num * dp < 0.f) return false;
+    // general ray against the triangle whose scene record starts at g
+    static RM_HD bool tri_hit(const R4<float>* __restrict__ g, const Vec3<float> o, const Vec3<float> d, float& t_out) {
+        const R4<float> a = g[0];
+        const float dp = fmaf(a.z, d.z, fmaf(a.y, d.y, a.x * d.x));
+        const float num = fmaf(-a.z, o.z, fmaf(-a.y, o.y, fmaf(-a.x, o.x, a.w)));   // (C - o).n
+        // triangle.rs:65: t = num / dp < 0 <=> numerator and denominator have strictly opposite signs -- the most
+        // frequent rejection comes first and needs neither the division nor the rest of the record
+        if (num * dp < 0.f) return false;
+        const R4<float> l = g[3];
+        if (!(fabsf(dp) > l.y)) return false;                  // triangle.rs:57 (parallel)
         const float t = fast_div(num, dp);                     // triangle.rs:62
-        if (t < 0.f) return false;
-        const R4<float> b = tri_g[4 * j + 1], c = tri_g[4 * j + 2];
+        const R4<float> b = g[1], c = g[2];
         const float qx = fmaf(t, d.x, o.x - b.x), qy = fmaf(t, d.y, o.y - b.y);   // hit point relative to vertex 0
         const float e0 = fmaf(b.z, qx, b.w * qy);
         const float e1 = fmaf(c.x, qx, fmaf(c.y, qy, c.z));
@@ -131,9 +131,10 @@ struct FastView {
             Cand<float> c;
             if (sphere_intersect<S>(sph[i], o, d, c, st)) keep(h, hit, c.key, i, sph_id[i]);
         }
-        for (int j = 0; j < n_tri; j++) {
+        const R4<float>* g = tri_g;
+        for (int j = 0; j < n_tri; j++, g += 4) {
             float t;
-            if (tri_hit(j, o, d, t)) keep(h, hit, t, n_sph + j, as_int(tri_g[4 * j + 3].z));
+            if (tri_hit(g, o, d, t)) keep(h, hit, t, n_sph + j, as_int(g[3].z));
         }
         for (int k = 0; k < n_poly; k++) {
             const int i = poly_slot[k];
@@ -149,8 +150,9 @@ struct FastView {
         for (int i = 0; i < n_sph; i++)
             if (sphere_intersect<S>(sph[i], o, d, c, st)) return true;
         float t;
-        for (int j = 0; j < n_tri; j++)
-            if (tri_hit(j, o, d, t)) return true;
+        const R4<float>* g = tri_g;
+        for (int j = 0; j < n_tri; j++, g += 4)
+            if (tri_hit(g, o, d, t)) return true;
         for (int k = 0; k < n_poly; k++) {
             const int i = poly_slot[k];
             if (plane_intersect<S>(pln_n[i], pln_c[i], pln_v[i], vert, o, d, c, st)) return true;
@@ -175,7 +177,9 @@ struct FastView {
 // best_*: ray parameter, slot and primitive id of the closest hit so far (slot < 0: none).
 template <int kPx> struct PrimaryState {
     float X[kPx], Y;
-    float t[kPx];
+    float len2[kPx];    // |D|^2 of the un-normalised pixel direction D = (X, Y, -1)
+    float t[kPx];       // triangles: ray parameter in units of |D| (the same for all candidates of a pixel); primary_rest
+                        // and the shading stage rescale to the unit direction
     int slot[kPx], id[kPx];
 };
 
@@ -190,6 +194,7 @@ template <int kPx> RM_HD void primary_begin(PrimaryState<kPx>& ps, const FramePa
     for (int k = 0; k < kPx; k++) {
         ps.X[k] = pixel_X(fp, x0 + k);
         RM_PIN(ps.X[k]);
+        ps.len2[k] = fmaf(ps.X[k], ps.X[k], fmaf(ps.Y, ps.Y, 1.f));
         ps.slot[k] = -1;
         ps.id[k] = -1;
         ps.t[k] = 0.f;
@@ -232,9 +237,9 @@ RM_HD void primary_tri(PrimaryState<kPx>& ps, const R4<float> r0, const R4<float
 #pragma unroll
         for (int k = 0; k < kPx; k++) {
             if (mk[k] > 0.f) {
-                const float lenD = sqrtf(fmaf(ps.X[k], ps.X[k], fmaf(Y, Y, 1.f)));
-                if (dpD[k] > r1.w * lenD) {                    // |d.n| >= 1e-6 (triangle.rs:57) on the unit direction
-                    const float t = fast_div(r0.w * lenD, dpD[k]);   // triangle.rs:62
+                // |d.n| > thr (triangle.rs:57) on the unit direction d = D/|D|: dpD > thr*|D|, squared (both sides >= 0)
+                if (dpD[k] * dpD[k] > r1.w * ps.len2[k]) {
+                    const float t = fast_div(r0.w, dpD[k]);      // triangle.rs:62 in units of |D|: t_unit = t * |D|
                     const int id = FastView::as_int(r2.w);
                     if (ps.slot[k] < 0 || t < ps.t[k] || (t == ps.t[k] && id < ps.id[k])) {
                         ps.t[k] = t;
@@ -251,11 +256,11 @@ RM_HD void primary_tri(PrimaryState<kPx>& ps, const R4<float> r0, const R4<float
 template <int kPx> RM_HD void primary_rest(PrimaryState<kPx>& ps, const FastView& fv, const FrameParams<float>& fp) {
 #pragma unroll
     for (int k = 0; k < kPx; k++) {
-        const float inv = fast_rsqrt(fmaf(ps.X[k], ps.X[k], fmaf(ps.Y, ps.Y, 1.f)));
+        const float inv = fast_rsqrt(ps.len2[k]);
         const Vec3<float> d = {ps.X[k] * inv, ps.Y * inv, -inv};
         bool hit = ps.slot[k] >= 0;
         HitRec<float> best;
-        best.dist = ps.t[k];
+        best.dist = ps.t[k] * (ps.len2[k] * inv);              // to the unit direction
         best.slot = ps.slot[k];
         best.id = ps.id[k];
         Counters<false> st;
@@ -269,20 +274,21 @@ template <int kPx> RM_HD void primary_rest(PrimaryState<kPx>& ps, const FastView
             if (plane_intersect<false>(fv.pln_n[i], fv.pln_c[i], fv.pln_v[i], fv.vert, fp.camera, d, c, st))
                 FastView::keep(best, hit, c.key, fv.n_sph + fv.n_tri + i, fv.pln_id[i]);
         }
-        ps.t[k] = best.dist;
+        ps.t[k] = best.dist * inv;                              // back to units of |D|, like the triangle hits
         ps.slot[k] = hit ? best.slot : -1;
         ps.id[k] = hit ? best.id : -1;
     }
 }
 
-// Shading + recursion of one pixel whose primary ray hit (t, slot, id): renderer.rs:254-309 from level 1.
+// Shading + recursion of one pixel whose primary ray hit (t in units of |D|, slot, id): renderer.rs:254-309 from level 1.
 RM_HD Vec3<float> fast_shade(FastView& fv, const FrameParams<float>& fp, const int x, const int y, const float t, const int slot,
                              const int id) {
-    const float X = (float(x) - fp.half_w) * fp.sx, Y = (float(y) - fp.half_h) * fp.sy;
-    const float inv = fast_rsqrt(fmaf(X, X, fmaf(Y, Y, 1.f)));     // geometry.rs:104-109: scale(1/norm)
+    const float X = pixel_X(fp, x), Y = pixel_Y(fp, y);
+    const float len2 = fmaf(X, X, fmaf(Y, Y, 1.f));
+    const float inv = fast_rsqrt(len2);                            // geometry.rs:104-109: scale(1/norm)
     const Vec3<float> d = {X * inv, Y * inv, -inv};
     fv.prim_got = true;
-    fv.prim_hit.dist = t;
+    fv.prim_hit.dist = t * (len2 * inv);                           // stage A reports t in units of |D|
     fv.prim_hit.slot = slot;
     fv.prim_hit.id = id;
     Counters<false> st;

@@ -128,6 +128,19 @@ template <> RM_HD Vec3<float> normalized<float>(Vec3<float> a) {
     return a;
 }
 
+// Keeps a value in its register across the code that follows: ptxas otherwise rematerialises cheap loop
+// invariants (selects, offsets, int->float conversions) inside inner loops when registers are tight.
+#if defined(__CUDA_ARCH__)
+RM_HD void pin(float& v) { asm volatile("" : "+f"(v)); }
+RM_HD void pin(double& v) { asm volatile("" : "+d"(v)); }
+RM_HD void pin(int& v) { asm volatile("" : "+r"(v)); }
+#else
+RM_HD void pin(float&) {}
+RM_HD void pin(double&) {}
+RM_HD void pin(int&) {}
+#endif
+template <typename R> RM_HD void pin(Vec3<R>& v) { pin(v.x); pin(v.y); pin(v.z); }
+
 template <typename R> RM_HD Vec3<R> xyz(const R4<R>& v) { return {v.x, v.y, v.z}; }
 
 }  // namespace rm

@@ -370,6 +370,8 @@ RM_HD Vec3<R> direct_lighting(const SC& sc, const Vec3<R> origin, const Vec3<R> 
         R side = dot(light_dir, normal);
         st.add(C_LIGHT_EVAL);
         Vec3<R> so = (side < R(0)) ? axmy(point, normal, R(1e-3)) : axpy(point, normal, R(1e-3)); // renderer.rs:168-172
+        pin(so);
+        pin(light_dir);
         if (sc.template anyhit<S>(so, light_dir, st)) continue;                                   // renderer.rs:174-177
         st.add(C_LIT);
         R diffusion = Num<R>::max_(side, R(0));                                                   // renderer.rs:138-140
