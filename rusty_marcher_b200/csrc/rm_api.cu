@@ -117,11 +117,16 @@ template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
     }
     if (sizeof(R) == 4) {
         if ((rc = upload_vec(ps.tri_src, &dp.tri_src)) != RM_OK) return rc;
-        CK(cudaMalloc(&dp.tri_r, (size_t)ps.lay.n_tri * 64 + 64 + 64));   // raster records + the tile counter behind them
-        CK(cudaMemset(dp.tri_r, 0, (size_t)ps.lay.n_tri * 64 + 64 + 64));
+        // raster records | frame control block | tile schedule
+        const size_t rec_bytes = (size_t)ps.lay.n_tri * 64 + 64;
+        const int order_cap = 1 << 16;                          // tiles of a frame up to 8192 x 8192
+        CK(cudaMalloc(&dp.tri_r, rec_bytes + 64 + (size_t)order_cap * sizeof(int)));
+        CK(cudaMemset(dp.tri_r, 0, rec_bytes + 64 + (size_t)order_cap * sizeof(int)));
         dp.ds.tri_src = static_cast<const double*>(dp.tri_src);
         dp.ds.tri_r = static_cast<rm::R4<float>*>(dp.tri_r);
-        dp.ds.tile_counter = reinterpret_cast<int*>(static_cast<char*>(dp.tri_r) + (size_t)ps.lay.n_tri * 64 + 64);
+        dp.ds.ctr = reinterpret_cast<int*>(static_cast<char*>(dp.tri_r) + rec_bytes);
+        dp.ds.tile_order = dp.ds.ctr + 16;
+        dp.ds.tile_order_cap = order_cap;
     }
     dp.ds.blob = static_cast<const unsigned char*>(dp.blob);
     dp.ds.lay = ps.lay;

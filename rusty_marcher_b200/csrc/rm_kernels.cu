@@ -121,9 +121,8 @@ render_kernel(const DeviceScene<R> ds, const FrameParams<R> fp, const int cull, 
 // K0: camera-specialised raster records of every fast-path triangle, in FP64, once per frame.
 __global__ void __launch_bounds__(128)
 prepare_raster_kernel(const double* __restrict__ tri_src, const int n_tri, const double cx, const double cy, const double cz,
-                      R4<float>* __restrict__ tri_r, int* __restrict__ tile_counter) {
+                      R4<float>* __restrict__ tri_r) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0) *tile_counter = 0;                              // work counter of the render kernel that follows
     if (j >= n_tri) return;
     const double cam[3] = {cx, cy, cz};
     R4<float> out[4];
@@ -132,29 +131,84 @@ prepare_raster_kernel(const double* __restrict__ tri_src, const int n_tri, const
     for (int k = 0; k < 4; k++) tri_r[4 * j + k] = out[k];
 }
 
-// K1, FP32 production kernel (rm_fast.cuh).  Persistent: the grid is (SMs x resident CTAs), every
-// CTA stages the scene into shared memory ONCE and then pulls 32x32-pixel tiles -- exactly the
-// reference's patches (renderer.rs:46-89) -- from an atomic counter, the GPU analogue of Rayon's
-// work stealing.  Each tile is processed as a two-stage wavefront:
-//   A  primary visibility, divergence-free: a warp owns a 32x4 strip, a thread 4 horizontally adjacent
-//      pixels.  First the warp bounds every triangle against its strip (one triangle per lane, exact
-//      corner test tri_may_touch, ballot), then all lanes walk the surviving triangles together
-//      (primary_tri<4>).  Misses are final (black) and are written at once with 128-bit stores; hits
-//      are appended to a shared-memory queue, compacted with ballot/popc, so that
-//   B  shading + shadow rays + the reflect/refract recursion (the divergent part) runs on warps that
-//      are fully populated with hit pixels: one queue entry per thread.
-// The channel maximum (framebuffer.rs:58-69) is kept per thread across all its tiles and reduced once:
+// K0 for scenes made of (few) triangles only: the raster records as above, and in the same launch the
+// tile schedule of the render kernel.  One thread per 32x32 tile bounds every triangle against the tile
+// (tri_may_touch: exact, see rm_fast.cuh); tiles some triangle may touch are "busy" and go to the front of
+// the schedule, the others are provably black and go to the back.  The render kernel hands the busy
+// tiles out first (longest work first, so the cheap tiles fill the tail) and only stores zeros for the rest.
+constexpr int kClassifyMaxTris = 256;
+__global__ void __launch_bounds__(256)
+prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, const double cx, const double cy, const double cz,
+                        R4<float>* __restrict__ tri_r, const FrameParams<float> fp, const int tiles_x, const int n_tiles,
+                        int* __restrict__ order, int* __restrict__ ctr) {
+    __shared__ R4<float> rec[4 * kClassifyMaxTris];
+    const double cam[3] = {cx, cy, cz};
+    for (int j = threadIdx.x; j < n_tri; j += blockDim.x) {      // every block rebuilds the (few) records; block 0 publishes them
+        R4<float> out[4];
+        prepare_raster(tri_src + (size_t)j * kTriSrcDoubles, cam, out);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            rec[4 * j + k] = out[k];
+            if (blockIdx.x == 0) tri_r[4 * j + k] = out[k];
+        }
+    }
+    __syncthreads();
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    bool busy = false;
+    if (tile < n_tiles) {
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int x0 = tx * 32, y0 = fp.row_begin + ty * 32;
+        const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + 31), Ya = pixel_Y(fp, y0), Yb = pixel_Y(fp, y0 + 31);
+        for (int j = 0; j < n_tri && !busy; j++) busy = tri_may_touch(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3], Xa, Xb, Ya, Yb);
+    }
+    // busy tiles fill the schedule from the front, empty ones from the back: one atomic per warp and class
+    const int lane = threadIdx.x & 31;
+    const unsigned lane_lt = (1u << lane) - 1u;
+    const unsigned mb = __ballot_sync(0xffffffffu, busy), me = __ballot_sync(0xffffffffu, tile < n_tiles && !busy);
+    int base_b = 0, base_e = 0;
+    if (lane == 0) {
+        if (mb) base_b = atomicAdd(ctr + 1, __popc(mb));
+        if (me) base_e = atomicAdd(ctr + 2, __popc(me));
+    }
+    base_b = __shfl_sync(0xffffffffu, base_b, 0);
+    base_e = __shfl_sync(0xffffffffu, base_e, 0);
+    if (busy) order[base_b + __popc(mb & lane_lt)] = tile;
+    else if (tile < n_tiles) order[n_tiles - 1 - (base_e + __popc(me & lane_lt))] = tile;
+}
+
+// K1, FP32 production kernel (rm_fast.cuh).  Persistent and warp-granular: the grid is (SMs x resident
+// CTAs); every CTA stages the scene into shared memory ONCE; after that its warps never meet at a
+// barrier again.  Work is handed out in two levels, the GPU analogue of Rayon's work stealing over the
+// reference's 32x32 patches (renderer.rs:46-89):
+//   * a CTA owns one 32x32 tile at a time, taken from a global atomic counter (one atomic per tile);
+//   * its warps take the tile's eight 32x4 strips from a shared-memory ticket counter.  The warp that
+//     draws strip 0 of a tile fetches the CTA's NEXT tile and publishes it in a small ring
+//     (tile id + sequence tag), so the global atomic's latency hides behind the current tile.
+// Per strip a warp runs a two-stage wavefront of its own:
+//   A  primary visibility, divergence-free: a thread owns 4 horizontally adjacent pixels.  First the
+//      warp bounds every triangle against the strip (one triangle per lane, exact corner test
+//      tri_may_touch, ballot), then all lanes walk the surviving triangles together (primary_tri<4>).
+//      Misses are final (black) and are written at once with 128-bit stores; hits are appended to the
+//      warp's private shared-memory queue, compacted with ballot/popc, so that
+//   B  shading + shadow rays + the reflect/refract recursion (the divergent part) runs on a fully
+//      populated warp: whenever the queue holds 32 entries or more, one entry per lane.  A remainder
+//      waits for the next strip's hits and is flushed when the work runs out.
+// The channel maximum (framebuffer.rs:58-69) is kept per thread across all its strips and reduced once:
 // REDUX over the warp, shared atomic, one global atomic per CTA.
 constexpr int kFastTile = 32;
+constexpr int kStripRows = 4, kStripsPerTile = kFastTile / kStripRows;
+constexpr int kWarpQueue = kFastTile * kStripRows + 32;         // one strip of hits on top of a partial round
+constexpr int kRing = 8;
 template <bool kSmem>
 __global__ void __launch_bounds__(kBlock, 3)
 render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
-                   float* __restrict__ dmax, int* __restrict__ tile_counter) {
+                   float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    __shared__ int cta_max, next_tile, q_count;
-    constexpr int kQueue = kFastTile * kFastTile + kBlock;     // one tile of hits on top of a partial round
-    __shared__ float4 queue[kQueue];                            // {t, slot, id, x | y << 16}
+    __shared__ int cta_max, strip_ticket;
+    __shared__ int ring_tile[kRing];
+    __shared__ int ring_seq[kRing];
+    __shared__ float4 queue[kBlock / 32][kWarpQueue];           // {t, slot, id, x | y << 16}
     const BlobLayout& L = ds.lay;
     const int n_tri = tri_count(L, cull != 0);
 
@@ -162,8 +216,10 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     const R4<float>* tri_r = ds.tri_r;
     if (threadIdx.x == 0) {
         cta_max = 0;
-        q_count = 0;
-        next_tile = atomicAdd(tile_counter, 1);
+        strip_ticket = 0;
+        for (int i = 1; i < kRing; i++) ring_seq[i] = -1;
+        ring_tile[0] = atomicAdd(ctr, 1);
+        ring_seq[0] = 0;
     }
     if (kSmem) {
         const uint4* src = reinterpret_cast<const uint4*>(ds.blob);
@@ -198,95 +254,122 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     fv.n_lgt = L.n_lgt;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lx = (lane & 7) * 4, ly = warp * 4 + (lane >> 3);
+    const int lx = (lane & 7) * 4, ly = lane >> 3;
     const unsigned lane_lt = (1u << lane) - 1u;
     const bool rest = fv.n_sph + fv.n_poly > 0;
+    const int n_busy = order ? ctr[1] : n_tiles;               // schedule positions >= n_busy hold provably empty tiles
+    float4* const wq = queue[warp];
+    volatile int* const vseq = ring_seq;
+    volatile int* const vtile = ring_tile;
+    int qn = 0;                                                 // entries in this warp's queue (warp-uniform)
     float m = 0.f;
+
+    auto shade_entry = [&](const float4 e) {
+        const unsigned xy = __float_as_uint(e.w);
+        const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+        const Vec3<float> c = fast_shade(fv, fp, x, y, e.x, __float_as_int(e.y), __float_as_int(e.z));
+        float* dst = rgb + 3 * ((size_t)(y - fp.buf_row0) * fp.width + x);
+        dst[0] = c.x;
+        dst[1] = c.y;
+        dst[2] = c.z;
+        m = fmaxf(m, fmaxf(fmaxf(c.x, c.y), c.z));
+    };
+
     for (;;) {
-        const int tile = next_tile;
-        const bool last = tile >= n_tiles;                      // no tile left: only flush the queue
-        if (!last) {
-            const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);      // exact for tile < 2^22
-            const int tx = tile - ty * tiles_x;
-            const int x0 = tx * kFastTile, y0 = fp.row_begin + ty * kFastTile;
-            // ---- stage A: primary visibility of this thread's 4 pixels
-            PrimaryState<4> ps;
-            primary_begin<4>(ps, fp, x0 + lx, y0 + ly);
-            {
-                // the warp's strip: pixels [x0, x0 + 31] x [y0 + 4 warp, y0 + 4 warp + 3]
-                const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + kFastTile - 1);
-                const float Ya = pixel_Y(fp, y0 + warp * 4), Yb = pixel_Y(fp, y0 + warp * 4 + 3);
-                for (int jb = 0; jb < n_tri; jb += 32) {
-                    const int j = jb + lane;
-                    bool cand = false;
-                    if (j < n_tri) cand = tri_may_touch(tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], Xa, Xb, Ya, Yb);
-                    unsigned cm = __ballot_sync(0xffffffffu, cand);
-                    while (cm) {                                // uniform across the warp
-                        const int jj = jb + __ffs(cm) - 1;
-                        cm &= cm - 1;
-                        primary_tri<4>(ps, tri_r[4 * jj], tri_r[4 * jj + 1], tri_r[4 * jj + 2], tri_r[4 * jj + 3], fv.n_sph + jj);
-                    }
+        // ---- next strip of the CTA's current tile
+        int s = 0;
+        if (lane == 0) s = atomicAdd(&strip_ticket, 1);
+        s = __shfl_sync(0xffffffffu, s, 0);
+        const int k = s / kStripsPerTile, strip = s % kStripsPerTile;
+        if (lane == 0) {
+            if (strip == 0) {                                   // first strip of tile k: fetch tile k + 1 for the CTA
+                vtile[(k + 1) % kRing] = atomicAdd(ctr, 1);
+                __threadfence_block();
+                vseq[(k + 1) % kRing] = k + 1;
+            }
+            while (vseq[k % kRing] != k) {}                     // published by whoever drew strip 0 of tile k - 1
+            __threadfence_block();
+        }
+        __syncwarp();
+        const int pos = vtile[k % kRing];                       // position in the tile schedule
+        if (pos >= n_tiles) break;
+        const int tile = order ? order[pos] : pos;
+        const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);          // exact for tile < 2^22
+        const int tx = tile - ty * tiles_x;
+        const int x0 = tx * kFastTile, ys = fp.row_begin + ty * kFastTile + strip * kStripRows;
+        const size_t px = (size_t)(ys + ly - fp.buf_row0) * fp.width + x0 + lx;
+        {
+            float4* dst = reinterpret_cast<float4*>(rgb + 3 * px);          // 48 contiguous bytes, 16-byte aligned (x % 4 == 0)
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);              // renderer.rs:300-306: a primary miss is black
+            __stcs(dst, z);
+            __stcs(dst + 1, z);
+            __stcs(dst + 2, z);
+        }
+        if (pos >= n_busy) {                                    // no triangle can touch this tile: all misses
+            if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + px), make_int4(-1, -1, -1, -1));
+            continue;
+        }
+        // ---- stage A: primary visibility of this thread's 4 pixels
+        PrimaryState<4> ps;
+        primary_begin<4>(ps, fp, x0 + lx, ys + ly);
+        {
+            // the strip: pixels [x0, x0 + 31] x [ys, ys + 3]
+            const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + kFastTile - 1);
+            const float Ya = pixel_Y(fp, ys), Yb = pixel_Y(fp, ys + kStripRows - 1);
+            for (int jb = 0; jb < n_tri; jb += 32) {
+                const int j = jb + lane;
+                bool cand = false;
+                if (j < n_tri) cand = tri_may_touch(tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], Xa, Xb, Ya, Yb);
+                unsigned cm = __ballot_sync(0xffffffffu, cand);
+                while (cm) {                                    // uniform across the warp
+                    const int jj = jb + __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    primary_tri<4>(ps, tri_r[4 * jj], tri_r[4 * jj + 1], tri_r[4 * jj + 2], tri_r[4 * jj + 3], fv.n_sph + jj);
                 }
-                if (rest) primary_rest<4>(ps, fv, fp);
             }
-            const size_t px = (size_t)(y0 + ly - fp.buf_row0) * fp.width + x0 + lx;
-            {
-                float4* dst = reinterpret_cast<float4*>(rgb + 3 * px);      // 48 contiguous bytes, 16-byte aligned (x % 4 == 0)
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);          // renderer.rs:300-306: a primary miss is black
-                __stcs(dst, z);
-                __stcs(dst + 1, z);
-                __stcs(dst + 2, z);
-                if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + px), make_int4(ps.id[0], ps.id[1], ps.id[2], ps.id[3]));
-            }
-            // ---- hits -> queue: one shared atomic per warp
-            const unsigned m0 = __ballot_sync(0xffffffffu, ps.slot[0] >= 0), m1 = __ballot_sync(0xffffffffu, ps.slot[1] >= 0);
-            const unsigned m2 = __ballot_sync(0xffffffffu, ps.slot[2] >= 0), m3 = __ballot_sync(0xffffffffu, ps.slot[3] >= 0);
-            if (m0 | m1 | m2 | m3) {
-                const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
-                int qb = 0;
-                if (lane == 0) qb = atomicAdd(&q_count, c0 + c1 + c2 + c3);
-                qb = __shfl_sync(0xffffffffu, qb, 0);
-                const unsigned xy = (unsigned)(x0 + lx) | ((unsigned)(y0 + ly) << 16);
-                if (ps.slot[0] >= 0) queue[qb + __popc(m0 & lane_lt)] = make_float4(ps.t[0], __int_as_float(ps.slot[0]), __int_as_float(ps.id[0]), __uint_as_float(xy));
-                qb += c0;
-                if (ps.slot[1] >= 0) queue[qb + __popc(m1 & lane_lt)] = make_float4(ps.t[1], __int_as_float(ps.slot[1]), __int_as_float(ps.id[1]), __uint_as_float(xy + 1));
-                qb += c1;
-                if (ps.slot[2] >= 0) queue[qb + __popc(m2 & lane_lt)] = make_float4(ps.t[2], __int_as_float(ps.slot[2]), __int_as_float(ps.id[2]), __uint_as_float(xy + 2));
-                qb += c2;
-                if (ps.slot[3] >= 0) queue[qb + __popc(m3 & lane_lt)] = make_float4(ps.t[3], __int_as_float(ps.slot[3]), __int_as_float(ps.id[3]), __uint_as_float(xy + 3));
-            }
+            if (rest) primary_rest<4>(ps, fv, fp);
         }
-        __syncthreads();                                        // queue complete; everyone has read next_tile
-        // ---- stage B: full rounds only (every warp fully populated); the remainder waits for the next
-        //      tile's hits, and is flushed after the last tile
-        const int n_hit = q_count;
-        const int n_full = last ? n_hit : (n_hit & ~(kBlock - 1));
-        for (int q = threadIdx.x; q < n_full; q += kBlock) {
-            const float4 e = queue[q];
-            const unsigned xy = __float_as_uint(e.w);
-            const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
-            const Vec3<float> c = fast_shade(fv, fp, x, y, e.x, __float_as_int(e.y), __float_as_int(e.z));
-            float* dst = rgb + 3 * ((size_t)(y - fp.buf_row0) * fp.width + x);
-            dst[0] = c.x;
-            dst[1] = c.y;
-            dst[2] = c.z;
-            m = fmaxf(m, fmaxf(fmaxf(c.x, c.y), c.z));
+        if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + px), make_int4(ps.id[0], ps.id[1], ps.id[2], ps.id[3]));
+        // ---- hits -> the warp's queue
+        const unsigned m0 = __ballot_sync(0xffffffffu, ps.slot[0] >= 0), m1 = __ballot_sync(0xffffffffu, ps.slot[1] >= 0);
+        const unsigned m2 = __ballot_sync(0xffffffffu, ps.slot[2] >= 0), m3 = __ballot_sync(0xffffffffu, ps.slot[3] >= 0);
+        if ((m0 | m1 | m2 | m3) == 0u) continue;
+        {
+            const unsigned xy = (unsigned)(x0 + lx) | ((unsigned)(ys + ly) << 16);
+            int qb = qn;
+            if (ps.slot[0] >= 0) wq[qb + __popc(m0 & lane_lt)] = make_float4(ps.t[0], __int_as_float(ps.slot[0]), __int_as_float(ps.id[0]), __uint_as_float(xy));
+            qb += __popc(m0);
+            if (ps.slot[1] >= 0) wq[qb + __popc(m1 & lane_lt)] = make_float4(ps.t[1], __int_as_float(ps.slot[1]), __int_as_float(ps.id[1]), __uint_as_float(xy + 1));
+            qb += __popc(m1);
+            if (ps.slot[2] >= 0) wq[qb + __popc(m2 & lane_lt)] = make_float4(ps.t[2], __int_as_float(ps.slot[2]), __int_as_float(ps.id[2]), __uint_as_float(xy + 2));
+            qb += __popc(m2);
+            if (ps.slot[3] >= 0) wq[qb + __popc(m3 & lane_lt)] = make_float4(ps.t[3], __int_as_float(ps.slot[3]), __int_as_float(ps.id[3]), __uint_as_float(xy + 3));
+            qn = qb + __popc(m3);
         }
-        if (last) break;
-        __syncthreads();                                        // full rounds consumed
-        const int left = n_hit - n_full;                        // < kBlock; source [n_full, n_hit) and target [0, left) are disjoint
-        if (n_full > 0 && (int)threadIdx.x < left) queue[threadIdx.x] = queue[n_full + threadIdx.x];
-        if (threadIdx.x == 0) {
-            q_count = left;
-            next_tile = atomicAdd(tile_counter, 1);
+        __syncwarp();
+        // ---- stage B: full warps only, from the tail of the queue
+        while (qn >= 32) {
+            qn -= 32;
+            shade_entry(wq[qn + lane]);
         }
-        __syncthreads();
+        __syncwarp();                                           // reads done before the next strip appends
     }
+    if (lane < qn) shade_entry(wq[lane]);                       // flush the remainder
     // values are >= 0, so the integer order of the bit patterns is the float order
     const int wm = __reduce_max_sync(0xffffffffu, __float_as_int(m));
     if (lane == 0 && wm > 0) atomicMax(&cta_max, wm);
     __syncthreads();
-    if (threadIdx.x == 0 && cta_max > 0) atomicMax(reinterpret_cast<int*>(dmax), cta_max);
+    if (threadIdx.x == 0) {
+        if (cta_max > 0) atomicMax(reinterpret_cast<int*>(dmax), cta_max);
+        // the last CTA out leaves the frame control block zeroed for the next frame
+        __threadfence();
+        if (atomicAdd(ctr + 3, 1) == (int)gridDim.x - 1) {
+            ctr[0] = 0;
+            ctr[1] = 0;
+            ctr[2] = 0;
+            ctr[3] = 0;
+        }
+    }
 }
 
 template <typename R> struct Tone;
@@ -355,11 +438,16 @@ namespace {
 cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& fp, bool cull, float* rgb, int* prim_id,
                         float* dmax, cudaStream_t stream, const double camera[3], int* launches, dim3 grid) {
     const int n_tri = tri_count(ds.lay, cull);
-    prepare_raster_kernel<<<(std::max(n_tri, 1) + 127) / 128, 128, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2],
-                                                                                ds.tri_r, ds.tile_counter);
+    const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * ((fp.row_end - fp.row_begin) / kFastTile);
+    const bool classify = ds.lay.n_sph + poly_count(ds.lay, cull) == 0 && n_tri <= kClassifyMaxTris && n_tiles <= ds.tile_order_cap;
+    if (classify)
+        prepare_classify_kernel<<<(n_tiles + 255) / 256, 256, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r,
+                                                                         fp, tiles_x, n_tiles, ds.tile_order, ds.ctr);
+    else
+        prepare_raster_kernel<<<(std::max(n_tri, 1) + 127) / 128, 128, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r);
+    const int* order = classify ? ds.tile_order : nullptr;
     if (launches) (*launches)++;
     const size_t smem = (size_t)ds.lay.bytes + (size_t)n_tri * 64;
-    const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * ((fp.row_end - fp.row_begin) / kFastTile);
     (void)grid;
     const float inv_tiles_x = 1.0f / (float)tiles_x;
     static int sm_count = 0;
@@ -375,13 +463,13 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
         int occ = 1;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, smem)) != cudaSuccess) return e;
         const int ctas = std::min(n_tiles, sm_count * std::max(occ, 1));
-        k<<<ctas, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.tile_counter);
+        k<<<ctas, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order);
     } else {
         auto k = render_fast_kernel<false>;
         int occ = 1;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, 0)) != cudaSuccess) return e;
         const int ctas = std::min(n_tiles, sm_count * std::max(occ, 1));
-        k<<<ctas, kBlock, 0, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.tile_counter);
+        k<<<ctas, kBlock, 0, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order);
     }
     if (launches) (*launches)++;
     return cudaGetLastError();

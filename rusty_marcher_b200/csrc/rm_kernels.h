@@ -21,7 +21,13 @@ template <typename R> struct DeviceScene {
     // camera-specialised raster records it writes (4 x R4<float> per triangle, rebuilt every frame)
     const double* tri_src = nullptr;
     R4<float>* tri_r = nullptr;
-    int* tile_counter = nullptr;   // work counter of the persistent render kernel (reset by the prepare kernel)
+    // frame control block of the persistent render kernel, zero between frames (the last CTA to finish resets it):
+    //   ctr[0] next tile to hand out   ctr[1] busy tiles   ctr[2] empty tiles   ctr[3] CTAs finished
+    int* ctr = nullptr;
+    // tile schedule written by the classify kernel: busy tiles (some triangle may touch them) first, then the
+    // tiles that are provably empty and only need their black pixels stored
+    int* tile_order = nullptr;
+    int tile_order_cap = 0;
 };
 
 // K0 + K1.  With counters == null and R = float this is the production path: prepare_raster_kernel

@@ -146,6 +146,23 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
                     const float Xa = rm::pixel_X(fp, xs), Xb = rm::pixel_X(fp, xs + 31);
                     const float Ya = rm::pixel_Y(fp, y0), Yb = rm::pixel_Y(fp, y0 + 3);
                     cand.clear();
+                    // the classify kernel's tile-level bound (32x32 tile around this strip): provably empty tiles are only zero-filled
+                    bool tile_busy = fv.n_sph + fv.n_poly > 0 || !g_strip_bound.load();
+                    {
+                        const int ty0 = fp.row_begin + ((y0 - fp.row_begin) / 32) * 32;
+                        const float TYa = rm::pixel_Y(fp, ty0), TYb = rm::pixel_Y(fp, ty0 + 31);
+                        for (int j = 0; j < n_tri && !tile_busy; j++)
+                            tile_busy = rm::tri_may_touch(tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], Xa, Xb, TYa, TYb);
+                    }
+                    if (!tile_busy) {
+                        for (int y = y0; y < y0 + 4; y++)
+                            for (int x = xs; x < xs + 32; x++) {
+                                size_t px = (size_t)y * fp.width + x;
+                                out_rgb[3 * px] = out_rgb[3 * px + 1] = out_rgb[3 * px + 2] = 0.f;
+                                if (prim) prim[px] = -1;
+                            }
+                        continue;
+                    }
                     for (int j = 0; j < n_tri; j++)
                         if (!g_strip_bound.load() || rm::tri_may_touch(tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], Xa, Xb, Ya, Yb)) cand.push_back(j);
                     for (int lane = 0; lane < 32; lane++) {
