@@ -91,25 +91,33 @@ struct FastView {
 #endif
     }
 
-    // general ray against the triangle whose scene record starts at g
-    static RM_HD bool tri_hit(const R4<float>* __restrict__ g, const Vec3<float> o, const Vec3<float> d, float& t_out) {
-        const R4<float> a = g[0];
-        const float dp = fmaf(a.z, d.z, fmaf(a.y, d.y, a.x * d.x));
-        const float num = fmaf(-a.z, o.z, fmaf(-a.y, o.y, fmaf(-a.x, o.x, a.w)));   // (C - o).n
-        // triangle.rs:65: t = num / dp < 0 <=> numerator and denominator have strictly opposite signs -- the most
-        // frequent rejection comes first and needs neither the division nor the rest of the record
-        if (num * dp < 0.f) return false;
+    // General ray against the triangle whose scene record starts at g, in two stages.
+    // Stage 1 (tri_front): d.n and (C - o).n from the first 16 bytes of the record.  triangle.rs:65 rejects
+    // t = num / dp < 0, i.e. numerator and denominator of triangle.rs:62 with strictly opposite signs -- the most
+    // frequent rejection needs neither the division nor the rest of the record.
+    static RM_HD bool tri_front(const R4<float> a, const Vec3<float> o, const Vec3<float> d, float& dp, float& num) {
+        dp = fmaf(a.z, d.z, fmaf(a.y, d.y, a.x * d.x));
+        num = fmaf(-a.z, o.z, fmaf(-a.y, o.y, fmaf(-a.x, o.x, a.w)));     // (C - o).n
+        return !(num * dp < 0.f);
+    }
+    // Stage 2 (tri_inside): parallel test, division, the three edge terms at the hit point relative to vertex 0.
+    static RM_HD bool tri_inside(const R4<float>* __restrict__ g, const Vec3<float> o, const Vec3<float> d, const float dp,
+                                 const float num, float& t_out) {
         const R4<float> l = g[3];
         if (!(fabsf(dp) > l.y)) return false;                  // triangle.rs:57 (parallel)
         const float t = fast_div(num, dp);                     // triangle.rs:62
         const R4<float> b = g[1], c = g[2];
-        const float qx = fmaf(t, d.x, o.x - b.x), qy = fmaf(t, d.y, o.y - b.y);   // hit point relative to vertex 0
+        const float qx = fmaf(t, d.x, o.x - b.x), qy = fmaf(t, d.y, o.y - b.y);
         const float e0 = fmaf(b.z, qx, b.w * qy);
         const float e1 = fmaf(c.x, qx, fmaf(c.y, qy, c.z));
         const float e2 = fmaf(c.w, qx, l.x * qy);
         if (!(fminf(fminf(e0, e1), e2) > 0.f)) return false;   // triangle.rs:72-76
         t_out = t;
         return true;
+    }
+    static RM_HD bool tri_hit(const R4<float>* __restrict__ g, const Vec3<float> o, const Vec3<float> d, float& t_out) {
+        float dp, num;
+        return tri_front(g[0], o, d, dp, num) && tri_inside(g, o, d, dp, num, t_out);
     }
 
     RM_HD static void keep(HitRec<float>& best, bool& hit, float t, int slot, int id) {
@@ -151,7 +159,22 @@ struct FastView {
             if (sphere_intersect<S>(sph[i], o, d, c, st)) return true;
         float t;
         const R4<float>* g = tri_g;
-        for (int j = 0; j < n_tri; j++, g += 4)
+        int j = 0;
+        // four triangles per round: the four record loads and the eight independent FFMA chains of stage 1 are in
+        // flight together (a single triangle per iteration leaves the warp waiting on each shared-memory load)
+        for (; j + 4 <= n_tri; j += 4, g += 16) {
+            float dp0, dp1, dp2, dp3, nm0, nm1, nm2, nm3;
+            const R4<float> a0 = g[0], a1 = g[4], a2 = g[8], a3 = g[12];
+            const bool f0 = tri_front(a0, o, d, dp0, nm0), f1 = tri_front(a1, o, d, dp1, nm1);
+            const bool f2 = tri_front(a2, o, d, dp2, nm2), f3 = tri_front(a3, o, d, dp3, nm3);
+            if (f0 | f1 | f2 | f3) {
+                if (f0 && tri_inside(g, o, d, dp0, nm0, t)) return true;
+                if (f1 && tri_inside(g + 4, o, d, dp1, nm1, t)) return true;
+                if (f2 && tri_inside(g + 8, o, d, dp2, nm2, t)) return true;
+                if (f3 && tri_inside(g + 12, o, d, dp3, nm3, t)) return true;
+            }
+        }
+        for (; j < n_tri; j++, g += 4)
             if (tri_hit(g, o, d, t)) return true;
         for (int k = 0; k < n_poly; k++) {
             const int i = poly_slot[k];
@@ -210,6 +233,17 @@ RM_HD float rect_max(const R4<float> r, const float Xa, const float Xb, const fl
     const float ba = fmaf(r.y, Ya, r.z), bb = fmaf(r.y, Yb, r.z);
     return fmaxf(fmaxf(fmaf(r.x, Xa, ba), fmaf(r.x, Xb, ba)), fmaxf(fmaf(r.x, Xa, bb), fmaf(r.x, Xb, bb)));
 }
+RM_HD float rect_min(const R4<float> r, const float Xa, const float Xb, const float Ya, const float Yb) {
+    const float ba = fmaf(r.y, Ya, r.z), bb = fmaf(r.y, Yb, r.z);
+    return fminf(fminf(fmaf(r.x, Xa, ba), fmaf(r.x, Xb, ba)), fminf(fmaf(r.x, Xa, bb), fmaf(r.x, Xb, bb)));
+}
+// All four functions positive at all four corners: every pixel of the rectangle lies inside the triangle (used only as
+// a cost estimate by the tile schedule -- such a tile is all hits -- never for a visibility decision).
+RM_HD bool tri_covers(const R4<float> r0, const R4<float> r1, const R4<float> r2, const R4<float> r3, const float Xa,
+                      const float Xb, const float Ya, const float Yb) {
+    return fminf(fminf(rect_min(r0, Xa, Xb, Ya, Yb), rect_min(r1, Xa, Xb, Ya, Yb)),
+                 fminf(rect_min(r2, Xa, Xb, Ya, Yb), rect_min(r3, Xa, Xb, Ya, Yb))) > 0.f;
+}
 RM_HD bool tri_may_touch(const R4<float> r0, const R4<float> r1, const R4<float> r2, const R4<float> r3, const float Xa,
                          const float Xb, const float Ya, const float Yb) {
     return fminf(fminf(rect_max(r0, Xa, Xb, Ya, Yb), rect_max(r1, Xa, Xb, Ya, Yb)),
@@ -252,17 +286,19 @@ RM_HD void primary_tri(PrimaryState<kPx>& ps, const R4<float> r0, const R4<float
     }
 }
 
-// spheres / n-gons: the general routines from the camera
+// spheres / n-gons: the general routines from the camera.  One copy of the code: the loop over the kPx pixels is
+// not unrolled and the pixel state rotates through index 0, so every array index stays a compile-time constant
+// (a dynamic index would push the arrays to local memory).
 template <int kPx> RM_HD void primary_rest(PrimaryState<kPx>& ps, const FastView& fv, const FrameParams<float>& fp) {
-#pragma unroll
-    for (int k = 0; k < kPx; k++) {
-        const float inv = fast_rsqrt(ps.len2[k]);
-        const Vec3<float> d = {ps.X[k] * inv, ps.Y * inv, -inv};
-        bool hit = ps.slot[k] >= 0;
+#pragma unroll 1
+    for (int r = 0; r < kPx; r++) {
+        const float inv = fast_rsqrt(ps.len2[0]);
+        const Vec3<float> d = {ps.X[0] * inv, ps.Y * inv, -inv};
+        bool hit = ps.slot[0] >= 0;
         HitRec<float> best;
-        best.dist = ps.t[k] * (ps.len2[k] * inv);              // to the unit direction
-        best.slot = ps.slot[k];
-        best.id = ps.id[k];
+        best.dist = ps.t[0] * (ps.len2[0] * inv);              // to the unit direction
+        best.slot = ps.slot[0];
+        best.id = ps.id[0];
         Counters<false> st;
         for (int i = 0; i < fv.n_sph; i++) {
             Cand<float> c;
@@ -274,9 +310,22 @@ template <int kPx> RM_HD void primary_rest(PrimaryState<kPx>& ps, const FastView
             if (plane_intersect<false>(fv.pln_n[i], fv.pln_c[i], fv.pln_v[i], fv.vert, fp.camera, d, c, st))
                 FastView::keep(best, hit, c.key, fv.n_sph + fv.n_tri + i, fv.pln_id[i]);
         }
-        ps.t[k] = best.dist * inv;                              // back to units of |D|, like the triangle hits
-        ps.slot[k] = hit ? best.slot : -1;
-        ps.id[k] = hit ? best.id : -1;
+        const float t_new = best.dist * inv;                   // back to units of |D|, like the triangle hits
+        const int slot_new = hit ? best.slot : -1, id_new = hit ? best.id : -1;
+        const float X0 = ps.X[0], L0 = ps.len2[0];
+#pragma unroll
+        for (int k = 0; k + 1 < kPx; k++) {                     // rotate left; the finished pixel goes to the end
+            ps.X[k] = ps.X[k + 1];
+            ps.len2[k] = ps.len2[k + 1];
+            ps.t[k] = ps.t[k + 1];
+            ps.slot[k] = ps.slot[k + 1];
+            ps.id[k] = ps.id[k + 1];
+        }
+        ps.X[kPx - 1] = X0;
+        ps.len2[kPx - 1] = L0;
+        ps.t[kPx - 1] = t_new;
+        ps.slot[kPx - 1] = slot_new;
+        ps.id[kPx - 1] = id_new;
     }
 }
 

@@ -137,10 +137,10 @@ prepare_raster_kernel(const double* __restrict__ tri_src, const int n_tri, const
 // the schedule, the others are provably black and go to the back.  The render kernel hands the busy
 // tiles out first (longest work first, so the cheap tiles fill the tail) and only stores zeros for the rest.
 constexpr int kClassifyMaxTris = 256;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64)
 prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, const double cx, const double cy, const double cz,
                         R4<float>* __restrict__ tri_r, const FrameParams<float> fp, const int tiles_x, const int n_tiles,
-                        int* __restrict__ order, int* __restrict__ ctr) {
+                        int* __restrict__ order, int* __restrict__ order2, int* __restrict__ ctr) {
     __shared__ R4<float> rec[4 * kClassifyMaxTris];
     const double cam[3] = {cx, cy, cz};
     for (int j = threadIdx.x; j < n_tri; j += blockDim.x) {      // every block rebuilds the (few) records; block 0 publishes them
@@ -154,36 +154,48 @@ prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, con
     }
     __syncthreads();
     const int tile = blockIdx.x * blockDim.x + threadIdx.x;
-    bool busy = false;
+    bool busy = false, full = false;
     if (tile < n_tiles) {
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const int x0 = tx * 32, y0 = fp.row_begin + ty * 32;
         const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + 31), Ya = pixel_Y(fp, y0), Yb = pixel_Y(fp, y0 + 31);
-        for (int j = 0; j < n_tri && !busy; j++) busy = tri_may_touch(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3], Xa, Xb, Ya, Yb);
+        for (int j = 0; j < n_tri && !full; j++) {
+            if (tri_may_touch(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3], Xa, Xb, Ya, Yb)) {
+                busy = true;
+                full = tri_covers(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3], Xa, Xb, Ya, Yb);
+            }
+        }
     }
-    // busy tiles fill the schedule from the front, empty ones from the back: one atomic per warp and class
+    // Three classes, one atomic per warp and class: fully covered tiles (1024 hits to shade: the longest jobs) at the
+    // front of `order`, partially covered ones in `order2` (handed out after the full ones), empty ones from the back
+    // of `order`.
     const int lane = threadIdx.x & 31;
     const unsigned lane_lt = (1u << lane) - 1u;
-    const unsigned mb = __ballot_sync(0xffffffffu, busy), me = __ballot_sync(0xffffffffu, tile < n_tiles && !busy);
-    int base_b = 0, base_e = 0;
+    const bool part = busy && !full, empty = tile < n_tiles && !busy;
+    const unsigned mf = __ballot_sync(0xffffffffu, full), mp = __ballot_sync(0xffffffffu, part), me = __ballot_sync(0xffffffffu, empty);
+    int base_f = 0, base_p = 0, base_e = 0;
     if (lane == 0) {
-        if (mb) base_b = atomicAdd(ctr + 1, __popc(mb));
+        if (mf) base_f = atomicAdd(ctr + 1, __popc(mf));
+        if (mp) base_p = atomicAdd(ctr + 5, __popc(mp));
         if (me) base_e = atomicAdd(ctr + 2, __popc(me));
     }
-    base_b = __shfl_sync(0xffffffffu, base_b, 0);
+    base_f = __shfl_sync(0xffffffffu, base_f, 0);
+    base_p = __shfl_sync(0xffffffffu, base_p, 0);
     base_e = __shfl_sync(0xffffffffu, base_e, 0);
-    if (busy) order[base_b + __popc(mb & lane_lt)] = tile;
-    else if (tile < n_tiles) order[n_tiles - 1 - (base_e + __popc(me & lane_lt))] = tile;
+    if (full) order[base_f + __popc(mf & lane_lt)] = tile;
+    else if (part) order2[base_p + __popc(mp & lane_lt)] = tile;
+    else if (empty) order[n_tiles - 1 - (base_e + __popc(me & lane_lt))] = tile;
 }
 
 // K1, FP32 production kernel (rm_fast.cuh).  Persistent and warp-granular: the grid is (SMs x resident
 // CTAs); every CTA stages the scene into shared memory ONCE; after that its warps never meet at a
 // barrier again.  Work is handed out in two levels, the GPU analogue of Rayon's work stealing over the
 // reference's 32x32 patches (renderer.rs:46-89):
-//   * a CTA owns one 32x32 tile at a time, taken from a global atomic counter (one atomic per tile);
+//   * a CTA owns one busy 32x32 tile at a time, taken from a global atomic counter (one atomic per tile);
 //   * its warps take the tile's eight 32x4 strips from a shared-memory ticket counter.  The warp that
-//     draws strip 0 of a tile fetches the CTA's NEXT tile and publishes it in a small ring
-//     (tile id + sequence tag), so the global atomic's latency hides behind the current tile.
+//     draws strip 0 of a tile fetches the tile the CTA will need kAhead tiles later and publishes it
+//     in a small ring (tile id + sequence tag), so the latency of the global atomic and of the
+//     schedule lookup hides behind the tiles in between.
 // Per strip a warp runs a two-stage wavefront of its own:
 //   A  primary visibility, divergence-free: a thread owns 4 horizontally adjacent pixels.  First the
 //      warp bounds every triangle against the strip (one triangle per lane, exact corner test
@@ -192,21 +204,28 @@ prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, con
 //      warp's private shared-memory queue, compacted with ballot/popc, so that
 //   B  shading + shadow rays + the reflect/refract recursion (the divergent part) runs on a fully
 //      populated warp: whenever the queue holds 32 entries or more, one entry per lane.  A remainder
-//      waits for the next strip's hits and is flushed when the work runs out.
+//      waits for the next strip's hits; when the busy tiles have run out the warps first zero-fill the
+//      tiles the classify kernel proved empty (drawn per warp, nothing to balance), then pool their
+//      leftovers across the CTA for one last round on full warps.
 // The channel maximum (framebuffer.rs:58-69) is kept per thread across all its strips and reduced once:
 // REDUX over the warp, shared atomic, one global atomic per CTA.
 constexpr int kFastTile = 32;
 constexpr int kStripRows = 4, kStripsPerTile = kFastTile / kStripRows;
 constexpr int kWarpQueue = kFastTile * kStripRows + 32;         // one strip of hits on top of a partial round
-constexpr int kRing = 8;
+constexpr int kRing = 16;                                        // published tiles (power of two)
+constexpr int kAhead = 1;                                       // tiles fetched ahead of the one being drawn
 template <bool kSmem>
 __global__ void __launch_bounds__(kBlock, 3)
 render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
-                   float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order) {
+                   float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order, const int* __restrict__ order2) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     __shared__ int cta_max, strip_ticket;
+    __shared__ int leftover[kBlock / 32];
+    __shared__ int fill_off[96];                                // float offset of each 16-byte chunk of a strip (see fill_strip)
+    __shared__ float4 pool[kBlock];                             // pooled leftovers of the eight warp queues (< 32 each)
     __shared__ int ring_tile[kRing];
+    __shared__ int ring_pos[kRing];
     __shared__ int ring_seq[kRing];
     __shared__ float4 queue[kBlock / 32][kWarpQueue];           // {t, slot, id, x | y << 16}
     const BlobLayout& L = ds.lay;
@@ -214,12 +233,18 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
 
     const unsigned char* base = ds.blob;
     const R4<float>* tri_r = ds.tri_r;
+    if (threadIdx.x < 96) fill_off[threadIdx.x] = (threadIdx.x / 24) * fp.width * 3 + (threadIdx.x % 24) * 4;
     if (threadIdx.x == 0) {
         cta_max = 0;
         strip_ticket = 0;
-        for (int i = 1; i < kRing; i++) ring_seq[i] = -1;
-        ring_tile[0] = atomicAdd(ctr, 1);
-        ring_seq[0] = 0;
+        for (int i = 0; i < kRing; i++) ring_seq[i] = -1;
+        const int n_full0 = order ? ctr[1] : n_tiles, n_busy0 = order ? n_full0 + ctr[5] : n_tiles;
+        for (int i = 0; i < kAhead; i++) {
+            const int pos = atomicAdd(ctr, 1);
+            ring_tile[i] = pos >= n_busy0 ? -1 : (!order ? pos : pos < n_full0 ? order[pos] : order2[pos - n_full0]);
+            ring_pos[i] = pos;
+            ring_seq[i] = i;
+        }
     }
     if (kSmem) {
         const uint4* src = reinterpret_cast<const uint4*>(ds.blob);
@@ -257,11 +282,13 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     const int lx = (lane & 7) * 4, ly = lane >> 3;
     const unsigned lane_lt = (1u << lane) - 1u;
     const bool rest = fv.n_sph + fv.n_poly > 0;
-    const int n_busy = order ? ctr[1] : n_tiles;               // schedule positions >= n_busy hold provably empty tiles
+    // schedule: [0, n_full) fully covered tiles (order), [n_full, n_busy) partially covered (order2), [n_busy, n_tiles) empty (order)
+    const int n_full = order ? ctr[1] : n_tiles, n_busy = order ? n_full + ctr[5] : n_tiles;
     float4* const wq = queue[warp];
     volatile int* const vseq = ring_seq;
     volatile int* const vtile = ring_tile;
     int qn = 0;                                                 // entries in this warp's queue (warp-uniform)
+    int final_take = 0;
     float m = 0.f;
 
     auto shade_entry = [&](const float4 e) {
@@ -275,86 +302,148 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         m = fmaxf(m, fmaxf(fmaxf(c.x, c.y), c.z));
     };
 
-    for (;;) {
-        // ---- next strip of the CTA's current tile
-        int s = 0;
-        if (lane == 0) s = atomicAdd(&strip_ticket, 1);
-        s = __shfl_sync(0xffffffffu, s, 0);
-        const int k = s / kStripsPerTile, strip = s % kStripsPerTile;
-        if (lane == 0) {
-            if (strip == 0) {                                   // first strip of tile k: fetch tile k + 1 for the CTA
-                vtile[(k + 1) % kRing] = atomicAdd(ctr, 1);
-                __threadfence_block();
-                vseq[(k + 1) % kRing] = k + 1;
-            }
-            while (vseq[k % kRing] != k) {}                     // published by whoever drew strip 0 of tile k - 1
-            __threadfence_block();
-        }
-        __syncwarp();
-        const int pos = vtile[k % kRing];                       // position in the tile schedule
-        if (pos >= n_tiles) break;
-        const int tile = order ? order[pos] : pos;
-        const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);          // exact for tile < 2^22
+    // Zero-fill (renderer.rs:300-306: a primary miss is black) of a 32-pixel wide strip of kStripRows rows by one warp,
+    // fully coalesced: a pixel row of the strip is 384 contiguous bytes = 24 chunks of 16 bytes, the strip 96 chunks,
+    // lane l stores chunks l, l + 32, l + 64 (each instruction writes 512 bytes in at most two contiguous runs).
+    auto fill_strip = [&](float* strip0) {                      // strip0: first float of the strip's first row
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 3; i++) __stcs(reinterpret_cast<float4*>(strip0 + fill_off[lane + 32 * i]), z);
+    };
+    auto fill_empty_tile = [&](const int tile) {
+        const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);
         const int tx = tile - ty * tiles_x;
-        const int x0 = tx * kFastTile, ys = fp.row_begin + ty * kFastTile + strip * kStripRows;
-        const size_t px = (size_t)(ys + ly - fp.buf_row0) * fp.width + x0 + lx;
-        {
-            float4* dst = reinterpret_cast<float4*>(rgb + 3 * px);          // 48 contiguous bytes, 16-byte aligned (x % 4 == 0)
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);              // renderer.rs:300-306: a primary miss is black
-            __stcs(dst, z);
-            __stcs(dst + 1, z);
-            __stcs(dst + 2, z);
+        const size_t p0 = (size_t)(fp.row_begin + ty * kFastTile - fp.buf_row0) * fp.width + tx * kFastTile;
+#pragma unroll
+        for (int r = 0; r < kStripsPerTile; r++) {
+            fill_strip(rgb + 3 * (p0 + (size_t)r * kStripRows * fp.width));
+            if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + p0 + (size_t)(r * kStripRows + ly) * fp.width + lx), make_int4(-1, -1, -1, -1));
         }
-        if (pos >= n_busy) {                                    // no triangle can touch this tile: all misses
-            if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + px), make_int4(-1, -1, -1, -1));
-            continue;
-        }
-        // ---- stage A: primary visibility of this thread's 4 pixels
-        PrimaryState<4> ps;
-        primary_begin<4>(ps, fp, x0 + lx, ys + ly);
-        {
-            // the strip: pixels [x0, x0 + 31] x [ys, ys + 3]
-            const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + kFastTile - 1);
-            const float Ya = pixel_Y(fp, ys), Yb = pixel_Y(fp, ys + kStripRows - 1);
-            for (int jb = 0; jb < n_tri; jb += 32) {
-                const int j = jb + lane;
-                bool cand = false;
-                if (j < n_tri) cand = tri_may_touch(tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], Xa, Xb, Ya, Yb);
-                unsigned cm = __ballot_sync(0xffffffffu, cand);
-                while (cm) {                                    // uniform across the warp
-                    const int jj = jb + __ffs(cm) - 1;
-                    cm &= cm - 1;
-                    primary_tri<4>(ps, tri_r[4 * jj], tri_r[4 * jj + 1], tri_r[4 * jj + 2], tri_r[4 * jj + 3], fv.n_sph + jj);
+    };
+    // The empty tiles' stores are pure HBM traffic and must overlap the busy tiles' arithmetic instead of forming a
+    // phase of their own.  Every warp of the grid owns a fixed share of the schedule's empty part (nothing to balance:
+    // tiles gw, gw + W, ... for global warp gw of W) and works it off at the pace of the busy strips it processes:
+    // n_empty / n_busy_strips empty tiles per busy strip, carried in a fraction accumulator.  What is left when the busy
+    // tiles run out (all of it for warps that never drew a busy strip) is filled in phase 2.
+    const int n_empty = n_tiles - n_busy;
+    const int n_busy_strips = n_busy * kStripsPerTile;
+    const int n_warps = gridDim.x * (kBlock / 32);
+    int next_empty = n_busy + blockIdx.x * (kBlock / 32) + warp;   // schedule position of this warp's next empty tile
+    int empty_acc = 0;
+
+    // ---- phase 1: busy tiles, dynamic.  phase 3 (below) reuses the shading code of the loop through `pooled`.
+    for (int phase = 1;;) {
+        if (phase == 1) {
+            // next strip of the CTA's current tile
+            int s = 0;
+            if (lane == 0) s = atomicAdd(&strip_ticket, 1);
+            s = __shfl_sync(0xffffffffu, s, 0);
+            const int k = s / kStripsPerTile, strip = s % kStripsPerTile;
+            if (lane == 0) {
+                if (strip == 0) {                               // first strip of tile k: fetch tile k + kAhead for the CTA
+                    const int pos = atomicAdd(ctr, 1);          // position in the tile schedule
+                    vtile[(k + kAhead) % kRing] = pos >= n_busy ? -1 : (!order ? pos : pos < n_full ? order[pos] : order2[pos - n_full]);
+                    ring_pos[(k + kAhead) % kRing] = pos;
+                    __threadfence_block();
+                    vseq[(k + kAhead) % kRing] = k + kAhead;
+                }
+                while (vseq[k % kRing] != k) {}                 // published by whoever drew strip 0 of tile k - kAhead
+                __threadfence_block();
+            }
+            __syncwarp();
+            const int tile = vtile[k % kRing];
+            if (tile < 0) {
+                phase = 2;
+            } else {
+                const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);          // exact for tile < 2^22
+                const int tx = tile - ty * tiles_x;
+                const int x0 = tx * kFastTile, ys = fp.row_begin + ty * kFastTile + strip * kStripRows;
+                const size_t px = (size_t)(ys + ly - fp.buf_row0) * fp.width + x0 + lx;
+                fill_strip(rgb + 3 * ((size_t)(ys - fp.buf_row0) * fp.width + x0));   // misses stay black; stage B overwrites the hits
+                // stage A: primary visibility of this thread's 4 pixels
+                PrimaryState<4> ps;
+                primary_begin<4>(ps, fp, x0 + lx, ys + ly);
+                {
+                    // the strip: pixels [x0, x0 + 31] x [ys, ys + 3]
+                    const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + kFastTile - 1);
+                    const float Ya = pixel_Y(fp, ys), Yb = pixel_Y(fp, ys + kStripRows - 1);
+                    for (int jb = 0; jb < n_tri; jb += 32) {
+                        const int j = jb + lane;
+                        bool cand = false;
+                        if (j < n_tri) cand = tri_may_touch(tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], Xa, Xb, Ya, Yb);
+                        unsigned cm = __ballot_sync(0xffffffffu, cand);
+                        while (cm) {                            // uniform across the warp
+                            const int jj = jb + __ffs(cm) - 1;
+                            cm &= cm - 1;
+                            primary_tri<4>(ps, tri_r[4 * jj], tri_r[4 * jj + 1], tri_r[4 * jj + 2], tri_r[4 * jj + 3], fv.n_sph + jj);
+                        }
+                    }
+                    if (rest) primary_rest<4>(ps, fv, fp);
+                }
+                if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + px), make_int4(ps.id[0], ps.id[1], ps.id[2], ps.id[3]));
+                // hits -> the warp's queue
+                const unsigned m0 = __ballot_sync(0xffffffffu, ps.slot[0] >= 0), m1 = __ballot_sync(0xffffffffu, ps.slot[1] >= 0);
+                const unsigned m2 = __ballot_sync(0xffffffffu, ps.slot[2] >= 0), m3 = __ballot_sync(0xffffffffu, ps.slot[3] >= 0);
+                if (m0 | m1 | m2 | m3) {
+                    const unsigned xy = (unsigned)(x0 + lx) | ((unsigned)(ys + ly) << 16);
+                    int qb = qn;
+                    if (ps.slot[0] >= 0) wq[qb + __popc(m0 & lane_lt)] = make_float4(ps.t[0], __int_as_float(ps.slot[0]), __int_as_float(ps.id[0]), __uint_as_float(xy));
+                    qb += __popc(m0);
+                    if (ps.slot[1] >= 0) wq[qb + __popc(m1 & lane_lt)] = make_float4(ps.t[1], __int_as_float(ps.slot[1]), __int_as_float(ps.id[1]), __uint_as_float(xy + 1));
+                    qb += __popc(m1);
+                    if (ps.slot[2] >= 0) wq[qb + __popc(m2 & lane_lt)] = make_float4(ps.t[2], __int_as_float(ps.slot[2]), __int_as_float(ps.id[2]), __uint_as_float(xy + 2));
+                    qb += __popc(m2);
+                    if (ps.slot[3] >= 0) wq[qb + __popc(m3 & lane_lt)] = make_float4(ps.t[3], __int_as_float(ps.slot[3]), __int_as_float(ps.id[3]), __uint_as_float(xy + 3));
+                    qn = qb + __popc(m3);
+                }
+                __syncwarp();
+                if (next_empty < n_tiles) {
+                    empty_acc += n_empty;
+                    while (empty_acc >= n_busy_strips && next_empty < n_tiles) {
+                        empty_acc -= n_busy_strips;
+                        fill_empty_tile(order[next_empty]);
+                        next_empty += n_warps;
+                    }
                 }
             }
-            if (rest) primary_rest<4>(ps, fv, fp);
         }
-        if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + px), make_int4(ps.id[0], ps.id[1], ps.id[2], ps.id[3]));
-        // ---- hits -> the warp's queue
-        const unsigned m0 = __ballot_sync(0xffffffffu, ps.slot[0] >= 0), m1 = __ballot_sync(0xffffffffu, ps.slot[1] >= 0);
-        const unsigned m2 = __ballot_sync(0xffffffffu, ps.slot[2] >= 0), m3 = __ballot_sync(0xffffffffu, ps.slot[3] >= 0);
-        if ((m0 | m1 | m2 | m3) == 0u) continue;
-        {
-            const unsigned xy = (unsigned)(x0 + lx) | ((unsigned)(ys + ly) << 16);
-            int qb = qn;
-            if (ps.slot[0] >= 0) wq[qb + __popc(m0 & lane_lt)] = make_float4(ps.t[0], __int_as_float(ps.slot[0]), __int_as_float(ps.id[0]), __uint_as_float(xy));
-            qb += __popc(m0);
-            if (ps.slot[1] >= 0) wq[qb + __popc(m1 & lane_lt)] = make_float4(ps.t[1], __int_as_float(ps.slot[1]), __int_as_float(ps.id[1]), __uint_as_float(xy + 1));
-            qb += __popc(m1);
-            if (ps.slot[2] >= 0) wq[qb + __popc(m2 & lane_lt)] = make_float4(ps.t[2], __int_as_float(ps.slot[2]), __int_as_float(ps.id[2]), __uint_as_float(xy + 2));
-            qb += __popc(m2);
-            if (ps.slot[3] >= 0) wq[qb + __popc(m3 & lane_lt)] = make_float4(ps.t[3], __int_as_float(ps.slot[3]), __int_as_float(ps.id[3]), __uint_as_float(xy + 3));
-            qn = qb + __popc(m3);
+        if (phase == 2) {
+            // ---- phase 2: the busy tiles have run out: the rest of this warp's share of the empty tiles
+            for (; next_empty < n_tiles; next_empty += n_warps) fill_empty_tile(order[next_empty]);
+            // ---- phase 3: pool the warps' leftovers (< 32 each) so the last round runs on full warps again
+            if (lane == 0) leftover[warp] = qn;
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kBlock / 32; w++) {
+                const int c = leftover[w];
+                if (w < warp) before += c;
+                total += c;
+            }
+            if (lane < qn) pool[before + lane] = wq[lane];
+            __syncthreads();
+            final_take = min(max(total - warp * 32, 0), 32);    // total < 256: at most one round, warp w takes entries [32 w, 32 w + 32)
+            phase = 3;
         }
-        __syncwarp();
-        // ---- stage B: full warps only, from the tail of the queue
-        while (qn >= 32) {
-            qn -= 32;
-            shade_entry(wq[qn + lane]);
+        // ---- stage B: full warps only, from the tail of the queue (phase 3: this warp's share of the pooled leftovers)
+        for (;;) {
+            const float4* src;
+            int take;
+            if (phase == 3) {
+                src = pool + warp * 32;
+                take = final_take;
+            } else {
+                if (qn < 32) break;
+                qn -= 32;
+                src = wq + qn;
+                take = 32;
+            }
+            if (lane < take) shade_entry(src[lane]);
+            if (phase == 3) break;
         }
+        if (phase == 3) break;
         __syncwarp();                                           // reads done before the next strip appends
     }
-    if (lane < qn) shade_entry(wq[lane]);                       // flush the remainder
     // values are >= 0, so the integer order of the bit patterns is the float order
     const int wm = __reduce_max_sync(0xffffffffu, __float_as_int(m));
     if (lane == 0 && wm > 0) atomicMax(&cta_max, wm);
@@ -368,6 +457,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
             ctr[1] = 0;
             ctr[2] = 0;
             ctr[3] = 0;
+            ctr[5] = 0;
         }
     }
 }
@@ -439,10 +529,10 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
                         float* dmax, cudaStream_t stream, const double camera[3], int* launches, dim3 grid) {
     const int n_tri = tri_count(ds.lay, cull);
     const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * ((fp.row_end - fp.row_begin) / kFastTile);
-    const bool classify = ds.lay.n_sph + poly_count(ds.lay, cull) == 0 && n_tri <= kClassifyMaxTris && n_tiles <= ds.tile_order_cap;
+    const bool classify = ds.lay.n_sph + poly_count(ds.lay, cull) == 0 && n_tri <= kClassifyMaxTris && n_tiles <= ds.tile_order_cap / 2;
     if (classify)
-        prepare_classify_kernel<<<(n_tiles + 255) / 256, 256, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r,
-                                                                         fp, tiles_x, n_tiles, ds.tile_order, ds.ctr);
+        prepare_classify_kernel<<<(n_tiles + 63) / 64, 64, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r,
+                                                                         fp, tiles_x, n_tiles, ds.tile_order, ds.tile_order + ds.tile_order_cap / 2, ds.ctr);
     else
         prepare_raster_kernel<<<(std::max(n_tri, 1) + 127) / 128, 128, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r);
     const int* order = classify ? ds.tile_order : nullptr;
@@ -463,13 +553,13 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
         int occ = 1;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, smem)) != cudaSuccess) return e;
         const int ctas = std::min(n_tiles, sm_count * std::max(occ, 1));
-        k<<<ctas, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order);
+        k<<<ctas, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr);
     } else {
         auto k = render_fast_kernel<false>;
         int occ = 1;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, 0)) != cudaSuccess) return e;
         const int ctas = std::min(n_tiles, sm_count * std::max(occ, 1));
-        k<<<ctas, kBlock, 0, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order);
+        k<<<ctas, kBlock, 0, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr);
     }
     if (launches) (*launches)++;
     return cudaGetLastError();

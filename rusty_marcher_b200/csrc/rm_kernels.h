@@ -22,7 +22,7 @@ template <typename R> struct DeviceScene {
     const double* tri_src = nullptr;
     R4<float>* tri_r = nullptr;
     // frame control block of the persistent render kernel, zero between frames (the last CTA to finish resets it):
-    //   ctr[0] next tile to hand out   ctr[1] busy tiles   ctr[2] empty tiles   ctr[3] CTAs finished
+    //   ctr[0] next busy tile   ctr[1] fully covered tiles   ctr[2] empty tiles   ctr[3] CTAs finished   ctr[5] partially covered tiles
     int* ctr = nullptr;
     // tile schedule written by the classify kernel: busy tiles (some triangle may touch them) first, then the
     // tiles that are provably empty and only need their black pixels stored
