@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RM_ABI_VERSION 1
+#define RM_ABI_VERSION 2
 
 typedef enum RmStatus {
     RM_OK = 0,
@@ -136,6 +136,9 @@ typedef struct RmParams {
     int32_t patch_row_end;
     int32_t cull_backfacing;  /* drop planar primitives that can never pass the reference's z-only
                                  inside test (projected winding not CCW); 0 = keep all             */
+    int32_t patch_row_stride; /* render patch rows begin, begin + stride, ... < end (0 and 1 = every
+                                 row).  Rank k of G renders rows k, k + G, ...: interleaved row tiles
+                                 balance scenes whose work sits in one part of the frame           */
 } RmParams;
 
 /* Event counters (same definitions as SURVEY.md 8d) + timings of one call. */
@@ -190,6 +193,16 @@ int rm_render_f64(RmScene scene, const RmParams* params, double* out_rgb, int32_
  * `stream` is a cudaStream_t (NULL = default stream).  Asynchronous. */
 int rm_render_device(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id,
                      void* d_max, void* stream);
+/* rm_render_device that also prepares the 8-bit frame d_rgb8 (H*W*3 bytes, may be a peer-mapped pointer of another
+ * GPU): when the frame can be rendered with a tile schedule (triangle-only scenes) the render kernel zeroes the bytes
+ * of every pixel it visits -- quantize(0 * 1/max) is 0 whatever the maximum (framebuffer.rs:71-82) -- and
+ * rm_tonemap_device_busy() then only converts the tiles that can hold anything else. */
+int rm_render_device_rgb8(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id,
+                          void* d_max, uint8_t* d_rgb8, void* stream);
+/* rm_tonemap_device for the frame `scene` rendered last through rm_render_device_rgb8 with the same params and
+ * d_rgb8; converts only the busy tiles when that render had a tile schedule, every tile otherwise. */
+int rm_tonemap_device_busy(RmScene scene, const RmParams* params, const void* d_rgb, const void* d_max,
+                           int normalise, uint8_t* d_rgb8, void* stream);
 /* Instrumented variant of rm_render_device: also accumulates the event counters (synchronous). */
 int rm_render_device_stats(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id,
                            void* d_max, void* stream, RmStats* stats);
@@ -204,6 +217,12 @@ void* rm_host_alloc(size_t bytes);
 void  rm_host_free(void* p);
 int   rm_host_register(void* p, size_t bytes);
 int   rm_host_unregister(void* p);
+
+/* ---- per-kernel device times (CUDA events on the launching stream around K0 and K1) ------------ *
+ * rm_set_profiling(1) makes every following device render record three events; rm_last_kernel_times() waits for the
+ * last one and returns the prepare (K0) and render (K1) kernel durations of that frame in milliseconds. */
+int rm_set_profiling(int on);
+int rm_last_kernel_times(double* ms_prepare, double* ms_render);
 
 /* ---- FP32 peak probe: a pure-FFMA kernel, returns measured TFLOP/s (roofline denominator) ----- */
 int rm_measure_fp32_peak(double* out_tflops, double* out_ms);

@@ -57,7 +57,7 @@ class RmParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fov", C.c_double), ("camera", d3),
                 ("max_depth", C.c_int32), ("background", C.c_double), ("patch_size", C.c_int32),
                 ("precision", C.c_int32), ("patch_row_begin", C.c_int32), ("patch_row_end", C.c_int32),
-                ("cull_backfacing", C.c_int32)]
+                ("cull_backfacing", C.c_int32), ("patch_row_stride", C.c_int32)]
 
 
 COUNTER_FIELDS = ["pixels", "closest_segments", "anyhit_segments", "sphere_tests", "sphere_disc", "sphere_hits",
@@ -96,7 +96,11 @@ SYMBOLS = {
     "rm_render_f64": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_void_p, _P(RmStats)]),
     "rm_render_device": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rm_render_device_stats": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _P(RmStats)]),
+    "rm_render_device_rgb8": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rm_tonemap_device": (C.c_int, [_P(RmParams), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "rm_tonemap_device_busy": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "rm_set_profiling": (C.c_int, [C.c_int]),
+    "rm_last_kernel_times": (C.c_int, [_P(C.c_double), _P(C.c_double)]),
     "rm_host_alloc": (C.c_void_p, [C.c_size_t]),
     "rm_host_free": (None, [C.c_void_p]),
     "rm_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),

@@ -54,11 +54,19 @@ template <typename R> struct DevicePack {
     }
 };
 
+// What the last FP32 render of a scene left behind, for rm_tonemap_device_busy().
+struct LastFrame {
+    bool scheduled = false;       // rendered with a tile schedule and the 8-bit frame zero-filled by the render kernel
+    int width = 0, height = 0, row_begin = 0, row_step = 0, n_bands = 0, buf_row0 = 0;
+    const void* rgb8 = nullptr;
+};
+
 struct SceneEntry {
     rm::OwnedFlatScene flat;
     int n_prims = 0;
     DevicePack<float> f32;
     DevicePack<double> f64;
+    LastFrame last;
 };
 
 struct Scratch {
@@ -82,6 +90,9 @@ struct Context {
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool profiling = false;       // rm_set_profiling: record events around K0 / K1 of every device render
+    cudaEvent_t pev[3] = {nullptr, nullptr, nullptr};
+    bool pev_valid = false;
     std::map<RmScene, SceneEntry> scenes;
     RmScene next_handle = 1;
     Scratch rgb, prim, rgb8, small;   // small: [0,8) max scalar, [64, 64+17*8) counters
@@ -160,7 +171,7 @@ void fill_counters(RmStats* st, const unsigned long long* c) {
 template <typename R>
 int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_prim, R* d_max, cudaStream_t stream,
                        int buf_row0_is_tile, unsigned long long* d_counters, rm::FrameParams<R>* out_fp, int* resident,
-                       int* launches = nullptr) {
+                       int* launches = nullptr, unsigned char* d_rgb8_zero = nullptr, bool* scheduled = nullptr) {
     if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
     int rc = check_params(params);
     if (rc != RM_OK) return rc;
@@ -173,7 +184,20 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
     if (out_fp) *out_fp = fp;
     const bool cull = params->cull_backfacing != 0;
     if (resident) *resident = dp.ds.lay.n_sph + rm::plane_count<R>(dp.ds.lay, cull);
-    CK(rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, stream, params->camera, launches));
+    rm::RenderExtras ex;
+    ex.rgb8_zero = d_rgb8_zero;
+    if (g.profiling && g.pev[0]) {
+        ex.ev_begin = g.pev[0];
+        ex.ev_prepared = g.pev[1];
+        ex.ev_rendered = g.pev[2];
+        g.pev_valid = true;
+    }
+    CK(rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, stream, params->camera, launches, &ex));
+    LastFrame& lf = it->second.last;
+    lf.scheduled = sizeof(R) == 4 && ex.scheduled && d_rgb8_zero != nullptr;
+    lf.width = fp.width; lf.height = fp.height; lf.row_begin = fp.row_begin; lf.row_step = fp.row_step;
+    lf.n_bands = fp.n_bands; lf.buf_row0 = fp.buf_row0; lf.rgb8 = d_rgb8_zero;
+    if (scheduled) *scheduled = lf.scheduled;
     return RM_OK;
 }
 
@@ -185,7 +209,8 @@ int render_host_impl(RmScene scene, const RmParams* params, R* out_rgb, int32_t*
     if (rc != RM_OK) return rc;
     const bool want_counters = stats && stats->pixels == 1;
     rm::FrameParams<R> fp = rm::make_frame_params<R>(*params);
-    const size_t rows = (size_t)(fp.row_end - fp.row_begin);
+    // scratch buffers hold the pixel-row span of the call, indexed from its first row (buf_row0 = row_begin)
+    const size_t rows = fp.n_bands > 0 ? (size_t)(fp.n_bands - 1) * fp.row_step + 32 : 0;
     const size_t n_px = rows * (size_t)fp.width;
     if ((rc = g.rgb.ensure(std::max<size_t>(n_px * 3 * sizeof(R), 16))) != RM_OK) return rc;
     if (out_prim && (rc = g.prim.ensure(std::max<size_t>(n_px * sizeof(int), 16))) != RM_OK) return rc;
@@ -200,18 +225,33 @@ int render_host_impl(RmScene scene, const RmParams* params, R* out_rgb, int32_t*
     CK(cudaEventRecord(g.ev[1], s));
     int resident = 0;
     int launches = 0;
+    bool scheduled = false;
     rc = render_device_impl<R>(scene, params, static_cast<R*>(g.rgb.p), out_prim ? static_cast<int*>(g.prim.p) : nullptr,
-                               d_max, s, 1, want_counters ? d_cnt : nullptr, &fp, &resident, &launches);
+                               d_max, s, 1, want_counters ? d_cnt : nullptr, &fp, &resident, &launches,
+                               out_rgb8 ? static_cast<unsigned char*>(g.rgb8.p) : nullptr, &scheduled);
     if (rc != RM_OK) return rc;
     CK(cudaEventRecord(g.ev[2], s));
-    const size_t first_px = (size_t)fp.row_begin * fp.width;
     if (out_rgb8 && rows) {
-        CK(rm::launch_tonemap<R>(fp, static_cast<const R*>(g.rgb.p), d_max, true, static_cast<unsigned char*>(g.rgb8.p), s));
+        if (scheduled) {
+            auto it = g.scenes.find(scene);
+            CK(rm::launch_tonemap_busy(it->second.f32.ds, reinterpret_cast<const rm::FrameParams<float>&>(fp),
+                                       reinterpret_cast<const float*>(g.rgb.p), reinterpret_cast<const float*>(d_max), true,
+                                       static_cast<unsigned char*>(g.rgb8.p), s));
+        } else {
+            CK(rm::launch_tonemap<R>(fp, static_cast<const R*>(g.rgb.p), d_max, true, static_cast<unsigned char*>(g.rgb8.p), s));
+        }
         launches++;
     }
-    if (out_rgb && rows) CK(cudaMemcpyAsync(out_rgb + first_px * 3, g.rgb.p, n_px * 3 * sizeof(R), cudaMemcpyDeviceToHost, s));
-    if (out_prim && rows) CK(cudaMemcpyAsync(out_prim + first_px, g.prim.p, n_px * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (out_rgb8 && rows) CK(cudaMemcpyAsync(out_rgb8 + first_px * 3, g.rgb8.p, n_px * 3, cudaMemcpyDeviceToHost, s));
+    // rendered bands -> host: one copy when they are contiguous, one per 32-row band otherwise
+    const int n_copies = fp.row_step == 32 ? (fp.n_bands > 0 ? 1 : 0) : fp.n_bands;
+    const size_t band_px = (size_t)(fp.row_step == 32 ? fp.n_bands * 32 : 32) * fp.width;
+    for (int b = 0; b < n_copies; b++) {
+        const size_t dev_px = (size_t)b * fp.row_step * fp.width;                 // scratch is indexed from row_begin
+        const size_t host_px = (size_t)fp.row_begin * fp.width + dev_px;
+        if (out_rgb) CK(cudaMemcpyAsync(out_rgb + host_px * 3, static_cast<R*>(g.rgb.p) + dev_px * 3, band_px * 3 * sizeof(R), cudaMemcpyDeviceToHost, s));
+        if (out_prim) CK(cudaMemcpyAsync(out_prim + host_px, static_cast<int*>(g.prim.p) + dev_px, band_px * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (out_rgb8) CK(cudaMemcpyAsync(out_rgb8 + host_px * 3, static_cast<unsigned char*>(g.rgb8.p) + dev_px * 3, band_px * 3, cudaMemcpyDeviceToHost, s));
+    }
     unsigned char small_host[1024];
     if (stats) CK(cudaMemcpyAsync(small_host, g.small.p, 64 + rm::C_COUNT * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(g.ev[3], s));
@@ -263,6 +303,7 @@ int rm_init(int device) {
     }
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     for (auto& ev : g.ev) CK(cudaEventCreate(&ev));
+    for (auto& ev : g.pev) CK(cudaEventCreate(&ev));
     g.device = device;
     g.ready = true;
     return RM_OK;
@@ -277,6 +318,8 @@ void rm_shutdown(void) {
     g.scenes.clear();
     g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release();
     for (auto& ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    for (auto& ev : g.pev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    g.pev_valid = false;
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
     g.ready = false;
@@ -309,6 +352,7 @@ void rm_params_default(RmParams* p, int width, int height) {
     p->patch_row_begin = 0;
     p->patch_row_end = -1;
     p->cull_backfacing = 1;
+    p->patch_row_stride = 1;
 }
 
 int rm_scene_upload(const RmFlatScene* scene, RmScene* out_handle) {
@@ -362,6 +406,60 @@ int rm_render_device(RmScene scene, const RmParams* params, void* d_rgb, int32_t
                                           static_cast<cudaStream_t>(stream), 0, nullptr, nullptr, nullptr);
     return render_device_impl<float>(scene, params, static_cast<float*>(d_rgb), d_prim_id, static_cast<float*>(d_max),
                                      static_cast<cudaStream_t>(stream), 0, nullptr, nullptr, nullptr);
+}
+
+int rm_render_device_rgb8(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id, void* d_max, uint8_t* d_rgb8,
+                          void* stream) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!d_rgb || !d_max || !d_rgb8) return fail(RM_ERR_INVALID_ARGUMENT, "d_rgb, d_max and d_rgb8 must be device pointers");
+    if (params && params->precision == RM_FP64)
+        return render_device_impl<double>(scene, params, static_cast<double*>(d_rgb), d_prim_id, static_cast<double*>(d_max),
+                                          static_cast<cudaStream_t>(stream), 0, nullptr, nullptr, nullptr, nullptr, d_rgb8);
+    return render_device_impl<float>(scene, params, static_cast<float*>(d_rgb), d_prim_id, static_cast<float*>(d_max),
+                                     static_cast<cudaStream_t>(stream), 0, nullptr, nullptr, nullptr, nullptr, d_rgb8);
+}
+
+int rm_tonemap_device_busy(RmScene scene, const RmParams* params, const void* d_rgb, const void* d_max, int normalise,
+                           uint8_t* d_rgb8, void* stream) {
+    {
+        std::lock_guard<std::mutex> lock(g.mu);
+        if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+        int rc = check_params(params);
+        if (rc != RM_OK) return rc;
+        if (!d_rgb || !d_rgb8 || (normalise && !d_max)) return fail(RM_ERR_INVALID_ARGUMENT, "null device pointer");
+        auto it = g.scenes.find(scene);
+        if (it == g.scenes.end()) return fail(RM_ERR_INVALID_ARGUMENT, "unknown scene handle");
+        const LastFrame& lf = it->second.last;
+        auto fp = rm::make_frame_params<float>(*params);
+        if (params->precision != RM_FP64 && lf.scheduled && lf.rgb8 == d_rgb8 && lf.width == fp.width && lf.height == fp.height &&
+            lf.row_begin == fp.row_begin && lf.row_step == fp.row_step && lf.n_bands == fp.n_bands && lf.buf_row0 == 0) {
+            CK(rm::launch_tonemap_busy(it->second.f32.ds, fp, static_cast<const float*>(d_rgb), static_cast<const float*>(d_max),
+                                       normalise != 0, d_rgb8, static_cast<cudaStream_t>(stream)));
+            return RM_OK;
+        }
+    }
+    return rm_tonemap_device(params, d_rgb, d_max, normalise, d_rgb8, stream);      // no schedule to lean on: every tile
+}
+
+int rm_set_profiling(int on) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    g.profiling = on != 0;
+    g.pev_valid = false;
+    return RM_OK;
+}
+
+int rm_last_kernel_times(double* ms_prepare, double* ms_render) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    if (!g.pev_valid) return fail(RM_ERR_INVALID_ARGUMENT, "no profiled render: call rm_set_profiling(1) and render first");
+    CK(cudaEventSynchronize(g.pev[2]));
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, g.pev[0], g.pev[1]));
+    CK(cudaEventElapsedTime(&b, g.pev[1], g.pev[2]));
+    if (ms_prepare) *ms_prepare = a;
+    if (ms_render) *ms_render = b;
+    return RM_OK;
 }
 
 int rm_render_device_stats(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id, void* d_max, void* stream,

@@ -80,13 +80,14 @@ render_kernel(const DeviceScene<R> ds, const FrameParams<R> fp, const int cull, 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = blockIdx.x * kTileW + (warp & 3) * 8 + (lane & 7);
-    const int y = fp.row_begin + blockIdx.y * kTileH + (warp >> 2) * 4 + (lane >> 3);
+    const int yl = blockIdx.y * kTileH + (warp >> 2) * 4 + (lane >> 3);   // row within this call's bands
+    const int y = frame_row(fp, yl);
 
     Counters<S> st;
     st.clear();
 
     R m = R(0);
-    if (x < fp.width && y < fp.row_end) {
+    if (x < fp.width && yl < fp.n_bands * 32) {
         st.add(C_PIXELS);
         int pid;
         const Vec3<R> dir = backproject<R>(fp, x, y);
@@ -157,7 +158,7 @@ prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, con
     bool busy = false, full = false;
     if (tile < n_tiles) {
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const int x0 = tx * 32, y0 = fp.row_begin + ty * 32;
+        const int x0 = tx * 32, y0 = fp.row_begin + ty * fp.row_step;
         const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + 31), Ya = pixel_Y(fp, y0), Yb = pixel_Y(fp, y0 + 31);
         for (int j = 0; j < n_tri && !full; j++) {
             if (tri_may_touch(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3], Xa, Xb, Ya, Yb)) {
@@ -218,7 +219,8 @@ template <bool kSmem>
 __global__ void __launch_bounds__(kBlock, 3)
 render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
-                   float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order, const int* __restrict__ order2) {
+                   float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order, const int* __restrict__ order2,
+                   unsigned char* __restrict__ rgb8) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     __shared__ int cta_max, strip_ticket;
     __shared__ int leftover[kBlock / 32];
@@ -305,18 +307,23 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     // Zero-fill (renderer.rs:300-306: a primary miss is black) of a 32-pixel wide strip of kStripRows rows by one warp,
     // fully coalesced: a pixel row of the strip is 384 contiguous bytes = 24 chunks of 16 bytes, the strip 96 chunks,
     // lane l stores chunks l, l + 32, l + 64 (each instruction writes 512 bytes in at most two contiguous runs).
-    auto fill_strip = [&](float* strip0) {                      // strip0: first float of the strip's first row
+    // With rgb8 given the strip's bytes of the 8-bit frame are zeroed as well: quantize(0 * 1/max) is 0 whatever the
+    // maximum turns out to be (framebuffer.rs:71-82), so only the busy tiles are left for the tone-map kernel.  A row of
+    // the strip is 96 bytes = 6 chunks of 16 bytes, the strip 24 chunks: one store of lanes 0..23.
+    auto fill_strip = [&](const size_t p0) {                    // p0: pixel index of the strip's first pixel
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* const strip0 = rgb + 3 * p0;
 #pragma unroll
         for (int i = 0; i < 3; i++) __stcs(reinterpret_cast<float4*>(strip0 + fill_off[lane + 32 * i]), z);
+        if (rgb8 && lane < 24) __stcs(reinterpret_cast<uint4*>(rgb8 + 3 * p0 + (size_t)(lane / 6) * fp.width * 3 + (lane % 6) * 16), make_uint4(0u, 0u, 0u, 0u));
     };
     auto fill_empty_tile = [&](const int tile) {
         const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);
         const int tx = tile - ty * tiles_x;
-        const size_t p0 = (size_t)(fp.row_begin + ty * kFastTile - fp.buf_row0) * fp.width + tx * kFastTile;
+        const size_t p0 = (size_t)(fp.row_begin + ty * fp.row_step - fp.buf_row0) * fp.width + tx * kFastTile;
 #pragma unroll
         for (int r = 0; r < kStripsPerTile; r++) {
-            fill_strip(rgb + 3 * (p0 + (size_t)r * kStripRows * fp.width));
+            fill_strip(p0 + (size_t)r * kStripRows * fp.width);
             if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + p0 + (size_t)(r * kStripRows + ly) * fp.width + lx), make_int4(-1, -1, -1, -1));
         }
     };
@@ -357,9 +364,9 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
             } else {
                 const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);          // exact for tile < 2^22
                 const int tx = tile - ty * tiles_x;
-                const int x0 = tx * kFastTile, ys = fp.row_begin + ty * kFastTile + strip * kStripRows;
+                const int x0 = tx * kFastTile, ys = fp.row_begin + ty * fp.row_step + strip * kStripRows;
                 const size_t px = (size_t)(ys + ly - fp.buf_row0) * fp.width + x0 + lx;
-                fill_strip(rgb + 3 * ((size_t)(ys - fp.buf_row0) * fp.width + x0));   // misses stay black; stage B overwrites the hits
+                fill_strip((size_t)(ys - fp.buf_row0) * fp.width + x0);         // misses stay black; stage B overwrites the hits
                 // stage A: primary visibility of this thread's 4 pixels
                 PrimaryState<4> ps;
                 primary_begin<4>(ps, fp, x0 + lx, ys + ly);
@@ -453,6 +460,8 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         // the last CTA out leaves the frame control block zeroed for the next frame
         __threadfence();
         if (atomicAdd(ctr + 3, 1) == (int)gridDim.x - 1) {
+            ctr[8] = order ? n_full : -1;                       // kept for the busy-tiles-only tone-map kernel of this frame
+            ctr[9] = n_busy - n_full;
             ctr[0] = 0;
             ctr[1] = 0;
             ctr[2] = 0;
@@ -475,13 +484,16 @@ template <> struct Tone<double> {
 };
 
 // 16 consecutive channel values per thread -> one 16-byte store.  Rows are W*3 values with W a
-// multiple of 32, so every thread's span is 16-byte aligned on both sides.
+// multiple of 32, so every thread's span is 16-byte aligned on both sides.  `band16` = 16-value chunks
+// of one 32-row band, `step16` = chunks from the start of one rendered band to the start of the next.
 template <typename R>
 __global__ void __launch_bounds__(256)
-tonemap_kernel(const R* __restrict__ rgb, const R* __restrict__ dmax, const int normalise, const size_t first,
-               const size_t count16, unsigned char* __restrict__ rgb8) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count16) return;
+tonemap_kernel(const R* __restrict__ rgb, const R* __restrict__ dmax, const int normalise, const size_t first16,
+               const size_t count16, const unsigned band16, const size_t step16, unsigned char* __restrict__ rgb8) {
+    const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= count16) return;
+    const size_t band = l / band16;
+    const size_t i = first16 + band * step16 + (l - band * band16);
     R inv = R(1);
     if (normalise) {
         const R mx = *dmax;
@@ -502,7 +514,36 @@ tonemap_kernel(const R* __restrict__ rgb, const R* __restrict__ dmax, const int 
         }
         w[k] = Tone<R>::q(v0, inv) | (Tone<R>::q(v1, inv) << 8) | (Tone<R>::q(v2, inv) << 16) | (Tone<R>::q(v3, inv) << 24);
     }
-    reinterpret_cast<uint4*>(rgb8 + first)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(rgb8)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// K4 for frames rendered with a tile schedule and rgb8 zero-fill: only the busy tiles (ctr[8] fully covered ones in
+// `order`, ctr[9] partially covered ones in `order2`) hold anything but zeros.  A block walks tiles; a thread converts
+// one float4 (4 channel values -> 4 bytes) at a time, lanes along a pixel row: 384-byte runs in, 96-byte runs out.
+__global__ void __launch_bounds__(256)
+tonemap_busy_kernel(const float* __restrict__ rgb, const float* __restrict__ dmax, const int normalise, const FrameParams<float> fp,
+                    const int tiles_x, const int* __restrict__ order, const int* __restrict__ order2, const int* __restrict__ ctr,
+                    unsigned char* __restrict__ rgb8) {
+    const int n_full = ctr[8], n_busy = n_full + ctr[9];
+    float inv = 1.f;
+    if (normalise) {
+        const float mx = *dmax;
+        if (mx > 0.f) inv = 1.f / mx;                           // framebuffer.rs:71-76: scale(1. / max_val)
+    }
+    for (int t = blockIdx.x; t < n_busy; t += gridDim.x) {
+        const int tile = t < n_full ? order[t] : order2[t - n_full];
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const size_t p0 = (size_t)(fp.row_begin + ty * fp.row_step - fp.buf_row0) * fp.width + tx * 32;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int c = threadIdx.x + 256 * i;                // 768 float4 per tile: 32 rows x 24
+            const int row = c / 24, col = c - row * 24;
+            const size_t v = 3 * (p0 + (size_t)row * fp.width) + 4 * col;
+            const float4 f = __ldcs(reinterpret_cast<const float4*>(rgb + v));
+            const unsigned w = Tone<float>::q(f.x, inv) | (Tone<float>::q(f.y, inv) << 8) | (Tone<float>::q(f.z, inv) << 16) | (Tone<float>::q(f.w, inv) << 24);
+            *reinterpret_cast<unsigned*>(rgb8 + v) = w;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) ffma_probe_kernel(float* __restrict__ sink, const int iters) {
@@ -526,9 +567,11 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(float* __restrict__ sin
 
 namespace {
 cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& fp, bool cull, float* rgb, int* prim_id,
-                        float* dmax, cudaStream_t stream, const double camera[3], int* launches, dim3 grid) {
+                        float* dmax, cudaStream_t stream, const double camera[3], int* launches, RenderExtras* ex) {
+    unsigned char* rgb8 = ex ? ex->rgb8_zero : nullptr;
+    if (ex && ex->ev_begin) cudaEventRecord(ex->ev_begin, stream);
     const int n_tri = tri_count(ds.lay, cull);
-    const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * ((fp.row_end - fp.row_begin) / kFastTile);
+    const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * fp.n_bands;
     const bool classify = ds.lay.n_sph + poly_count(ds.lay, cull) == 0 && n_tri <= kClassifyMaxTris && n_tiles <= ds.tile_order_cap / 2;
     if (classify)
         prepare_classify_kernel<<<(n_tiles + 63) / 64, 64, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r,
@@ -536,9 +579,11 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     else
         prepare_raster_kernel<<<(std::max(n_tri, 1) + 127) / 128, 128, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r);
     const int* order = classify ? ds.tile_order : nullptr;
+    if (ex) ex->scheduled = classify;
+    if (!classify) rgb8 = nullptr;                              // without a schedule the tone-map kernel converts every tile
+    if (ex && ex->ev_prepared) cudaEventRecord(ex->ev_prepared, stream);
     if (launches) (*launches)++;
     const size_t smem = (size_t)ds.lay.bytes + (size_t)n_tri * 64;
-    (void)grid;
     const float inv_tiles_x = 1.0f / (float)tiles_x;
     static int sm_count = 0;
     cudaError_t e;
@@ -553,28 +598,33 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
         int occ = 1;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, smem)) != cudaSuccess) return e;
         const int ctas = std::min(n_tiles, sm_count * std::max(occ, 1));
-        k<<<ctas, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr);
+        k<<<ctas, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr, rgb8);
     } else {
         auto k = render_fast_kernel<false>;
         int occ = 1;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, 0)) != cudaSuccess) return e;
         const int ctas = std::min(n_tiles, sm_count * std::max(occ, 1));
-        k<<<ctas, kBlock, 0, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr);
+        k<<<ctas, kBlock, 0, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr, rgb8);
     }
     if (launches) (*launches)++;
+    if (ex && ex->ev_rendered) cudaEventRecord(ex->ev_rendered, stream);
     return cudaGetLastError();
 }
 cudaError_t launch_fast(const DeviceScene<double>&, const FrameParams<double>&, bool, double*, int*, double*, cudaStream_t,
-                        const double*, int*, dim3) { return cudaErrorInvalidValue; }
+                        const double*, int*, RenderExtras*) { return cudaErrorInvalidValue; }
 }  // namespace
 
 template <typename R>
 cudaError_t launch_render(const DeviceScene<R>& ds, const FrameParams<R>& fp, bool cull, R* rgb, int* prim_id, R* dmax,
-                          unsigned long long* counters, cudaStream_t stream, const double camera[3], int* launches) {
-    const int rows = fp.row_end - fp.row_begin;
+                          unsigned long long* counters, cudaStream_t stream, const double camera[3], int* launches,
+                          RenderExtras* ex) {
+    const int rows = fp.n_bands * 32;
+    if (ex) ex->scheduled = false;
     if (rows <= 0 || fp.width <= 0) return cudaSuccess;
     const dim3 grid((fp.width + kTileW - 1) / kTileW, (rows + kTileH - 1) / kTileH);
-    if (sizeof(R) == 4 && !counters && camera && ds.tri_r) return launch_fast(ds, fp, cull, rgb, prim_id, dmax, stream, camera, launches, grid);
+    if (sizeof(R) == 4 && !counters && camera && ds.tri_r) return launch_fast(ds, fp, cull, rgb, prim_id, dmax, stream, camera, launches, ex);
+    if (ex && ex->ev_begin) cudaEventRecord(ex->ev_begin, stream);
+    if (ex && ex->ev_prepared) cudaEventRecord(ex->ev_prepared, stream);
     if (launches) (*launches)++;
     const int use_smem = ds.lay.bytes <= kSmemLimit;
     const size_t smem = use_smem ? (size_t)ds.lay.bytes : 0;
@@ -588,19 +638,32 @@ cudaError_t launch_render(const DeviceScene<R>& ds, const FrameParams<R>& fp, bo
         if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<grid, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, use_smem, rgb, prim_id, dmax, nullptr);
     }
+    if (ex && ex->ev_rendered) cudaEventRecord(ex->ev_rendered, stream);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tonemap_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, const float* dmax,
+                                bool normalise, unsigned char* rgb8, cudaStream_t stream) {
+    const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * fp.n_bands;
+    if (n_tiles <= 0) return cudaSuccess;
+    const int blocks = std::min(n_tiles, 148 * 8);
+    tonemap_busy_kernel<<<blocks, 256, 0, stream>>>(rgb, dmax, normalise ? 1 : 0, fp, tiles_x, ds.tile_order,
+                                                    ds.tile_order + ds.tile_order_cap / 2, ds.ctr, rgb8);
     return cudaGetLastError();
 }
 
 template <typename R>
 cudaError_t launch_tonemap(const FrameParams<R>& fp, const R* rgb, const R* dmax, bool normalise, unsigned char* rgb8,
                            cudaStream_t stream) {
-    const int rows = fp.row_end - fp.row_begin;
+    const int rows = fp.n_bands * 32;
     if (rows <= 0) return cudaSuccess;
     // both buffers are indexed from pixel row fp.buf_row0
-    const size_t first = (size_t)(fp.row_begin - fp.buf_row0) * fp.width * 3;
-    const size_t count16 = (size_t)rows * fp.width * 3 / 16;
+    const size_t row16 = (size_t)fp.width * 3 / 16;
+    const size_t first16 = (size_t)(fp.row_begin - fp.buf_row0) * row16;
+    const size_t count16 = (size_t)rows * row16;
     const int blocks = (int)((count16 + 255) / 256);
-    tonemap_kernel<R><<<blocks, 256, 0, stream>>>(rgb + first, dmax, normalise ? 1 : 0, first, count16, rgb8);
+    tonemap_kernel<R><<<blocks, 256, 0, stream>>>(rgb, dmax, normalise ? 1 : 0, first16, count16, (unsigned)(32 * row16),
+                                                  (size_t)fp.row_step * row16, rgb8);
     return cudaGetLastError();
 }
 
@@ -610,8 +673,8 @@ cudaError_t launch_ffma_probe(float* sink, int iters, int blocks, cudaStream_t s
     return cudaGetLastError();
 }
 
-template cudaError_t launch_render<float>(const DeviceScene<float>&, const FrameParams<float>&, bool, float*, int*, float*, unsigned long long*, cudaStream_t, const double*, int*);
-template cudaError_t launch_render<double>(const DeviceScene<double>&, const FrameParams<double>&, bool, double*, int*, double*, unsigned long long*, cudaStream_t, const double*, int*);
+template cudaError_t launch_render<float>(const DeviceScene<float>&, const FrameParams<float>&, bool, float*, int*, float*, unsigned long long*, cudaStream_t, const double*, int*, RenderExtras*);
+template cudaError_t launch_render<double>(const DeviceScene<double>&, const FrameParams<double>&, bool, double*, int*, double*, unsigned long long*, cudaStream_t, const double*, int*, RenderExtras*);
 template cudaError_t launch_tonemap<float>(const FrameParams<float>&, const float*, const float*, bool, unsigned char*, cudaStream_t);
 template cudaError_t launch_tonemap<double>(const FrameParams<double>&, const double*, const double*, bool, unsigned char*, cudaStream_t);
 

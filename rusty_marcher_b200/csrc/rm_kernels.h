@@ -30,6 +30,17 @@ template <typename R> struct DeviceScene {
     int tile_order_cap = 0;
 };
 
+// Optional extras of a render launch.
+struct RenderExtras {
+    // in: the 8-bit frame (indexed like rgb).  When the frame gets a tile schedule the render kernel zeroes the bytes of
+    // every pixel it visits, so that launch_tonemap_busy() only has to convert the busy tiles afterwards.
+    unsigned char* rgb8_zero = nullptr;
+    // in: events recorded on the stream before K0, between K0 and K1, after K1 (profiling; may be null)
+    cudaEvent_t ev_begin = nullptr, ev_prepared = nullptr, ev_rendered = nullptr;
+    // out: the frame was rendered with a tile schedule (and rgb8_zero, if given, has been zero-filled)
+    bool scheduled = false;
+};
+
 // K0 + K1.  With counters == null and R = float this is the production path: prepare_raster_kernel
 // (one thread per triangle, FP64) followed by render_fast_kernel; otherwise the generic kernel.
 // K1: render rows [fp.row_begin, fp.row_end).  rgb: H*W*3 of R; prim_id optional; dmax: scalar R that
@@ -37,12 +48,16 @@ template <typename R> struct DeviceScene {
 template <typename R>
 cudaError_t launch_render(const DeviceScene<R>& ds, const FrameParams<R>& fp, bool cull, R* rgb, int* prim_id, R* dmax,
                           unsigned long long* counters, cudaStream_t stream, const double camera[3] = nullptr,
-                          int* launches = nullptr);
+                          int* launches = nullptr, RenderExtras* extras = nullptr);
 
 // K4: FrameBuffer::normalize + to_vec (framebuffer.rs:40-82) over rows [fp.row_begin, fp.row_end).
 template <typename R>
 cudaError_t launch_tonemap(const FrameParams<R>& fp, const R* rgb, const R* dmax, bool normalise, unsigned char* rgb8,
                            cudaStream_t stream);
+
+// K4 over the busy tiles of the frame `ds` rendered last with a schedule and RenderExtras::rgb8_zero (same fp).
+cudaError_t launch_tonemap_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, const float* dmax,
+                                bool normalise, unsigned char* rgb8, cudaStream_t stream);
 
 // Pure-FFMA probe: `iters` x 16 dependent-chain FFMAs per thread on every SM; returns flop count.
 cudaError_t launch_ffma_probe(float* sink, int iters, int blocks, cudaStream_t stream, double* flops);

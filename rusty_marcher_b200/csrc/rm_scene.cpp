@@ -347,8 +347,11 @@ template <typename R> FrameParams<R> make_frame_params(const RmParams& p) {
     int r0 = p.patch_row_begin < 0 ? 0 : p.patch_row_begin;
     int r1 = (p.patch_row_end < 0 || p.patch_row_end > n_rows) ? n_rows : p.patch_row_end;
     if (r0 > r1) r0 = r1;
+    const int stride = p.patch_row_stride < 1 ? 1 : p.patch_row_stride;
     fp.row_begin = r0 * patch;
     fp.row_end = r1 * patch;
+    fp.row_step = stride * patch;
+    fp.n_bands = (r1 - r0 + stride - 1) / stride;
     // renderer.rs:25-33
     const double half_fov = std::tan(p.fov / 2.);
     const double width = (double)p.width, height = (double)p.height;

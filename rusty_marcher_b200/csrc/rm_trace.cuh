@@ -479,7 +479,10 @@ RM_HD Vec3<R> cast_ray(const SC& sc, Vec3<R> o, Vec3<R> d, R background, int max
 //   x = 2*(j/W - 0.5)*half_fov*ratio, y = -2*(i/H - 0.5)*half_fov, z = -1, then normalised.
 template <typename R> struct FrameParams {
     int width, height;
-    int row_begin, row_end;       // pixel rows of this tile
+    int row_begin, row_end;       // pixel-row span of this call
+    int row_step;                 // pixel rows from one rendered 32-row band to the next (32 = contiguous; 32*G when the
+                                  // bands of a frame are dealt round-robin to G ranks)
+    int n_bands;                  // rendered 32-row bands: rows row_begin + b*row_step + [0, 32), b < n_bands
     int buf_row0;                 // pixel row stored at offset 0 of the output buffers
     R width_r, height_r, half_fov, ratio;   // f64 path: the reference's own operands
     R half_w, half_h, sx, sy;     // f32 path: x = (j - W/2)*sx, y = (i - H/2)*sy, folded on the host in f64
@@ -487,6 +490,9 @@ template <typename R> struct FrameParams {
     R background;
     int max_depth;
 };
+
+// pixel row of the l-th rendered row of this call (l in [0, 32 * n_bands))
+template <typename R> RM_HD int frame_row(const FrameParams<R>& fp, int l) { return fp.row_begin + (l >> 5) * fp.row_step + (l & 31); }
 
 template <typename R> RM_HD Vec3<R> backproject(const FrameParams<R>& fp, int j, int i) {
     Vec3<R> v = {(R(j) - fp.half_w) * fp.sx, (R(i) - fp.half_h) * fp.sy, R(-1)};

@@ -214,6 +214,85 @@ def test_device_api_with_torch_buffers(rm_gpu):
     assert float(tr.dmax.item()) == host["max"]
 
 
+@pytest.mark.parametrize("name,w,h", [("cornell_box", 1920, 1080), ("dodecahedron", 640, 480), ("demo", 800, 600)])
+def test_fused_rgb8_and_interleaved_bands_on_device(rm_gpu, name, w, h):
+    """Device API: (1) rm_render_device_rgb8 + rm_tonemap_device_busy (render kernel zero-fills the 8-bit frame, tone map
+    converts the busy tiles only) gives the very bytes of rm_render_device + rm_tonemap_device; (2) patch rows dealt
+    round-robin (patch_row_stride) to 2 and 3 'ranks' reassemble to the frame rendered in one piece, bit for bit."""
+    import torch
+    from rusty_marcher_b200 import tiled
+    dev = torch.device("cuda:0")
+    scene = workloads.scene(name)
+    r = rm_gpu.create_renderer(1.5, h, w)
+    be = tiled.CudaBackend(scene, r, w, h, dev)
+    n_patch = h // 32
+
+    def frame(rows_list, fused):
+        rgb = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+        rgb8 = torch.full((h, w, 3), 7, dtype=torch.uint8, device=dev)      # poisoned: every rendered byte must be written
+        ids = torch.full((h, w), -2, dtype=torch.int32, device=dev)
+        dmax = torch.zeros(1, dtype=torch.float32, device=dev)
+        for rows in rows_list:
+            be.render_rows(rows, rgb, dmax, prim=ids, rgb8=rgb8 if fused else None)
+            if fused:           # the schedule of a scene handle describes its LAST render: convert before the next one
+                be.tonemap_rows(rows, rgb, dmax, rgb8, busy=True, normalise=False)
+        if not fused:
+            for rows in rows_list:
+                be.tonemap_rows(rows, rgb, dmax, rgb8, normalise=False)
+        torch.cuda.synchronize()
+        return rgb.cpu().numpy(), rgb8.cpu().numpy(), ids.cpu().numpy(), float(dmax.item())
+
+    whole = frame([(0, n_patch)], fused=False)
+    rows = n_patch * 32
+    assert np.all(whole[1][rows:] == 7) and np.all(whole[2][rows:] == -2)       # rows below the last patch row stay untouched
+    for rows_list, fused in (([(0, n_patch)], True), ([(k, n_patch, 2) for k in range(2)], False),
+                             ([(k, n_patch, 3) for k in range(3)], True), ([(0, 1), (1, n_patch)], True)):
+        got = frame(rows_list, fused)
+        assert np.array_equal(got[0], whole[0]), (rows_list, fused)
+        assert np.array_equal(got[1], whole[1]), (rows_list, fused)
+        assert np.array_equal(got[2], whole[2]) and got[3] == whole[3]
+
+
+def test_host_api_interleaved_bands(rm_gpu):
+    scene = workloads.scene("cornell_box")
+    w, h = 640, 480
+    whole = gpu_render(rm_gpu, scene, w, h, "f32")
+    acc_rgb, acc8, acc_id = np.zeros_like(whole["rgb"]), np.zeros_like(whole["rgb8"]), np.full_like(whole["prim_id"], -1)
+    for k in range(3):
+        r = rm_gpu.create_renderer(1.5, h, w)
+        fb = rm_gpu.create_frame_buffer(w, h, dtype=np.float32)
+        ids = np.full((h, w), -1, dtype=np.int32)
+        rgb8 = np.zeros((h, w, 3), dtype=np.uint8)
+        p = r.params(fb, scene, (k, -1))
+        p.patch_row_stride = 3
+        st = _abi.RmStats()
+        _abi.check(_abi.load().rm_render(scene.device_handle(), C.byref(p), fb.buffer.ctypes.data, ids.ctypes.data, rgb8.ctypes.data, C.byref(st)))
+        band = np.zeros(h, dtype=bool)
+        for pr in range(k, h // 32, 3):
+            band[pr * 32:(pr + 1) * 32] = True
+        assert np.all(fb.buffer[~band] == 0) and np.all(ids[~band] == -1)     # other ranks' rows are not touched
+        acc_rgb[band], acc_id[band] = fb.buffer[band], ids[band]
+    assert np.array_equal(acc_rgb, whole["rgb"]) and np.array_equal(acc_id, whole["prim_id"])
+
+
+def test_kernel_profiling_events(rm_gpu):
+    import torch
+    from rusty_marcher_b200 import tiled
+    L = _abi.load()
+    a, b = C.c_double(0), C.c_double(0)
+    assert L.rm_set_profiling(1) == 0
+    assert L.rm_last_kernel_times(C.byref(a), C.byref(b)) != 0                  # nothing rendered yet
+    dev = torch.device("cuda:0")
+    w, h = 640, 480
+    be = tiled.CudaBackend(workloads.scene("cornell_box"), rm_gpu.create_renderer(1.5, h, w), w, h, dev)
+    rgb = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+    dmax = torch.zeros(1, dtype=torch.float32, device=dev)
+    be.render_rows((0, h // 32), rgb, dmax)
+    _abi.check(L.rm_last_kernel_times(C.byref(a), C.byref(b)))
+    assert 0 < a.value < 50 and 0 < b.value < 50
+    assert L.rm_set_profiling(0) == 0
+
+
 def test_fp32_peak_probe(rm_gpu):
     t, ms = C.c_double(0), C.c_double(0)
     _abi.check(_abi.load().rm_measure_fp32_peak(C.byref(t), C.byref(ms)))

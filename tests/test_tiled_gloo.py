@@ -22,21 +22,26 @@ class EmuBackend:
     def __init__(self, scene):
         self.scene = scene
 
-    def render_rows(self, rows, rgb, dmax, prim=None):
-        from tests.emu import emu
-        if rows[1] <= rows[0]:
-            return
-        r = emu.render(self.scene, W, H, "f32", patch_rows=rows, threads=2)
-        a, b = rows[0] * 32, rows[1] * 32
-        rgb[a:b] = torch.from_numpy(r["rgb"][a:b])
-        dmax[0] = max(float(dmax[0]), float(r["rgb"][a:b].max()))
+    @staticmethod
+    def _bands(rows):
+        stride = rows[2] if len(rows) > 2 else 1
+        return [(p, p + 1) for p in range(rows[0], rows[1], stride)]
 
-    def tonemap_rows(self, rows, rgb, dmax, rgb8, normalise=True):
-        a, b = rows[0] * 32, rows[1] * 32
+    def render_rows(self, rows, rgb, dmax, prim=None, rgb8=None):
+        from tests.emu import emu
+        for pr in self._bands(rows):
+            r = emu.render(self.scene, W, H, "f32", patch_rows=pr, threads=2)
+            a, b = pr[0] * 32, pr[1] * 32
+            rgb[a:b] = torch.from_numpy(r["rgb"][a:b])
+            dmax[0] = max(float(dmax[0]), float(r["rgb"][a:b].max()))
+
+    def tonemap_rows(self, rows, rgb, dmax, rgb8, normalise=True, busy=False):
         m = np.float32(dmax[0].item())
         inv = np.float32(1) / m if (normalise and m > 0) else np.float32(1)
-        x = rgb[a:b].numpy()
-        rgb8[a:b] = torch.from_numpy((np.float32(255) * np.clip(x * inv, 0, 1)).astype(np.uint8))
+        for pr in self._bands(rows):
+            a, b = pr[0] * 32, pr[1] * 32
+            x = rgb[a:b].numpy()
+            rgb8[a:b] = torch.from_numpy((np.float32(255) * np.clip(x * inv, 0, 1)).astype(np.uint8))
 
 
 def _worker(rank, world, port, out_path):
@@ -74,6 +79,10 @@ def test_tile_partition_covers_all_patch_rows():
             sizes = [b - a for a, b in tiles]
             assert max(sizes) - min(sizes) <= 1
     assert tiled.tile_of(67, 3, 8) == (25, 33)
+    for p in (1, 5, 67, 135):
+        for g in (1, 2, 3, 4, 8):
+            seen = sorted(r for k in range(g) for r in range(*tiled.bands_of(p, k, g)))
+            assert seen == list(range(p))
 
 
 @pytest.mark.parametrize("world", [2, 3])
