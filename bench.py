@@ -220,6 +220,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # per-kernel CUDA events on the launching stream (K0 | K1 | K4), kept by the library for the last 256 frames
+    _abi.check(L.rm_set_profiling(1))
     for _ in range(max(args.warmup, 3)):
         flush.fill_(1)
         tr.render()
@@ -228,31 +230,36 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    for a, k1_done, b in ev:
+    for a, b in ev:
         flush.fill_(0)                       # L2 flush between timed iterations, outside the step's events
         a.record()
-        tr.dmax.zero_()
-        backend.render_rows(tr.rows, tr.rgb, tr.dmax)
-        k1_done.record()
-        if world > 1:
-            dist.all_reduce(tr.dmax, op=dist.ReduceOp.MAX)
-        backend.tonemap_rows(tr.rows, tr.rgb, tr.dmax, tr.rgb8)
-        if world > 1:
-            n = (tr.rows[1] - tr.rows[0]) * 32
-            tr.slot[:n].copy_(tr.rgb8[tr.rows[0] * 32:tr.rows[1] * 32])
-            dist.gather(tr.slot, tr.gathered, dst=0)
+        tr.render()                          # one frame: K0 + K1 + K4 incl. the exchange (rm_render_frame)
         b.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    step_ms = [a.elapsed_time(b) for a, _k, b in ev]
-    k1_ms = [a.elapsed_time(k) for a, k, _b in ev]
-    total = torch.tensor([sum(step_ms), sum(k1_ms)], dtype=torch.float64, device=dev)
+    if tr.peer is not None:
+        tr.peer.status()                     # raises if a wait on a peer timed out
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    k0_ms, k1_ms, k4_ms = [], [], []
+    if tr.exchange == "peer":
+        t0, t1, t4 = C.c_double(0), C.c_double(0), C.c_double(0)
+        for back in range(min(args.steps, 256)):
+            _abi.check(L.rm_kernel_times(back, C.byref(t0), C.byref(t1), C.byref(t4)))
+            k0_ms.append(t0.value)
+            k1_ms.append(t1.value)
+            k4_ms.append(0.0)                # K4 is fused into K1 on this path
+    else:                                    # torch.distributed exchange: two library calls per frame, K1 is the first
+        t0, t1 = C.c_double(0), C.c_double(0)
+        _abi.check(L.rm_last_kernel_times(C.byref(t0), C.byref(t1)))
+        k0_ms, k1_ms, k4_ms = [t0.value], [t1.value], [0.0]
+    _abi.check(L.rm_set_profiling(0))
+    n_k = len(k1_ms)
+    total = torch.tensor([sum(step_ms), sum(k1_ms) / n_k, sum(k0_ms) / n_k, sum(k4_ms) / n_k], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total, op=dist.ReduceOp.MAX)
-    total_ms, k1_total_ms = float(total[0]), float(total[1])
+    total_ms, k1_ms_avg, k0_ms_avg, k4_ms_avg = (float(x) for x in total)
     ms_per_step = total_ms / args.steps
     value = segs / (ms_per_step * 1e-3)
 
@@ -288,13 +295,12 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t[0]) * 1e3 / args.steps
-    tile_rows = (tr.rows[1] - tr.rows[0]) * 32
+    tile_rows = len(range(*tr.rows)) * 32
     d2h = tile_rows * w * 12
 
     line = None
     if rank == 0:
-        k1_ms_avg = k1_total_ms / args.steps
-        # K1 of rank 0's share: with N ranks each kernel processes ~1/N of the frame's work
+        # K1 of the slowest rank's share: with N ranks each kernel processes ~1/N of the frame's work
         ach_tflops = flops / world / (k1_ms_avg * 1e-3) / 1e12
         issue_frac = (slots / world / (k1_ms_avg * 1e-3)) / (peak_t.value * 1e12 / 2.0)
         cpu = None
@@ -309,8 +315,11 @@ def run_ours(args):
             "config": config_of(args, {
                 "segments_per_frame": segs, "pixels_per_frame": rows * w, "resident_prims": st.resident_prims,
                 "cull_backfacing": bool(renderer.cull_backfacing),
-                "step": "K1 render + fused max, K4 normalise+quantise RGB8" + (", max all-reduce + RGB8 gather to rank 0 (NCCL)" if world > 1 else ""),
-                "parallelism": "row tiles x%d" % world,
+                "step": ("K0 per-frame records + tile schedule; K1 render + channel max + (fused K4) normalise+quantise of the busy tiles to RGB8"
+                         + ("" if world == 1 else ", the exchange inside K1 over NVLink peer memory: max of one float per rank, RGB8 tiles stored straight into rank 0's frame"))
+                        if tr.exchange == "peer" else "K0, K1 render + fused max, max all-reduce (NCCL), K4 normalise+quantise RGB8, RGB8 gather to rank 0 (NCCL)",
+                "exchange": tr.exchange,
+                "parallelism": "32-row bands dealt round-robin to %d rank%s" % (world, "" if world == 1 else "s"),
                 "l2": "flushed between steps (256 MiB fill, outside each step's CUDA events)"}),
             "ms_per_frame": ms_per_step,
             "clocks": clocks,
@@ -318,10 +327,12 @@ def run_ours(args):
                     "h2d_bytes_per_step": flat_bytes, "d2h_bytes_per_step": d2h,
                     "path": "Renderer.render(frame, scene) -> rm_scene_upload + rm_render, float32 framebuffer into pinned host memory"
                             + ("; each rank delivers its own row tile" if world > 1 else "")},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": tr.launches_per_frame() * args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak_t.value, "unit": "TFLOP/s",
                          "frac": ach_tflops / peak_t.value, "traffic": None,
-                         "kernel": "render_kernel<float,false>", "kernel_ms": k1_ms_avg,
+                         "kernel": "render_fast_kernel<true>", "kernel_ms": k1_ms_avg,
+                         "prepare_kernel_ms": k0_ms_avg,
+                         "kernel_includes": "K0 (prepare) + K1: render + exchange wait + fused K4, CUDA events around both launches" if tr.exchange == "peer" else "render only",
                          "algorithmic_flops_per_frame": flops, "algorithmic_issue_slots_per_frame": slots,
                          "issue_slot_frac": issue_frac,
                          "peak_source": "measured live: ffma_probe_kernel (pure dependent-chain FFMA, all SMs); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
@@ -332,6 +343,7 @@ def run_ours(args):
     if pinned:
         frame.buffer = None
         L.rm_host_free(pinned)
+    tr.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

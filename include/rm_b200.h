@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RM_ABI_VERSION 2
+#define RM_ABI_VERSION 3
 
 typedef enum RmStatus {
     RM_OK = 0,
@@ -36,7 +36,8 @@ typedef enum RmStatus {
     RM_ERR_DIMENSIONS = -4,       /* width not a multiple of the patch size (renderer.rs:107 panics)  */
     RM_ERR_SCENE = -5,            /* malformed flat scene (index out of range, polygon with <3 verts) */
     RM_ERR_CUDA = -6,             /* a CUDA runtime call failed; see rm_last_error()                  */
-    RM_ERR_OUT_OF_MEMORY = -7
+    RM_ERR_OUT_OF_MEMORY = -7,
+    RM_ERR_PEER = -8              /* a rank of the box did not answer within 2 s during a frame's exchange */
 } RmStatus;
 
 /* ---- scene PODs: field-for-field mirrors of the reference structs (all f64) ------------------ */
@@ -218,11 +219,57 @@ void  rm_host_free(void* p);
 int   rm_host_register(void* p, size_t bytes);
 int   rm_host_unregister(void* p);
 
+/* ---- one frame on the GPUs of one box: render + the path's single exchange step, in two launches ---------- *
+ * The reference's Rayon loop splits the frame into independent 32x32 patches (renderer.rs:46-89); across GPUs the
+ * frame is split into 32-row bands (RmParams.patch_row_begin/end/stride; rank k of G renders bands k, k+G, ...), one
+ * process per GPU.  The only data the ranks must exchange is what FrameBuffer::normalize (framebuffer.rs:58-76) needs
+ * -- ONE float, the global channel maximum -- and the finished 8-bit rows, which go to rank 0.  Both travel over
+ * NVLink peer memory from inside the render kernel (no NCCL call on the path, two launches per frame and rank):
+ *   K0  per-frame triangle records + tile schedule; zeroes d_max
+ *   K1  renders this rank's bands (float rows stay local).  Rank 0 also clears the bytes of every provably black pixel of
+ *       the 8-bit frame, its own and the other ranks' whole bands (local HBM stores: zeros never cross NVLink).  The last
+ *       CTA to retire from rendering stores {seq, max} into every rank's mailbox.  Then every CTA waits for the G mailbox
+ *       words of frame `seq` (which doubles as the grid-wide barrier of this persistent kernel), takes their maximum,
+ *       quantises this rank's busy tiles (normalize + to_vec, framebuffer.rs:40-82) straight into rank 0's 8-bit frame
+ *       and the last CTA signals rank 0; rank 0's kernel retires only when all G ranks have signalled, so whatever
+ *       follows it on rank 0's stream sees the complete frame.
+ * Memory shared between the processes is allocated with rm_peer_alloc (cudaMalloc + CUDA IPC handle), the 64-byte
+ * handle is passed to the other ranks by any means (torch.distributed / MPI / a pipe) and mapped with rm_peer_open.
+ * world == 1 needs no peers: mailbox[0] and frame8[] are local allocations. */
+#define RM_MAX_RANKS 16
+#define RM_IPC_HANDLE_BYTES 64
+#define RM_MAILBOX_BYTES 512
+typedef struct RmExchange {
+    int32_t  rank, world;
+    void*    mailbox[RM_MAX_RANKS];  /* mailbox[r]: rank r's mailbox (RM_MAILBOX_BYTES, zeroed once), mapped on this GPU */
+    uint8_t* frame8[2];              /* rank 0's 8-bit frames (H*W*3 bytes each); frame `seq` goes to frame8[seq & 1], so a
+                                        reader of frame n on rank 0 never races the writers of frame n+1            */
+} RmExchange;
+int rm_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle[RM_IPC_HANDLE_BYTES]);  /* zero-filled */
+int rm_peer_open(const unsigned char handle[RM_IPC_HANDLE_BYTES], void** d_ptr);
+int rm_peer_close(void* d_ptr);                                                           /* of rm_peer_open  */
+int rm_peer_free(void* d_ptr);                                                            /* of rm_peer_alloc */
+/* One frame (FP32).  d_rgb: this rank's float frame (H*W*3, rows of other ranks are not touched); d_max: device float,
+ * receives this rank's maximum; seq >= 1 and equal on all ranks, incremented by one per frame.  Asynchronous on
+ * `stream`.  After a synchronisation rm_peer_status() tells whether any wait on this GPU timed out (RM_ERR_PEER). */
+int rm_render_frame(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id, void* d_max,
+                    const RmExchange* exchange, uint32_t seq, int normalise, void* stream);
+int rm_peer_status(const RmExchange* exchange);
+/* %globaltimer stamps (ns) the render kernel left in this rank's mailbox during its last frame: [0] kernel start,
+ * [1] rendering done (last CTA), [2] all ranks' maxima gathered, [3] this rank's 8-bit tiles stored, [4] rank 0 only:
+ * every rank has signalled, frame complete.  Synchronous (a small device-to-host copy); for phase breakdowns. */
+int rm_peer_stamps(const RmExchange* exchange, uint64_t out_ns[5]);
+
 /* ---- per-kernel device times (CUDA events on the launching stream around K0 and K1) ------------ *
  * rm_set_profiling(1) makes every following device render record three events; rm_last_kernel_times() waits for the
  * last one and returns the prepare (K0) and render (K1) kernel durations of that frame in milliseconds. */
 int rm_set_profiling(int on);
 int rm_last_kernel_times(double* ms_prepare, double* ms_render);
+/* The same for the frame `back` frames before the last one (a ring of 256 frames is kept).  On the rm_render_frame path
+ * K1 is launched programmatically dependent on K0 (its prologue overlaps K0) and ends with the exchange and the fused
+ * K4: there ms_prepare is 0 and ms_render covers K0 + K1 + exchange + K4, ms_tonemap is -1.  On the other paths the
+ * tone-map kernel is a separate call that is not timed here (ms_tonemap -1). */
+int rm_kernel_times(int back, double* ms_prepare, double* ms_render, double* ms_tonemap);
 
 /* ---- FP32 peak probe: a pure-FFMA kernel, returns measured TFLOP/s (roofline denominator) ----- */
 int rm_measure_fp32_peak(double* out_tflops, double* out_ms);

@@ -74,10 +74,17 @@ class RmStats(C.Structure):
         return {n: int(getattr(self, n)) for n in COUNTER_FIELDS}
 
 
+RM_MAX_RANKS, RM_IPC_HANDLE_BYTES, RM_MAILBOX_BYTES = 16, 64, 512
+
+
+class RmExchange(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("mailbox", C.c_void_p * RM_MAX_RANKS), ("frame8", C.c_void_p * 2)]
+
+
 RM_FP32, RM_FP64 = 0, 1
 RM_OK = 0
 STATUS_NAMES = {0: "RM_OK", -1: "RM_ERR_NO_DEVICE", -2: "RM_ERR_NOT_INITIALISED", -3: "RM_ERR_INVALID_ARGUMENT",
-                -4: "RM_ERR_DIMENSIONS", -5: "RM_ERR_SCENE", -6: "RM_ERR_CUDA", -7: "RM_ERR_OUT_OF_MEMORY"}
+                -4: "RM_ERR_DIMENSIONS", -5: "RM_ERR_SCENE", -6: "RM_ERR_CUDA", -7: "RM_ERR_OUT_OF_MEMORY", -8: "RM_ERR_PEER"}
 
 # every symbol include/rm_b200.h and include/rm_b200_host.h declare: name -> (restype, argtypes)
 _P = C.POINTER
@@ -101,6 +108,14 @@ SYMBOLS = {
     "rm_tonemap_device_busy": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "rm_set_profiling": (C.c_int, [C.c_int]),
     "rm_last_kernel_times": (C.c_int, [_P(C.c_double), _P(C.c_double)]),
+    "rm_kernel_times": (C.c_int, [C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_double)]),
+    "rm_peer_alloc": (C.c_int, [C.c_size_t, _P(C.c_void_p), C.c_char_p]),
+    "rm_peer_open": (C.c_int, [C.c_char_p, _P(C.c_void_p)]),
+    "rm_peer_close": (C.c_int, [C.c_void_p]),
+    "rm_peer_free": (C.c_int, [C.c_void_p]),
+    "rm_render_frame": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_void_p, _P(RmExchange), C.c_uint32, C.c_int, C.c_void_p]),
+    "rm_peer_status": (C.c_int, [_P(RmExchange)]),
+    "rm_peer_stamps": (C.c_int, [_P(RmExchange), _P(C.c_uint64)]),
     "rm_host_alloc": (C.c_void_p, [C.c_size_t]),
     "rm_host_free": (None, [C.c_void_p]),
     "rm_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),

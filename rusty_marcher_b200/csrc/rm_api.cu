@@ -84,15 +84,24 @@ struct Scratch {
     void release() { cudaFree(p); p = nullptr; cap = 0; }
 };
 
+constexpr int kProfRing = 256;
+struct ProfSlot {
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};   // before K0, K0|K1, after K1, after K4
+    bool has_tone = false;
+    bool split = true;                                          // e[1] was recorded between K0 and K1
+};
+
 struct Context {
     bool ready = false;
     int device = -1;
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool profiling = false;       // rm_set_profiling: record events around K0 / K1 of every device render
-    cudaEvent_t pev[3] = {nullptr, nullptr, nullptr};
-    bool pev_valid = false;
+    // rm_set_profiling: events around K0 / K1 / K4 of every device render, a ring of kProfRing frames
+    bool profiling = false;
+    std::vector<ProfSlot> prof;
+    int prof_head = -1;           // slot of the last recorded frame
+    long long prof_frames = 0;    // frames recorded since profiling was switched on
     std::map<RmScene, SceneEntry> scenes;
     RmScene next_handle = 1;
     Scratch rgb, prim, rgb8, small;   // small: [0,8) max scalar, [64, 64+17*8) counters
@@ -171,7 +180,8 @@ void fill_counters(RmStats* st, const unsigned long long* c) {
 template <typename R>
 int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_prim, R* d_max, cudaStream_t stream,
                        int buf_row0_is_tile, unsigned long long* d_counters, rm::FrameParams<R>* out_fp, int* resident,
-                       int* launches = nullptr, unsigned char* d_rgb8_zero = nullptr, bool* scheduled = nullptr) {
+                       int* launches = nullptr, unsigned char* d_rgb8_zero = nullptr, bool* scheduled = nullptr,
+                       const rm::PeerLink* link = nullptr, unsigned char* d_rgb8_out = nullptr, bool normalise = true) {
     if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
     int rc = check_params(params);
     if (rc != RM_OK) return rc;
@@ -186,11 +196,21 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
     if (resident) *resident = dp.ds.lay.n_sph + rm::plane_count<R>(dp.ds.lay, cull);
     rm::RenderExtras ex;
     ex.rgb8_zero = d_rgb8_zero;
-    if (g.profiling && g.pev[0]) {
-        ex.ev_begin = g.pev[0];
-        ex.ev_prepared = g.pev[1];
-        ex.ev_rendered = g.pev[2];
-        g.pev_valid = true;
+    if (link) {
+        ex.link = *link;
+        ex.zero_dmax = true;
+        ex.rgb8_out = d_rgb8_out;
+        ex.normalise = normalise;
+    }
+    if (g.profiling && !g.prof.empty()) {
+        g.prof_head = (g.prof_head + 1) % kProfRing;
+        g.prof_frames++;
+        ProfSlot& ps = g.prof[g.prof_head];
+        ps.has_tone = false;
+        ps.split = link == nullptr;                             // frame-level calls keep K0 -> K1 a programmatic launch edge
+        ex.ev_begin = ps.e[0];
+        ex.ev_prepared = ps.split ? ps.e[1] : nullptr;
+        ex.ev_rendered = ps.e[2];
     }
     CK(rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, stream, params->camera, launches, &ex));
     LastFrame& lf = it->second.last;
@@ -303,7 +323,6 @@ int rm_init(int device) {
     }
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     for (auto& ev : g.ev) CK(cudaEventCreate(&ev));
-    for (auto& ev : g.pev) CK(cudaEventCreate(&ev));
     g.device = device;
     g.ready = true;
     return RM_OK;
@@ -318,8 +337,12 @@ void rm_shutdown(void) {
     g.scenes.clear();
     g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release();
     for (auto& ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
-    for (auto& ev : g.pev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
-    g.pev_valid = false;
+    for (auto& ps : g.prof)
+        for (auto& ev : ps.e) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+    g.prof.clear();
+    g.profiling = false;
+    g.prof_head = -1;
+    g.prof_frames = 0;
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
     g.ready = false;
@@ -444,21 +467,148 @@ int rm_tonemap_device_busy(RmScene scene, const RmParams* params, const void* d_
 int rm_set_profiling(int on) {
     std::lock_guard<std::mutex> lock(g.mu);
     if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    if (on && g.prof.empty()) {
+        g.prof.resize(kProfRing);
+        for (auto& ps : g.prof)
+            for (auto& ev : ps.e) CK(cudaEventCreate(&ev));
+    }
     g.profiling = on != 0;
-    g.pev_valid = false;
+    g.prof_head = -1;
+    g.prof_frames = 0;
     return RM_OK;
 }
 
-int rm_last_kernel_times(double* ms_prepare, double* ms_render) {
+int rm_kernel_times(int back, double* ms_prepare, double* ms_render, double* ms_tonemap) {
     std::lock_guard<std::mutex> lock(g.mu);
     if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
-    if (!g.pev_valid) return fail(RM_ERR_INVALID_ARGUMENT, "no profiled render: call rm_set_profiling(1) and render first");
-    CK(cudaEventSynchronize(g.pev[2]));
-    float a = 0.f, b = 0.f;
-    CK(cudaEventElapsedTime(&a, g.pev[0], g.pev[1]));
-    CK(cudaEventElapsedTime(&b, g.pev[1], g.pev[2]));
+    if (back < 0 || back >= kProfRing || back >= g.prof_frames || g.prof_head < 0)
+        return fail(RM_ERR_INVALID_ARGUMENT, "no such profiled frame: call rm_set_profiling(1) and render first (256 frames are kept)");
+    const ProfSlot& ps = g.prof[(g.prof_head - back + kProfRing) % kProfRing];
+    CK(cudaEventSynchronize(ps.e[ps.has_tone ? 3 : 2]));
+    float a = 0.f, b = 0.f, c = -1.f;
+    if (ps.split) {
+        CK(cudaEventElapsedTime(&a, ps.e[0], ps.e[1]));
+        CK(cudaEventElapsedTime(&b, ps.e[1], ps.e[2]));
+    } else {
+        CK(cudaEventElapsedTime(&b, ps.e[0], ps.e[2]));        // K0 and K1 overlap: one figure for both
+    }
+    if (ps.has_tone) CK(cudaEventElapsedTime(&c, ps.e[2], ps.e[3]));
     if (ms_prepare) *ms_prepare = a;
     if (ms_render) *ms_render = b;
+    if (ms_tonemap) *ms_tonemap = c;
+    return RM_OK;
+}
+
+int rm_last_kernel_times(double* ms_prepare, double* ms_render) { return rm_kernel_times(0, ms_prepare, ms_render, nullptr); }
+
+// ---- one frame across the GPUs of a box (include/rm_b200.h) ---------------------------------------------------------
+
+int rm_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle[RM_IPC_HANDLE_BYTES]) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    if (!d_ptr || !bytes) return fail(RM_ERR_INVALID_ARGUMENT, "d_ptr is null or bytes is 0");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RM_IPC_HANDLE_BYTES, "RM_IPC_HANDLE_BYTES must equal sizeof(cudaIpcMemHandle_t)");
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess && handle) {
+        cudaIpcMemHandle_t h;
+        e = cudaIpcGetMemHandle(&h, p);
+        if (e == cudaSuccess) std::memcpy(handle, &h, sizeof h);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail_cuda(e, "rm_peer_alloc");
+    }
+    *d_ptr = p;
+    return RM_OK;
+}
+
+int rm_peer_open(const unsigned char handle[RM_IPC_HANDLE_BYTES], void** d_ptr) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    if (!handle || !d_ptr) return fail(RM_ERR_INVALID_ARGUMENT, "handle or d_ptr is null");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RM_OK;
+}
+
+int rm_peer_close(void* d_ptr) {
+    if (!d_ptr) return RM_OK;
+    CK(cudaIpcCloseMemHandle(d_ptr));
+    return RM_OK;
+}
+
+int rm_peer_free(void* d_ptr) {
+    if (!d_ptr) return RM_OK;
+    CK(cudaFree(d_ptr));
+    return RM_OK;
+}
+
+int rm_render_frame(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id, void* d_max, const RmExchange* x,
+                    uint32_t seq, int normalise, void* stream) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
+    if (!d_rgb || !d_max || !x) return fail(RM_ERR_INVALID_ARGUMENT, "d_rgb, d_max and exchange are required");
+    if (params && params->precision != RM_FP32) return fail(RM_ERR_INVALID_ARGUMENT, "rm_render_frame computes in RM_FP32");
+    if (x->world < 1 || x->world > RM_MAX_RANKS || x->rank < 0 || x->rank >= x->world)
+        return fail(RM_ERR_INVALID_ARGUMENT, "exchange: need 0 <= rank < world <= RM_MAX_RANKS");
+    if (seq == 0) return fail(RM_ERR_INVALID_ARGUMENT, "frame sequence numbers start at 1 (mailboxes are zero-initialised)");
+    rm::PeerLink link;
+    link.rank = x->rank;
+    link.world = x->world;
+    link.seq = seq;
+    for (int r = 0; r < x->world; r++) {
+        if (!x->mailbox[r]) return fail(RM_ERR_INVALID_ARGUMENT, "exchange: mailbox pointer of a rank is null");
+        link.box[r] = static_cast<unsigned long long*>(x->mailbox[r]);
+    }
+    unsigned char* frame8 = x->frame8[seq & 1u];
+    if (!frame8) return fail(RM_ERR_INVALID_ARGUMENT, "exchange: frame8[seq & 1] is null");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rm::FrameParams<float> fp;
+    // K0 + K1; K1 ends with the exchange and the conversion to 8 bits (K4 fused).  Only rank 0 clears bytes of the 8-bit
+    // frame (its own black pixels and the whole bands of the other ranks): zeros never travel over NVLink.
+    int rc = render_device_impl<float>(scene, params, static_cast<float*>(d_rgb), d_prim_id, static_cast<float*>(d_max), s, 0,
+                                       nullptr, &fp, nullptr, nullptr, x->rank == 0 ? frame8 : nullptr, nullptr, &link, frame8,
+                                       normalise != 0);
+    if (rc != RM_OK) return rc;
+    auto it = g.scenes.find(scene);
+    const rm::DeviceScene<float>& ds = it->second.f32.ds;
+    if (fp.n_bands <= 0) {
+        // a rank without bands (more ranks than patch rows) still owes the others its word -- a maximum of zero -- and
+        // rank 0 its signal (on rank 0: still has to wait for everybody else)
+        CK(rm::launch_publish_zero(link, static_cast<float*>(d_max), s));
+        CK(rm::launch_tonemap_peer(ds, fp, static_cast<const float*>(d_rgb), static_cast<const float*>(d_max), normalise != 0, frame8, s, link));
+    }
+    if (g.profiling && g.prof_head >= 0) {
+        ProfSlot& ps = g.prof[g.prof_head];
+        if (fp.n_bands <= 0) {                                  // nothing rendered: K0 and K1 take no time
+            CK(cudaEventRecord(ps.e[0], s));
+            CK(cudaEventRecord(ps.e[2], s));
+        }
+        ps.has_tone = false;                                    // K4 is part of K1 on this path
+    }
+    return RM_OK;
+}
+
+int rm_peer_stamps(const RmExchange* x, uint64_t out_ns[5]) {
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    if (!x || !out_ns || x->rank < 0 || x->rank >= RM_MAX_RANKS || !x->mailbox[x->rank]) return fail(RM_ERR_INVALID_ARGUMENT, "exchange, out_ns or own mailbox is null");
+    CK(cudaMemcpy(out_ns, static_cast<const unsigned long long*>(x->mailbox[x->rank]) + 56, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return RM_OK;
+}
+
+int rm_peer_status(const RmExchange* x) {
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    if (!x || x->rank < 0 || x->rank >= RM_MAX_RANKS || !x->mailbox[x->rank]) return fail(RM_ERR_INVALID_ARGUMENT, "exchange or own mailbox is null");
+    unsigned long long w = 0;
+    CK(cudaMemcpy(&w, static_cast<const unsigned long long*>(x->mailbox[x->rank]) + 48, sizeof w, cudaMemcpyDeviceToHost));
+    if (w) {
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "a rank of the box did not answer within 2 s during the exchange of frame %u", (unsigned)(w >> 32));
+        return fail(RM_ERR_PEER, buf);
+    }
     return RM_OK;
 }
 

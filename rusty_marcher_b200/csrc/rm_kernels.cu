@@ -60,6 +60,96 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
     atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
+// ---- programmatic dependent launch: the render kernel is launched while the prepare kernel (K0) still runs; its CTAs
+// become resident, stage the static scene into shared memory and then wait here for K0's results (raster records, tile
+// schedule, zeroed maximum) -- the launch latency and the prologue of K1 hide behind K0.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---- peer-memory exchange (PeerLink, rm_kernels.h): system-scope words in mailboxes every GPU of the box has mapped ----
+constexpr unsigned long long kPeerTimeoutNs = 2000000000ull;    // a wait gives up after 2 s (a peer died): flag it, go on
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spins until the upper half of *p is `seq`; returns the word.
+__device__ __noinline__ unsigned long long wait_word(const unsigned long long* p, const unsigned seq, unsigned long long* err) {
+    unsigned long long v = ld_sys(p);
+    if ((unsigned)(v >> 32) == seq) return v;
+    const unsigned long long t0 = now_ns();
+    for (int spins = 0;; spins++) {
+        v = ld_sys(p);
+        if ((unsigned)(v >> 32) == seq) return v;
+        if (spins > 64) __nanosleep(64);
+        if ((spins & 1023) == 1023 && now_ns() - t0 > kPeerTimeoutNs) {
+            st_sys(err, ((unsigned long long)seq << 32) | 1ull);
+            return v;
+        }
+    }
+}
+// Render kernel, last CTA out: this rank's channel maximum of frame link.seq to every rank's mailbox (its own included).
+__device__ __forceinline__ void publish_max(const PeerLink& link, const float m) {
+    const unsigned long long w = ((unsigned long long)link.seq << 32) | (unsigned long long)__float_as_uint(m);
+    for (int r = 0; r < link.world; r++) st_sys(link.box[r] + (link.seq & 1u) * 16 + link.rank, w);
+}
+// Tone-map kernels, every block: the frame's maximum = max over the ranks' published words (FrameBuffer::normalize is a
+// global maximum, framebuffer.rs:58-69).  Lane r of warp 0 waits for rank r's word.
+__device__ __forceinline__ float gather_max(const PeerLink& link, float* slot) {
+    if (threadIdx.x < 32) {
+        float m = 0.f;
+        unsigned long long* mine = link.box[link.rank];
+        if ((int)threadIdx.x < link.world)
+            m = __uint_as_float((unsigned)wait_word(mine + (link.seq & 1u) * 16 + threadIdx.x, link.seq, mine + 48));
+        m = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(m)));     // values >= 0: int order == float order
+        if (threadIdx.x == 0) *slot = m;
+    }
+    __syncthreads();
+    return *slot;
+}
+// Tone-map kernels, after a block's last store: the last block of the grid to get here tells rank 0 that this rank's
+// bytes of the frame are in place; on rank 0 it waits for everybody else's signal, so the kernel retires with the whole
+// frame assembled.  `done` is a zero-initialised local counter, left at zero.
+__device__ __forceinline__ void signal_frame_done(const PeerLink& link, int* done) {
+    __syncthreads();
+    if (threadIdx.x != 0 || link.world < 1) return;
+    // This block's stores (peer memory included) are ordered before its count by a device-scope fence; the one system-
+    // scope fence of the last block then covers them all (fences are cumulative) -- a fence.sys per block costs ~5 us.
+    __threadfence();
+    if (atomicAdd(done, 1) != (int)gridDim.x - 1) return;
+    *done = 0;
+    link.box[link.rank][59] = now_ns();                        // stamp: this rank's bytes stored
+    if (link.world == 1) return;
+    __threadfence_system();
+    if (link.rank != 0) {
+        st_sys(link.box[0] + 32 + link.rank, ((unsigned long long)link.seq << 32) | 1ull);
+    } else {
+        for (int r = 1; r < link.world; r++) wait_word(link.box[0] + 32 + r, link.seq, link.box[0] + 48);
+        __threadfence_system();
+        link.box[0][60] = now_ns();                            // stamp: frame complete on rank 0
+    }
+}
+
+template <typename R> struct Tone;
+template <> struct Tone<float> {
+    static __device__ __forceinline__ unsigned q(float v, float inv) {
+        return (unsigned)(unsigned char)(255.f * fminf(fmaxf(v * inv, 0.f), 1.f));     // framebuffer.rs:80-82
+    }
+};
+template <> struct Tone<double> {
+    static __device__ __forceinline__ unsigned q(double v, double inv) {
+        return (unsigned)(unsigned char)(255. * fmin(fmax(v * inv, 0.), 1.));
+    }
+};
+
 template <typename R, bool S>
 __global__ void __launch_bounds__(kBlock)
 render_kernel(const DeviceScene<R> ds, const FrameParams<R> fp, const int cull, const int use_smem,
@@ -122,8 +212,10 @@ render_kernel(const DeviceScene<R> ds, const FrameParams<R> fp, const int cull, 
 // K0: camera-specialised raster records of every fast-path triangle, in FP64, once per frame.
 __global__ void __launch_bounds__(128)
 prepare_raster_kernel(const double* __restrict__ tri_src, const int n_tri, const double cx, const double cy, const double cz,
-                      R4<float>* __restrict__ tri_r) {
+                      R4<float>* __restrict__ tri_r, float* __restrict__ dmax_zero) {
+    pdl_launch_dependents();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0 && dmax_zero) *dmax_zero = 0.f;
     if (j >= n_tri) return;
     const double cam[3] = {cx, cy, cz};
     R4<float> out[4];
@@ -141,9 +233,11 @@ constexpr int kClassifyMaxTris = 256;
 __global__ void __launch_bounds__(64)
 prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, const double cx, const double cy, const double cz,
                         R4<float>* __restrict__ tri_r, const FrameParams<float> fp, const int tiles_x, const int n_tiles,
-                        int* __restrict__ order, int* __restrict__ order2, int* __restrict__ ctr) {
+                        int* __restrict__ order, int* __restrict__ order2, int* __restrict__ ctr, float* __restrict__ dmax_zero) {
     __shared__ R4<float> rec[4 * kClassifyMaxTris];
     const double cam[3] = {cx, cy, cz};
+    pdl_launch_dependents();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && dmax_zero) *dmax_zero = 0.f;
     for (int j = threadIdx.x; j < n_tri; j += blockDim.x) {      // every block rebuilds the (few) records; block 0 publishes them
         R4<float> out[4];
         prepare_raster(tri_src + (size_t)j * kTriSrcDoubles, cam, out);
@@ -190,13 +284,12 @@ prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, con
 
 // K1, FP32 production kernel (rm_fast.cuh).  Persistent and warp-granular: the grid is (SMs x resident
 // CTAs); every CTA stages the scene into shared memory ONCE; after that its warps never meet at a
-// barrier again.  Work is handed out in two levels, the GPU analogue of Rayon's work stealing over the
-// reference's 32x32 patches (renderer.rs:46-89):
-//   * a CTA owns one busy 32x32 tile at a time, taken from a global atomic counter (one atomic per tile);
-//   * its warps take the tile's eight 32x4 strips from a shared-memory ticket counter.  The warp that
-//     draws strip 0 of a tile fetches the tile the CTA will need kAhead tiles later and publishes it
-//     in a small ring (tile id + sequence tag), so the latency of the global atomic and of the
-//     schedule lookup hides behind the tiles in between.
+// barrier again.  Work is handed out per WARP, the GPU analogue of Rayon's work stealing over the
+// reference's 32x32 patches (renderer.rs:46-89) at a granularity that suits 3552 resident warps: a warp
+// draws one 32x4 strip (an eighth of a patch) at a time from a global atomic counter that walks the tile
+// schedule, fully covered tiles first.  (Handing whole tiles to CTAs quantised the kernel's duration to
+// ceil(busy tiles / CTAs) tile times: 3 rounds instead of 2.7 on the cornell frame, and no gain at all
+// from splitting the frame over two GPUs.)
 // Per strip a warp runs a two-stage wavefront of its own:
 //   A  primary visibility, divergence-free: a thread owns 4 horizontally adjacent pixels.  First the
 //      warp bounds every triangle against the strip (one triangle per lane, exact corner test
@@ -213,22 +306,19 @@ prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, con
 constexpr int kFastTile = 32;
 constexpr int kStripRows = 4, kStripsPerTile = kFastTile / kStripRows;
 constexpr int kWarpQueue = kFastTile * kStripRows + 32;         // one strip of hits on top of a partial round
-constexpr int kRing = 16;                                        // published tiles (power of two)
-constexpr int kAhead = 1;                                       // tiles fetched ahead of the one being drawn
 template <bool kSmem>
 __global__ void __launch_bounds__(kBlock, 3)
 render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
                    float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order, const int* __restrict__ order2,
-                   unsigned char* __restrict__ rgb8) {
+                   unsigned char* rgb8, const PeerLink link, unsigned char* rgb8_out, const int normalise,
+                   const int zero_foreign) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    __shared__ int cta_max, strip_ticket;
+    __shared__ int cta_max;
+    __shared__ float frame_max;
     __shared__ int leftover[kBlock / 32];
     __shared__ int fill_off[96];                                // float offset of each 16-byte chunk of a strip (see fill_strip)
     __shared__ float4 pool[kBlock];                             // pooled leftovers of the eight warp queues (< 32 each)
-    __shared__ int ring_tile[kRing];
-    __shared__ int ring_pos[kRing];
-    __shared__ int ring_seq[kRing];
     __shared__ float4 queue[kBlock / 32][kWarpQueue];           // {t, slot, id, x | y << 16}
     const BlobLayout& L = ds.lay;
     const int n_tri = tri_count(L, cull != 0);
@@ -236,23 +326,18 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     const unsigned char* base = ds.blob;
     const R4<float>* tri_r = ds.tri_r;
     if (threadIdx.x < 96) fill_off[threadIdx.x] = (threadIdx.x / 24) * fp.width * 3 + (threadIdx.x % 24) * 4;
-    if (threadIdx.x == 0) {
-        cta_max = 0;
-        strip_ticket = 0;
-        for (int i = 0; i < kRing; i++) ring_seq[i] = -1;
-        const int n_full0 = order ? ctr[1] : n_tiles, n_busy0 = order ? n_full0 + ctr[5] : n_tiles;
-        for (int i = 0; i < kAhead; i++) {
-            const int pos = atomicAdd(ctr, 1);
-            ring_tile[i] = pos >= n_busy0 ? -1 : (!order ? pos : pos < n_full0 ? order[pos] : order2[pos - n_full0]);
-            ring_pos[i] = pos;
-            ring_seq[i] = i;
-        }
-    }
-    if (kSmem) {
+    if (threadIdx.x == 0) cta_max = 0;
+    if (kSmem) {                                                // the static part of the scene: does not depend on K0
         const uint4* src = reinterpret_cast<const uint4*>(ds.blob);
         uint4* dst = reinterpret_cast<uint4*>(smem_raw);
         const int n16 = L.bytes / 16;
         for (int i = threadIdx.x; i < n16; i += kBlock) dst[i] = __ldg(src + i);
+    }
+    pdl_wait_primary();                                         // K0 has retired: raster records, schedule, zeroed maximum
+    if (threadIdx.x == 0 && blockIdx.x == 0 && link.world > 0) link.box[link.rank][56] = now_ns();  // stamp: start of the work
+    if (kSmem) {
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+        const int n16 = L.bytes / 16;
         const uint4* rsrc = reinterpret_cast<const uint4*>(ds.tri_r);
         for (int i = threadIdx.x; i < n_tri * 4; i += kBlock) dst[n16 + i] = rsrc[i];
         base = smem_raw;
@@ -287,8 +372,6 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     // schedule: [0, n_full) fully covered tiles (order), [n_full, n_busy) partially covered (order2), [n_busy, n_tiles) empty (order)
     const int n_full = order ? ctr[1] : n_tiles, n_busy = order ? n_full + ctr[5] : n_tiles;
     float4* const wq = queue[warp];
-    volatile int* const vseq = ring_seq;
-    volatile int* const vtile = ring_tile;
     int qn = 0;                                                 // entries in this warp's queue (warp-uniform)
     int final_take = 0;
     float m = 0.f;
@@ -338,30 +421,36 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     int next_empty = n_busy + blockIdx.x * (kBlock / 32) + warp;   // schedule position of this warp's next empty tile
     int empty_acc = 0;
 
+    // ---- phase 0 (rank 0 of a multi-GPU frame only)
+    if (zero_foreign) {
+        // Rank 0 of a multi-GPU frame: the bands of the other ranks are black wherever those ranks store nothing
+        // (they only send their busy tiles, after the exchange of the maxima, i.e. after this kernel's stores), so
+        // the 8-bit frame's foreign bands are cleared here, from local HBM bandwidth, instead of sending zeros over
+        // NVLink.  A band is 32 full rows = 96 W contiguous bytes; 512-byte pieces are dealt to the grid's warps.
+        const int S = fp.row_step >> 5, f = (fp.row_begin >> 5) % S, P = fp.height >> 5;
+        const int per_band = fp.width * 96 / 512;                  // W is a multiple of 32: 6 W / 32 pieces
+        const int n_foreign = P - (P - f + S - 1) / S;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int c = blockIdx.x * (kBlock / 32) + warp; c < n_foreign * per_band; c += n_warps) {
+            const int fb = c / per_band, piece = c - fb * per_band;
+            const int g = fb / (S - 1), r = fb - g * (S - 1);
+            const int band = g * S + (r < f ? r : r + 1);
+            __stcs(reinterpret_cast<uint4*>(rgb8 + ((size_t)band * fp.width * 96 + (size_t)piece * 512)) + lane, z);
+        }
+    }
     // ---- phase 1: busy tiles, dynamic.  phase 3 (below) reuses the shading code of the loop through `pooled`.
     for (int phase = 1;;) {
         if (phase == 1) {
-            // next strip of the CTA's current tile
+            // next strip of the schedule: strip s & 7 of the (s >> 3)-th busy tile.  One global atomic per 128 pixels;
+            // its latency hides behind the other warps of the SM, and no warp ever holds work another one could do.
             int s = 0;
-            if (lane == 0) s = atomicAdd(&strip_ticket, 1);
+            if (lane == 0) s = atomicAdd(ctr, 1);
             s = __shfl_sync(0xffffffffu, s, 0);
             const int k = s / kStripsPerTile, strip = s % kStripsPerTile;
-            if (lane == 0) {
-                if (strip == 0) {                               // first strip of tile k: fetch tile k + kAhead for the CTA
-                    const int pos = atomicAdd(ctr, 1);          // position in the tile schedule
-                    vtile[(k + kAhead) % kRing] = pos >= n_busy ? -1 : (!order ? pos : pos < n_full ? order[pos] : order2[pos - n_full]);
-                    ring_pos[(k + kAhead) % kRing] = pos;
-                    __threadfence_block();
-                    vseq[(k + kAhead) % kRing] = k + kAhead;
-                }
-                while (vseq[k % kRing] != k) {}                 // published by whoever drew strip 0 of tile k - kAhead
-                __threadfence_block();
-            }
-            __syncwarp();
-            const int tile = vtile[k % kRing];
-            if (tile < 0) {
+            if (k >= n_busy) {
                 phase = 2;
             } else {
+                const int tile = !order ? k : k < n_full ? __ldg(order + k) : __ldg(order2 + (k - n_full));
                 const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);          // exact for tile < 2^22
                 const int tx = tile - ty * tiles_x;
                 const int x0 = tx * kFastTile, ys = fp.row_begin + ty * fp.row_step + strip * kStripRows;
@@ -467,67 +556,97 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
             ctr[2] = 0;
             ctr[3] = 0;
             ctr[5] = 0;
+            // every CTA's stores and its atomicMax happened before its count (fence above): the maximum of this rank's
+            // rows is final, and so are its float rows and (rank 0) the cleared bytes of the 8-bit frame
+            if (link.world > 0) {
+                link.box[link.rank][57] = now_ns();                                                 // stamp: rendering done
+                __threadfence_system();
+                publish_max(link, __int_as_float(atomicMax(reinterpret_cast<int*>(dmax), 0)));
+            }
         }
     }
+    if (!rgb8_out) return;
+    // ---- phase 4: FrameBuffer::normalize + to_vec (framebuffer.rs:40-82), fused.  Every CTA waits for the words of all
+    // ranks in this rank's mailbox -- its own word is only published once every CTA of this grid has retired from
+    // rendering, so the wait is also the grid-wide barrier that makes the float rows readable (the grid is persistent:
+    // all its CTAs are resident, nobody waits for a CTA that cannot start) -- takes the maximum, and converts the busy
+    // tiles, one tile per CTA and round, straight into rank 0's 8-bit frame (peer memory on ranks > 0).
+    float inv = 1.f;
+    {
+        const float mx = gather_max(link, &frame_max);
+        if (normalise && mx > 0.f) inv = 1.f / mx;              // framebuffer.rs:71-76: scale(1. / max_val)
+        if (blockIdx.x == 0 && threadIdx.x == 0) link.box[link.rank][58] = now_ns();                // stamp: maxima gathered
+    }
+    __threadfence();
+    for (int t = blockIdx.x; t < n_busy; t += gridDim.x) {
+        const int tile = !order ? t : t < n_full ? __ldg(order + t) : __ldg(order2 + (t - n_full));
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const size_t p0 = (size_t)(fp.row_begin + ty * fp.row_step - fp.buf_row0) * fp.width + tx * 32;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int c = threadIdx.x + 256 * i;                // 768 float4 per tile: 32 rows x 24
+            const int row = c / 24, col = c - row * 24;
+            const size_t v = 3 * (p0 + (size_t)row * fp.width) + 4 * col;
+            const float4 q = __ldcg(reinterpret_cast<const float4*>(rgb + v));
+            const unsigned w = Tone<float>::q(q.x, inv) | (Tone<float>::q(q.y, inv) << 8) | (Tone<float>::q(q.z, inv) << 16) | (Tone<float>::q(q.w, inv) << 24);
+            *reinterpret_cast<unsigned*>(rgb8_out + v) = w;
+        }
+    }
+    signal_frame_done(link, ctr + 10);
 }
-
-template <typename R> struct Tone;
-template <> struct Tone<float> {
-    static __device__ __forceinline__ unsigned q(float v, float inv) {
-        return (unsigned)(unsigned char)(255.f * fminf(fmaxf(v * inv, 0.f), 1.f));     // framebuffer.rs:80-82
-    }
-};
-template <> struct Tone<double> {
-    static __device__ __forceinline__ unsigned q(double v, double inv) {
-        return (unsigned)(unsigned char)(255. * fmin(fmax(v * inv, 0.), 1.));
-    }
-};
 
 // 16 consecutive channel values per thread -> one 16-byte store.  Rows are W*3 values with W a
 // multiple of 32, so every thread's span is 16-byte aligned on both sides.  `band16` = 16-value chunks
 // of one 32-row band, `step16` = chunks from the start of one rendered band to the start of the next.
-template <typename R>
+// kPeer: the maximum comes from the ranks' mailboxes and the end of the kernel is signalled (PeerLink).
+template <typename R, bool kPeer>
 __global__ void __launch_bounds__(256)
 tonemap_kernel(const R* __restrict__ rgb, const R* __restrict__ dmax, const int normalise, const size_t first16,
-               const size_t count16, const unsigned band16, const size_t step16, unsigned char* __restrict__ rgb8) {
+               const size_t count16, const unsigned band16, const size_t step16, unsigned char* __restrict__ rgb8,
+               const PeerLink link, int* __restrict__ done) {
+    __shared__ float peer_max;
     const size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= count16) return;
-    const size_t band = l / band16;
-    const size_t i = first16 + band * step16 + (l - band * band16);
     R inv = R(1);
     if (normalise) {
-        const R mx = *dmax;
+        const R mx = kPeer ? R(gather_max(link, &peer_max)) : *dmax;
         if (mx > R(0)) inv = R(1) / mx;                         // framebuffer.rs:71-76: scale(1. / max_val)
     }
-    const R* src = rgb + i * 16;
-    unsigned w[4];
+    if (l < count16) {
+        const size_t band = l / band16;
+        const size_t i = first16 + band * step16 + (l - band * band16);
+        const R* src = rgb + i * 16;
+        unsigned w[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        R v0, v1, v2, v3;
-        if (sizeof(R) == 4) {
-            const float4 f = __ldcs(reinterpret_cast<const float4*>(src) + k);
-            v0 = f.x; v1 = f.y; v2 = f.z; v3 = f.w;
-        } else {
-            const double2 a = __ldcs(reinterpret_cast<const double2*>(src) + 2 * k);
-            const double2 b = __ldcs(reinterpret_cast<const double2*>(src) + 2 * k + 1);
-            v0 = a.x; v1 = a.y; v2 = b.x; v3 = b.y;
+        for (int k = 0; k < 4; k++) {
+            R v0, v1, v2, v3;
+            if (sizeof(R) == 4) {
+                const float4 f = __ldcs(reinterpret_cast<const float4*>(src) + k);
+                v0 = f.x; v1 = f.y; v2 = f.z; v3 = f.w;
+            } else {
+                const double2 a = __ldcs(reinterpret_cast<const double2*>(src) + 2 * k);
+                const double2 b = __ldcs(reinterpret_cast<const double2*>(src) + 2 * k + 1);
+                v0 = a.x; v1 = a.y; v2 = b.x; v3 = b.y;
+            }
+            w[k] = Tone<R>::q(v0, inv) | (Tone<R>::q(v1, inv) << 8) | (Tone<R>::q(v2, inv) << 16) | (Tone<R>::q(v3, inv) << 24);
         }
-        w[k] = Tone<R>::q(v0, inv) | (Tone<R>::q(v1, inv) << 8) | (Tone<R>::q(v2, inv) << 16) | (Tone<R>::q(v3, inv) << 24);
+        reinterpret_cast<uint4*>(rgb8)[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    reinterpret_cast<uint4*>(rgb8)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    if (kPeer) signal_frame_done(link, done);
 }
 
 // K4 for frames rendered with a tile schedule and rgb8 zero-fill: only the busy tiles (ctr[8] fully covered ones in
 // `order`, ctr[9] partially covered ones in `order2`) hold anything but zeros.  A block walks tiles; a thread converts
 // one float4 (4 channel values -> 4 bytes) at a time, lanes along a pixel row: 384-byte runs in, 96-byte runs out.
+template <bool kPeer>
 __global__ void __launch_bounds__(256)
 tonemap_busy_kernel(const float* __restrict__ rgb, const float* __restrict__ dmax, const int normalise, const FrameParams<float> fp,
-                    const int tiles_x, const int* __restrict__ order, const int* __restrict__ order2, const int* __restrict__ ctr,
-                    unsigned char* __restrict__ rgb8) {
+                    const int tiles_x, const int* __restrict__ order, const int* __restrict__ order2, int* __restrict__ ctr,
+                    unsigned char* __restrict__ rgb8, const PeerLink link) {
+    __shared__ float peer_max;
     const int n_full = ctr[8], n_busy = n_full + ctr[9];
     float inv = 1.f;
     if (normalise) {
-        const float mx = *dmax;
+        const float mx = kPeer ? gather_max(link, &peer_max) : *dmax;
         if (mx > 0.f) inv = 1.f / mx;                           // framebuffer.rs:71-76: scale(1. / max_val)
     }
     for (int t = blockIdx.x; t < n_busy; t += gridDim.x) {
@@ -544,6 +663,12 @@ tonemap_busy_kernel(const float* __restrict__ rgb, const float* __restrict__ dma
             *reinterpret_cast<unsigned*>(rgb8 + v) = w;
         }
     }
+    if (kPeer) signal_frame_done(link, ctr + 10);
+}
+
+__global__ void publish_zero_kernel(const PeerLink link, float* __restrict__ dmax) {
+    *dmax = 0.f;
+    publish_max(link, 0.f);
 }
 
 __global__ void __launch_bounds__(256) ffma_probe_kernel(float* __restrict__ sink, const int iters) {
@@ -575,13 +700,21 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     const bool classify = ds.lay.n_sph + poly_count(ds.lay, cull) == 0 && n_tri <= kClassifyMaxTris && n_tiles <= ds.tile_order_cap / 2;
     if (classify)
         prepare_classify_kernel<<<(n_tiles + 63) / 64, 64, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r,
-                                                                         fp, tiles_x, n_tiles, ds.tile_order, ds.tile_order + ds.tile_order_cap / 2, ds.ctr);
+                                                                         fp, tiles_x, n_tiles, ds.tile_order, ds.tile_order + ds.tile_order_cap / 2, ds.ctr,
+                                                                         ex && ex->zero_dmax ? dmax : nullptr);
     else
-        prepare_raster_kernel<<<(std::max(n_tri, 1) + 127) / 128, 128, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r);
+        prepare_raster_kernel<<<(std::max(n_tri, 1) + 127) / 128, 128, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r,
+                                                                                     ex && ex->zero_dmax ? dmax : nullptr);
+    const PeerLink link = ex ? ex->link : PeerLink();
     const int* order = classify ? ds.tile_order : nullptr;
     if (ex) ex->scheduled = classify;
     if (!classify) rgb8 = nullptr;                              // without a schedule the tone-map kernel converts every tile
-    if (ex && ex->ev_prepared) cudaEventRecord(ex->ev_prepared, stream);
+    unsigned char* rgb8_out = ex ? ex->rgb8_out : nullptr;     // fused K4 (needs a link: the mailbox wait is its barrier)
+    if (link.world <= 0) rgb8_out = nullptr;
+    const int normalise = ex && ex->normalise ? 1 : 0;
+    const int zero_foreign = (rgb8_out && link.world > 1 && link.rank == 0 && ex->rgb8_zero) ? 1 : 0;
+    if (zero_foreign) rgb8 = ex->rgb8_zero;                     // scheduled or not: rank 0 clears the foreign bands
+    if (ex && ex->ev_prepared) cudaEventRecord(ex->ev_prepared, stream);      // (an event here gives up the overlap of K1's launch with K0)
     if (launches) (*launches)++;
     const size_t smem = (size_t)ds.lay.bytes + (size_t)n_tri * 64;
     const float inv_tiles_x = 1.0f / (float)tiles_x;
@@ -592,20 +725,29 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     }
-    if (smem <= (size_t)kSmemLimit) {
-        auto k = render_fast_kernel<true>;
-        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        int occ = 1;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, smem)) != cudaSuccess) return e;
-        const int ctas = std::min(n_tiles, sm_count * std::max(occ, 1));
-        k<<<ctas, kBlock, smem, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr, rgb8);
-    } else {
-        auto k = render_fast_kernel<false>;
-        int occ = 1;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, 0)) != cudaSuccess) return e;
-        const int ctas = std::min(n_tiles, sm_count * std::max(occ, 1));
-        k<<<ctas, kBlock, 0, stream>>>(ds, fp, cull ? 1 : 0, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr, rgb8);
-    }
+    // launched with programmatic stream serialisation: the CTAs may become resident while K0 still runs (pdl_wait_primary)
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kBlock);
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int cull_i = cull ? 1 : 0;
+    const int* order2 = order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr;
+    const bool use_smem = smem <= (size_t)kSmemLimit;
+    auto k = use_smem ? render_fast_kernel<true> : render_fast_kernel<false>;
+    cfg.dynamicSmemBytes = use_smem ? smem : 0;
+    if (cfg.dynamicSmemBytes > 48 * 1024 &&
+        (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes)) != cudaSuccess)
+        return e;
+    int occ = 1;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;
+    cfg.gridDim = dim3(std::min(n_tiles, sm_count * std::max(occ, 1)));
+    if ((e = cudaLaunchKernelEx(&cfg, k, ds, fp, cull_i, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order2, rgb8,
+                                link, rgb8_out, normalise, zero_foreign)) != cudaSuccess)
+        return e;
     if (launches) (*launches)++;
     if (ex && ex->ev_rendered) cudaEventRecord(ex->ev_rendered, stream);
     return cudaGetLastError();
@@ -643,27 +785,50 @@ cudaError_t launch_render(const DeviceScene<R>& ds, const FrameParams<R>& fp, bo
 }
 
 cudaError_t launch_tonemap_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, const float* dmax,
-                                bool normalise, unsigned char* rgb8, cudaStream_t stream) {
+                                bool normalise, unsigned char* rgb8, cudaStream_t stream, const PeerLink* link) {
     const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * fp.n_bands;
-    if (n_tiles <= 0) return cudaSuccess;
-    const int blocks = std::min(n_tiles, 148 * 8);
-    tonemap_busy_kernel<<<blocks, 256, 0, stream>>>(rgb, dmax, normalise ? 1 : 0, fp, tiles_x, ds.tile_order,
-                                                    ds.tile_order + ds.tile_order_cap / 2, ds.ctr, rgb8);
+    const bool peer = link && link->world > 0;
+    if (n_tiles <= 0 && !peer) return cudaSuccess;
+    const int blocks = std::max(std::min(n_tiles, 148 * 8), 1);
+    int* order = ds.tile_order;
+    int* order2 = ds.tile_order + ds.tile_order_cap / 2;
+    if (peer)
+        tonemap_busy_kernel<true><<<blocks, 256, 0, stream>>>(rgb, dmax, normalise ? 1 : 0, fp, tiles_x, order, order2, ds.ctr, rgb8, *link);
+    else
+        tonemap_busy_kernel<false><<<blocks, 256, 0, stream>>>(rgb, dmax, normalise ? 1 : 0, fp, tiles_x, order, order2, ds.ctr, rgb8, PeerLink());
     return cudaGetLastError();
 }
+
+namespace {
+template <typename R, bool kPeer>
+cudaError_t launch_tonemap_impl(const FrameParams<R>& fp, const R* rgb, const R* dmax, bool normalise, unsigned char* rgb8,
+                                cudaStream_t stream, const PeerLink& link, int* done) {
+    const int rows = fp.n_bands * 32;
+    if (rows <= 0 && !kPeer) return cudaSuccess;
+    // both buffers are indexed from pixel row fp.buf_row0
+    const size_t row16 = (size_t)fp.width * 3 / 16;
+    const size_t first16 = (size_t)(fp.row_begin - fp.buf_row0) * row16;
+    const size_t count16 = (size_t)std::max(rows, 0) * row16;
+    const int blocks = std::max((int)((count16 + 255) / 256), 1);
+    tonemap_kernel<R, kPeer><<<blocks, 256, 0, stream>>>(rgb, dmax, normalise ? 1 : 0, first16, count16, (unsigned)std::max<size_t>(32 * row16, 1),
+                                                         (size_t)fp.row_step * row16, rgb8, link, done);
+    return cudaGetLastError();
+}
+}  // namespace
 
 template <typename R>
 cudaError_t launch_tonemap(const FrameParams<R>& fp, const R* rgb, const R* dmax, bool normalise, unsigned char* rgb8,
                            cudaStream_t stream) {
-    const int rows = fp.n_bands * 32;
-    if (rows <= 0) return cudaSuccess;
-    // both buffers are indexed from pixel row fp.buf_row0
-    const size_t row16 = (size_t)fp.width * 3 / 16;
-    const size_t first16 = (size_t)(fp.row_begin - fp.buf_row0) * row16;
-    const size_t count16 = (size_t)rows * row16;
-    const int blocks = (int)((count16 + 255) / 256);
-    tonemap_kernel<R><<<blocks, 256, 0, stream>>>(rgb, dmax, normalise ? 1 : 0, first16, count16, (unsigned)(32 * row16),
-                                                  (size_t)fp.row_step * row16, rgb8);
+    return launch_tonemap_impl<R, false>(fp, rgb, dmax, normalise, rgb8, stream, PeerLink(), nullptr);
+}
+
+cudaError_t launch_tonemap_peer(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, const float* dmax,
+                                bool normalise, unsigned char* rgb8, cudaStream_t stream, const PeerLink& link) {
+    return launch_tonemap_impl<float, true>(fp, rgb, dmax, normalise, rgb8, stream, link, ds.ctr + 10);
+}
+
+cudaError_t launch_publish_zero(const PeerLink& link, float* dmax, cudaStream_t stream) {
+    publish_zero_kernel<<<1, 1, 0, stream>>>(link, dmax);
     return cudaGetLastError();
 }
 

@@ -30,11 +30,35 @@ template <typename R> struct DeviceScene {
     int tile_order_cap = 0;
 };
 
+// The path's one exchange step done by the kernels themselves over peer memory (NVLink): every rank owns
+// a mailbox of kMailboxWords 64-bit words that all ranks of the box have mapped (CUDA IPC).
+//   word [(seq & 1) * 16 + src]   {seq, max bits} published by rank src's render kernel (double buffered by frame parity:
+//                                 a rank may be at most one frame ahead of the slowest reader)
+//   word [32 + src]               {seq, 1} on rank 0 only: rank src's tone-map kernel has stored all its bytes of the frame
+//   word [48]                     non-zero when a wait gave up after kPeerTimeoutNs (a peer died); sticky
+//   words [56, 61)                %globaltimer stamps (ns) of the rank's last frame: kernel start, rendering done, maxima
+//                                 gathered, own bytes stored, (rank 0) frame complete -- rm_peer_stamps()
+constexpr int kMaxRanks = 16;
+constexpr int kMailboxWords = 64;
+struct PeerLink {
+    int rank = 0, world = 0;            // world == 0: no exchange (single-GPU calls)
+    unsigned seq = 0;                   // frame sequence number, >= 1, the same on every rank
+    unsigned long long* box[kMaxRanks] = {};
+};
+
 // Optional extras of a render launch.
 struct RenderExtras {
+    // in: let K0 zero *dmax (saves the memset launch of frame-level calls)
+    bool zero_dmax = false;
+    // in: publish the channel maximum of this rank's rows to every rank's mailbox when the render kernel retires
+    PeerLink link;
     // in: the 8-bit frame (indexed like rgb).  When the frame gets a tile schedule the render kernel zeroes the bytes of
     // every pixel it visits, so that launch_tonemap_busy() only has to convert the busy tiles afterwards.
     unsigned char* rgb8_zero = nullptr;
+    // in: fuse K4 into the render kernel (needs `link`): once every rank's maximum is in this rank's mailbox the kernel
+    // converts its busy tiles (all its tiles without a schedule) into rgb8_out, which may be peer memory, and signals rank 0
+    unsigned char* rgb8_out = nullptr;
+    bool normalise = true;
     // in: events recorded on the stream before K0, between K0 and K1, after K1 (profiling; may be null)
     cudaEvent_t ev_begin = nullptr, ev_prepared = nullptr, ev_rendered = nullptr;
     // out: the frame was rendered with a tile schedule (and rgb8_zero, if given, has been zero-filled)
@@ -56,8 +80,17 @@ cudaError_t launch_tonemap(const FrameParams<R>& fp, const R* rgb, const R* dmax
                            cudaStream_t stream);
 
 // K4 over the busy tiles of the frame `ds` rendered last with a schedule and RenderExtras::rgb8_zero (same fp).
+// With a link (world >= 1) the kernel takes the frame maximum from this rank's mailbox instead of dmax (waiting for every
+// rank's word of frame link.seq), and signals rank 0 when its bytes are stored; on rank 0 it returns only once every rank
+// has signalled, i.e. when the whole 8-bit frame is in place.
 cudaError_t launch_tonemap_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, const float* dmax,
-                                bool normalise, unsigned char* rgb8, cudaStream_t stream);
+                                bool normalise, unsigned char* rgb8, cudaStream_t stream, const PeerLink* link = nullptr);
+// launch_tonemap<float> with the same exchange (frames without a tile schedule).
+cudaError_t launch_tonemap_peer(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, const float* dmax,
+                                bool normalise, unsigned char* rgb8, cudaStream_t stream, const PeerLink& link);
+
+// A rank without rows: zero maximum to every mailbox (the others wait for a word of every rank).
+cudaError_t launch_publish_zero(const PeerLink& link, float* dmax, cudaStream_t stream);
 
 // Pure-FFMA probe: `iters` x 16 dependent-chain FFMAs per thread on every SM; returns flop count.
 cudaError_t launch_ffma_probe(float* sink, int iters, int blocks, cudaStream_t stream, double* flops);

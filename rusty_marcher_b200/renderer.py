@@ -30,7 +30,8 @@ class Renderer:
         p.max_depth = self.max_depth
         p.background = self.background
         p.precision = self.precision
-        p.patch_row_begin, p.patch_row_end = patch_rows
+        p.patch_row_begin, p.patch_row_end = patch_rows[:2]     # (begin, end[, stride]) in 32-row patch rows
+        p.patch_row_stride = patch_rows[2] if len(patch_rows) > 2 else 1
         p.cull_backfacing = int(self.cull_backfacing)
         return p
 

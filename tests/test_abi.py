@@ -30,19 +30,19 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in decl:
         assert hasattr(L, name), "librm_b200.so does not export %s" % name
     assert sorted(_abi.SYMBOLS) == decl, "ctypes table and headers disagree"
-    assert L.rm_abi_version() == 2
+    assert L.rm_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header(tmp_path):
     src = tmp_path / "sizes.c"
-    src.write_text('#include <stdio.h>\n#include "rm_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "rm_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(RmReflectance),sizeof(RmSphere),sizeof(RmPolygon),sizeof(RmTriangle),sizeof(RmObj),"
-                   "sizeof(RmLight),sizeof(RmShapeRef),sizeof(RmFlatScene),sizeof(RmParams),sizeof(RmStats));return 0;}\n")
+                   "sizeof(RmLight),sizeof(RmShapeRef),sizeof(RmFlatScene),sizeof(RmParams),sizeof(RmStats),sizeof(RmExchange));return 0;}\n")
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(t) for t in (_abi.RmReflectance, _abi.RmSphere, _abi.RmPolygon, _abi.RmTriangle, _abi.RmObj,
-                                  _abi.RmLight, _abi.RmShapeRef, _abi.RmFlatScene, _abi.RmParams, _abi.RmStats)]
+                                  _abi.RmLight, _abi.RmShapeRef, _abi.RmFlatScene, _abi.RmParams, _abi.RmStats, _abi.RmExchange)]
     assert got == want
 
 

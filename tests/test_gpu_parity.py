@@ -297,3 +297,116 @@ def test_fp32_peak_probe(rm_gpu):
     t, ms = C.c_double(0), C.c_double(0)
     _abi.check(_abi.load().rm_measure_fp32_peak(C.byref(t), C.byref(ms)))
     assert 20. < t.value < 90., t.value                        # 148 SMs x 128 lanes x 2 x ~1.9 GHz = 72 TFLOP/s nominal
+
+
+@pytest.mark.parametrize("name,w,h", [("cornell_box", 1920, 1080), ("demo", 800, 600), ("dodecahedron", 640, 480)])
+def test_frame_level_call_equals_the_two_step_path(rm_gpu, name, w, h):
+    """rm_render_frame (K0 + K1 + K4, the exchange done by the kernels through the mailbox) with world = 1 against
+    rm_render: same floats, same ids, same bytes; consecutive frames alternate between the two 8-bit buffers."""
+    import torch
+    from rusty_marcher_b200 import tiled
+    dev = torch.device("cuda:0")
+    scene = workloads.scene(name)
+    whole = gpu_render(rm_gpu, scene, w, h, "f32")
+    be = tiled.CudaBackend(scene, rm_gpu.create_renderer(1.5, h, w), w, h, dev)
+    tr = tiled.TiledRenderer(be, w, h, dev)
+    assert tr.exchange == "peer" and tr.world == 1
+    try:
+        frames, ptrs = [], []
+        for _ in range(3):
+            f = tr.render()
+            torch.cuda.synchronize()
+            tr.peer.status()
+            ptrs.append(f.data_ptr())
+            frames.append(f.cpu().numpy().copy())
+            assert np.array_equal(tr.rgb.cpu().numpy(), whole["rgb"])
+            assert float(tr.dmax.item()) == np.float32(whole["max"])
+        assert ptrs[0] != ptrs[1] and ptrs[0] == ptrs[2]
+        for f in frames:
+            assert np.array_equal(f, whole["rgb8"])
+    finally:
+        tr.close()
+
+
+def test_frame_level_call_argument_checks(rm_gpu):
+    import torch
+    from rusty_marcher_b200 import tiled
+    dev = torch.device("cuda:0")
+    w, h = 64, 64
+    scene = workloads.scene("demo")
+    be = tiled.CudaBackend(scene, rm_gpu.create_renderer(1.5, h, w), w, h, dev)
+    tr = tiled.TiledRenderer(be, w, h, dev)
+    L = _abi.load()
+    try:
+        stream = torch.cuda.current_stream().cuda_stream
+        args = (be.handle, C.byref(tr.params), tr.rgb.data_ptr(), None, tr.dmax.data_ptr())
+        assert L.rm_render_frame(*args, C.byref(tr.peer.x), 0, 1, stream) == -3            # sequence numbers start at 1
+        assert L.rm_render_frame(*args, None, 1, 1, stream) == -3
+        bad = _abi.RmExchange()
+        bad.rank, bad.world = 0, 2                                                           # second mailbox missing
+        bad.mailbox[0] = tr.peer.x.mailbox[0]
+        bad.frame8[0], bad.frame8[1] = tr.peer.x.frame8[0], tr.peer.x.frame8[1]
+        assert L.rm_render_frame(*args, C.byref(bad), 1, 1, stream) == -3
+        bad.world, bad.rank = 1, 1
+        assert L.rm_render_frame(*args, C.byref(bad), 1, 1, stream) == -3
+        p64 = be.frame_params(tr.rows)
+        p64.precision = _abi.RM_FP64
+        assert L.rm_render_frame(be.handle, C.byref(p64), tr.rgb.data_ptr(), None, tr.dmax.data_ptr(), C.byref(tr.peer.x), 1, 1, stream) == -3
+        h64 = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        assert L.rm_peer_alloc(0, C.byref(ptr), h64) == -3
+        assert L.rm_peer_close(None) == 0 and L.rm_peer_free(None) == 0
+    finally:
+        tr.close()
+
+
+def _two_rank_worker(rank, world, port, out_path, name, w, h):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import rusty_marcher_b200 as rm
+    from rusty_marcher_b200 import tiled
+    try:
+        rm.init(rank)
+        scene = workloads.scene(name)
+        be = tiled.CudaBackend(scene, rm.create_renderer(1.5, h, w), w, h, dev)
+        tr = tiled.TiledRenderer(be, w, h, dev, exchange="peer")
+        frames = []
+        for _ in range(5):                                     # back to back: exercises the double buffering
+            f = tr.render()
+            if rank == 0:
+                frames.append(f.clone())
+        torch.cuda.synchronize()
+        tr.peer.status()
+        if rank == 0:
+            for f in frames[1:]:
+                assert torch.equal(f, frames[0])
+            np.save(out_path, frames[0].cpu().numpy())
+        tr.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,w,h", [("cornell_box", 1920, 1080), ("demo", 800, 600)])
+def test_peer_exchange_across_gpus_equals_single_gpu_frame(rm_gpu, tmp_path, name, w, h):
+    """world = all visible GPUs (>= 2): the frame assembled on rank 0 by the kernels' peer stores is byte-identical to the
+    single-GPU frame.  Skipped on a one-GPU box (the driver's round-end run); run with gpurun --gpus 2."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    whole = gpu_render(rm_gpu, workloads.scene(name), w, h, "f32")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "frame.npy")
+    mp.spawn(_two_rank_worker, args=(world, port, out, name, w, h), nprocs=world, join=True)
+    assert np.array_equal(np.load(out), whole["rgb8"])
