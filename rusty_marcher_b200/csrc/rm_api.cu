@@ -153,6 +153,7 @@ template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
     dp.ds.mat_a = static_cast<const rm::R4<R>*>(dp.mat_a);
     dp.ds.mat_b = static_cast<const rm::R4<R>*>(dp.mat_b);
     dp.ds.mat_f = dp.mat_f;
+    dp.ds.n_mat = ps.n_prims;
     se.n_prims = ps.n_prims;
     dp.ready = true;
     return RM_OK;

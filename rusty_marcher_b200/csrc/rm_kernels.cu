@@ -303,16 +303,19 @@ prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, con
 //      leftovers across the CTA for one last round on full warps.
 // The channel maximum (framebuffer.rs:58-69) is kept per thread across all its strips and reduced once:
 // REDUX over the warp, shared atomic, one global atomic per CTA.
+#ifndef RM_K1_MIN_BLOCKS
+#define RM_K1_MIN_BLOCKS 3                                      // resident CTAs per SM the register allocation aims at
+#endif
 constexpr int kFastTile = 32;
 constexpr int kStripRows = 4, kStripsPerTile = kFastTile / kStripRows;
 constexpr int kWarpQueue = kFastTile * kStripRows + 32;         // one strip of hits on top of a partial round
 template <bool kSmem>
-__global__ void __launch_bounds__(kBlock, 3)
+__global__ void __launch_bounds__(kBlock, RM_K1_MIN_BLOCKS)
 render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
                    float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order, const int* __restrict__ order2,
                    unsigned char* rgb8, const PeerLink link, unsigned char* rgb8_out, const int normalise,
-                   const int zero_foreign) {
+                   const int zero_foreign, const int stage_mat) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     __shared__ int cta_max;
     __shared__ float frame_max;
@@ -332,6 +335,16 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         uint4* dst = reinterpret_cast<uint4*>(smem_raw);
         const int n16 = L.bytes / 16;
         for (int i = threadIdx.x; i < n16; i += kBlock) dst[i] = __ldg(src + i);
+        if (stage_mat) {                                        // materials behind the raster records: mat_a | mat_b | mat_f
+            uint4* m = dst + n16 + L.n_tri * 4;
+            const uint4* a = reinterpret_cast<const uint4*>(ds.mat_a);
+            const uint4* b = reinterpret_cast<const uint4*>(ds.mat_b);
+            for (int i = threadIdx.x; i < ds.n_mat; i += kBlock) {
+                m[i] = __ldg(a + i);
+                m[ds.n_mat + i] = __ldg(b + i);
+                reinterpret_cast<int*>(m + 2 * ds.n_mat)[i] = __ldg(ds.mat_f + i);
+            }
+        }
     }
     pdl_wait_primary();                                         // K0 has retired: raster records, schedule, zeroed maximum
     if (threadIdx.x == 0 && blockIdx.x == 0 && link.world > 0) link.box[link.rank][56] = now_ns();  // stamp: start of the work
@@ -361,6 +374,11 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     fv.mat_a = ds.mat_a;
     fv.mat_b = ds.mat_b;
     fv.mat_f = ds.mat_f;
+    if (kSmem && stage_mat) {
+        fv.mat_a = reinterpret_cast<const R4<float>*>(smem_raw + L.bytes + (size_t)L.n_tri * 64);
+        fv.mat_b = fv.mat_a + ds.n_mat;
+        fv.mat_f = reinterpret_cast<const int*>(fv.mat_b + ds.n_mat);
+    }
     fv.lgt_p = reinterpret_cast<const R4<float>*>(base + L.off_lgt_p);
     fv.lgt_c = reinterpret_cast<const R4<float>*>(base + L.off_lgt_c);
     fv.n_lgt = L.n_lgt;
@@ -560,7 +578,10 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
             // rows is final, and so are its float rows and (rank 0) the cleared bytes of the 8-bit frame
             if (link.world > 0) {
                 link.box[link.rank][57] = now_ns();                                                 // stamp: rendering done
-                __threadfence_system();
+                // Rank 0's cleared bytes must be in place before a peer, having seen this word, stores its tiles over them:
+                // system-scope fence (cumulative over the CTAs counted above).  Nothing a peer touches depends on the
+                // other ranks' stores, and a fence.sys costs microseconds.
+                if (link.world > 1 && link.rank == 0) __threadfence_system();
                 publish_max(link, __int_as_float(atomicMax(reinterpret_cast<int*>(dmax), 0)));
             }
         }
@@ -716,7 +737,11 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     if (zero_foreign) rgb8 = ex->rgb8_zero;                     // scheduled or not: rank 0 clears the foreign bands
     if (ex && ex->ev_prepared) cudaEventRecord(ex->ev_prepared, stream);      // (an event here gives up the overlap of K1's launch with K0)
     if (launches) (*launches)++;
-    const size_t smem = (size_t)ds.lay.bytes + (size_t)n_tri * 64;
+    // shared memory: scene blob | raster records of every fast-path triangle | materials (if they fit as well)
+    const size_t smem_geo = (size_t)ds.lay.bytes + (size_t)ds.lay.n_tri * 64;
+    const size_t smem_mat = (((size_t)ds.n_mat * 36) + 15) / 16 * 16;
+    const int stage_mat = smem_geo + smem_mat <= (size_t)kSmemLimit ? 1 : 0;
+    const size_t smem = smem_geo + (stage_mat ? smem_mat : 0);
     const float inv_tiles_x = 1.0f / (float)tiles_x;
     static int sm_count = 0;
     cudaError_t e;
@@ -739,14 +764,16 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     const bool use_smem = smem <= (size_t)kSmemLimit;
     auto k = use_smem ? render_fast_kernel<true> : render_fast_kernel<false>;
     cfg.dynamicSmemBytes = use_smem ? smem : 0;
-    if (cfg.dynamicSmemBytes > 48 * 1024 &&
-        (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes)) != cudaSuccess)
-        return e;
+    static bool opted_in = false;                              // static + dynamic shared memory may exceed 48 KB: opt in once
+    if (use_smem && !opted_in) {
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
+        opted_in = true;
+    }
     int occ = 1;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;
     cfg.gridDim = dim3(std::min(n_tiles, sm_count * std::max(occ, 1)));
     if ((e = cudaLaunchKernelEx(&cfg, k, ds, fp, cull_i, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order2, rgb8,
-                                link, rgb8_out, normalise, zero_foreign)) != cudaSuccess)
+                                link, rgb8_out, normalise, zero_foreign, stage_mat)) != cudaSuccess)
         return e;
     if (launches) (*launches)++;
     if (ex && ex->ev_rendered) cudaEventRecord(ex->ev_rendered, stream);

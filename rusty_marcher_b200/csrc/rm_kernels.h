@@ -14,6 +14,7 @@ template <typename R> struct DeviceScene {
     const R4<R>* mat_a = nullptr;
     const R4<R>* mat_b = nullptr;
     const int* mat_f = nullptr;
+    int n_mat = 0;                                   // entries of mat_a / mat_b / mat_f (= primitives of the scene)
     const int* order[2] = {nullptr, nullptr};        // [0] every primitive, [1] after culling
     const int* order_shape[2] = {nullptr, nullptr};
     int n_order[2] = {0, 0};

@@ -52,9 +52,12 @@ RM_HD float fast_div(float a, float b) {
     asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
 }
-// MUFU.RSQ (2 ulp) + one Newton step: 1/sqrt(a) to ~1 ulp in a handful of instructions instead of IEEE sqrt + IEEE divide
+// MUFU.RSQ (2 ulp) + one Newton step: 1/sqrt(a) to ~1 ulp in four instructions instead of IEEE sqrt + IEEE divide.
+// rsqrt.approx.ftz is the bare MUFU (rsqrtf() wraps it in a rescue sequence for subnormal arguments; the arguments here
+// are squared lengths of scene-scale vectors).
 RM_HD float fast_rsqrt(float a) {
-    const float r = rsqrtf(a);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
     return r * fmaf(-0.5f * a * r, r, 1.5f);
 }
 #else
@@ -70,6 +73,19 @@ RM_HD float pow_nonneg(float x, float e) {
     const int n = (int)e;
     if ((float)n == e && n >= 0 && n <= 1024) {
         float r = 1.f;
+        if (n < 128) {
+            // straight-line square-and-multiply: six squarings, then the factors picked by the bits of n (no loop
+            // counter, no branch; n is the same for every pixel of a material)
+            const float x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8, x32 = x16 * x16, x64 = x32 * x32;
+            if (n & 1) r *= x;
+            if (n & 2) r *= x2;
+            if (n & 4) r *= x4;
+            if (n & 8) r *= x8;
+            if (n & 16) r *= x16;
+            if (n & 32) r *= x32;
+            if (n & 64) r *= x64;
+            return r;
+        }
         for (int k = n; k; k >>= 1) {
             if (k & 1) r *= x;
             x *= x;

@@ -362,6 +362,7 @@ template <typename R, bool S, typename SC>
 RM_HD Vec3<R> direct_lighting(const SC& sc, const Vec3<R> origin, const Vec3<R> point, const Vec3<R> normal,
                               const R4<R> ma, const R4<R> mb, Counters<S>& st) {
     Vec3<R> acc = {R(0), R(0), R(0)};
+    const Vec3<R> to_viewer = normalized(origin - point);                                         // renderer.rs:149 (the same for every light)
     for (int l = 0; l < sc.n_lgt; l++) {
         R4<R> lp = sc.lgt_p[l];
         R4<R> lc4 = sc.lgt_c[l];
@@ -378,7 +379,6 @@ RM_HD Vec3<R> direct_lighting(const SC& sc, const Vec3<R> origin, const Vec3<R> 
         Vec3<R> kd = {ma.x, ma.y, ma.z};
         acc = acc + scaled(scaled(lc * kd, diffusion), lp.w);                                     // renderer.rs:181-183
         Vec3<R> reflected = reflect(-light_dir, normal);                                          // renderer.rs:144-145
-        Vec3<R> to_viewer = normalized(origin - point);                                           // renderer.rs:149
         R sf = Num<R>::max_(dot(reflected, to_viewer), R(0));                                     // renderer.rs:150
         R specular = Num<R>::pow_(sf * mb.x, mb.y);                                               // renderer.rs:186-188
         acc = acc + scaled(lc, specular);                                                         // renderer.rs:189
