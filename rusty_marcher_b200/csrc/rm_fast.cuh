@@ -183,6 +183,112 @@ struct FastView {
         return false;
     }
 
+    // Branch-free tri_inside: the predicate of stage 2 as a value, for the paired shadow rays below (a garbage quotient
+    // of a near-parallel ray is masked by the |d.n| test; NaNs compare false).
+    static RM_HD bool tri_inside_pred(const R4<float> b, const R4<float> c, const R4<float> l, const Vec3<float> o,
+                                      const Vec3<float> d, const float dp, const float num) {
+        const float t = fast_div(num, dp);                     // triangle.rs:62
+        const float qx = fmaf(t, d.x, o.x - b.x), qy = fmaf(t, d.y, o.y - b.y);
+        const float e0 = fmaf(b.z, qx, b.w * qy);
+        const float e1 = fmaf(c.x, qx, fmaf(c.y, qy, c.z));
+        const float e2 = fmaf(c.w, qx, l.x * qy);
+        return (fabsf(dp) > l.y) & (fminf(fminf(e0, e1), e2) > 0.f);   // triangle.rs:57, 72-76
+    }
+
+    // The shadow rays of TWO lights from one surface point together (renderer.rs:174-177, twice): every triangle record is
+    // loaded once and tested against both rays, which puts two independent dependency chains per lane in flight -- the
+    // shading stage is bound by instruction latency, not by issue slots.  The same arithmetic per (ray, triangle) as
+    // anyhit(), so the same decisions.  `need`: bit 0 / bit 1 = ray A / B exists; returns the rays that are blocked.
+    RM_HD unsigned anyhit2(const Vec3<float> oA, const Vec3<float> dA, const Vec3<float> oB, const Vec3<float> dB,
+                           unsigned need) const {
+        unsigned blocked = 0;
+        if (n_sph + n_poly > 0) {                               // spheres and n-gons: ray by ray (any-hit: the order of the
+            Counters<false> st;                                 // primitives does not matter for the boolean)
+            Cand<float> c;
+            for (int r = 0; r < 2; r++) {
+                if (!(need >> r & 1)) continue;
+                const Vec3<float> o = r ? oB : oA, d = r ? dB : dA;
+                bool hit = false;
+                for (int i = 0; i < n_sph && !hit; i++) hit = sphere_intersect<false>(sph[i], o, d, c, st);
+                for (int k = 0; k < n_poly && !hit; k++) {
+                    const int i = poly_slot[k];
+                    hit = plane_intersect<false>(pln_n[i], pln_c[i], pln_v[i], vert, o, d, c, st);
+                }
+                if (hit) blocked |= 1u << r;
+            }
+            need &= ~blocked;
+        }
+        const R4<float>* g = tri_g;
+        int j = 0;
+        for (; j + 2 <= n_tri && need; j += 2, g += 8) {
+            const R4<float> a0 = g[0], a1 = g[4];
+            float dpA0, nmA0, dpB0, nmB0, dpA1, nmA1, dpB1, nmB1;
+            const bool fA0 = tri_front(a0, oA, dA, dpA0, nmA0), fB0 = tri_front(a0, oB, dB, dpB0, nmB0);
+            const bool fA1 = tri_front(a1, oA, dA, dpA1, nmA1), fB1 = tri_front(a1, oB, dB, dpB1, nmB1);
+            const unsigned f0 = ((unsigned)fA0 | (unsigned)fB0 << 1) & need, f1 = ((unsigned)fA1 | (unsigned)fB1 << 1) & need;
+            if (f0 | f1) {
+                if (f0) {
+                    const R4<float> b = g[1], c = g[2], l = g[3];
+                    const unsigned in = (unsigned)tri_inside_pred(b, c, l, oA, dA, dpA0, nmA0) |
+                                        (unsigned)tri_inside_pred(b, c, l, oB, dB, dpB0, nmB0) << 1;
+                    blocked |= in & f0;
+                }
+                if (f1) {
+                    const R4<float> b = g[5], c = g[6], l = g[7];
+                    const unsigned in = (unsigned)tri_inside_pred(b, c, l, oA, dA, dpA1, nmA1) |
+                                        (unsigned)tri_inside_pred(b, c, l, oB, dB, dpB1, nmB1) << 1;
+                    blocked |= in & f1;
+                }
+                need &= ~blocked;
+            }
+        }
+        if (j < n_tri && need) {
+            const R4<float> a0 = g[0];
+            float dpA, nmA, dpB, nmB;
+            const bool fA = tri_front(a0, oA, dA, dpA, nmA), fB = tri_front(a0, oB, dB, dpB, nmB);
+            const unsigned f0 = ((unsigned)fA | (unsigned)fB << 1) & need;
+            if (f0) {
+                const R4<float> b = g[1], c = g[2], l = g[3];
+                const unsigned in = (unsigned)tri_inside_pred(b, c, l, oA, dA, dpA, nmA) |
+                                    (unsigned)tri_inside_pred(b, c, l, oB, dB, dpB, nmB) << 1;
+                blocked |= in & f0;
+            }
+        }
+        return blocked;
+    }
+
+    // renderer.rs:138-193 for the production path: lights taken two at a time (anyhit2), contributions added in the
+    // reference's order (light l before light l + 1).
+    template <bool S> RM_HD Vec3<float> direct(const Vec3<float> origin, const Vec3<float> point, const Vec3<float> normal,
+                                               const R4<float> ma, const R4<float> mb, Counters<S>&) const {
+        Vec3<float> acc = {0.f, 0.f, 0.f};
+        const Vec3<float> to_viewer = normalized(origin - point);                                  // renderer.rs:149
+        const Vec3<float> kd = {ma.x, ma.y, ma.z};
+        for (int l0 = 0; l0 < n_lgt; l0 += 2) {
+            const bool two = l0 + 1 < n_lgt;
+            const R4<float> lpA = lgt_p[l0], lpB = lgt_p[two ? l0 + 1 : l0];
+            const Vec3<float> ldA = normalized(Vec3<float>{lpA.x - point.x, lpA.y - point.y, lpA.z - point.z});   // renderer.rs:166
+            const Vec3<float> ldB = normalized(Vec3<float>{lpB.x - point.x, lpB.y - point.y, lpB.z - point.z});
+            const float sideA = dot(ldA, normal), sideB = dot(ldB, normal);
+            const float offA = sideA < 0.f ? -1e-3f : 1e-3f, offB = sideB < 0.f ? -1e-3f : 1e-3f;    // renderer.rs:168-172
+            const Vec3<float> soA = axpy(point, normal, offA), soB = axpy(point, normal, offB);
+            const unsigned blocked = anyhit2(soA, ldA, soB, ldB, two ? 3u : 1u);                     // renderer.rs:174-177
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                if ((r && !two) || (blocked >> r & 1)) continue;
+                const R4<float> lp = r ? lpB : lpA;
+                const Vec3<float> ld = r ? ldB : ldA;
+                const float side = r ? sideB : sideA;
+                const Vec3<float> lc = xyz(lgt_c[l0 + r]);
+                acc = acc + scaled(scaled(lc * kd, fmaxf(side, 0.f)), lp.w);                          // renderer.rs:138-140, 181-183
+                const Vec3<float> reflected = reflect(-ld, normal);                                   // renderer.rs:144-145
+                const float sf = fmaxf(dot(reflected, to_viewer), 0.f);                               // renderer.rs:150
+                acc = acc + scaled(lc, pow_nonneg(sf * mb.x, mb.y));                                  // renderer.rs:186-189
+            }
+        }
+        return scaled(acc, ma.w);                                                                     // renderer.rs:192
+    }
+
     RM_HD void surface(HitRec<float>& h, const Vec3<float> o, const Vec3<float> d, Vec3<float>& normal) const {
         if (h.slot < n_sph) {
             sphere_point_normal(sph[h.slot], o, d, h.p, h.p, normal);

@@ -303,14 +303,27 @@ prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, con
 //      leftovers across the CTA for one last round on full warps.
 // The channel maximum (framebuffer.rs:58-69) is kept per thread across all its strips and reduced once:
 // REDUX over the warp, shared atomic, one global atomic per CTA.
-#ifndef RM_K1_MIN_BLOCKS
-#define RM_K1_MIN_BLOCKS 3                                      // resident CTAs per SM the register allocation aims at
+// CTA shape of the render kernel.  The shading stage wants ~116 registers to run without spills, and it is bound by
+// instruction latency and spill traffic rather than by the number of resident warps: measured on the cornell / demo /
+// dodecahedron frames (render phase, us) -- 3 CTAs x 8 warps at 80 registers 55 / 205 / 49, 5 x 4 warps at 96 registers
+// 54 / 194 / 44, 2 x 8 warps at 128 registers 53 / 174 / 40 (gpurun_out/ab_r2a.log).  Hence two CTAs of eight warps.
+#ifndef RM_K1_BLOCK
+#define RM_K1_BLOCK 256
 #endif
+#ifndef RM_K1_MIN_BLOCKS
+#define RM_K1_MIN_BLOCKS 2                                      // resident CTAs per SM the register allocation aims at
+#endif
+constexpr int kFastBlock = RM_K1_BLOCK;
 constexpr int kFastTile = 32;
 constexpr int kStripRows = 4, kStripsPerTile = kFastTile / kStripRows;
 constexpr int kWarpQueue = kFastTile * kStripRows + 32;         // one strip of hits on top of a partial round
+#ifdef RM_K1_MAXREG
+#define RM_K1_BOUNDS __maxnreg__(RM_K1_MAXREG)
+#else
+#define RM_K1_BOUNDS __launch_bounds__(kFastBlock, RM_K1_MIN_BLOCKS)
+#endif
 template <bool kSmem>
-__global__ void __launch_bounds__(kBlock, RM_K1_MIN_BLOCKS)
+__global__ void RM_K1_BOUNDS
 render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
                    float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order, const int* __restrict__ order2,
@@ -319,10 +332,10 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     extern __shared__ __align__(32) unsigned char smem_raw[];
     __shared__ int cta_max;
     __shared__ float frame_max;
-    __shared__ int leftover[kBlock / 32];
+    __shared__ int leftover[kFastBlock / 32];
     __shared__ int fill_off[96];                                // float offset of each 16-byte chunk of a strip (see fill_strip)
-    __shared__ float4 pool[kBlock];                             // pooled leftovers of the eight warp queues (< 32 each)
-    __shared__ float4 queue[kBlock / 32][kWarpQueue];           // {t, slot, id, x | y << 16}
+    __shared__ float4 pool[kFastBlock];                             // pooled leftovers of the eight warp queues (< 32 each)
+    __shared__ float4 queue[kFastBlock / 32][kWarpQueue];           // {t, slot, id, x | y << 16}
     const BlobLayout& L = ds.lay;
     const int n_tri = tri_count(L, cull != 0);
 
@@ -334,12 +347,12 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         const uint4* src = reinterpret_cast<const uint4*>(ds.blob);
         uint4* dst = reinterpret_cast<uint4*>(smem_raw);
         const int n16 = L.bytes / 16;
-        for (int i = threadIdx.x; i < n16; i += kBlock) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < n16; i += kFastBlock) dst[i] = __ldg(src + i);
         if (stage_mat) {                                        // materials behind the raster records: mat_a | mat_b | mat_f
             uint4* m = dst + n16 + L.n_tri * 4;
             const uint4* a = reinterpret_cast<const uint4*>(ds.mat_a);
             const uint4* b = reinterpret_cast<const uint4*>(ds.mat_b);
-            for (int i = threadIdx.x; i < ds.n_mat; i += kBlock) {
+            for (int i = threadIdx.x; i < ds.n_mat; i += kFastBlock) {
                 m[i] = __ldg(a + i);
                 m[ds.n_mat + i] = __ldg(b + i);
                 reinterpret_cast<int*>(m + 2 * ds.n_mat)[i] = __ldg(ds.mat_f + i);
@@ -352,7 +365,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         uint4* dst = reinterpret_cast<uint4*>(smem_raw);
         const int n16 = L.bytes / 16;
         const uint4* rsrc = reinterpret_cast<const uint4*>(ds.tri_r);
-        for (int i = threadIdx.x; i < n_tri * 4; i += kBlock) dst[n16 + i] = rsrc[i];
+        for (int i = threadIdx.x; i < n_tri * 4; i += kFastBlock) dst[n16 + i] = rsrc[i];
         base = smem_raw;
         tri_r = reinterpret_cast<const R4<float>*>(smem_raw + L.bytes);
     }
@@ -435,8 +448,8 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     // tiles run out (all of it for warps that never drew a busy strip) is filled in phase 2.
     const int n_empty = n_tiles - n_busy;
     const int n_busy_strips = n_busy * kStripsPerTile;
-    const int n_warps = gridDim.x * (kBlock / 32);
-    int next_empty = n_busy + blockIdx.x * (kBlock / 32) + warp;   // schedule position of this warp's next empty tile
+    const int n_warps = gridDim.x * (kFastBlock / 32);
+    int next_empty = n_busy + blockIdx.x * (kFastBlock / 32) + warp;   // schedule position of this warp's next empty tile
     int empty_acc = 0;
 
     // ---- phase 0 (rank 0 of a multi-GPU frame only)
@@ -449,7 +462,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         const int per_band = fp.width * 96 / 512;                  // W is a multiple of 32: 6 W / 32 pieces
         const int n_foreign = P - (P - f + S - 1) / S;
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int c = blockIdx.x * (kBlock / 32) + warp; c < n_foreign * per_band; c += n_warps) {
+        for (int c = blockIdx.x * (kFastBlock / 32) + warp; c < n_foreign * per_band; c += n_warps) {
             const int fb = c / per_band, piece = c - fb * per_band;
             const int g = fb / (S - 1), r = fb - g * (S - 1);
             const int band = g * S + (r < f ? r : r + 1);
@@ -529,7 +542,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
             __syncthreads();
             int before = 0, total = 0;
 #pragma unroll
-            for (int w = 0; w < kBlock / 32; w++) {
+            for (int w = 0; w < kFastBlock / 32; w++) {
                 const int c = leftover[w];
                 if (w < warp) before += c;
                 total += c;
@@ -599,18 +612,38 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         if (blockIdx.x == 0 && threadIdx.x == 0) link.box[link.rank][58] = now_ns();                // stamp: maxima gathered
     }
     __threadfence();
-    for (int t = blockIdx.x; t < n_busy; t += gridDim.x) {
-        const int tile = !order ? t : t < n_full ? __ldg(order + t) : __ldg(order2 + (t - n_full));
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const size_t p0 = (size_t)(fp.row_begin + ty * fp.row_step - fp.buf_row0) * fp.width + tx * 32;
+    // Work unit: a 32x4 strip of a busy tile = 96 float4 in, 96 words out, three per lane; a warp takes four units per
+    // round and issues their twelve loads before the first conversion (the phase is bound by L2 latency, not by bytes).
+    {
+        const int n_units = n_busy * kStripsPerTile;
+        const int gw = blockIdx.x * (kFastBlock / 32) + warp;
+        for (int u0 = gw; u0 < n_units; u0 += 4 * n_warps) {
+            float4 q[4][3];
+            size_t base_v[4];
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const int c = threadIdx.x + 256 * i;                // 768 float4 per tile: 32 rows x 24
-            const int row = c / 24, col = c - row * 24;
-            const size_t v = 3 * (p0 + (size_t)row * fp.width) + 4 * col;
-            const float4 q = __ldcg(reinterpret_cast<const float4*>(rgb + v));
-            const unsigned w = Tone<float>::q(q.x, inv) | (Tone<float>::q(q.y, inv) << 8) | (Tone<float>::q(q.z, inv) << 16) | (Tone<float>::q(q.w, inv) << 24);
-            *reinterpret_cast<unsigned*>(rgb8_out + v) = w;
+            for (int k = 0; k < 4; k++) {
+                const int u = u0 + k * n_warps;
+                base_v[k] = 0;
+                if (u < n_units) {
+                    const int t = u / kStripsPerTile, strip = u - t * kStripsPerTile;
+                    const int tile = !order ? t : t < n_full ? __ldg(order + t) : __ldg(order2 + (t - n_full));
+                    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                    base_v[k] = 3 * ((size_t)(fp.row_begin + ty * fp.row_step + strip * kStripRows - fp.buf_row0) * fp.width + tx * 32);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) q[k][i] = __ldcg(reinterpret_cast<const float4*>(rgb + base_v[k] + fill_off[lane + 32 * i]));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (u0 + k * n_warps < n_units) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        const float4 f = q[k][i];
+                        const unsigned w = Tone<float>::q(f.x, inv) | (Tone<float>::q(f.y, inv) << 8) | (Tone<float>::q(f.z, inv) << 16) | (Tone<float>::q(f.w, inv) << 24);
+                        *reinterpret_cast<unsigned*>(rgb8_out + base_v[k] + fill_off[lane + 32 * i]) = w;
+                    }
+                }
+            }
         }
     }
     signal_frame_done(link, ctr + 10);
@@ -755,7 +788,7 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(kBlock);
+    cfg.blockDim = dim3(kFastBlock);
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
@@ -770,7 +803,7 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
         opted_in = true;
     }
     int occ = 1;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kFastBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;
     cfg.gridDim = dim3(std::min(n_tiles, sm_count * std::max(occ, 1)));
     if ((e = cudaLaunchKernelEx(&cfg, k, ds, fp, cull_i, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order2, rgb8,
                                 link, rgb8_out, normalise, zero_foreign, stage_mat)) != cudaSuccess)
