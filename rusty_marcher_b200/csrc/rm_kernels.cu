@@ -225,19 +225,22 @@ prepare_raster_kernel(const double* __restrict__ tri_src, const int n_tri, const
 }
 
 // K0 for scenes made of (few) triangles only: the raster records as above, and in the same launch the
-// tile schedule of the render kernel.  One thread per 32x32 tile bounds every triangle against the tile
-// (tri_may_touch: exact, see rm_fast.cuh); tiles some triangle may touch are "busy" and go to the front of
+// tile schedule of the render kernel.  Eight lanes per 32x32 tile bound the triangles against the tile, one
+// triangle per lane and round (tri_may_touch: exact, see rm_fast.cuh); tiles some triangle may touch are "busy" and go to the front of
 // the schedule, the others are provably black and go to the back.  The render kernel hands the busy
 // tiles out first (longest work first, so the cheap tiles fill the tail) and only stores zeros for the rest.
 constexpr int kClassifyMaxTris = 256;
-__global__ void __launch_bounds__(64)
+constexpr int kClassifyBlock = 512, kClassifyLanes = 8;         // 8 lanes per tile: 64 tiles per block
+__global__ void __launch_bounds__(kClassifyBlock)
 prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, const double cx, const double cy, const double cz,
                         R4<float>* __restrict__ tri_r, const FrameParams<float> fp, const int tiles_x, const int n_tiles,
                         int* __restrict__ order, int* __restrict__ order2, int* __restrict__ ctr, float* __restrict__ dmax_zero) {
     __shared__ R4<float> rec[4 * kClassifyMaxTris];
+    __shared__ int cnt[3], base[3];
     const double cam[3] = {cx, cy, cz};
     pdl_launch_dependents();
     if (blockIdx.x == 0 && threadIdx.x == 0 && dmax_zero) *dmax_zero = 0.f;
+    if (threadIdx.x < 3) cnt[threadIdx.x] = 0;
     for (int j = threadIdx.x; j < n_tri; j += blockDim.x) {      // every block rebuilds the (few) records; block 0 publishes them
         R4<float> out[4];
         prepare_raster(tri_src + (size_t)j * kTriSrcDoubles, cam, out);
@@ -248,38 +251,39 @@ prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, con
         }
     }
     __syncthreads();
-    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
-    bool busy = false, full = false;
+    // a tile is tested by kClassifyLanes lanes, lane s against triangles s, s + 8, ...; the group's verdict is read off a ballot
+    const int lane = threadIdx.x & 31, sub = lane & (kClassifyLanes - 1);
+    const int tile = (blockIdx.x * kClassifyBlock + threadIdx.x) / kClassifyLanes;
+    bool touch = false, cover = false;
     if (tile < n_tiles) {
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const int x0 = tx * 32, y0 = fp.row_begin + ty * fp.row_step;
         const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + 31), Ya = pixel_Y(fp, y0), Yb = pixel_Y(fp, y0 + 31);
-        for (int j = 0; j < n_tri && !full; j++) {
+        for (int j = sub; j < n_tri && !cover; j += kClassifyLanes) {
             if (tri_may_touch(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3], Xa, Xb, Ya, Yb)) {
-                busy = true;
-                full = tri_covers(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3], Xa, Xb, Ya, Yb);
+                touch = true;
+                cover = tri_covers(rec[4 * j], rec[4 * j + 1], rec[4 * j + 2], rec[4 * j + 3], Xa, Xb, Ya, Yb);
             }
         }
     }
-    // Three classes, one atomic per warp and class: fully covered tiles (1024 hits to shade: the longest jobs) at the
-    // front of `order`, partially covered ones in `order2` (handed out after the full ones), empty ones from the back
-    // of `order`.
-    const int lane = threadIdx.x & 31;
-    const unsigned lane_lt = (1u << lane) - 1u;
-    const bool part = busy && !full, empty = tile < n_tiles && !busy;
-    const unsigned mf = __ballot_sync(0xffffffffu, full), mp = __ballot_sync(0xffffffffu, part), me = __ballot_sync(0xffffffffu, empty);
-    int base_f = 0, base_p = 0, base_e = 0;
-    if (lane == 0) {
-        if (mf) base_f = atomicAdd(ctr + 1, __popc(mf));
-        if (mp) base_p = atomicAdd(ctr + 5, __popc(mp));
-        if (me) base_e = atomicAdd(ctr + 2, __popc(me));
+    const unsigned group = ((1u << kClassifyLanes) - 1u) << (lane & ~(kClassifyLanes - 1));
+    const bool busy = (__ballot_sync(0xffffffffu, touch) & group) != 0u;
+    const bool full = (__ballot_sync(0xffffffffu, cover) & group) != 0u;
+    // Three classes: fully covered tiles (1024 hits to shade: the longest jobs) at the front of `order`, partially covered
+    // ones in `order2` (handed out after the full ones), empty ones from the back of `order`.  The group leaders take a
+    // place within the block from shared counters; three global atomics per block reserve the block's ranges.
+    const bool leader = sub == 0 && tile < n_tiles;
+    const int cls = full ? 0 : busy ? 1 : 2;
+    int local = 0;
+    if (leader) local = atomicAdd(&cnt[cls], 1);
+    __syncthreads();
+    if (threadIdx.x < 3 && cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(ctr + (threadIdx.x == 0 ? 1 : threadIdx.x == 1 ? 5 : 2), cnt[threadIdx.x]);
+    __syncthreads();
+    if (leader) {
+        if (cls == 0) order[base[0] + local] = tile;
+        else if (cls == 1) order2[base[1] + local] = tile;
+        else order[n_tiles - 1 - (base[2] + local)] = tile;
     }
-    base_f = __shfl_sync(0xffffffffu, base_f, 0);
-    base_p = __shfl_sync(0xffffffffu, base_p, 0);
-    base_e = __shfl_sync(0xffffffffu, base_e, 0);
-    if (full) order[base_f + __popc(mf & lane_lt)] = tile;
-    else if (part) order2[base_p + __popc(mp & lane_lt)] = tile;
-    else if (empty) order[n_tiles - 1 - (base_e + __popc(me & lane_lt))] = tile;
 }
 
 // K1, FP32 production kernel (rm_fast.cuh).  Persistent and warp-granular: the grid is (SMs x resident
@@ -753,7 +757,7 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * fp.n_bands;
     const bool classify = ds.lay.n_sph + poly_count(ds.lay, cull) == 0 && n_tri <= kClassifyMaxTris && n_tiles <= ds.tile_order_cap / 2;
     if (classify)
-        prepare_classify_kernel<<<(n_tiles + 63) / 64, 64, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r,
+        prepare_classify_kernel<<<(n_tiles * kClassifyLanes + kClassifyBlock - 1) / kClassifyBlock, kClassifyBlock, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r,
                                                                          fp, tiles_x, n_tiles, ds.tile_order, ds.tile_order + ds.tile_order_cap / 2, ds.ctr,
                                                                          ex && ex->zero_dmax ? dmax : nullptr);
     else
