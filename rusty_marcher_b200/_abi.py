@@ -159,11 +159,12 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing:
+    path = os.environ.get("RM_B200_LIB") or _build.LIB           # RM_B200_LIB: another build of the same library (A/B runs)
+    if build_if_missing and path == _build.LIB:
         _build.build()
-    if not os.path.exists(_build.LIB):
+    if not os.path.exists(path):
         raise RuntimeError("librm_b200.so is missing and could not be built; there is no CPU fallback")
-    L = C.CDLL(_build.LIB)
+    L = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(L, name)      # AttributeError if the library does not export a declared symbol
         fn.restype = res

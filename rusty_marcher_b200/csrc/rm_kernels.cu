@@ -319,13 +319,13 @@ prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, con
 #endif
 constexpr int kFastBlock = RM_K1_BLOCK;
 constexpr int kFastTile = 32;
-constexpr int kStripRows = 4, kStripsPerTile = kFastTile / kStripRows;
-constexpr int kWarpQueue = kFastTile * kStripRows + 32;         // one strip of hits on top of a partial round
+constexpr int kWarpQueue = kFastTile * 4 + 32;                  // one strip of hits on top of a partial round
 #ifdef RM_K1_MAXREG
 #define RM_K1_BOUNDS __maxnreg__(RM_K1_MAXREG)
 #else
 #define RM_K1_BOUNDS __launch_bounds__(kFastBlock, RM_K1_MIN_BLOCKS)
 #endif
+template <int kPx> struct PxTag { static constexpr int value = kPx; };
 template <bool kSmem>
 __global__ void RM_K1_BOUNDS
 render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
@@ -401,7 +401,6 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     fv.n_lgt = L.n_lgt;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lx = (lane & 7) * 4, ly = lane >> 3;
     const unsigned lane_lt = (1u << lane) - 1u;
     const bool rest = fv.n_sph + fv.n_poly > 0;
     // schedule: [0, n_full) fully covered tiles (order), [n_full, n_busy) partially covered (order2), [n_busy, n_tiles) empty (order)
@@ -428,21 +427,22 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     // With rgb8 given the strip's bytes of the 8-bit frame are zeroed as well: quantize(0 * 1/max) is 0 whatever the
     // maximum turns out to be (framebuffer.rs:71-82), so only the busy tiles are left for the tone-map kernel.  A row of
     // the strip is 96 bytes = 6 chunks of 16 bytes, the strip 24 chunks: one store of lanes 0..23.
-    auto fill_strip = [&](const size_t p0) {                    // p0: pixel index of the strip's first pixel
+    auto fill_rows = [&](const size_t p0, const int rows) {     // p0: pixel index of the first pixel; rows: 2 or 4
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         float* const strip0 = rgb + 3 * p0;
 #pragma unroll
-        for (int i = 0; i < 3; i++) __stcs(reinterpret_cast<float4*>(strip0 + fill_off[lane + 32 * i]), z);
-        if (rgb8 && lane < 24) __stcs(reinterpret_cast<uint4*>(rgb8 + 3 * p0 + (size_t)(lane / 6) * fp.width * 3 + (lane % 6) * 16), make_uint4(0u, 0u, 0u, 0u));
+        for (int i = 0; i < 3; i++)
+            if (lane + 32 * i < 24 * rows) __stcs(reinterpret_cast<float4*>(strip0 + fill_off[lane + 32 * i]), z);
+        if (rgb8 && lane < 6 * rows) __stcs(reinterpret_cast<uint4*>(rgb8 + 3 * p0 + (size_t)(lane / 6) * fp.width * 3 + (lane % 6) * 16), make_uint4(0u, 0u, 0u, 0u));
     };
-    auto fill_empty_tile = [&](const int tile) {
+    auto fill_empty_tile = [&](const int tile) {                // always in pieces of four rows, whatever the strip height
         const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);
         const int tx = tile - ty * tiles_x;
         const size_t p0 = (size_t)(fp.row_begin + ty * fp.row_step - fp.buf_row0) * fp.width + tx * kFastTile;
 #pragma unroll
-        for (int r = 0; r < kStripsPerTile; r++) {
-            fill_strip(p0 + (size_t)r * kStripRows * fp.width);
-            if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + p0 + (size_t)(r * kStripRows + ly) * fp.width + lx), make_int4(-1, -1, -1, -1));
+        for (int r = 0; r < 8; r++) {
+            fill_rows(p0 + (size_t)r * 4 * fp.width, 4);
+            if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + p0 + (size_t)(r * 4 + (lane >> 3)) * fp.width + (lane & 7) * 4), make_int4(-1, -1, -1, -1));
         }
     };
     // The empty tiles' stores are pure HBM traffic and must overlap the busy tiles' arithmetic instead of forming a
@@ -451,8 +451,15 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     // n_empty / n_busy_strips empty tiles per busy strip, carried in a fraction accumulator.  What is left when the busy
     // tiles run out (all of it for warps that never drew a busy strip) is filled in phase 2.
     const int n_empty = n_tiles - n_busy;
-    const int n_busy_strips = n_busy * kStripsPerTile;
-    const int n_warps = gridDim.x * (kFastBlock / 32);
+    const int n_warps_grid = gridDim.x * (kFastBlock / 32);
+    // Strip height (a strip is 32 pixels wide and kPx rows high: 32 lanes x kPx horizontally adjacent pixels of a thread in
+    // stage A).  Four rows amortise the record loads of stage A best, but a fully covered strip is then four shading rounds
+    // in a row on one warp, and on a GPU with few strips -- its share of a frame split over several GPUs, a sparsely
+    // covered frame -- the longest such chain sets the kernel's duration.  Two-row strips halve it.  Decided per launch
+    // from the schedule: four rows when there are at least two fully covered four-row strips per warp of the grid.
+    const bool tall = order && n_full * 8 >= 2 * n_warps_grid;
+    const int n_busy_strips = n_busy * (tall ? 8 : 16);
+    const int n_warps = n_warps_grid;
     int next_empty = n_busy + blockIdx.x * (kFastBlock / 32) + warp;   // schedule position of this warp's next empty tile
     int empty_acc = 0;
 
@@ -473,6 +480,10 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
             __stcs(reinterpret_cast<uint4*>(rgb8 + ((size_t)band * fp.width * 96 + (size_t)piece * 512)) + lane, z);
         }
     }
+    auto warp_loop = [&](auto px_tag) {
+    constexpr int kPx = decltype(px_tag)::value;
+    constexpr int kStripRows = kPx, kStripsPerTile = kFastTile / kStripRows, kRowLanes = 32 / kPx;
+    const int lx = (lane % kRowLanes) * kPx, ly = lane / kRowLanes;
     // ---- phase 1: busy tiles, dynamic.  phase 3 (below) reuses the shading code of the loop through `pooled`.
     for (int phase = 1;;) {
         if (phase == 1) {
@@ -490,10 +501,10 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                 const int tx = tile - ty * tiles_x;
                 const int x0 = tx * kFastTile, ys = fp.row_begin + ty * fp.row_step + strip * kStripRows;
                 const size_t px = (size_t)(ys + ly - fp.buf_row0) * fp.width + x0 + lx;
-                fill_strip((size_t)(ys - fp.buf_row0) * fp.width + x0);         // misses stay black; stage B overwrites the hits
+                fill_rows((size_t)(ys - fp.buf_row0) * fp.width + x0, kStripRows);         // misses stay black; stage B overwrites the hits
                 // stage A: primary visibility of this thread's 4 pixels
-                PrimaryState<4> ps;
-                primary_begin<4>(ps, fp, x0 + lx, ys + ly);
+                PrimaryState<kPx> ps;
+                primary_begin<kPx>(ps, fp, x0 + lx, ys + ly);
                 {
                     // the strip: pixels [x0, x0 + 31] x [ys, ys + 3]
                     const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + kFastTile - 1);
@@ -506,26 +517,22 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                         while (cm) {                            // uniform across the warp
                             const int jj = jb + __ffs(cm) - 1;
                             cm &= cm - 1;
-                            primary_tri<4>(ps, tri_r[4 * jj], tri_r[4 * jj + 1], tri_r[4 * jj + 2], tri_r[4 * jj + 3], fv.n_sph + jj);
+                            primary_tri<kPx>(ps, tri_r[4 * jj], tri_r[4 * jj + 1], tri_r[4 * jj + 2], tri_r[4 * jj + 3], fv.n_sph + jj);
                         }
                     }
-                    if (rest) primary_rest<4>(ps, fv, fp);
+                    if (rest) primary_rest<kPx>(ps, fv, fp);
                 }
-                if (prim_id) __stcs(reinterpret_cast<int4*>(prim_id + px), make_int4(ps.id[0], ps.id[1], ps.id[2], ps.id[3]));
-                // hits -> the warp's queue
-                const unsigned m0 = __ballot_sync(0xffffffffu, ps.slot[0] >= 0), m1 = __ballot_sync(0xffffffffu, ps.slot[1] >= 0);
-                const unsigned m2 = __ballot_sync(0xffffffffu, ps.slot[2] >= 0), m3 = __ballot_sync(0xffffffffu, ps.slot[3] >= 0);
-                if (m0 | m1 | m2 | m3) {
-                    const unsigned xy = (unsigned)(x0 + lx) | ((unsigned)(ys + ly) << 16);
-                    int qb = qn;
-                    if (ps.slot[0] >= 0) wq[qb + __popc(m0 & lane_lt)] = make_float4(ps.t[0], __int_as_float(ps.slot[0]), __int_as_float(ps.id[0]), __uint_as_float(xy));
-                    qb += __popc(m0);
-                    if (ps.slot[1] >= 0) wq[qb + __popc(m1 & lane_lt)] = make_float4(ps.t[1], __int_as_float(ps.slot[1]), __int_as_float(ps.id[1]), __uint_as_float(xy + 1));
-                    qb += __popc(m1);
-                    if (ps.slot[2] >= 0) wq[qb + __popc(m2 & lane_lt)] = make_float4(ps.t[2], __int_as_float(ps.slot[2]), __int_as_float(ps.id[2]), __uint_as_float(xy + 2));
-                    qb += __popc(m2);
-                    if (ps.slot[3] >= 0) wq[qb + __popc(m3 & lane_lt)] = make_float4(ps.t[3], __int_as_float(ps.slot[3]), __int_as_float(ps.id[3]), __uint_as_float(xy + 3));
-                    qn = qb + __popc(m3);
+                if (prim_id) {
+                    if (kPx == 4) __stcs(reinterpret_cast<int4*>(prim_id + px), make_int4(ps.id[0], ps.id[1], ps.id[kPx - 2], ps.id[kPx - 1]));
+                    else __stcs(reinterpret_cast<int2*>(prim_id + px), make_int2(ps.id[0], ps.id[1]));
+                }
+                // hits -> the warp's queue, pixel column by pixel column, compacted with ballot / popc
+                const unsigned xy = (unsigned)(x0 + lx) | ((unsigned)(ys + ly) << 16);
+#pragma unroll
+                for (int c = 0; c < kPx; c++) {
+                    const unsigned mc = __ballot_sync(0xffffffffu, ps.slot[c] >= 0);
+                    if (ps.slot[c] >= 0) wq[qn + __popc(mc & lane_lt)] = make_float4(ps.t[c], __int_as_float(ps.slot[c]), __int_as_float(ps.id[c]), __uint_as_float(xy + c));
+                    qn += __popc(mc);
                 }
                 __syncwarp();
                 if (next_empty < n_tiles) {
@@ -575,6 +582,9 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         if (phase == 3) break;
         __syncwarp();                                           // reads done before the next strip appends
     }
+    };
+    if (tall) warp_loop(PxTag<4>());
+    else warp_loop(PxTag<2>());
     // values are >= 0, so the integer order of the bit patterns is the float order
     const int wm = __reduce_max_sync(0xffffffffu, __float_as_int(m));
     if (lane == 0 && wm > 0) atomicMax(&cta_max, wm);
@@ -619,7 +629,8 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     // Work unit: a 32x4 strip of a busy tile = 96 float4 in, 96 words out, three per lane; a warp takes four units per
     // round and issues their twelve loads before the first conversion (the phase is bound by L2 latency, not by bytes).
     {
-        const int n_units = n_busy * kStripsPerTile;
+        constexpr int kToneRows = 4, kTonePerTile = kFastTile / kToneRows;
+        const int n_units = n_busy * kTonePerTile;
         const int gw = blockIdx.x * (kFastBlock / 32) + warp;
         for (int u0 = gw; u0 < n_units; u0 += 4 * n_warps) {
             float4 q[4][3];
@@ -629,10 +640,10 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                 const int u = u0 + k * n_warps;
                 base_v[k] = 0;
                 if (u < n_units) {
-                    const int t = u / kStripsPerTile, strip = u - t * kStripsPerTile;
+                    const int t = u / kTonePerTile, strip = u - t * kTonePerTile;
                     const int tile = !order ? t : t < n_full ? __ldg(order + t) : __ldg(order2 + (t - n_full));
                     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-                    base_v[k] = 3 * ((size_t)(fp.row_begin + ty * fp.row_step + strip * kStripRows - fp.buf_row0) * fp.width + tx * 32);
+                    base_v[k] = 3 * ((size_t)(fp.row_begin + ty * fp.row_step + strip * kToneRows - fp.buf_row0) * fp.width + tx * 32);
 #pragma unroll
                     for (int i = 0; i < 3; i++) q[k][i] = __ldcg(reinterpret_cast<const float4*>(rgb + base_v[k] + fill_off[lane + 32 * i]));
                 }
@@ -774,19 +785,25 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     if (zero_foreign) rgb8 = ex->rgb8_zero;                     // scheduled or not: rank 0 clears the foreign bands
     if (ex && ex->ev_prepared) cudaEventRecord(ex->ev_prepared, stream);      // (an event here gives up the overlap of K1's launch with K0)
     if (launches) (*launches)++;
-    // shared memory: scene blob | raster records of every fast-path triangle | materials (if they fit as well)
-    const size_t smem_geo = (size_t)ds.lay.bytes + (size_t)ds.lay.n_tri * 64;
-    const size_t smem_mat = (((size_t)ds.n_mat * 36) + 15) / 16 * 16;
-    const int stage_mat = smem_geo + smem_mat <= (size_t)kSmemLimit ? 1 : 0;
-    const size_t smem = smem_geo + (stage_mat ? smem_mat : 0);
-    const float inv_tiles_x = 1.0f / (float)tiles_x;
-    static int sm_count = 0;
+    // shared memory: scene blob | raster records of every fast-path triangle | materials (if they fit as well), next to the
+    // kernel's static arrays (hit queues etc.) within the opt-in limit of the device
+    static int sm_count = 0, dyn_limit = 0;
     cudaError_t e;
     if (!sm_count) {
-        int dev = 0;
+        int dev = 0, optin = 0;
+        cudaFuncAttributes fa;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+        if ((e = cudaFuncGetAttributes(&fa, render_fast_kernel<true>)) != cudaSuccess) return e;
+        dyn_limit = std::min(kSmemLimit, optin - (int)fa.sharedSizeBytes - 1024);
+        if ((e = cudaFuncSetAttribute(render_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     }
+    const size_t smem_geo = (size_t)ds.lay.bytes + (size_t)ds.lay.n_tri * 64;
+    const size_t smem_mat = (((size_t)ds.n_mat * 36) + 15) / 16 * 16;
+    const int stage_mat = smem_geo + smem_mat <= (size_t)dyn_limit ? 1 : 0;
+    const size_t smem = smem_geo + (stage_mat ? smem_mat : 0);
+    const float inv_tiles_x = 1.0f / (float)tiles_x;
     // launched with programmatic stream serialisation: the CTAs may become resident while K0 still runs (pdl_wait_primary)
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -798,14 +815,9 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     cfg.numAttrs = 1;
     const int cull_i = cull ? 1 : 0;
     const int* order2 = order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr;
-    const bool use_smem = smem <= (size_t)kSmemLimit;
+    const bool use_smem = smem <= (size_t)dyn_limit;
     auto k = use_smem ? render_fast_kernel<true> : render_fast_kernel<false>;
     cfg.dynamicSmemBytes = use_smem ? smem : 0;
-    static bool opted_in = false;                              // static + dynamic shared memory may exceed 48 KB: opt in once
-    if (use_smem && !opted_in) {
-        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
-        opted_in = true;
-    }
     int occ = 1;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kFastBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;
     cfg.gridDim = dim3(std::min(n_tiles, sm_count * std::max(occ, 1)));
