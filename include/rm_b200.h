@@ -257,8 +257,9 @@ int rm_render_frame(RmScene scene, const RmParams* params, void* d_rgb, int32_t*
 int rm_peer_status(const RmExchange* exchange);
 /* %globaltimer stamps (ns) the render kernel left in this rank's mailbox during its last frame: [0] kernel start,
  * [1] rendering done (last CTA), [2] all ranks' maxima gathered, [3] this rank's 8-bit tiles stored, [4] rank 0 only:
- * every rank has signalled, frame complete.  Synchronous (a small device-to-host copy); for phase breakdowns. */
-int rm_peer_stamps(const RmExchange* exchange, uint64_t out_ns[5]);
+ * every rank has signalled, frame complete, [5] / [6] start and end of the frame's prepare kernel (K0; 0 when the scene has
+ * no tile schedule).  Synchronous (a small device-to-host copy); for phase breakdowns. */
+int rm_peer_stamps(const RmExchange* exchange, uint64_t out_ns[7]);
 
 /* ---- per-kernel device times (CUDA events on the launching stream around K0 and K1) ------------ *
  * rm_set_profiling(1) makes every following device render record three events; rm_last_kernel_times() waits for the

@@ -593,10 +593,10 @@ int rm_render_frame(RmScene scene, const RmParams* params, void* d_rgb, int32_t*
     return RM_OK;
 }
 
-int rm_peer_stamps(const RmExchange* x, uint64_t out_ns[5]) {
+int rm_peer_stamps(const RmExchange* x, uint64_t out_ns[7]) {
     if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
     if (!x || !out_ns || x->rank < 0 || x->rank >= RM_MAX_RANKS || !x->mailbox[x->rank]) return fail(RM_ERR_INVALID_ARGUMENT, "exchange, out_ns or own mailbox is null");
-    CK(cudaMemcpy(out_ns, static_cast<const unsigned long long*>(x->mailbox[x->rank]) + 56, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_ns, static_cast<const unsigned long long*>(x->mailbox[x->rank]) + 56, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return RM_OK;
 }
 

@@ -229,6 +229,9 @@ prepare_raster_kernel(const double* __restrict__ tri_src, const int n_tri, const
 // triangle per lane and round (tri_may_touch: exact, see rm_fast.cuh); tiles some triangle may touch are "busy" and go to the front of
 // the schedule, the others are provably black and go to the back.  The render kernel hands the busy
 // tiles out first (longest work first, so the cheap tiles fill the tail) and only stores zeros for the rest.
+// (K0 was also tried fused into the render kernel behind a grid-wide barrier: 4.2 us inside the kernel -- the barrier
+// exposes the launch ramp of the 296 CTAs -- against 2.3 us of K0 plus a 3 to 4.6 us hand-over here, whose first part
+// overlaps K1's launch thanks to the programmatic dependent launch.  No gain; not kept.)
 constexpr int kClassifyMaxTris = 256;
 constexpr int kClassifyBlock = 512, kClassifyLanes = 8;         // 8 lanes per tile: 64 tiles per block
 __global__ void __launch_bounds__(kClassifyBlock)
@@ -239,7 +242,12 @@ prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, con
     __shared__ int cnt[3], base[3];
     const double cam[3] = {cx, cy, cz};
     pdl_launch_dependents();
-    if (blockIdx.x == 0 && threadIdx.x == 0 && dmax_zero) *dmax_zero = 0.f;
+    unsigned long long* const stamp = reinterpret_cast<unsigned long long*>(ctr + 12);   // [0] K0 start, [1] K0 end (ns)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (dmax_zero) *dmax_zero = 0.f;
+        stamp[0] = now_ns();
+        stamp[1] = 0ull;
+    }
     if (threadIdx.x < 3) cnt[threadIdx.x] = 0;
     for (int j = threadIdx.x; j < n_tri; j += blockDim.x) {      // every block rebuilds the (few) records; block 0 publishes them
         R4<float> out[4];
@@ -284,6 +292,7 @@ prepare_classify_kernel(const double* __restrict__ tri_src, const int n_tri, con
         else if (cls == 1) order2[base[1] + local] = tile;
         else order[n_tiles - 1 - (base[2] + local)] = tile;
     }
+    if (threadIdx.x == 0) atomicMax(stamp + 1, now_ns());
 }
 
 // K1, FP32 production kernel (rm_fast.cuh).  Persistent and warp-granular: the grid is (SMs x resident
@@ -364,7 +373,12 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         }
     }
     pdl_wait_primary();                                         // K0 has retired: raster records, schedule, zeroed maximum
-    if (threadIdx.x == 0 && blockIdx.x == 0 && link.world > 0) link.box[link.rank][56] = now_ns();  // stamp: start of the work
+    if (threadIdx.x == 0 && blockIdx.x == 0 && link.world > 0) {
+        unsigned long long* const box = link.box[link.rank];
+        box[56] = now_ns();                                     // stamp: start of the work
+        box[61] = reinterpret_cast<const unsigned long long*>(ctr + 12)[0];     // K0's own stamps, for the phase breakdown
+        box[62] = reinterpret_cast<const unsigned long long*>(ctr + 12)[1];     // (tile-scheduled scenes only)
+    }
     if (kSmem) {
         uint4* dst = reinterpret_cast<uint4*>(smem_raw);
         const int n16 = L.bytes / 16;

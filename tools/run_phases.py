@@ -39,18 +39,18 @@ for i in range(frames):
     torch.cuda.synchronize()
     tr.render()
     torch.cuda.synchronize()
-    st = (C.c_uint64 * 5)()
+    st = (C.c_uint64 * 7)()
     _abi.check(L.rm_peer_stamps(C.byref(tr.peer.x), st))
     k0, k1, k4 = C.c_double(0), C.c_double(0), C.c_double(0)
     _abi.check(L.rm_kernel_times(0, C.byref(k0), C.byref(k1), C.byref(k4)))
     t = [int(x) for x in st]
-    rows.append((k0.value * 1e3, k1.value * 1e3, (t[1] - t[0]) / 1e3, (t[2] - t[1]) / 1e3, (t[3] - t[2]) / 1e3, (t[4] - t[3]) / 1e3 if rank == 0 and world > 1 else 0.0))
+    rows.append(((t[6] - t[5]) / 1e3 if t[5] else 0.0, (t[0] - t[6]) / 1e3 if t[5] else 0.0, k1.value * 1e3, (t[1] - t[0]) / 1e3, (t[2] - t[1]) / 1e3, (t[3] - t[2]) / 1e3, (t[4] - t[3]) / 1e3 if rank == 0 and world > 1 else 0.0))
 for rk in range(world):
     if world > 1:
         dist.barrier()
     if rk == rank:
         for i, x in enumerate(rows[2:]):
-            print("rank %d frame %d: K0 %.1f us  K0+K1 events %.1f us; in K1: render %.1f + wait-max %.1f + tone %.1f + wait-done %.1f" % ((rank, i + 2) + x), flush=True)
+            print("rank %d frame %d: K0 %.1f us, gap %.1f us to K1's work; K0+K1 events %.1f us; in K1: render %.1f + wait-max %.1f + tone %.1f + wait-done %.1f" % ((rank, i + 2) + x), flush=True)
 tr.close()
 if world > 1:
     dist.destroy_process_group()
