@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -303,6 +303,15 @@ def run_ours(args):
         # K1 of the slowest rank's share: with N ranks each kernel processes ~1/N of the frame's work
         ach_tflops = flops / world / (k1_ms_avg * 1e-3) / 1e12
         issue_frac = (slots / world / (k1_ms_avg * 1e-3)) / (peak_t.value * 1e12 / 2.0)
+        # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture of the same workload
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f).get(args.workload)
+            if tj and world == 1:
+                traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+        except (OSError, ValueError, KeyError):
+            pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             full_s, threads, sample = cpu_reference_frame_time(desc, w, h, depth, budget_s=25.0, reps=3)
@@ -329,7 +338,7 @@ def run_ours(args):
                             + ("; each rank delivers its own row tile" if world > 1 else "")},
             "gpu_launches": tr.launches_per_frame() * args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak_t.value, "unit": "TFLOP/s",
-                         "frac": ach_tflops / peak_t.value, "traffic": None,
+                         "frac": ach_tflops / peak_t.value, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "render_fast_kernel<true>", "kernel_ms": k1_ms_avg,
                          "prepare_kernel_ms": k0_ms_avg,
                          "kernel_includes": "K0 (prepare) + K1: render + exchange wait + fused K4, CUDA events around both launches" if tr.exchange == "peer" else "render only",
@@ -353,8 +362,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cornell_4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cull", action="store_true", help="trace every primitive like the reference's brute force")

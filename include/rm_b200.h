@@ -226,13 +226,14 @@ int   rm_host_unregister(void* p);
  * -- ONE float, the global channel maximum -- and the finished 8-bit rows, which go to rank 0.  Both travel over
  * NVLink peer memory from inside the render kernel (no NCCL call on the path, two launches per frame and rank):
  *   K0  per-frame triangle records + tile schedule; zeroes d_max
- *   K1  renders this rank's bands (float rows stay local).  Rank 0 also clears the bytes of every provably black pixel of
- *       the 8-bit frame, its own and the other ranks' whole bands (local HBM stores: zeros never cross NVLink).  The last
- *       CTA to retire from rendering stores {seq, max} into every rank's mailbox.  Then every CTA waits for the G mailbox
- *       words of frame `seq` (which doubles as the grid-wide barrier of this persistent kernel), takes their maximum,
- *       quantises this rank's busy tiles (normalize + to_vec, framebuffer.rs:40-82) straight into rank 0's 8-bit frame
- *       and the last CTA signals rank 0; rank 0's kernel retires only when all G ranks have signalled, so whatever
- *       follows it on rank 0's stream sees the complete frame.
+ *   K1  renders this rank's bands (float rows stay local); rank 0 also clears the bytes of its own provably black pixels
+ *       in the 8-bit frame.  The last CTA to retire from rendering stores {seq, max} into every rank's mailbox.  Then every
+ *       CTA waits for the G mailbox words of frame `seq` (which doubles as the grid-wide barrier of this persistent
+ *       kernel), takes their maximum, quantises this rank's busy tiles (normalize + to_vec, framebuffer.rs:40-82) straight
+ *       into rank 0's 8-bit frame, and the last CTA signals rank 0.  While the tiles of the other ranks arrive, rank 0
+ *       clears those ranks' bands in the OTHER 8-bit buffer, the one the next frame will use (local HBM stores: zeros
+ *       never cross NVLink); its kernel retires only when all G ranks have signalled, so whatever follows it on rank 0's
+ *       stream sees the complete frame.
  * Memory shared between the processes is allocated with rm_peer_alloc (cudaMalloc + CUDA IPC handle), the 64-byte
  * handle is passed to the other ranks by any means (torch.distributed / MPI / a pipe) and mapped with rm_peer_open.
  * world == 1 needs no peers: mailbox[0] and frame8[] are local allocations. */
@@ -242,8 +243,9 @@ int   rm_host_unregister(void* p);
 typedef struct RmExchange {
     int32_t  rank, world;
     void*    mailbox[RM_MAX_RANKS];  /* mailbox[r]: rank r's mailbox (RM_MAILBOX_BYTES, zeroed once), mapped on this GPU */
-    uint8_t* frame8[2];              /* rank 0's 8-bit frames (H*W*3 bytes each); frame `seq` goes to frame8[seq & 1], so a
-                                        reader of frame n on rank 0 never races the writers of frame n+1            */
+    uint8_t* frame8[2];              /* rank 0's 8-bit frames (H*W*3 bytes each, zeroed once by rm_peer_alloc); frame `seq` goes
+                                        to frame8[seq & 1] and is valid until the next rm_render_frame is issued on rank 0's
+                                        stream (that launch prepares the buffer for the frame after it)                  */
 } RmExchange;
 int rm_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle[RM_IPC_HANDLE_BYTES]);  /* zero-filled */
 int rm_peer_open(const unsigned char handle[RM_IPC_HANDLE_BYTES], void** d_ptr);

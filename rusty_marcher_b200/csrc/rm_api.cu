@@ -182,7 +182,8 @@ template <typename R>
 int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_prim, R* d_max, cudaStream_t stream,
                        int buf_row0_is_tile, unsigned long long* d_counters, rm::FrameParams<R>* out_fp, int* resident,
                        int* launches = nullptr, unsigned char* d_rgb8_zero = nullptr, bool* scheduled = nullptr,
-                       const rm::PeerLink* link = nullptr, unsigned char* d_rgb8_out = nullptr, bool normalise = true) {
+                       const rm::PeerLink* link = nullptr, unsigned char* d_rgb8_out = nullptr, bool normalise = true,
+                       unsigned char* d_rgb8_next = nullptr) {
     if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
     int rc = check_params(params);
     if (rc != RM_OK) return rc;
@@ -202,6 +203,7 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
         ex.zero_dmax = true;
         ex.rgb8_out = d_rgb8_out;
         ex.normalise = normalise;
+        ex.rgb8_next = d_rgb8_next;
     }
     if (g.profiling && !g.prof.empty()) {
         g.prof_head = (g.prof_head + 1) % kProfRing;
@@ -565,14 +567,16 @@ int rm_render_frame(RmScene scene, const RmParams* params, void* d_rgb, int32_t*
         link.box[r] = static_cast<unsigned long long*>(x->mailbox[r]);
     }
     unsigned char* frame8 = x->frame8[seq & 1u];
-    if (!frame8) return fail(RM_ERR_INVALID_ARGUMENT, "exchange: frame8[seq & 1] is null");
+    unsigned char* frame8_next = x->frame8[(seq + 1u) & 1u];
+    if (!frame8 || (x->rank == 0 && x->world > 1 && !frame8_next)) return fail(RM_ERR_INVALID_ARGUMENT, "exchange: frame8[] is null");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rm::FrameParams<float> fp;
     // K0 + K1; K1 ends with the exchange and the conversion to 8 bits (K4 fused).  Only rank 0 clears bytes of the 8-bit
-    // frame (its own black pixels and the whole bands of the other ranks): zeros never travel over NVLink.
+    // frames (its own black pixels in this frame's buffer, the whole bands of the other ranks in the next frame's buffer):
+    // zeros never travel over NVLink.
     int rc = render_device_impl<float>(scene, params, static_cast<float*>(d_rgb), d_prim_id, static_cast<float*>(d_max), s, 0,
                                        nullptr, &fp, nullptr, nullptr, x->rank == 0 ? frame8 : nullptr, nullptr, &link, frame8,
-                                       normalise != 0);
+                                       normalise != 0, frame8_next);
     if (rc != RM_OK) return rc;
     auto it = g.scenes.find(scene);
     const rm::DeviceScene<float>& ds = it->second.f32.ds;

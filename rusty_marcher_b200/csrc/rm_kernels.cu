@@ -341,7 +341,8 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
                    float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order, const int* __restrict__ order2,
                    unsigned char* rgb8, const PeerLink link, unsigned char* rgb8_out, const int normalise,
-                   const int zero_foreign, const int stage_mat) {
+                   unsigned char* rgb8_next, const int stage_mat) {
+    const int zero_foreign = rgb8_next != nullptr;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     __shared__ int cta_max;
     __shared__ float frame_max;
@@ -477,23 +478,6 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     int next_empty = n_busy + blockIdx.x * (kFastBlock / 32) + warp;   // schedule position of this warp's next empty tile
     int empty_acc = 0;
 
-    // ---- phase 0 (rank 0 of a multi-GPU frame only)
-    if (zero_foreign) {
-        // Rank 0 of a multi-GPU frame: the bands of the other ranks are black wherever those ranks store nothing
-        // (they only send their busy tiles, after the exchange of the maxima, i.e. after this kernel's stores), so
-        // the 8-bit frame's foreign bands are cleared here, from local HBM bandwidth, instead of sending zeros over
-        // NVLink.  A band is 32 full rows = 96 W contiguous bytes; 512-byte pieces are dealt to the grid's warps.
-        const int S = fp.row_step >> 5, f = (fp.row_begin >> 5) % S, P = fp.height >> 5;
-        const int per_band = fp.width * 96 / 512;                  // W is a multiple of 32: 6 W / 32 pieces
-        const int n_foreign = P - (P - f + S - 1) / S;
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int c = blockIdx.x * (kFastBlock / 32) + warp; c < n_foreign * per_band; c += n_warps) {
-            const int fb = c / per_band, piece = c - fb * per_band;
-            const int g = fb / (S - 1), r = fb - g * (S - 1);
-            const int band = g * S + (r < f ? r : r + 1);
-            __stcs(reinterpret_cast<uint4*>(rgb8 + ((size_t)band * fp.width * 96 + (size_t)piece * 512)) + lane, z);
-        }
-    }
     auto warp_loop = [&](auto px_tag) {
     constexpr int kPx = decltype(px_tag)::value;
     constexpr int kStripRows = kPx, kStripsPerTile = kFastTile / kStripRows, kRowLanes = 32 / kPx;
@@ -675,6 +659,24 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
             }
         }
     }
+    // ---- rank 0 of a multi-GPU frame, while the other ranks' tiles are still arriving: the bands of the other ranks are
+    // black wherever those ranks store nothing (they only send their busy tiles), so somebody has to clear them -- here,
+    // from local HBM bandwidth instead of zeros over NVLink, and for the NEXT frame's buffer (frames alternate between two
+    // buffers), in the microseconds this GPU would otherwise spend waiting for the last rank's signal.  The next frame's
+    // peers store into that buffer only after this rank has published its next maximum, i.e. after this kernel.
+    // A band is 32 full rows = 96 W contiguous bytes; 512-byte pieces are dealt to the grid's warps.
+    if (zero_foreign) {
+        const int S = fp.row_step >> 5, f = (fp.row_begin >> 5) % S, P = fp.height >> 5;
+        const int per_band = fp.width * 96 / 512;                  // W is a multiple of 32: 6 W / 32 pieces
+        const int n_foreign = P - (P - f + S - 1) / S;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int c = blockIdx.x * (kFastBlock / 32) + warp; c < n_foreign * per_band; c += n_warps) {
+            const int fb = c / per_band, piece = c - fb * per_band;
+            const int g = fb / (S - 1), r = fb - g * (S - 1);
+            const int band = g * S + (r < f ? r : r + 1);
+            __stcs(reinterpret_cast<uint4*>(rgb8_next + ((size_t)band * fp.width * 96 + (size_t)piece * 512)) + lane, z);
+        }
+    }
     signal_frame_done(link, ctr + 10);
 }
 
@@ -795,8 +797,8 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     unsigned char* rgb8_out = ex ? ex->rgb8_out : nullptr;     // fused K4 (needs a link: the mailbox wait is its barrier)
     if (link.world <= 0) rgb8_out = nullptr;
     const int normalise = ex && ex->normalise ? 1 : 0;
-    const int zero_foreign = (rgb8_out && link.world > 1 && link.rank == 0 && ex->rgb8_zero) ? 1 : 0;
-    if (zero_foreign) rgb8 = ex->rgb8_zero;                     // scheduled or not: rank 0 clears the foreign bands
+    // rank 0 of a multi-GPU frame clears the other ranks' bands of the NEXT frame's buffer at the end of this kernel
+    unsigned char* rgb8_next = (rgb8_out && link.world > 1 && link.rank == 0) ? ex->rgb8_next : nullptr;
     if (ex && ex->ev_prepared) cudaEventRecord(ex->ev_prepared, stream);      // (an event here gives up the overlap of K1's launch with K0)
     if (launches) (*launches)++;
     // shared memory: scene blob | raster records of every fast-path triangle | materials (if they fit as well), next to the
@@ -836,7 +838,7 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kFastBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;
     cfg.gridDim = dim3(std::min(n_tiles, sm_count * std::max(occ, 1)));
     if ((e = cudaLaunchKernelEx(&cfg, k, ds, fp, cull_i, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order2, rgb8,
-                                link, rgb8_out, normalise, zero_foreign, stage_mat)) != cudaSuccess)
+                                link, rgb8_out, normalise, rgb8_next, stage_mat)) != cudaSuccess)
         return e;
     if (launches) (*launches)++;
     if (ex && ex->ev_rendered) cudaEventRecord(ex->ev_rendered, stream);

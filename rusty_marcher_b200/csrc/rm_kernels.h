@@ -60,6 +60,8 @@ struct RenderExtras {
     // converts its busy tiles (all its tiles without a schedule) into rgb8_out, which may be peer memory, and signals rank 0
     unsigned char* rgb8_out = nullptr;
     bool normalise = true;
+    // in (rank 0 of a multi-GPU frame): the 8-bit buffer of the NEXT frame, whose foreign bands this launch clears
+    unsigned char* rgb8_next = nullptr;
     // in: events recorded on the stream before K0, between K0 and K1, after K1 (profiling; may be null)
     cudaEvent_t ev_begin = nullptr, ev_prepared = nullptr, ev_rendered = nullptr;
     // out: the frame was rendered with a tile schedule (and rgb8_zero, if given, has been zero-filled)

@@ -245,6 +245,13 @@ class TiledRenderer:
                 self.bands8[r::self.world].copy_(self.gathered[r][:self.counts[r]])
         return self.rgb8
 
+    def set_camera(self, camera):
+        """Camera of the following frames (the scene stays resident on the device; main.rs:124-171 moves the camera only)."""
+        if self.exchange == "peer":
+            self.params.camera[:] = [float(c) for c in camera]
+        else:
+            self.backend.scene.camera = type(self.backend.scene.camera)(*[float(c) for c in camera])
+
     def launches_per_frame(self):
         """Kernels of this repo launched per frame on this rank: K0 and K1 (K4 fused) on the peer path, K0, K1, K4 otherwise."""
         return 2 if self.exchange == "peer" else 3

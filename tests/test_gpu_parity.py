@@ -360,6 +360,9 @@ def test_frame_level_call_argument_checks(rm_gpu):
         tr.close()
 
 
+CAMERAS = [(0., 0., 0.), (30., -20., 10.), (-45., 15., 0.)]      # the frames of the multi-GPU test alternate between them
+
+
 def _two_rank_worker(rank, world, port, out_path, name, w, h):
     import os
     import torch
@@ -377,16 +380,15 @@ def _two_rank_worker(rank, world, port, out_path, name, w, h):
         be = tiled.CudaBackend(scene, rm.create_renderer(1.5, h, w), w, h, dev)
         tr = tiled.TiledRenderer(be, w, h, dev, exchange="peer")
         frames = []
-        for _ in range(5):                                     # back to back: exercises the double buffering
+        for i in range(7):                                     # back to back, the camera moving: exercises the two buffers
+            tr.set_camera(CAMERAS[i % len(CAMERAS)])
             f = tr.render()
             if rank == 0:
-                frames.append(f.clone())
+                frames.append(f.clone())                       # (stream-ordered: valid until the next render is issued)
         torch.cuda.synchronize()
         tr.peer.status()
         if rank == 0:
-            for f in frames[1:]:
-                assert torch.equal(f, frames[0])
-            np.save(out_path, frames[0].cpu().numpy())
+            np.save(out_path, torch.stack(frames).cpu().numpy())
         tr.close()
     finally:
         dist.destroy_process_group()
@@ -402,11 +404,19 @@ def test_peer_exchange_across_gpus_equals_single_gpu_frame(rm_gpu, tmp_path, nam
     world = min(torch.cuda.device_count(), 8)
     if world < 2:
         pytest.skip("needs at least two GPUs")
-    whole = gpu_render(rm_gpu, workloads.scene(name), w, h, "f32")
+    whole = []
+    for cam in CAMERAS:
+        scene = workloads.scene(name)
+        scene.offset_camera(cam)
+        whole.append(gpu_render(rm_gpu, scene, w, h, "f32")["rgb8"])
+    assert not np.array_equal(whole[0], whole[1])
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    out = str(tmp_path / "frame.npy")
+    out = str(tmp_path / "frames.npy")
     mp.spawn(_two_rank_worker, args=(world, port, out, name, w, h), nprocs=world, join=True)
-    assert np.array_equal(np.load(out), whole["rgb8"])
+    frames = np.load(out)
+    assert len(frames) == 7
+    for i, f in enumerate(frames):
+        assert np.array_equal(f, whole[i % len(CAMERAS)]), "frame %d differs from the single-GPU frame" % i

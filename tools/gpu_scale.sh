@@ -5,9 +5,9 @@ nvidia-smi topo -m > gpurun_out/topo_$TAG.log 2>&1
 for n in 1 2 4 8; do
   if [ $n -le $N ]; then
     if [ $n -eq 1 ]; then
-      timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_${TAG}_n$n.log 2> gpurun_out/bench_${TAG}_n$n.err
+      timeout 300 python bench.py  --no-cpu-baseline > gpurun_out/bench_${TAG}_n$n.log 2> gpurun_out/bench_${TAG}_n$n.err
     else
-      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/bench_${TAG}_n$n.log 2> gpurun_out/bench_${TAG}_n$n.err
+      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n  > gpurun_out/bench_${TAG}_n$n.log 2> gpurun_out/bench_${TAG}_n$n.err
     fi
     echo "bench n$n rc=$?"
   fi
