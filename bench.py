@@ -295,6 +295,24 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_t[0]) * 1e3 / args.steps
+    # the same call when the caller only wants what main.rs shows or saves: render + normalize + to_vec, the 8-bit frame
+    # (24.9 MB instead of 98.8 MB over PCIe); extra information next to the headline e2e figure (single GPU only)
+    rgb8_ms = None
+    if world == 1:
+        nb8 = h * w * 3
+        pin8 = L.rm_host_alloc(nb8)
+        if pin8:
+            st8 = _abi.RmStats()
+            t8 = []
+            for i in range(5 + min(args.steps, 50)):
+                flush.fill_(0)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                _abi.check(L.rm_render(scene.device_handle(), C.byref(p_all), None, None, pin8, C.byref(st8)))
+                if i >= 5:
+                    t8.append(time.perf_counter() - t0)
+            rgb8_ms = 1e3 * sum(t8) / len(t8)
+            L.rm_host_free(pin8)
     tile_rows = len(range(*tr.rows)) * 32
     d2h = tile_rows * w * 12
 
@@ -335,7 +353,9 @@ def run_ours(args):
             "e2e": {"value": segs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_frame": e2e_ms,
                     "h2d_bytes_per_step": flat_bytes, "d2h_bytes_per_step": d2h,
                     "path": "Renderer.render(frame, scene) -> rm_scene_upload + rm_render, float32 framebuffer into pinned host memory"
-                            + ("; each rank delivers its own row tile" if world > 1 else "")},
+                            + ("; each rank delivers its own row tile" if world > 1 else ""),
+                    "pcie_gbs": d2h / (e2e_ms * 1e-3) / 1e9,
+                    "rgb8_only_ms_per_frame": rgb8_ms},
             "gpu_launches": tr.launches_per_frame() * args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak_t.value, "unit": "TFLOP/s",
                          "frac": ach_tflops / peak_t.value, "traffic": traffic, "traffic_source": traffic_src,

@@ -59,6 +59,10 @@ const RmFlatScene* rm_builder_flatten(RmSceneBuilder* b);
 /* rm_scene_upload(rm_builder_flatten(b)) */
 int rm_builder_upload(RmSceneBuilder* b, RmScene* out_handle);
 
+/* FrameBuffer::write_ppm (framebuffer.rs:26-38) for the 8-bit frame the kernels deliver (rm_render's out_rgb8, or
+ * rm_render_frame's frame on rank 0 after a copy to the host): "P6\n{W} {H}\n255\n" followed by H*W*3 bytes. */
+int rm_write_ppm(const char* path, int width, int height, const uint8_t* rgb8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -139,6 +139,7 @@ SYMBOLS = {
     "rm_builder_shape_name": (C.c_char_p, [C.c_void_p, C.c_int]),
     "rm_builder_flatten": (_P(RmFlatScene), [C.c_void_p]),
     "rm_builder_upload": (C.c_int, [C.c_void_p, _P(C.c_int64)]),
+    "rm_write_ppm": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_void_p]),
 }
 
 _lib = None

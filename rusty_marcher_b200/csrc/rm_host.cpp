@@ -5,6 +5,7 @@
 // Compiled with -ffp-contract=off: no FMA may sneak into these f64 precomputations.
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -271,6 +272,17 @@ const RmFlatScene* rm_builder_flatten(RmSceneBuilder* b) {
 int rm_builder_upload(RmSceneBuilder* b, RmScene* out_handle) {
     if (!b) return RM_ERR_INVALID_ARGUMENT;
     return rm_scene_upload(rm_builder_flatten(b), out_handle);
+}
+
+// framebuffer.rs:26-38
+int rm_write_ppm(const char* path, int width, int height, const uint8_t* rgb8) {
+    if (!path || !rgb8 || width <= 0 || height <= 0) return RM_ERR_INVALID_ARGUMENT;
+    std::FILE* f = std::fopen(path, "wb");
+    if (!f) return RM_ERR_INVALID_ARGUMENT;
+    std::fprintf(f, "P6\n%d %d\n255\n", width, height);       // framebuffer.rs:32
+    const size_t n = (size_t)width * (size_t)height * 3;
+    const bool ok = std::fwrite(rgb8, 1, n, f) == n;
+    return (std::fclose(f) == 0 && ok) ? RM_OK : RM_ERR_INVALID_ARGUMENT;
 }
 
 // scene.rs:28-211.  The reference threads ONE mutable Reflectance through the whole function, so

@@ -196,3 +196,24 @@ def test_framebuffer_normalize_to_vec_write_ppm(tmp_path):
     assert np.array_equal(fb.to_vec(), O.to_vec(ref))
     fb.write_ppm(str(tmp_path / "o.ppm"))
     assert (tmp_path / "o.ppm").read_bytes() == O.ppm_bytes(ref)
+
+
+def test_rm_write_ppm_reproduces_the_reference_golden_file(tmp_path):
+    """rm_write_ppm (the C-ABI FrameBuffer::write_ppm) on the oracle's normalised 800x600 demo frame: the file hashes to
+    the reference's golden engine/out.ppm."""
+    import hashlib
+    import json
+    from oracle import oracle as O
+    from tests.oracle_scenes import build_oracle_scene
+    from rusty_marcher_b200 import _abi
+    r = O.render(build_oracle_scene(workloads.describe("demo")), 800, 600, want_ids=False, want_fragile=False, want_counters=False)
+    rgb = r["rgb"].copy()
+    O.normalize(rgb)
+    rgb8 = np.ascontiguousarray(O.to_vec(rgb))
+    path = str(tmp_path / "out.ppm")
+    assert _abi.load().rm_write_ppm(path.encode(), 800, 600, rgb8.ctypes.data) == 0
+    meta = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "out_ppm.json")))
+    data = open(path, "rb").read()
+    assert len(data) == meta["size"] and hashlib.sha256(data).hexdigest() == meta["sha256"]
+    assert _abi.load().rm_write_ppm(None, 800, 600, rgb8.ctypes.data) == -3
+    assert _abi.load().rm_write_ppm(str(tmp_path / "no" / "dir.ppm").encode(), 8, 8, rgb8.ctypes.data) == -3
