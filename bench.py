@@ -34,6 +34,10 @@ WORKLOADS = {
     "demo": ("demo", 1600, 1280, 3, {}),
     "dodecahedron_4k": ("dodecahedron", 3840, 2160, 3, {}),
     "stress_small": ("stress", 1920, 1080, 6, dict(n_spheres=512, grid=32)),
+    # BASELINE.json configs[4] scaled to fit a bench run (1024 spheres + 8192 triangles instead of 4096 + 100,352, 4K instead
+    # of 8K, same generator and depth cap 6): brute force over ~9k primitives per segment, ~0.1-0.2 s per frame on one GPU
+    # -- the regime in which the row-band split can be expected to scale
+    "stress_4k": ("stress", 3840, 2160, 6, dict(n_spheres=1024, grid=64)),
 }
 
 
