@@ -719,19 +719,18 @@ tonemap_kernel(const R* __restrict__ rgb, const R* __restrict__ dmax, const int 
     if (kPeer) signal_frame_done(link, done);
 }
 
-// K4 for frames rendered with a tile schedule and rgb8 zero-fill: only the busy tiles (ctr[8] fully covered ones in
+// K4 for frames rendered with a tile schedule and rgb8 zero-fill (host API rm_render with out_rgb8, rm_tonemap_device_busy;
+// on the frame path this work is the last phase of the render kernel): only the busy tiles (ctr[8] fully covered ones in
 // `order`, ctr[9] partially covered ones in `order2`) hold anything but zeros.  A block walks tiles; a thread converts
 // one float4 (4 channel values -> 4 bytes) at a time, lanes along a pixel row: 384-byte runs in, 96-byte runs out.
-template <bool kPeer>
 __global__ void __launch_bounds__(256)
 tonemap_busy_kernel(const float* __restrict__ rgb, const float* __restrict__ dmax, const int normalise, const FrameParams<float> fp,
-                    const int tiles_x, const int* __restrict__ order, const int* __restrict__ order2, int* __restrict__ ctr,
-                    unsigned char* __restrict__ rgb8, const PeerLink link) {
-    __shared__ float peer_max;
+                    const int tiles_x, const int* __restrict__ order, const int* __restrict__ order2, const int* __restrict__ ctr,
+                    unsigned char* __restrict__ rgb8) {
     const int n_full = ctr[8], n_busy = n_full + ctr[9];
     float inv = 1.f;
     if (normalise) {
-        const float mx = kPeer ? gather_max(link, &peer_max) : *dmax;
+        const float mx = *dmax;
         if (mx > 0.f) inv = 1.f / mx;                           // framebuffer.rs:71-76: scale(1. / max_val)
     }
     for (int t = blockIdx.x; t < n_busy; t += gridDim.x) {
@@ -748,7 +747,6 @@ tonemap_busy_kernel(const float* __restrict__ rgb, const float* __restrict__ dma
             *reinterpret_cast<unsigned*>(rgb8 + v) = w;
         }
     }
-    if (kPeer) signal_frame_done(link, ctr + 10);
 }
 
 __global__ void publish_zero_kernel(const PeerLink link, float* __restrict__ dmax) {
@@ -877,17 +875,12 @@ cudaError_t launch_render(const DeviceScene<R>& ds, const FrameParams<R>& fp, bo
 }
 
 cudaError_t launch_tonemap_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, const float* dmax,
-                                bool normalise, unsigned char* rgb8, cudaStream_t stream, const PeerLink* link) {
+                                bool normalise, unsigned char* rgb8, cudaStream_t stream) {
     const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * fp.n_bands;
-    const bool peer = link && link->world > 0;
-    if (n_tiles <= 0 && !peer) return cudaSuccess;
-    const int blocks = std::max(std::min(n_tiles, 148 * 8), 1);
-    int* order = ds.tile_order;
-    int* order2 = ds.tile_order + ds.tile_order_cap / 2;
-    if (peer)
-        tonemap_busy_kernel<true><<<blocks, 256, 0, stream>>>(rgb, dmax, normalise ? 1 : 0, fp, tiles_x, order, order2, ds.ctr, rgb8, *link);
-    else
-        tonemap_busy_kernel<false><<<blocks, 256, 0, stream>>>(rgb, dmax, normalise ? 1 : 0, fp, tiles_x, order, order2, ds.ctr, rgb8, PeerLink());
+    if (n_tiles <= 0) return cudaSuccess;
+    const int blocks = std::min(n_tiles, 148 * 8);
+    tonemap_busy_kernel<<<blocks, 256, 0, stream>>>(rgb, dmax, normalise ? 1 : 0, fp, tiles_x, ds.tile_order,
+                                                    ds.tile_order + ds.tile_order_cap / 2, ds.ctr, rgb8);
     return cudaGetLastError();
 }
 

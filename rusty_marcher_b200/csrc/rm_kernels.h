@@ -83,12 +83,11 @@ cudaError_t launch_tonemap(const FrameParams<R>& fp, const R* rgb, const R* dmax
                            cudaStream_t stream);
 
 // K4 over the busy tiles of the frame `ds` rendered last with a schedule and RenderExtras::rgb8_zero (same fp).
-// With a link (world >= 1) the kernel takes the frame maximum from this rank's mailbox instead of dmax (waiting for every
-// rank's word of frame link.seq), and signals rank 0 when its bytes are stored; on rank 0 it returns only once every rank
-// has signalled, i.e. when the whole 8-bit frame is in place.
 cudaError_t launch_tonemap_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, const float* dmax,
-                                bool normalise, unsigned char* rgb8, cudaStream_t stream, const PeerLink* link = nullptr);
-// launch_tonemap<float> with the same exchange (frames without a tile schedule).
+                                bool normalise, unsigned char* rgb8, cudaStream_t stream);
+// launch_tonemap<float> that takes the frame maximum from this rank's mailbox (waiting for every rank's word of frame
+// link.seq) and signals rank 0 when its bytes are stored -- the exchange of a rank that has no rows to render (its render
+// kernel, which normally does both, is not launched).
 cudaError_t launch_tonemap_peer(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, const float* dmax,
                                 bool normalise, unsigned char* rgb8, cudaStream_t stream, const PeerLink& link);
 

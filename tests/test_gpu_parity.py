@@ -394,7 +394,7 @@ def _two_rank_worker(rank, world, port, out_path, name, w, h):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,w,h", [("cornell_box", 1920, 1080), ("demo", 800, 600)])
+@pytest.mark.parametrize("name,w,h", [("cornell_box", 1920, 1080), ("demo", 800, 600), ("demo", 64, 32)])   # last: ranks without rows
 def test_peer_exchange_across_gpus_equals_single_gpu_frame(rm_gpu, tmp_path, name, w, h):
     """world = all visible GPUs (>= 2): the frame assembled on rank 0 by the kernels' peer stores is byte-identical to the
     single-GPU frame.  Skipped on a one-GPU box (the driver's round-end run); run with gpurun --gpus 2."""
