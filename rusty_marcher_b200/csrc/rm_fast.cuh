@@ -259,10 +259,13 @@ struct FastView {
 
     // renderer.rs:138-193 for the production path: lights taken two at a time (anyhit2), contributions added in the
     // reference's order (light l before light l + 1).
-    template <bool S> RM_HD Vec3<float> direct(const Vec3<float> origin, const Vec3<float> point, const Vec3<float> normal,
-                                               const R4<float> ma, const R4<float> mb, Counters<S>&) const {
+    template <bool S> RM_HD Vec3<float> direct(const Vec3<float> /*origin*/, const Vec3<float> dir, const Vec3<float> point,
+                                               const Vec3<float> normal, const R4<float> ma, const R4<float> mb, Counters<S>&) const {
         Vec3<float> acc = {0.f, 0.f, 0.f};
-        const Vec3<float> to_viewer = normalized(origin - point);                                  // renderer.rs:149
+        // renderer.rs:149 normalises origin - point; the point lies on the ray, origin - point = -t * dir with t > 0 and dir
+        // a unit vector, so the view vector IS -dir -- exactly, whereas the subtraction of two far-away points in FP32 only
+        // approximates it (|origin| 2^-24 against a short t)
+        const Vec3<float> to_viewer = -dir;
         const Vec3<float> kd = {ma.x, ma.y, ma.z};
         for (int l0 = 0; l0 < n_lgt; l0 += 2) {
             const bool two = l0 + 1 < n_lgt;

@@ -73,6 +73,16 @@ RM_HD float pow_nonneg(float x, float e) {
     const int n = (int)e;
     if ((float)n == e && n >= 0 && n <= 1024) {
         float r = 1.f;
+        // the two exponents the reference's scenes use most (30: Reflectance::create_default, shapes.rs:55; 100: scene.rs)
+        // by their shortest addition chains: 6 and 8 multiplications
+        if (n == 30) {
+            const float x2 = x * x, x3 = x2 * x, x5 = x3 * x2, x10 = x5 * x5, x15 = x10 * x5;
+            return x15 * x15;
+        }
+        if (n == 100) {
+            const float x2 = x * x, x3 = x2 * x, x6 = x3 * x3, x12 = x6 * x6, x24 = x12 * x12, x25 = x24 * x, x50 = x25 * x25;
+            return x50 * x50;
+        }
         if (n < 128) {
             // straight-line square-and-multiply: six squarings, then the factors picked by the bits of n (no loop
             // counter, no branch; n is the same for every pixel of a material)

@@ -68,8 +68,8 @@ template <typename R> struct SceneView {
         return intersect_shape_set<R, S>(*this, o, d, st);
     }
     RM_HD void surface(HitRec<R>& h, const Vec3<R> o, const Vec3<R> d, Vec3<R>& normal) const { surface_of(*this, h, o, d, normal); }
-    template <bool S> RM_HD Vec3<R> direct(const Vec3<R> origin, const Vec3<R> point, const Vec3<R> normal, const R4<R> ma,
-                                           const R4<R> mb, Counters<S>& st) const {
+    template <bool S> RM_HD Vec3<R> direct(const Vec3<R> origin, const Vec3<R> /*dir*/, const Vec3<R> point, const Vec3<R> normal,
+                                           const R4<R> ma, const R4<R> mb, Counters<S>& st) const {
         return direct_lighting<R, S, SceneView<R>>(*this, origin, point, normal, ma, mb, st);
     }
 
@@ -427,7 +427,7 @@ RM_HD Vec3<R> cast_ray(const SC& sc, Vec3<R> o, Vec3<R> d, R background, int max
                 sc.surface(h, o, d, normal);
                 const R4<R> ma = sc.mat_a[h.id];
                 const R4<R> mb = sc.mat_b[h.id];
-                Vec3<R> c = bg + sc.template direct<S>(o, h.p, normal, ma, mb, st);           // renderer.rs:272-275
+                Vec3<R> c = bg + sc.template direct<S>(o, d, h.p, normal, ma, mb, st);        // renderer.rs:272-275
                 bool pushed = false;
                 if (sc.mat_f[h.id] & 1) {                       // renderer.rs:277
                     st.add(C_GLASS);
