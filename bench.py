@@ -334,6 +334,13 @@ def run_ours(args):
                 traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
         except (OSError, ValueError, KeyError):
             pass
+        # the HBM view of the same kernel (it is not the bound): driver-measured copy bandwidth of this pool's B200s
+        hbm_peak, hbm_src = 6538.9, "fallback: MEASURED_PEAKS.json absent; the figure the driver measured on this pool (torch copy, 2026-10-18)"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json:hbm_gbs"
+        except (OSError, ValueError, KeyError):
+            pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             full_s, threads, sample = cpu_reference_frame_time(desc, w, h, depth, budget_s=25.0, reps=3)
@@ -369,7 +376,10 @@ def run_ours(args):
                          "algorithmic_flops_per_frame": flops, "algorithmic_issue_slots_per_frame": slots,
                          "issue_slot_frac": issue_frac,
                          "peak_source": "measured live: ffma_probe_kernel (pure dependent-chain FFMA, all SMs); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
-                         "hbm_gbs_achieved": (rows * w * 12 / world) / (k1_ms_avg * 1e-3) / 1e9},
+                         "hbm_gbs_achieved": (rows * w * 15 / world) / (k1_ms_avg * 1e-3) / 1e9,
+                         "hbm_gbs_peak": hbm_peak, "hbm_peak_source": hbm_src,
+                         "hbm_frac": (rows * w * 15 / world) / (k1_ms_avg * 1e-3) / 1e9 / hbm_peak,
+                         "hbm_bytes": "12 B/px float rows + 3 B/px RGB8 stored by this kernel (algorithmic)"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
