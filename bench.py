@@ -20,6 +20,7 @@ import os
 import statistics
 import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -52,15 +53,52 @@ def config_of(args, extra=None):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / clock-event (throttle) reasons during the timed region (B200_PROFILING.md's clocks line).
+
+    Sampled in-process through NVML (nvidia_ml_py) from a thread every ~2 ms -- `nvidia-smi -lms` needs ~100 ms to come
+    up and delivers one or two lines in a region this short; it is kept as the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.proc, self.thread = index, None, None
+        self.sm, self.mx, self.reasons, self.busy = [], [], set(), []
+        self._stop = threading.Event()
+
+    def _nvml_loop(self, nv, h):
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                 ("hw_power_brake_slowdown", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for name, bit in names:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:               # one failed query must not end the sampling
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.index
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.source = "nvml, 2 ms period"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.source = "nvidia-smi -lms 20"
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -68,26 +106,30 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        out = self.proc.communicate()[0]
-        sm, mx, reasons = [], [], set()
-        for line in out.splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower() == "active":
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=1.0)
+        elif self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            for line in self.proc.communicate()[0].splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    self.sm.append(float(f[1]))
+                    self.mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower() == "active":
+                        self.reasons.add(name)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        sm, mx = self.sm, self.mx
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": self.source}
 
 
 def cpu_reference_frame_time(desc, w, h, depth, budget_s, reps):
@@ -224,6 +266,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks / throttle reasons: nvidia-smi needs ~100 ms to come up and the device-timed region is a few tens of ms, so
+    # the sampler runs from here -- warm-up, device-timed region, end-to-end region -- to the end of the e2e loop
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # per-kernel CUDA events on the launching stream (K0 | K1 | K4), kept by the library for the last 256 frames
     _abi.check(L.rm_set_profiling(1))
     for _ in range(max(args.warmup, 3)):
@@ -231,9 +278,6 @@ def run_ours(args):
         tr.render()
     barrier()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for a, b in ev:
@@ -242,7 +286,6 @@ def run_ours(args):
         tr.render()                          # one frame: K0 + K1 + K4 incl. the exchange (rm_render_frame)
         b.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     if tr.peer is not None:
         tr.peer.status()                     # raises if a wait on a peer timed out
     step_ms = [a.elapsed_time(b) for a, b in ev]
@@ -291,6 +334,7 @@ def run_ours(args):
                 e2e_times.append(dt)
     finally:
         sys.stdout = stdout
+    clocks = sampler.stop() if rank == 0 else None
     flat = scene.flatten()
     flat_bytes = (C.sizeof(_abi.RmSphere) * flat.c.n_spheres + C.sizeof(_abi.RmPolygon) * flat.c.n_polygons
                   + 24 * flat.c.n_polygon_vertices + (C.sizeof(_abi.RmTriangle) + C.sizeof(_abi.RmReflectance)) * flat.c.n_triangles
