@@ -39,14 +39,35 @@ WORKLOADS = {
     # of 8K, same generator and depth cap 6): brute force over ~9k primitives per segment, ~0.1-0.2 s per frame on one GPU
     # -- the regime in which the row-band split can be expected to scale
     "stress_4k": ("stress", 3840, 2160, 6, dict(n_spheres=1024, grid=64)),
+    # the same frame with RmParams.accel = 1: scene queries walk the bounding-volume hierarchy instead
+    # of every primitive -- bit-identical frame, O(log n) tests per segment.  Reported separately: the algorithmic work of
+    # SURVEY.md 8d is defined by the reference's brute-force traversal, which this mode does not execute.
+    "stress_4k_bvh": ("stress", 3840, 2160, 6, dict(n_spheres=1024, grid=64, accel=True)),
+    # BASELINE.json configs[4] at full size: 4096 spheres + 100,352 triangles, 7680x4320, depth cap 6
+    "stress_8k_bvh": ("stress", 7680, 4320, 6, dict(n_spheres=4096, grid=224, accel=True)),
 }
 
 
+def workload_of(name):
+    """(scene, width, height, max_depth, scene kwargs, accel)"""
+    scene, w, h, depth, kw = WORKLOADS[name]
+    kw = dict(kw)
+    accel = bool(kw.pop("accel", False))
+    return scene, w, h, depth, kw, accel
+
+
+def n_prims_of(desc):
+    if desc.get("default"):
+        return 6
+    return len(desc["spheres"]) + sum(len(v) for _n, v, _o in desc["meshes"])
+
+
 def config_of(args, extra=None):
-    scene, w, h, depth, _kw = WORKLOADS[args.workload]
-    cfg = {"workload": "%s %dx%d fov 1.5 camera origin depth-cap %d (reference semantics: rows >= floor(H/32)*32 not rendered)"
-                       % (scene, w, h, depth),
-           "width": w, "height": h, "max_depth": depth, "scene": scene}
+    scene, w, h, depth, kw, accel = workload_of(args.workload)
+    cfg = {"workload": "%s%s %dx%d fov 1.5 camera origin depth-cap %d (reference semantics: rows >= floor(H/32)*32 not rendered)"
+                       % (scene, " " + json.dumps(kw, sort_keys=True) if kw else "", w, h, depth),
+           "width": w, "height": h, "max_depth": depth, "scene": scene,
+           "accel": "bvh (RmParams.accel = 1)" if accel else "none (the reference's brute-force traversal)"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -142,12 +163,17 @@ def cpu_reference_frame_time(desc, w, h, depth, budget_s, reps):
     threads = O.hardware_threads()
     out = np.zeros((h, w, 3), dtype=np.float64)
     n_patches = (h // 32) * (w // 32)
-    # calibrate on every 16th patch
+    # calibrate on every 16th patch -- on fewer when pixels x primitives says the brute-force frame takes minutes (the
+    # reference tests every primitive for every segment: configs[4] is ~3e12 primary tests alone)
+    cal, max_stride = 16, 64
+    while w * h * n_prims_of(desc) / cal > 4e9 and cal < 1024:
+        cal *= 2
+        max_stride = 1024
     t0 = time.perf_counter()
-    O.render(osc, w, h, max_depth=depth, threads=threads, patch_stride=16, want_ids=False, want_fragile=False, want_counters=False, out=out)
-    full_est = (time.perf_counter() - t0) * 16
+    O.render(osc, w, h, max_depth=depth, threads=threads, patch_stride=cal, want_ids=False, want_fragile=False, want_counters=False, out=out)
+    full_est = (time.perf_counter() - t0) * cal
     stride = 1
-    while full_est / stride * reps > budget_s and stride < 64:
+    while full_est / stride * reps > budget_s and stride < max_stride:
         stride *= 2
     best = None
     for _ in range(reps):
@@ -166,9 +192,13 @@ def oracle_segments(desc, w, h, depth):
     """Segments of one frame from the oracle's counters (reference arm only)."""
     from oracle import oracle as O
     from tests.oracle_scenes import build_oracle_scene
-    r = O.render(build_oracle_scene(desc), w, h, max_depth=depth, want_ids=False, want_fragile=False, want_counters=True)
+    stride = 1
+    while w * h * n_prims_of(desc) / stride > 4e10 and stride < 1024:
+        stride *= 2                     # a frame the oracle cannot finish in minutes: count a patch sample and scale it
+    r = O.render(build_oracle_scene(desc), w, h, max_depth=depth, patch_stride=stride, want_ids=False, want_fragile=False, want_counters=True)
     c = r["counters"]
-    return c["closest_segments"] + c["anyhit_segments"]
+    n_patches = (h // 32) * (w // 32)
+    return int((c["closest_segments"] + c["anyhit_segments"]) * n_patches / len(range(0, n_patches, stride)))
 
 
 def run_reference(args):
@@ -176,7 +206,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     from rusty_marcher_b200 import workloads
-    scene, w, h, depth, kw = WORKLOADS[args.workload]
+    scene, w, h, depth, kw, _accel = workload_of(args.workload)
     desc = workloads.describe(scene, **kw)
     segs = oracle_segments(desc, w, h, depth)
     # one "step" = one (possibly patch-sampled) frame; keep the whole run within a few minutes
@@ -189,7 +219,7 @@ def run_reference(args):
     out = np.zeros((h, w, 3), dtype=np.float64)
     n_patches = (h // 32) * (w // 32)
     stride = 1
-    while full / stride * total_steps > 150.0 and stride < 64:
+    while full / stride * total_steps > 150.0 and stride < (64 if w * h * n_prims_of(desc) <= 6.4e10 else 1024):
         stride *= 2
     n_sampled = len(range(0, n_patches, stride))
     times = []
@@ -231,12 +261,13 @@ def run_ours(args):
     rm.init(local_rank)
     L = _abi.load()
 
-    scene_name, w, h, depth, kw = WORKLOADS[args.workload]
+    scene_name, w, h, depth, kw, accel = workload_of(args.workload)
     desc = workloads.describe(scene_name, **kw)
     scene = workloads.build_scene(desc)
     renderer = rm.create_renderer(1.5, h, w)
     renderer.max_depth = depth
     renderer.cull_backfacing = not args.no_cull
+    renderer.accel = accel
     backend = tiled.CudaBackend(scene, renderer, w, h, dev)
     tr = tiled.TiledRenderer(backend, w, h, dev)
     rows = (h // 32) * 32
@@ -248,11 +279,43 @@ def run_ours(args):
     st = _abi.RmStats()
     scratch = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
     smax = torch.zeros(1, dtype=torch.float32, device=dev)
-    _abi.check(L.rm_render_device_stats(backend.handle, C.byref(p_all), scratch.data_ptr(), None, smax.data_ptr(),
-                                        torch.cuda.current_stream().cuda_stream, C.byref(st)))
-    counters = st.counters()
-    segs = work.segments(counters)
-    flops, slots = work.algorithmic_work(counters)
+    # (the instrumented kernel walks every primitive like the reference; a frame of configs[4]'s size would take minutes)
+    instrumented = rows * w * n_prims_of(desc) <= 1e11
+    flops = slots = None
+    brute_ms = None
+    if instrumented:
+        _abi.check(L.rm_render_device_stats(backend.handle, C.byref(p_all), scratch.data_ptr(), None, smax.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream, C.byref(st)))
+        counters = st.counters()
+        segs = work.segments(counters)
+        flops, slots = work.algorithmic_work(counters)
+    if accel:
+        # segments of the frame from the hierarchy kernel itself: rendered pixels (one primary query each) + the queries it
+        # counted behind them (rm_scene_query_count); cross-checked against the instrumented count when there is one
+        q = C.c_uint64(0)
+        _abi.check(L.rm_scene_query_count(backend.handle, C.byref(q), 1))
+        smax.zero_()
+        _abi.check(L.rm_render_device(backend.handle, C.byref(p_all), scratch.data_ptr(), None, smax.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream))
+        _abi.check(L.rm_scene_query_count(backend.handle, C.byref(q), 1))
+        segs_accel = rows * w + int(q.value)
+        if instrumented and abs(segs_accel - segs) > 1e-3 * segs:
+            raise SystemExit("bench.py: segment count of the hierarchy kernel (%d) disagrees with the instrumented kernel (%d)" % (segs_accel, segs))
+        segs = segs_accel
+        if not instrumented:
+            st.resident_prims = n_prims_of(desc)
+        if instrumented and world == 1:
+            # the same frame by brute force (accel = 0), once: what the hierarchy saves
+            p_bf = renderer.params(fb, scene, (0, -1))
+            p_bf.accel = 0
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            smax.zero_()
+            e0.record()
+            _abi.check(L.rm_render_device(backend.handle, C.byref(p_bf), scratch.data_ptr(), None, smax.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream))
+            e1.record()
+            torch.cuda.synchronize()
+            brute_ms = e0.elapsed_time(e1)
     del scratch
 
     # ---- FP32 FMA peak, measured live (roofline denominator)
@@ -367,8 +430,11 @@ def run_ours(args):
     line = None
     if rank == 0:
         # K1 of the slowest rank's share: with N ranks each kernel processes ~1/N of the frame's work
-        ach_tflops = flops / world / (k1_ms_avg * 1e-3) / 1e12
-        issue_frac = (slots / world / (k1_ms_avg * 1e-3)) / (peak_t.value * 1e12 / 2.0)
+        # (accel workloads: flops / slots are the algorithmic work of the reference's brute-force traversal, SURVEY.md 8d,
+        # most of which the hierarchy skips -- the fractions then say how much faster than a perfect brute-force kernel the
+        # frame is, not how busy the FP32 pipes are; null when the frame is too large for the instrumented kernel)
+        ach_tflops = flops / world / (k1_ms_avg * 1e-3) / 1e12 if flops is not None else None
+        issue_frac = (slots / world / (k1_ms_avg * 1e-3)) / (peak_t.value * 1e12 / 2.0) if slots is not None else None
         # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture of the same workload
         traffic, traffic_src = None, None
         try:
@@ -413,8 +479,10 @@ def run_ours(args):
                     "rgb8_only_ms_per_frame": rgb8_ms},
             "gpu_launches": tr.launches_per_frame() * args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak_t.value, "unit": "TFLOP/s",
-                         "frac": ach_tflops / peak_t.value, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "render_fast_kernel<true>", "kernel_ms": k1_ms_avg,
+                         "frac": ach_tflops / peak_t.value if ach_tflops is not None else None, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "render_fast_kernel<false, true> (hierarchy walk)" if accel else "render_fast_kernel<true, false>", "kernel_ms": k1_ms_avg,
+                         "work_definition": ("reference brute-force traversal (SURVEY.md 8d); the hierarchy skips most of it, so frac is a speed-up over a perfect brute-force kernel, not pipe utilisation" if accel else "reference traversal, resident primitives (SURVEY.md 8d)"),
+                         "brute_force_ms_same_frame": brute_ms,
                          "prepare_kernel_ms": k0_ms_avg,
                          "kernel_includes": "K0 (prepare) + K1: render + exchange wait + fused K4, CUDA events around both launches" if tr.exchange == "peer" else "render only",
                          "algorithmic_flops_per_frame": flops, "algorithmic_issue_slots_per_frame": slots,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RM_ABI_VERSION 3
+#define RM_ABI_VERSION 4
 
 typedef enum RmStatus {
     RM_OK = 0,
@@ -140,6 +140,12 @@ typedef struct RmParams {
     int32_t patch_row_stride; /* render patch rows begin, begin + stride, ... < end (0 and 1 = every
                                  row).  Rank k of G renders rows k, k + G, ...: interleaved row tiles
                                  balance scenes whose work sits in one part of the frame           */
+    int32_t accel;            /* 0 = every scene query tests every resident primitive, the reference's
+                                 traversal (shapes.rs:92-143, obj.rs:186-216); 1 = queries walk a bounding-
+                                 volume hierarchy over the hittable primitives (the bounding boxes the
+                                 reference carries but never uses, shapes.rs:34-38,63-86).  Same tests per
+                                 (ray, primitive), same winner: the FP32 frame is bit-identical, the work per
+                                 segment drops from O(n) to O(log n).  RM_FP32 production kernel only       */
 } RmParams;
 
 /* Event counters (same definitions as SURVEY.md 8d) + timings of one call. */
@@ -273,6 +279,11 @@ int rm_last_kernel_times(double* ms_prepare, double* ms_render);
  * K4: there ms_prepare is 0 and ms_render covers K0 + K1 + exchange + K4, ms_tonemap is -1.  On the other paths the
  * tone-map kernel is a separate call that is not timed here (ms_tonemap -1). */
 int rm_kernel_times(int back, double* ms_prepare, double* ms_render, double* ms_tonemap);
+/* Scene queries behind the primary rays -- closest-hit calls of the reflect/refract recursion (renderer.rs:266 at
+ * level > 1) plus shadow rays (renderer.rs:174) -- issued by the accel = 1 renders of `scene` since the last reset.
+ * Ray segments of a frame = rendered pixels + this count: the figure the instrumented brute-force kernel (RmStats)
+ * gives for scenes small enough to run through it.  Synchronises the device. */
+int rm_scene_query_count(RmScene scene, uint64_t* out_queries, int reset);
 
 /* ---- FP32 peak probe: a pure-FFMA kernel, returns measured TFLOP/s (roofline denominator) ----- */
 int rm_measure_fp32_peak(double* out_tflops, double* out_ms);

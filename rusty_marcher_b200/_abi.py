@@ -57,7 +57,7 @@ class RmParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fov", C.c_double), ("camera", d3),
                 ("max_depth", C.c_int32), ("background", C.c_double), ("patch_size", C.c_int32),
                 ("precision", C.c_int32), ("patch_row_begin", C.c_int32), ("patch_row_end", C.c_int32),
-                ("cull_backfacing", C.c_int32), ("patch_row_stride", C.c_int32)]
+                ("cull_backfacing", C.c_int32), ("patch_row_stride", C.c_int32), ("accel", C.c_int32)]
 
 
 COUNTER_FIELDS = ["pixels", "closest_segments", "anyhit_segments", "sphere_tests", "sphere_disc", "sphere_hits",
@@ -109,6 +109,7 @@ SYMBOLS = {
     "rm_set_profiling": (C.c_int, [C.c_int]),
     "rm_last_kernel_times": (C.c_int, [_P(C.c_double), _P(C.c_double)]),
     "rm_kernel_times": (C.c_int, [C.c_int, _P(C.c_double), _P(C.c_double), _P(C.c_double)]),
+    "rm_scene_query_count": (C.c_int, [C.c_int64, _P(C.c_uint64), C.c_int]),
     "rm_peer_alloc": (C.c_int, [C.c_size_t, _P(C.c_void_p), C.c_char_p]),
     "rm_peer_open": (C.c_int, [C.c_char_p, _P(C.c_void_p)]),
     "rm_peer_close": (C.c_int, [C.c_void_p]),

@@ -46,9 +46,12 @@ template <typename R> struct DevicePack {
     int* order_shape[2] = {nullptr, nullptr};
     void* tri_src = nullptr;
     void* tri_r = nullptr;
+    void* bvh_nodes = nullptr;
+    void* bvh_prims = nullptr;
     rm::DeviceScene<R> ds;
     void release() {
         cudaFree(blob); cudaFree(mat_a); cudaFree(mat_b); cudaFree(mat_f); cudaFree(tri_src); cudaFree(tri_r);
+        cudaFree(bvh_nodes); cudaFree(bvh_prims);
         for (int i = 0; i < 2; i++) { cudaFree(order[i]); cudaFree(order_shape[i]); }
         *this = DevicePack<R>();
     }
@@ -147,6 +150,11 @@ template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
         dp.ds.ctr = reinterpret_cast<int*>(static_cast<char*>(dp.tri_r) + rec_bytes);
         dp.ds.tile_order = dp.ds.ctr + 16;
         dp.ds.tile_order_cap = order_cap;
+        if ((rc = upload_vec(ps.bvh_nodes, &dp.bvh_nodes)) != RM_OK) return rc;
+        if ((rc = upload_vec(ps.bvh_prims, &dp.bvh_prims)) != RM_OK) return rc;
+        dp.ds.bvh.nodes = static_cast<const rm::R4<float>*>(dp.bvh_nodes);
+        dp.ds.bvh.prims = static_cast<const int*>(dp.bvh_prims);
+        dp.ds.bvh.n_nodes = (int)(ps.bvh_nodes.size() / 4);
     }
     dp.ds.blob = static_cast<const unsigned char*>(dp.blob);
     dp.ds.lay = ps.lay;
@@ -503,6 +511,20 @@ int rm_kernel_times(int back, double* ms_prepare, double* ms_render, double* ms_
 }
 
 int rm_last_kernel_times(double* ms_prepare, double* ms_render) { return rm_kernel_times(0, ms_prepare, ms_render, nullptr); }
+
+int rm_scene_query_count(RmScene scene, uint64_t* out_queries, int reset) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    auto it = g.scenes.find(scene);
+    if (it == g.scenes.end()) return fail(RM_ERR_INVALID_ARGUMENT, "unknown scene handle");
+    if (!it->second.f32.ready || !it->second.f32.ds.ctr) return fail(RM_ERR_INVALID_ARGUMENT, "scene has no FP32 pack");
+    CK(cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    CK(cudaMemcpy(&v, it->second.f32.ds.ctr + 6, sizeof v, cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(it->second.f32.ds.ctr + 6, 0, sizeof v));
+    if (out_queries) *out_queries = v;
+    return RM_OK;
+}
 
 // ---- one frame across the GPUs of a box (include/rm_b200.h) ---------------------------------------------------------
 

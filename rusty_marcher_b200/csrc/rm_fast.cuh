@@ -18,6 +18,7 @@
 //  * Spheres and n-gons (n > 3) reuse the routines of rm_trace.cuh.
 #pragma once
 
+#include "rm_bvh.cuh"
 #include "rm_trace.cuh"
 
 namespace rm {
@@ -53,7 +54,9 @@ RM_HD void prepare_raster(const double* __restrict__ src, const double cam[3], R
     }
 }
 
-struct FastView {
+// kBvh: scene queries walk the hierarchy of rm_bvh.cuh instead of every primitive (RmParams.accel).  The tests per
+// (ray, primitive) and the rule that picks the winner are the same code either way.
+template <bool kBvh> struct FastViewT {
     // spheres
     const R4<float>* sph;
     const int* sph_id;
@@ -80,6 +83,11 @@ struct FastView {
     // primary hit of this thread's pixel
     bool prim_got;
     HitRec<float> prim_hit;
+    // hierarchy over the hittable primitives (kBvh only), and this thread's count of scene queries behind the primary
+    // one (closest-hit calls of the recursion + shadow rays): the segment count of a frame too large to run through the
+    // instrumented brute-force kernel (rm_scene_query_count)
+    BvhView bvh;
+    mutable unsigned n_queries = 0;
 
     static RM_HD int as_int(float f) {
 #if defined(__CUDA_ARCH__)
@@ -135,6 +143,19 @@ struct FastView {
             return prim_got;
         }
         bool hit = false;
+        if constexpr (kBvh) {
+            h.dist = INFINITY;
+            n_queries++;
+            bvh_walk(bvh, o, d,
+                     [&](const int e) {
+                         float t;
+                         int slot, id;
+                         if (leaf_hit(e, o, d, t, slot, id)) keep(h, hit, t, slot, id);
+                         return false;
+                     },
+                     [&]() { return h.dist * 1.00001f; });
+            return hit;
+        }
         for (int i = 0; i < n_sph; i++) {
             Cand<float> c;
             if (sphere_intersect<S>(sph[i], o, d, c, st)) keep(h, hit, c.key, i, sph_id[i]);
@@ -153,7 +174,45 @@ struct FastView {
         return hit;
     }
 
+    // One leaf entry of the hierarchy against a general ray: the routine the brute-force loops run for that kind of
+    // primitive, and the slot / id they would report.
+    RM_HD bool leaf_hit(const int e, const Vec3<float> o, const Vec3<float> d, float& t, int& slot, int& id) const {
+        const unsigned kind = (unsigned)e >> 30;
+        const int i = e & 0x3fffffff;
+        Counters<false> st;
+        Cand<float> c;
+        if (kind == BVH_TRI) {
+            const R4<float>* g = tri_g + 4 * (size_t)i;
+            if (!tri_hit(g, o, d, t)) return false;
+            slot = n_sph + i;
+            id = as_int(g[3].z);
+            return true;
+        }
+        if (kind == BVH_SPHERE) {
+            if (!sphere_intersect<false>(sph[i], o, d, c, st)) return false;
+            slot = i;
+            id = sph_id[i];
+        } else {
+            if (!plane_intersect<false>(pln_n[i], pln_c[i], pln_v[i], vert, o, d, c, st)) return false;
+            slot = n_sph + n_tri + i;
+            id = pln_id[i];
+        }
+        t = c.key;
+        return true;
+    }
+    RM_HD bool anyhit_bvh(const Vec3<float> o, const Vec3<float> d) const {
+        n_queries++;
+        return bvh_walk(bvh, o, d,
+                        [&](const int e) {
+                            float t;
+                            int slot, id;
+                            return leaf_hit(e, o, d, t, slot, id);
+                        },
+                        []() { return INFINITY; });
+    }
+
     template <bool S> RM_HD bool anyhit(const Vec3<float> o, const Vec3<float> d, Counters<S>& st) const {
+        if constexpr (kBvh) return anyhit_bvh(o, d);
         Cand<float> c;
         for (int i = 0; i < n_sph; i++)
             if (sphere_intersect<S>(sph[i], o, d, c, st)) return true;
@@ -202,6 +261,11 @@ struct FastView {
     RM_HD unsigned anyhit2(const Vec3<float> oA, const Vec3<float> dA, const Vec3<float> oB, const Vec3<float> dB,
                            unsigned need) const {
         unsigned blocked = 0;
+        if constexpr (kBvh) {                                   // any-hit is a boolean per ray: one walk each
+            if ((need & 1u) && anyhit_bvh(oA, dA)) blocked |= 1u;
+            if ((need & 2u) && anyhit_bvh(oB, dB)) blocked |= 2u;
+            return blocked;
+        }
         if (n_sph + n_poly > 0) {                               // spheres and n-gons: ray by ray (any-hit: the order of the
             Counters<false> st;                                 // primitives does not matter for the boolean)
             Cand<float> c;
@@ -301,6 +365,8 @@ struct FastView {
         }
     }
 };
+using FastView = FastViewT<false>;
+using FastViewBvh = FastViewT<true>;
 
 // ---- primary visibility (stage A of the render kernel) ------------------------------------------
 // kPx horizontally adjacent pixels of one thread (the CUDA kernel uses 4; they share Y, so each affine
@@ -398,7 +464,7 @@ RM_HD void primary_tri(PrimaryState<kPx>& ps, const R4<float> r0, const R4<float
 // spheres / n-gons: the general routines from the camera.  One copy of the code: the loop over the kPx pixels is
 // not unrolled and the pixel state rotates through index 0, so every array index stays a compile-time constant
 // (a dynamic index would push the arrays to local memory).
-template <int kPx> RM_HD void primary_rest(PrimaryState<kPx>& ps, const FastView& fv, const FrameParams<float>& fp) {
+template <int kPx, class FV> RM_HD void primary_rest(PrimaryState<kPx>& ps, const FV& fv, const FrameParams<float>& fp) {
 #pragma unroll 1
     for (int r = 0; r < kPx; r++) {
         const float inv = fast_rsqrt(ps.len2[0]);
@@ -438,8 +504,82 @@ template <int kPx> RM_HD void primary_rest(PrimaryState<kPx>& ps, const FastView
     }
 }
 
+// Primary visibility of a thread's kPx pixels through the hierarchy (RmParams.accel), one pixel at a time.  A
+// triangle leaf runs primary_tri on the triangle's raster record, a sphere / n-gon leaf the general routine from the
+// camera, and the two partial winners are merged the way primary_rest merges them -- the same arithmetic per (pixel,
+// primitive) and the same (distance, id) order as the brute-force stage A, hence the same t / slot / id, bit for bit.
+template <int kPx> RM_HD void primary_bvh(PrimaryState<kPx>& ps, const FastViewBvh& fv, const FrameParams<float>& fp) {
+    const bool rest = fv.n_sph + fv.n_poly > 0;
+#pragma unroll 1
+    for (int r = 0; r < kPx; r++) {
+        PrimaryState<1> p1;
+        p1.X[0] = ps.X[0];
+        p1.Y = ps.Y;
+        p1.len2[0] = ps.len2[0];
+        p1.t[0] = 0.f;
+        p1.slot[0] = -1;
+        p1.id[0] = -1;
+        const float inv = fast_rsqrt(p1.len2[0]);
+        const float len = p1.len2[0] * inv;                    // |D|: stage A's triangle distances are in units of it
+        const Vec3<float> d = {p1.X[0] * inv, p1.Y * inv, -inv};
+        HitRec<float> other;                                   // closest sphere / n-gon, unit-direction distance
+        other.dist = INFINITY;
+        other.slot = -1;
+        other.id = -1;
+        bool hit_other = false;
+        float tcut = INFINITY;
+        bvh_walk(fv.bvh, fp.camera, d,
+                 [&](const int e) {
+                     const unsigned kind = (unsigned)e >> 30;
+                     const int i = e & 0x3fffffff;
+                     if (kind == BVH_TRI) {
+                         const R4<float>* q = fv.tri_r + 4 * (size_t)i;
+                         primary_tri<1>(p1, q[0], q[1], q[2], q[3], fv.n_sph + i);
+                         if (p1.slot[0] >= 0) tcut = fminf(tcut, p1.t[0] * len);
+                     } else {
+                         float t;
+                         int slot, id;
+                         if (fv.leaf_hit(e, fp.camera, d, t, slot, id)) {
+                             FastViewBvh::keep(other, hit_other, t, slot, id);
+                             tcut = fminf(tcut, other.dist);
+                         }
+                     }
+                     return false;
+                 },
+                 [&]() { return tcut * 1.00001f; });
+        float t_new = p1.t[0];
+        int slot_new = p1.slot[0], id_new = p1.id[0];
+        if (rest) {                                            // primary_rest's merge and its round trip through unit distances
+            bool hit = p1.slot[0] >= 0;
+            HitRec<float> best;
+            best.dist = p1.t[0] * len;
+            best.slot = p1.slot[0];
+            best.id = p1.id[0];
+            if (hit_other) FastViewBvh::keep(best, hit, other.dist, other.slot, other.id);
+            t_new = best.dist * inv;
+            slot_new = hit ? best.slot : -1;
+            id_new = hit ? best.id : -1;
+        }
+        const float X0 = ps.X[0], L0 = ps.len2[0];
+#pragma unroll
+        for (int k = 0; k + 1 < kPx; k++) {                     // rotate left; the finished pixel goes to the end
+            ps.X[k] = ps.X[k + 1];
+            ps.len2[k] = ps.len2[k + 1];
+            ps.t[k] = ps.t[k + 1];
+            ps.slot[k] = ps.slot[k + 1];
+            ps.id[k] = ps.id[k + 1];
+        }
+        ps.X[kPx - 1] = X0;
+        ps.len2[kPx - 1] = L0;
+        ps.t[kPx - 1] = t_new;
+        ps.slot[kPx - 1] = slot_new;
+        ps.id[kPx - 1] = id_new;
+    }
+}
+
 // Shading + recursion of one pixel whose primary ray hit (t in units of |D|, slot, id): renderer.rs:254-309 from level 1.
-RM_HD Vec3<float> fast_shade(FastView& fv, const FrameParams<float>& fp, const int x, const int y, const float t, const int slot,
+template <class FV>
+RM_HD Vec3<float> fast_shade(FV& fv, const FrameParams<float>& fp, const int x, const int y, const float t, const int slot,
                              const int id) {
     const float X = pixel_X(fp, x), Y = pixel_Y(fp, y);
     const float len2 = fmaf(X, X, fmaf(Y, Y, 1.f));
@@ -451,7 +591,7 @@ RM_HD Vec3<float> fast_shade(FastView& fv, const FrameParams<float>& fp, const i
     fv.prim_hit.id = id;
     Counters<false> st;
     int pid;
-    return cast_ray<float, false, FastView>(fv, fp.camera, d, fp.background, fp.max_depth, pid, st);
+    return cast_ray<float, false, FV>(fv, fp.camera, d, fp.background, fp.max_depth, pid, st);
 }
 
 }  // namespace rm

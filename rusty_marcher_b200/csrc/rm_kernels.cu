@@ -335,7 +335,9 @@ constexpr int kWarpQueue = kFastTile * 4 + 32;                  // one strip of 
 #define RM_K1_BOUNDS __launch_bounds__(kFastBlock, RM_K1_MIN_BLOCKS)
 #endif
 template <int kPx> struct PxTag { static constexpr int value = kPx; };
-template <bool kSmem>
+// kBvh (RmParams.accel): scene queries walk the hierarchy of rm_bvh.cuh (read through the read-only path; the nodes near
+// the root stay in L1) instead of every primitive; stage A then handles a thread's pixels one after the other.
+template <bool kSmem, bool kBvh>
 __global__ void RM_K1_BOUNDS
 render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
@@ -389,7 +391,8 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         tri_r = reinterpret_cast<const R4<float>*>(smem_raw + L.bytes);
     }
     __syncthreads();
-    FastView fv;
+    FastViewT<kBvh> fv;
+    fv.bvh = ds.bvh;
     fv.sph = reinterpret_cast<const R4<float>*>(base + L.off_sph);
     fv.sph_id = reinterpret_cast<const int*>(base + L.off_sph_id);
     fv.n_sph = L.n_sph;
@@ -503,7 +506,9 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                 // stage A: primary visibility of this thread's 4 pixels
                 PrimaryState<kPx> ps;
                 primary_begin<kPx>(ps, fp, x0 + lx, ys + ly);
-                {
+                if constexpr (kBvh) {
+                    primary_bvh<kPx>(ps, fv, fp);
+                } else {
                     // the strip: pixels [x0, x0 + 31] x [ys, ys + 3]
                     const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + kFastTile - 1);
                     const float Ya = pixel_Y(fp, ys), Yb = pixel_Y(fp, ys + kStripRows - 1);
@@ -583,6 +588,10 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     };
     if (tall) warp_loop(PxTag<4>());
     else warp_loop(PxTag<2>());
+    if constexpr (kBvh) {                                       // ctr[6..7]: u64 count of secondary + shadow queries, kept across frames
+        const unsigned q = __reduce_add_sync(0xffffffffu, fv.n_queries);
+        if (lane == 0 && q) atomicAdd(reinterpret_cast<unsigned long long*>(ctr + 6), (unsigned long long)q);
+    }
     // values are >= 0, so the integer order of the bit patterns is the float order
     const int wm = __reduce_max_sync(0xffffffffu, __float_as_int(m));
     if (lane == 0 && wm > 0) atomicMax(&cta_max, wm);
@@ -780,7 +789,8 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     if (ex && ex->ev_begin) cudaEventRecord(ex->ev_begin, stream);
     const int n_tri = tri_count(ds.lay, cull);
     const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * fp.n_bands;
-    const bool classify = ds.lay.n_sph + poly_count(ds.lay, cull) == 0 && n_tri <= kClassifyMaxTris && n_tiles <= ds.tile_order_cap / 2;
+    const bool bvh = fp.accel != 0 && ds.bvh.n_nodes > 0;
+    const bool classify = !bvh && ds.lay.n_sph + poly_count(ds.lay, cull) == 0 && n_tri <= kClassifyMaxTris && n_tiles <= ds.tile_order_cap / 2;
     if (classify)
         prepare_classify_kernel<<<(n_tiles * kClassifyLanes + kClassifyBlock - 1) / kClassifyBlock, kClassifyBlock, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r,
                                                                          fp, tiles_x, n_tiles, ds.tile_order, ds.tile_order + ds.tile_order_cap / 2, ds.ctr,
@@ -808,9 +818,9 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
         cudaFuncAttributes fa;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-        if ((e = cudaFuncGetAttributes(&fa, render_fast_kernel<true>)) != cudaSuccess) return e;
+        if ((e = cudaFuncGetAttributes(&fa, render_fast_kernel<true, false>)) != cudaSuccess) return e;
         dyn_limit = std::min(kSmemLimit, optin - (int)fa.sharedSizeBytes - 1024);
-        if ((e = cudaFuncSetAttribute(render_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     }
     const size_t smem_geo = (size_t)ds.lay.bytes + (size_t)ds.lay.n_tri * 64;
@@ -829,8 +839,8 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     cfg.numAttrs = 1;
     const int cull_i = cull ? 1 : 0;
     const int* order2 = order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr;
-    const bool use_smem = smem <= (size_t)dyn_limit;
-    auto k = use_smem ? render_fast_kernel<true> : render_fast_kernel<false>;
+    const bool use_smem = !bvh && smem <= (size_t)dyn_limit;
+    auto k = bvh ? render_fast_kernel<false, true> : use_smem ? render_fast_kernel<true, false> : render_fast_kernel<false, false>;
     cfg.dynamicSmemBytes = use_smem ? smem : 0;
     int occ = 1;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kFastBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;

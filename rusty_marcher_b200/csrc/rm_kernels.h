@@ -24,11 +24,14 @@ template <typename R> struct DeviceScene {
     R4<float>* tri_r = nullptr;
     // frame control block of the persistent render kernel, zero between frames (the last CTA to finish resets it):
     //   ctr[0] next busy tile   ctr[1] fully covered tiles   ctr[2] empty tiles   ctr[3] CTAs finished   ctr[5] partially covered tiles
+    //   ctr[6..7] u64: scene queries behind the primary rays, accumulated by the hierarchy kernel (rm_scene_query_count)
     int* ctr = nullptr;
     // tile schedule written by the classify kernel: busy tiles (some triangle may touch them) first, then the
     // tiles that are provably empty and only need their black pixels stored
     int* tile_order = nullptr;
     int tile_order_cap = 0;
+    // hierarchy over the hittable primitives (rm_bvh.cuh), walked instead of the flat arrays when RmParams.accel is set
+    BvhView bvh;
 };
 
 // The path's one exchange step done by the kernels themselves over peer memory (NVLink): every rank owns

@@ -167,21 +167,64 @@ void write_triangle(const PlaneTmp& p, double* src, R4<float>* g) {
     g[2] = {(float)A[1], (float)B[1], (float)C[1], (float)A[2]};
     g[3] = {(float)B[2], thr, idf, 0.f};
 }
+// Bounds of the region a planar primitive can be hit in: the points of its plane whose XY projection lies inside the
+// XY-projected polygon (triangle.rs:13-15,72-76 only ever look at x and y).  z is affine in (x, y) on the plane, so its
+// range over the polygon is its range over the vertices; taken from the plane equation rather than from the vertices'
+// own z, so that the box bounds what the intersection routine accepts even for a caller-supplied normal / plane point.
+BvhPrimBox plane_bounds(const PlaneTmp& p, int code) {
+    BvhPrimBox b;
+    b.code = code;
+    for (int a = 0; a < 3; a++) {
+        b.lo[a] = INFINITY;
+        b.hi[a] = -INFINITY;
+    }
+    for (size_t v = 0; v < p.vxy.size() / 2; v++) {
+        const double x = p.vxy[2 * v], y = p.vxy[2 * v + 1];
+        const double z = p.c[2] - (p.n[0] * (x - p.c[0]) + p.n[1] * (y - p.c[1])) / p.n[2];   // non-finite for n.z == 0: unbounded box
+        const double q[3] = {x, y, z};
+        for (int a = 0; a < 3; a++) {
+            b.lo[a] = std::fmin(b.lo[a], q[a]);      // fmin/fmax drop a NaN; build_bvh() treats lo > hi as unbounded
+            b.hi[a] = std::fmax(b.hi[a], q[a]);
+            if (!std::isfinite(q[a])) {
+                b.lo[a] = -INFINITY;
+                b.hi[a] = INFINITY;
+            }
+        }
+    }
+    return b;
+}
+
 template <typename R> void write_fast(const std::vector<PlaneTmp>&, BlobLayout&, unsigned char*, PackedScene<R>&) {}
 template <> void write_fast<float>(const std::vector<PlaneTmp>& pln, BlobLayout& L, unsigned char* b, PackedScene<float>& out) {
     auto* g = reinterpret_cast<R4<float>*>(b + L.off_tri_g);
     auto* slot = reinterpret_cast<int*>(b + L.off_poly_slot);
     out.tri_src.assign((size_t)L.n_tri * kTriSrcDoubles + kTriSrcDoubles, 0.);
     int t = 0, k = 0;
+    std::vector<BvhPrimBox> boxes;
+    const auto* sph = reinterpret_cast<const R4<float>*>(b + L.off_sph);
+    for (int i = 0; i < L.n_sph; i++) {
+        // the sphere as the kernels see it: centre and r^2 already rounded to f32 (sphere.rs:6-11)
+        const double r = std::sqrt((double)sph[i].w), c[3] = {sph[i].x, sph[i].y, sph[i].z};
+        BvhPrimBox bx;
+        for (int a = 0; a < 3; a++) {
+            bx.lo[a] = c[a] - r;
+            bx.hi[a] = c[a] + r;
+        }
+        bx.code = (BVH_SPHERE << 30) | i;
+        boxes.push_back(bx);
+    }
     for (size_t i = 0; i < pln.size(); i++) {
         if (pln[i].cls == 2) continue;
         if (pln[i].vxy.size() == 6) {
             write_triangle(pln[i], out.tri_src.data() + (size_t)t * kTriSrcDoubles, g + 4 * t);
+            if (pln[i].cls == 0) boxes.push_back(plane_bounds(pln[i], (BVH_TRI << 30) | t));
             t++;
         } else {
+            if (pln[i].cls == 0) boxes.push_back(plane_bounds(pln[i], (int)((unsigned)BVH_POLY << 30 | (unsigned)i)));
             slot[k++] = (int)i;
         }
     }
+    out.bvh_depth = build_bvh(boxes, out.bvh_nodes, out.bvh_prims);
 }
 
 template <typename R> void push_material(PackedScene<R>& out, const RmReflectance& r) {
@@ -367,6 +410,7 @@ template <typename R> FrameParams<R> make_frame_params(const RmParams& p) {
     fp.camera = {(R)p.camera[0], (R)p.camera[1], (R)p.camera[2]};
     fp.background = (R)p.background;
     fp.max_depth = p.max_depth < 0 ? 0 : (p.max_depth > kMaxDepth ? kMaxDepth : p.max_depth);
+    fp.accel = p.accel != 0 ? 1 : 0;
     return fp;
 }
 

@@ -54,7 +54,19 @@ template <typename R> struct PackedScene {
     // scene-order traversal lists: [0] = every primitive, [1] = after culling
     std::vector<int> order[2], order_shape[2];
     int n_prims = 0;
+    // FP32 pack only: hierarchy over the hittable primitives (rm_bvh.cuh), used when RmParams.accel is set
+    std::vector<R4<float>> bvh_nodes;
+    std::vector<int> bvh_prims;
+    int bvh_depth = 0;
 };
+
+// Bounds of one hittable primitive (f64, unpadded) and its entry code kind << 30 | index for the hierarchy's leaves.
+struct BvhPrimBox {
+    double lo[3], hi[3];
+    int code;
+};
+// Builds the hierarchy of rm_bvh.cuh (nodes: 4 x R4<float> each; prims: leaf entries).  Returns its depth.
+int build_bvh(const std::vector<BvhPrimBox>& boxes, std::vector<R4<float>>& nodes, std::vector<int>& prims);
 
 // Validates `fs` and packs it.  Returns RM_OK or RM_ERR_SCENE / RM_ERR_INVALID_ARGUMENT with `err` set.
 template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out, std::string& err);

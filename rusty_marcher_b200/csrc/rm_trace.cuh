@@ -496,6 +496,7 @@ template <typename R> struct FrameParams {
     Vec3<R> camera;
     R background;
     int max_depth;
+    int accel;                    // RmParams.accel: scene queries through the hierarchy (FP32 production kernel)
 };
 
 // pixel row of the l-th rendered row of this call (l in [0, 32 * n_bands))

@@ -12,6 +12,8 @@ from .geometry import Vec3f
 
 
 class Renderer:
+    ACCEL_AUTO_PRIMS = 256
+
     def __init__(self, fov, height, width):                     # renderer.rs:25-33
         self.fov = float(fov)
         self.height = float(height)
@@ -19,6 +21,10 @@ class Renderer:
         self.max_depth = 3                                      # renderer.rs:262
         self.background = 0.1                                   # renderer.rs:40-44
         self.cull_backfacing = True
+        # scene queries through the bounding-volume hierarchy (RmParams.accel; the reference's unused bounding boxes,
+        # shapes.rs:34-38): False = the reference's brute-force traversal, True, or "auto" = for scenes of more than
+        # ACCEL_AUTO_PRIMS primitives.  The FP32 frame is bit-identical either way.
+        self.accel = False
         self.precision = _abi.RM_FP32
         self.last_stats = None
 
@@ -33,6 +39,10 @@ class Renderer:
         p.patch_row_begin, p.patch_row_end = patch_rows[:2]     # (begin, end[, stride]) in 32-row patch rows
         p.patch_row_stride = patch_rows[2] if len(patch_rows) > 2 else 1
         p.cull_backfacing = int(self.cull_backfacing)
+        accel = self.accel
+        if accel == "auto":
+            accel = _abi.load().rm_scene_num_prims(scene.device_handle()) > self.ACCEL_AUTO_PRIMS
+        p.accel = int(bool(accel)) if self.precision == _abi.RM_FP32 else 0
         return p
 
     def render(self, frame, scene, prim_id=None, rgb8=None, counters=False, patch_rows=(0, -1)):

@@ -15,7 +15,7 @@ _lib = None
 
 def build(force=False):
     srcs = [os.path.join(HERE, "rm_emu.cpp")] + [os.path.join(ROOT, "rusty_marcher_b200", "csrc", f) for f in
-                                                 ("rm_trace.cuh", "rm_fast.cuh", "rm_math.cuh", "rm_scene.cpp", "rm_scene.h", "rm_host.cpp")]
+                                                 ("rm_trace.cuh", "rm_fast.cuh", "rm_math.cuh", "rm_scene.cpp", "rm_scene.h", "rm_host.cpp", "rm_bvh.cuh", "rm_bvh.cpp")]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(s) for s in srcs):
         return LIB
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-pthread",
@@ -36,7 +36,7 @@ def lib():
     return _lib
 
 
-def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=True, threads=8, patch_rows=(0, -1), strip_bound=True):
+def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=True, threads=8, patch_rows=(0, -1), strip_bound=True, accel=False):
     lib().emu_set_strip_bound(int(strip_bound))
     flat = scene.flatten()
     p = _abi.RmParams()
@@ -45,6 +45,7 @@ def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=Tru
     p.max_depth, p.background, p.patch_size = max_depth, 0.1, 32
     p.patch_row_begin, p.patch_row_end = patch_rows
     p.cull_backfacing = int(cull)
+    p.accel = int(accel)
     dt = np.float32 if precision in ("f32", "fast") else np.float64
     rgb = np.zeros((height, width, 3), dtype=dt)
     ids = np.full((height, width), -1, dtype=np.int32)
@@ -54,3 +55,20 @@ def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=Tru
     if rc != 0:
         raise RuntimeError("emu rc %d" % rc)
     return {"rgb": rgb, "prim_id": ids, "counters": st.counters(), "max": st.max_value, "resident": st.resident_prims}
+
+
+def bvh(scene):
+    """The hierarchy rm_scene.cpp builds for the scene's FP32 pack: (nodes (n, 16) float32, leaf entries int32, depth)."""
+    L = lib()
+    flat = scene.flatten()
+    cap = 4 * (flat.c.n_spheres + flat.c.n_polygons + flat.c.n_triangles) + 16
+    nodes = np.zeros((cap, 16), dtype=np.float32)
+    prims = np.zeros(cap, dtype=np.int32)
+    n_nodes, n_prims, depth = C.c_int(), C.c_int(), C.c_int()
+    L.emu_bvh.restype = C.c_int
+    L.emu_bvh.argtypes = [C.POINTER(_abi.RmFlatScene), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rc = L.emu_bvh(C.byref(flat.c), nodes.ctypes.data, cap, prims.ctypes.data, cap, C.byref(n_nodes), C.byref(n_prims), C.byref(depth))
+    if rc != 0:
+        raise RuntimeError("emu_bvh rc %d" % rc)
+    return nodes[:n_nodes.value], prims[:n_prims.value], depth.value

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../rusty_marcher_b200/csrc/rm_scene.cpp"
+#include "../../rusty_marcher_b200/csrc/rm_bvh.cpp"
 #include "../../rusty_marcher_b200/csrc/rm_host.cpp"
 
 // rm_host.cpp's rm_builder_upload needs this symbol; the emulator has no device.
@@ -97,6 +98,8 @@ int emu_render_impl(const RmFlatScene* fs, const RmParams* p, R* out_rgb, int32_
 static std::atomic<int> g_strip_bound{1};   // 0: walk every triangle in every strip (to prove the bound changes no pixel)
 
 // the FP32 production path (rm_fast.cuh): prepare_raster + fast_pixel, as the CUDA kernels run them
+// (kBvh: RmParams.accel -- every query through the hierarchy of rm_bvh.cuh, stage A pixel by pixel)
+template <bool kBvh>
 int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
     rm::PackedScene<float> ps;
     std::string err;
@@ -109,7 +112,10 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
     const int n_tri = rm::tri_count(L, cull);
     std::vector<rm::R4<float>> tri_r((size_t)n_tri * 4 + 4);
     for (int j = 0; j < n_tri; j++) rm::prepare_raster(ps.tri_src.data() + (size_t)j * rm::kTriSrcDoubles, p->camera, tri_r.data() + 4 * j);
-    rm::FastView fv0;
+    rm::FastViewT<kBvh> fv0;
+    fv0.bvh.nodes = ps.bvh_nodes.data();
+    fv0.bvh.prims = ps.bvh_prims.data();
+    fv0.bvh.n_nodes = (int)(ps.bvh_nodes.size() / 4);
     fv0.sph = reinterpret_cast<const rm::R4<float>*>(base + L.off_sph);
     fv0.sph_id = reinterpret_cast<const int*>(base + L.off_sph_id);
     fv0.n_sph = L.n_sph;
@@ -135,7 +141,7 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
     std::vector<std::thread> pool;
     for (int t = 0; t < n_threads; t++) {
         pool.emplace_back([&, t] {
-            rm::FastView fv = fv0;
+            rm::FastViewT<kBvh> fv = fv0;
             std::vector<int> cand;
             for (;;) {
                 // one 4-row band per grab; inside it the kernel's 32x4 warp strips, each with its own exact
@@ -147,7 +153,7 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
                     const float Ya = rm::pixel_Y(fp, y0), Yb = rm::pixel_Y(fp, y0 + 3);
                     cand.clear();
                     // the classify kernel's tile-level bound (32x32 tile around this strip): provably empty tiles are only zero-filled
-                    bool tile_busy = fv.n_sph + fv.n_poly > 0 || !g_strip_bound.load();
+                    bool tile_busy = kBvh || fv.n_sph + fv.n_poly > 0 || !g_strip_bound.load();
                     {
                         const int ty0 = fp.row_begin + ((y0 - fp.row_begin) / 32) * 32;
                         const float TYa = rm::pixel_Y(fp, ty0), TYb = rm::pixel_Y(fp, ty0 + 31);
@@ -163,14 +169,18 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
                             }
                         continue;
                     }
-                    for (int j = 0; j < n_tri; j++)
+                    for (int j = 0; j < n_tri && !kBvh; j++)
                         if (!g_strip_bound.load() || rm::tri_may_touch(tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], Xa, Xb, Ya, Yb)) cand.push_back(j);
                     for (int lane = 0; lane < 32; lane++) {
                         const int x = xs + (lane & 7) * 4, y = y0 + (lane >> 3);
                         rm::PrimaryState<4> ps;
                         rm::primary_begin<4>(ps, fp, x, y);
-                        for (int j : cand) rm::primary_tri<4>(ps, tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], fv.n_sph + j);
-                        if (fv.n_sph + fv.n_poly > 0) rm::primary_rest<4>(ps, fv, fp);
+                        if constexpr (kBvh) {
+                            rm::primary_bvh<4>(ps, fv, fp);
+                        } else {
+                            for (int j : cand) rm::primary_tri<4>(ps, tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], fv.n_sph + j);
+                            if (fv.n_sph + fv.n_poly > 0) rm::primary_rest<4>(ps, fv, fp);
+                        }
                         for (int k = 0; k < 4; k++) {
                             rm::Vec3<float> c = ps.slot[k] >= 0 ? rm::fast_shade(fv, fp, x + k, y, ps.t[k], ps.slot[k], ps.id[k])
                                                                 : rm::Vec3<float>{0.f, 0.f, 0.f};
@@ -199,7 +209,22 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
 extern "C" {
 void emu_set_strip_bound(int on) { g_strip_bound.store(on); }
 int emu_render_fast(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
-    return emu_render_fast_impl(fs, p, out_rgb, prim, stats, n_threads);
+    return p->accel ? emu_render_fast_impl<true>(fs, p, out_rgb, prim, stats, n_threads)
+                    : emu_render_fast_impl<false>(fs, p, out_rgb, prim, stats, n_threads);
+}
+// the hierarchy of a scene's FP32 pack, for the builder's invariants: nodes (16 floats each) and leaf entries
+int emu_bvh(const RmFlatScene* fs, float* nodes, int nodes_cap, int* prims, int prims_cap, int* n_nodes, int* n_prims, int* depth) {
+    rm::PackedScene<float> ps;
+    std::string err;
+    int rc = rm::pack_scene<float>(*fs, ps, err);
+    if (rc != RM_OK) return rc;
+    *n_nodes = (int)(ps.bvh_nodes.size() / 4);
+    *n_prims = (int)ps.bvh_prims.size();
+    *depth = ps.bvh_depth;
+    if (*n_nodes > nodes_cap || *n_prims > prims_cap) return RM_ERR_INVALID_ARGUMENT;
+    std::memcpy(nodes, ps.bvh_nodes.data(), ps.bvh_nodes.size() * sizeof(rm::R4<float>));
+    std::memcpy(prims, ps.bvh_prims.data(), ps.bvh_prims.size() * sizeof(int));
+    return RM_OK;
 }
 int emu_render_f32(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
     return emu_render_impl<float>(fs, p, out_rgb, prim, stats, n_threads);

@@ -20,9 +20,9 @@ from tests.oracle_scenes import build_oracle_scene
 pytestmark = pytest.mark.gpu
 
 
-def gpu_render(rm, scene, w, h, precision="f32", depth=3, cull=True, counters=False, rows=(0, -1), want_rgb8=True):
+def gpu_render(rm, scene, w, h, precision="f32", depth=3, cull=True, counters=False, rows=(0, -1), want_rgb8=True, accel=False):
     r = rm.create_renderer(1.5, h, w)
-    r.max_depth, r.cull_backfacing = depth, cull
+    r.max_depth, r.cull_backfacing, r.accel = depth, cull, accel
     r.precision = rm.RM_FP64 if precision == "f64" else rm.RM_FP32
     fb = rm.create_frame_buffer(w, h, dtype=np.float64 if precision == "f64" else np.float32)
     ids = np.full((h, w), -1, dtype=np.int32)
@@ -70,6 +70,51 @@ def test_fp32_kernels_meet_the_north_star_tolerance(rm_gpu, case, cull):
     rep = parity.check_fp32(got, ref, (h // 32) * 32, got["rgb8"])
     print(name, "cull", cull, rep)
     assert np.all(got["rgb"][(h // 32) * 32:] == 0)            # renderer.rs:47-55: rows never rendered stay untouched
+
+
+@pytest.mark.parametrize("cull", [False, True])
+def test_hierarchy_changes_no_pixel(rm_gpu, case, cull):
+    """RmParams.accel = 1 (scene queries walk the bounding-volume hierarchy, rm_bvh.cuh): the same tests per (ray,
+    primitive) and the same winner as the brute-force traversal, so the FP32 frame -- floats, primary ids, max, 8-bit
+    bytes -- is bit-identical, and meets the north-star tolerance against the oracle like the brute-force frame."""
+    name, w, h, depth, scene, ref = case
+    a = gpu_render(rm_gpu, scene, w, h, "f32", depth, cull)
+    b = gpu_render(rm_gpu, scene, w, h, "f32", depth, cull, accel=True)
+    assert np.array_equal(a["prim_id"], b["prim_id"])
+    assert np.array_equal(a["rgb"], b["rgb"]) and np.array_equal(a["rgb8"], b["rgb8"]) and a["max"] == b["max"]
+    parity.check_fp32(b, ref, (h // 32) * 32, b["rgb8"])
+
+
+def test_hierarchy_on_the_stress_scene(rm_gpu):
+    """The bench's stress scene (1024 spheres + 8192 triangles, depth cap 6) at 1280x704, camera off the origin: hierarchy
+    against brute force bit for bit, whole frame and interleaved bands, host call and frame-level call."""
+    import torch
+    from rusty_marcher_b200 import tiled
+    w, h = 1280, 704
+    scene = workloads.build_scene(workloads.describe("stress", n_spheres=1024, grid=64))
+    scene.offset_camera((7.5, -3.25, 20.0))
+    a = gpu_render(rm_gpu, scene, w, h, "f32", depth=6)
+    b = gpu_render(rm_gpu, scene, w, h, "f32", depth=6, accel=True)
+    assert (a["prim_id"] >= 0).sum() > 50000
+    assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["rgb"], b["rgb"]) and np.array_equal(a["rgb8"], b["rgb8"])
+    acc = np.zeros_like(a["rgb"])
+    for k in range(3):
+        t = gpu_render(rm_gpu, scene, w, h, "f32", depth=6, accel=True, rows=(k, -1, 3), want_rgb8=False)
+        for pr in range(k, h // 32, 3):
+            acc[pr * 32:(pr + 1) * 32] = t["rgb"][pr * 32:(pr + 1) * 32]
+    assert np.array_equal(acc, a["rgb"])
+    dev = torch.device("cuda:0")
+    r = rm_gpu.create_renderer(1.5, h, w)
+    r.max_depth, r.accel = 6, "auto"
+    tr = tiled.TiledRenderer(tiled.CudaBackend(scene, r, w, h, dev), w, h, dev)
+    try:
+        assert tr.params.accel == 1
+        f = tr.render()
+        torch.cuda.synchronize()
+        tr.peer.status()
+        assert np.array_equal(f.cpu().numpy(), a["rgb8"]) and np.array_equal(tr.rgb.cpu().numpy(), a["rgb"])
+    finally:
+        tr.close()
 
 
 def test_demo_golden_image_on_gpu(rm_gpu):

@@ -99,3 +99,66 @@ def test_empty_scene_and_camera_offset():
     osc = O.Scene.create_default()
     osc.offset_camera((5., 0., -5.))
     parity.check_exact(emu.render(scene, 96, 64, "f64"), O.render(osc, 96, 64))
+
+
+@pytest.mark.parametrize("cull", [False, True])
+def test_hierarchy_changes_no_pixel(case, cull):
+    """RmParams.accel: queries through the bounding-volume hierarchy (rm_bvh.cuh) test a superset of the primitives a
+    ray can hit with the same routines and pick the winner by the same (distance, id) order -- the frame must be
+    bit-identical to the brute-force FP32 frame, primary ids included."""
+    name, w, h, depth, scene, ref = case
+    a = emu.render(scene, w, h, "fast", max_depth=depth, cull=cull)
+    b = emu.render(scene, w, h, "fast", max_depth=depth, cull=cull, accel=True)
+    assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["rgb"], b["rgb"])
+
+
+def test_hierarchy_on_a_large_scene_and_a_moved_camera():
+    """1024 spheres + 8192 triangles (the bench's stress_4k scene), depth cap 6, camera off the origin."""
+    scene = workloads.build_scene(workloads.describe("stress", n_spheres=1024, grid=64))
+    scene.offset_camera((7.5, -3.25, 20.0))
+    a = emu.render(scene, 320, 192, "fast", max_depth=6)
+    b = emu.render(scene, 320, 192, "fast", max_depth=6, accel=True)
+    assert (a["prim_id"] >= 0).sum() > 5000
+    assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["rgb"], b["rgb"])
+
+
+@pytest.mark.parametrize("name,kw", [("demo", {}), ("cornell_box", {}), ("stress", dict(n_spheres=512, grid=32))])
+def test_hierarchy_invariants(name, kw):
+    """Builder (rm_bvh.cpp): every hittable primitive sits in exactly one leaf, leaves hold at most four, a child's box
+    lies inside the box its parent records for it, and the depth fits the traversal stack."""
+    scene = workloads.build_scene(workloads.describe(name, **kw))
+    nodes, prims, depth = emu.bvh(scene)
+    assert 1 <= depth < 64 and len(nodes) >= 1
+    assert len(set(prims.tolist())) == len(prims)              # no primitive twice
+    kinds = prims.view(np.uint32) >> 30
+    flat = scene.flatten().c
+    assert (kinds == 0).sum() == flat.n_spheres
+    assert (kinds > 0).sum() <= flat.n_polygons + flat.n_triangles
+    seen = np.zeros(len(prims), dtype=np.int32)
+
+    def boxes(n):
+        a, b, z = n[0:4], n[4:8], n[8:12]
+        return ((a[0], a[1], a[2], a[3], z[0], z[1]), (b[0], b[1], b[2], b[3], z[2], z[3]))
+
+    def inside(inner, outer):
+        return all(inner[k] >= outer[k] for k in (0, 2, 4)) and all(inner[k] <= outer[k] for k in (1, 3, 5))
+
+    stack = [(0, None, 1)]
+    deepest = 0
+    while stack:
+        i, bound, d = stack.pop()
+        deepest = max(deepest, d)
+        n = nodes[i]
+        b0, b1 = boxes(n)
+        for box, child in ((b0, int(n[12:13].view(np.int32)[0])), (b1, int(n[13:14].view(np.int32)[0]))):
+            if bound is not None:
+                assert inside(box, bound)
+            if child >= 0:
+                stack.append((child, box, d + 1))
+            else:
+                code = ~child
+                first, cnt = code >> 3, code & 7
+                assert cnt <= 4
+                seen[first:first + cnt] += 1
+    assert np.all(seen == 1)
+    assert deepest <= depth
