@@ -284,6 +284,11 @@ int rm_kernel_times(int back, double* ms_prepare, double* ms_render, double* ms_
  * Ray segments of a frame = rendered pixels + this count: the figure the instrumented brute-force kernel (RmStats)
  * gives for scenes small enough to run through it.  Synchronises the device. */
 int rm_scene_query_count(RmScene scene, uint64_t* out_queries, int reset);
+/* A walk of the hierarchy visits every node at most once; one that exceeds that budget (possible only with corrupt
+ * hierarchy memory) gives up instead of hanging the GPU and raises a sticky flag.  Returns RM_OK while the flag is down,
+ * RM_ERR_CUDA once it is up; out_words (optional): [0] flag, [1..6] origin and direction of the first such ray (float
+ * bits), [7] node, [8] stack depth.  Synchronises the device. */
+int rm_scene_accel_status(RmScene scene, int32_t out_words[16]);
 
 /* ---- FP32 peak probe: a pure-FFMA kernel, returns measured TFLOP/s (roofline denominator) ----- */
 int rm_measure_fp32_peak(double* out_tflops, double* out_ms);

@@ -141,10 +141,11 @@ template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
     if (sizeof(R) == 4) {
         if ((rc = upload_vec(ps.tri_src, &dp.tri_src)) != RM_OK) return rc;
         // raster records | frame control block | tile schedule
+        // raster records | frame control block | tile schedule | status words of the hierarchy walk
         const size_t rec_bytes = (size_t)ps.lay.n_tri * 64 + 64;
         const int order_cap = 1 << 16;                          // tiles of a frame up to 8192 x 8192
-        CK(cudaMalloc(&dp.tri_r, rec_bytes + 64 + (size_t)order_cap * sizeof(int)));
-        CK(cudaMemset(dp.tri_r, 0, rec_bytes + 64 + (size_t)order_cap * sizeof(int)));
+        CK(cudaMalloc(&dp.tri_r, rec_bytes + 64 + (size_t)order_cap * sizeof(int) + 64));
+        CK(cudaMemset(dp.tri_r, 0, rec_bytes + 64 + (size_t)order_cap * sizeof(int) + 64));
         dp.ds.tri_src = static_cast<const double*>(dp.tri_src);
         dp.ds.tri_r = static_cast<rm::R4<float>*>(dp.tri_r);
         dp.ds.ctr = reinterpret_cast<int*>(static_cast<char*>(dp.tri_r) + rec_bytes);
@@ -155,6 +156,7 @@ template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
         dp.ds.bvh.nodes = static_cast<const rm::R4<float>*>(dp.bvh_nodes);
         dp.ds.bvh.prims = static_cast<const int*>(dp.bvh_prims);
         dp.ds.bvh.n_nodes = (int)(ps.bvh_nodes.size() / 4);
+        dp.ds.bvh.status = dp.ds.tile_order + order_cap;
     }
     dp.ds.blob = static_cast<const unsigned char*>(dp.blob);
     dp.ds.lay = ps.lay;
@@ -163,6 +165,10 @@ template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
     dp.ds.mat_f = dp.mat_f;
     dp.ds.n_mat = ps.n_prims;
     se.n_prims = ps.n_prims;
+    // The copies and the memset above ran on the legacy default stream, the kernels run on non-blocking streams that it
+    // does not order: a copy from pageable memory returns once the data is staged, a memset is asynchronous.  Everything
+    // must have landed before the first frame reads it.
+    CK(cudaDeviceSynchronize());
     dp.ready = true;
     return RM_OK;
 }
@@ -511,6 +517,20 @@ int rm_kernel_times(int back, double* ms_prepare, double* ms_render, double* ms_
 }
 
 int rm_last_kernel_times(double* ms_prepare, double* ms_render) { return rm_kernel_times(0, ms_prepare, ms_render, nullptr); }
+
+int rm_scene_accel_status(RmScene scene, int32_t out_words[16]) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    auto it = g.scenes.find(scene);
+    if (it == g.scenes.end()) return fail(RM_ERR_INVALID_ARGUMENT, "unknown scene handle");
+    if (!it->second.f32.ready || !it->second.f32.ds.bvh.status) return fail(RM_ERR_INVALID_ARGUMENT, "scene has no FP32 pack");
+    CK(cudaDeviceSynchronize());
+    int32_t w[16];
+    CK(cudaMemcpy(w, it->second.f32.ds.bvh.status, sizeof w, cudaMemcpyDeviceToHost));
+    if (out_words) std::memcpy(out_words, w, sizeof w);
+    if (w[0]) return fail(RM_ERR_CUDA, "a walk of the scene's hierarchy exceeded its node budget (corrupt hierarchy memory?): the frame is not valid");
+    return RM_OK;
+}
 
 int rm_scene_query_count(RmScene scene, uint64_t* out_queries, int reset) {
     std::lock_guard<std::mutex> lock(g.mu);

@@ -35,6 +35,8 @@ struct BvhView {
     const R4<float>* nodes = nullptr;
     const int* prims = nullptr;
     int n_nodes = 0;
+    // device only: 16 words a walk writes when it gives up (see bvh_walk); word 0 is the flag
+    int* status = nullptr;
 };
 
 RM_HD int bvh_int(float f) {
@@ -73,8 +75,21 @@ RM_HD bool bvh_walk(const BvhView& bv, const Vec3<float> o, const Vec3<float> d,
     const BvhRay r = bvh_ray(o, d);
     int stack[kBvhStack];
     int sp = 0, cur = 0;
+    // A walk visits every node at most once.  Corrupt node memory must not be able to hang the GPU: past that bound the
+    // walk gives up (reports a miss), raises the scene's status flag and leaves the ray behind for the host to report.
+    int budget = 2 * bv.n_nodes + 8;
     for (;;) {
         while (cur >= 0) {
+            if (--budget < 0 || sp >= kBvhStack - 1 || cur >= bv.n_nodes) {
+#if defined(__CUDA_ARCH__)
+                if (bv.status && atomicExch(bv.status, 1) == 0) {
+                    float* f = reinterpret_cast<float*>(bv.status);
+                    f[1] = o.x; f[2] = o.y; f[3] = o.z; f[4] = d.x; f[5] = d.y; f[6] = d.z;
+                    bv.status[7] = cur; bv.status[8] = sp; bv.status[9] = budget;
+                }
+#endif
+                return false;
+            }
             const R4<float>* n = bv.nodes + 4 * (size_t)cur;
             const R4<float> a = n[0], b = n[1], z = n[2], c = n[3];
             const float tc = cut();

@@ -510,7 +510,13 @@ template <int kPx, class FV> RM_HD void primary_rest(PrimaryState<kPx>& ps, cons
 // primitive) and the same (distance, id) order as the brute-force stage A, hence the same t / slot / id, bit for bit.
 template <int kPx> RM_HD void primary_bvh(PrimaryState<kPx>& ps, const FastViewBvh& fv, const FrameParams<float>& fp) {
     const bool rest = fv.n_sph + fv.n_poly > 0;
-#pragma unroll 1
+    // One walk per pixel, the loop over the thread's pixels fully unrolled.  As a rolled loop (`#pragma unroll 1`, like
+    // primary_rest) it went wrong on the B200 for scenes with deep hierarchies: ptxas keeps the trip counter of such a
+    // loop in a uniform register behind a uniform branch, the walks inside run a different number of steps in every
+    // lane, and the frames showed lanes that had skipped an iteration (results shifted by one pixel, pixels left
+    // unprocessed) and, once, a kernel that never left the loop.  Unrolled there is no counter to share; the rotation
+    // of the pixel state becomes a compile-time renaming.
+#pragma unroll
     for (int r = 0; r < kPx; r++) {
         PrimaryState<1> p1;
         p1.X[0] = ps.X[0];
@@ -574,6 +580,9 @@ template <int kPx> RM_HD void primary_bvh(PrimaryState<kPx>& ps, const FastViewB
         ps.t[kPx - 1] = t_new;
         ps.slot[kPx - 1] = slot_new;
         ps.id[kPx - 1] = id_new;
+#if defined(__CUDA_ARCH__) && defined(RM_BVH_SYNC_EACH_PIXEL)
+        __syncwarp();
+#endif
     }
 }
 
