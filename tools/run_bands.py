@@ -8,18 +8,19 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import rusty_marcher_b200 as rm  # noqa: E402
-from bench import WORKLOADS  # noqa: E402
+from bench import workload_of  # noqa: E402
 from rusty_marcher_b200 import _abi, tiled, workloads  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cornell_4k"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-scene_name, w, h, depth, kw = WORKLOADS[name]
+scene_name, w, h, depth, kw, accel = workload_of(name)
 rm.init(0)
 L = _abi.load()
 dev = torch.device("cuda:0")
 scene = workloads.scene(scene_name, **kw)
 r = rm.create_renderer(1.5, h, w)
 r.max_depth = depth
+r.accel = accel
 be = tiled.CudaBackend(scene, r, w, h, dev)
 rgb = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
 dmax = torch.zeros(1, dtype=torch.float32, device=dev)

@@ -7,17 +7,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import rusty_marcher_b200 as rm  # noqa: E402
-from bench import WORKLOADS  # noqa: E402
+from bench import workload_of  # noqa: E402
 from rusty_marcher_b200 import tiled, workloads  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "cornell_4k"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 and not sys.argv[2].startswith("-") else 5
-scene_name, w, h, depth, kw = WORKLOADS[name]
+scene_name, w, h, depth, kw, accel = workload_of(name)
 rm.init(0)
 dev = torch.device("cuda:0")
 scene = workloads.scene(scene_name, **kw)
 r = rm.create_renderer(1.5, h, w)
 r.max_depth = depth
+r.accel = accel
 r.cull_backfacing = "--no-cull" not in sys.argv
 if "--f64" in sys.argv:
     r.precision = rm.RM_FP64

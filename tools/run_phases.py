@@ -9,7 +9,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import rusty_marcher_b200 as rm  # noqa: E402
-from bench import WORKLOADS  # noqa: E402
+from bench import workload_of  # noqa: E402
 from rusty_marcher_b200 import _abi, tiled, workloads  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "cornell_4k"
@@ -21,12 +21,13 @@ torch.cuda.set_device(lr)
 dev = torch.device("cuda", lr)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-scene_name, w, h, depth, kw = WORKLOADS[name]
+scene_name, w, h, depth, kw, accel = workload_of(name)
 rm.init(lr)
 L = _abi.load()
 scene = workloads.scene(scene_name, **kw)
 r = rm.create_renderer(1.5, h, w)
 r.max_depth = depth
+r.accel = accel
 be = tiled.CudaBackend(scene, r, w, h, dev)
 tr = tiled.TiledRenderer(be, w, h, dev, exchange="peer")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
