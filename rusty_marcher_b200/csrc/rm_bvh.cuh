@@ -29,6 +29,7 @@ namespace rm {
 
 constexpr int kBvhStack = 64;      // the builder switches to median splits below depth 40: 40 + log2(n) < 64
 constexpr int kBvhLeafMax = 4;
+constexpr int kBvhMaxLights = 8;   // lights the hierarchy kernel shades (unrolled pairs, rm_fast.cuh direct())
 enum BvhKind { BVH_SPHERE = 0, BVH_TRI = 1, BVH_POLY = 2 };
 
 struct BvhView {

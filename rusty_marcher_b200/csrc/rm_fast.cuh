@@ -331,7 +331,7 @@ template <bool kBvh> struct FastViewT {
         // approximates it (|origin| 2^-24 against a short t)
         const Vec3<float> to_viewer = -dir;
         const Vec3<float> kd = {ma.x, ma.y, ma.z};
-        for (int l0 = 0; l0 < n_lgt; l0 += 2) {
+        auto pair = [&](const int l0) {
             const bool two = l0 + 1 < n_lgt;
             const R4<float> lpA = lgt_p[l0], lpB = lgt_p[two ? l0 + 1 : l0];
             const Vec3<float> ldA = normalized(Vec3<float>{lpA.x - point.x, lpA.y - point.y, lpA.z - point.z});   // renderer.rs:166
@@ -352,6 +352,15 @@ template <bool kBvh> struct FastViewT {
                 const float sf = fmaxf(dot(reflected, to_viewer), 0.f);                               // renderer.rs:150
                 acc = acc + scaled(lc, pow_nonneg(sf * mb.x, mb.y));                                  // renderer.rs:186-189
             }
+        };
+        if constexpr (kBvh) {
+            // No rolled loop around the walks (see primary_bvh for what a shared trip counter did on the B200): the lights
+            // as unrolled, guarded pairs.  Scenes with more than kBvhMaxLights lights stay on the brute-force kernel.
+#pragma unroll
+            for (int k = 0; k < kBvhMaxLights / 2; k++)
+                if (2 * k < n_lgt) pair(2 * k);
+        } else {
+            for (int l0 = 0; l0 < n_lgt; l0 += 2) pair(l0);
         }
         return scaled(acc, ma.w);                                                                     // renderer.rs:192
     }

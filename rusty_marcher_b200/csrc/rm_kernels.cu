@@ -789,7 +789,7 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     if (ex && ex->ev_begin) cudaEventRecord(ex->ev_begin, stream);
     const int n_tri = tri_count(ds.lay, cull);
     const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * fp.n_bands;
-    const bool bvh = fp.accel != 0 && ds.bvh.n_nodes > 0;
+    const bool bvh = fp.accel != 0 && ds.bvh.n_nodes > 0 && ds.lay.n_lgt <= kBvhMaxLights;
     const bool classify = !bvh && ds.lay.n_sph + poly_count(ds.lay, cull) == 0 && n_tri <= kClassifyMaxTris && n_tiles <= ds.tile_order_cap / 2;
     if (classify)
         prepare_classify_kernel<<<(n_tiles * kClassifyLanes + kClassifyBlock - 1) / kClassifyBlock, kClassifyBlock, 0, stream>>>(ds.tri_src, n_tri, camera[0], camera[1], camera[2], ds.tri_r,

@@ -209,7 +209,8 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
 extern "C" {
 void emu_set_strip_bound(int on) { g_strip_bound.store(on); }
 int emu_render_fast(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
-    return p->accel ? emu_render_fast_impl<true>(fs, p, out_rgb, prim, stats, n_threads)
+    // (the device keeps scenes with more than kBvhMaxLights lights on the brute-force kernel: launch_fast)
+    return p->accel && fs->n_lights <= rm::kBvhMaxLights ? emu_render_fast_impl<true>(fs, p, out_rgb, prim, stats, n_threads)
                     : emu_render_fast_impl<false>(fs, p, out_rgb, prim, stats, n_threads);
 }
 // the hierarchy of a scene's FP32 pack, for the builder's invariants: nodes (16 floats each) and leaf entries

@@ -83,6 +83,17 @@ def test_hierarchy_changes_no_pixel(rm_gpu, case, cull):
     assert np.array_equal(a["prim_id"], b["prim_id"])
     assert np.array_equal(a["rgb"], b["rgb"]) and np.array_equal(a["rgb8"], b["rgb8"]) and a["max"] == b["max"]
     parity.check_fp32(b, ref, (h // 32) * 32, b["rgb8"])
+    # the kernel's own query count: rendered pixels + queries behind the primary rays = the oracle's segments, up to the
+    # handful of near-tie pixels where FP32 and f64 take different branches
+    L = _abi.load()
+    q = C.c_uint64(0)
+    _abi.check(L.rm_scene_query_count(scene.device_handle(), C.byref(q), 1))
+    gpu_render(rm_gpu, scene, w, h, "f32", depth, cull, accel=True, want_rgb8=False)
+    _abi.check(L.rm_scene_query_count(scene.device_handle(), C.byref(q), 1))
+    want = ref["counters"]["closest_segments"] + ref["counters"]["anyhit_segments"]
+    assert abs((h // 32) * 32 * w + q.value - want) <= 2e-3 * want
+    words = (C.c_int32 * 16)()
+    assert L.rm_scene_accel_status(scene.device_handle(), words) == 0 and words[0] == 0
 
 
 def test_hierarchy_on_the_stress_scene(rm_gpu):
@@ -115,6 +126,24 @@ def test_hierarchy_on_the_stress_scene(rm_gpu):
         assert np.array_equal(f.cpu().numpy(), a["rgb8"]) and np.array_equal(tr.rgb.cpu().numpy(), a["rgb"])
     finally:
         tr.close()
+
+
+@pytest.mark.parametrize("n_lights", [3, 4, 8, 9])
+def test_hierarchy_with_more_lights(rm_gpu, n_lights):
+    """Several pairs of lights through the hierarchy kernel (unrolled pairs up to 8 lights; 9 lights: the call stays on
+    the brute-force kernel) against brute force, bit for bit, twice (the frame must also be reproducible)."""
+    from tests.test_kernel_emulation import _with_lights
+    w, h = 640, 352
+    scene = workloads.build_scene(_with_lights(workloads.describe("stress", n_spheres=512, grid=32), n_lights))
+    scene.offset_camera((7.5, -3.25, 20.0))
+    a = gpu_render(rm_gpu, scene, w, h, "f32", depth=4)
+    b = gpu_render(rm_gpu, scene, w, h, "f32", depth=4, accel=True)
+    c = gpu_render(rm_gpu, scene, w, h, "f32", depth=4, accel=True)
+    assert (a["prim_id"] >= 0).sum() > 10000
+    assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["rgb"], b["rgb"]) and np.array_equal(a["rgb8"], b["rgb8"])
+    assert np.array_equal(b["prim_id"], c["prim_id"]) and np.array_equal(b["rgb"], c["rgb"])
+    words = (C.c_int32 * 16)()
+    assert _abi.load().rm_scene_accel_status(scene.device_handle(), words) == 0 and words[0] == 0
 
 
 def test_demo_golden_image_on_gpu(rm_gpu):

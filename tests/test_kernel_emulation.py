@@ -122,6 +122,27 @@ def test_hierarchy_on_a_large_scene_and_a_moved_camera():
     assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["rgb"], b["rgb"])
 
 
+def _with_lights(desc, n):
+    """The stress scene lit by n lights (the reference's two, main.rs:293-315, plus more of the same kind)."""
+    extra = [((-40., 30., 10.), (.5, 1., .5), .6), ((35., -25., -20.), (.6, .6, 1.), .7), ((0., 60., -90.), (1., 1., .4), .5),
+             ((-70., -10., -60.), (1., .3, 1.), .4), ((10., 5., -100.), (.9, .9, .9), .3), ((55., 40., -140.), (.3, 1., 1.), .5),
+             ((-5., -45., -40.), (1., .7, .2), .6)]
+    desc = dict(desc)
+    desc["lights"] = (list(desc["lights"]) + extra)[:n]
+    return desc
+
+
+@pytest.mark.parametrize("n_lights", [1, 3, 4, 8, 9])
+def test_hierarchy_with_more_lights(n_lights):
+    """The hierarchy kernel shades its lights as unrolled pairs (up to 8; a 9-light scene stays on the brute-force
+    kernel on the device): odd counts, several pairs."""
+    scene = workloads.build_scene(_with_lights(workloads.describe("stress", n_spheres=128, grid=12), n_lights))
+    a = emu.render(scene, 224, 128, "fast", max_depth=4)
+    b = emu.render(scene, 224, 128, "fast", max_depth=4, accel=True)
+    assert (a["prim_id"] >= 0).sum() > 2000
+    assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["rgb"], b["rgb"])
+
+
 @pytest.mark.parametrize("name,kw", [("demo", {}), ("cornell_box", {}), ("stress", dict(n_spheres=512, grid=32))])
 def test_hierarchy_invariants(name, kw):
     """Builder (rm_bvh.cpp): every hittable primitive sits in exactly one leaf, leaves hold at most four, a child's box
