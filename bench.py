@@ -193,7 +193,7 @@ def oracle_segments(desc, w, h, depth):
     from oracle import oracle as O
     from tests.oracle_scenes import build_oracle_scene
     stride = 1
-    while w * h * n_prims_of(desc) / stride > 4e10 and stride < 1024:
+    while w * h * n_prims_of(desc) / stride > 1e10 and stride < 1024:
         stride *= 2                     # a frame the oracle cannot finish in minutes: count a patch sample and scale it
     r = O.render(build_oracle_scene(desc), w, h, max_depth=depth, patch_stride=stride, want_ids=False, want_fragile=False, want_counters=True)
     c = r["counters"]
@@ -211,7 +211,9 @@ def run_reference(args):
     segs = oracle_segments(desc, w, h, depth)
     # one "step" = one (possibly patch-sampled) frame; keep the whole run within a few minutes
     total_steps = args.steps + args.warmup
-    full, threads, sample = cpu_reference_frame_time(desc, w, h, depth, budget_s=150.0 / max(total_steps, 1) * 3, reps=3)
+    heavy = w * h * n_prims_of(desc) > 6.4e10       # minutes per brute-force frame: one bounded estimation pass only
+    full, threads, sample = cpu_reference_frame_time(desc, w, h, depth, budget_s=min(150.0 / max(total_steps, 1) * 3, 60.0 if heavy else 1e9),
+                                                     reps=1 if heavy else 3)
     from oracle import oracle as O
     from tests.oracle_scenes import build_oracle_scene
     import numpy as np
@@ -219,7 +221,7 @@ def run_reference(args):
     out = np.zeros((h, w, 3), dtype=np.float64)
     n_patches = (h // 32) * (w // 32)
     stride = 1
-    while full / stride * total_steps > 150.0 and stride < (64 if w * h * n_prims_of(desc) <= 6.4e10 else 1024):
+    while full / stride * total_steps > 150.0 and stride < (1024 if heavy else 64):
         stride *= 2
     n_sampled = len(range(0, n_patches, stride))
     times = []
@@ -234,7 +236,9 @@ def run_reference(args):
         n_sampled, n_patches, stride, "th, time extrapolated to the frame" if stride > 1 else "", threads)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config_of(args, {"segments_per_frame": segs}),
+            "dtype": "f64", "data": "synthetic",
+            "config": config_of(args, {"segments_per_frame": segs,
+                                       "accel": "none: this arm is the reference's brute-force traversal (shapes.rs:92-143), whatever the workload's own arm uses"}),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
