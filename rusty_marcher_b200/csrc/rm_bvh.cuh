@@ -40,6 +40,16 @@ struct BvhView {
     int* status = nullptr;
 };
 
+// Walk statistics of the host emulation (tests/emu, -DRM_EMU_STATS): node visits and primitive tests per walk -- the
+// algorithmic cost of a hierarchy, comparable across builder settings without a GPU.  Compiles to nothing elsewhere.
+#if defined(RM_EMU_STATS) && !defined(__CUDA_ARCH__)
+struct BvhStats { unsigned long long walks = 0, nodes = 0, prims = 0; };
+inline BvhStats& bvh_stats() { static thread_local BvhStats s; return s; }
+#define RM_BVH_STAT(field) (bvh_stats().field++)
+#else
+#define RM_BVH_STAT(field) ((void)0)
+#endif
+
 RM_HD int bvh_int(float f) {
 #if defined(__CUDA_ARCH__)
     return __float_as_int(f);
@@ -79,6 +89,7 @@ RM_HD bool bvh_walk(const BvhView& bv, const Vec3<float> o, const Vec3<float> d,
     // A walk visits every node at most once.  Corrupt node memory must not be able to hang the GPU: past that bound the
     // walk gives up (reports a miss), raises the scene's status flag and leaves the ray behind for the host to report.
     int budget = 2 * bv.n_nodes + 8;
+    RM_BVH_STAT(walks);
     for (;;) {
         while (cur >= 0) {
             if (--budget < 0 || sp >= kBvhStack - 1 || cur >= bv.n_nodes) {
@@ -91,6 +102,7 @@ RM_HD bool bvh_walk(const BvhView& bv, const Vec3<float> o, const Vec3<float> d,
 #endif
                 return false;
             }
+            RM_BVH_STAT(nodes);
             const R4<float>* n = bv.nodes + 4 * (size_t)cur;
             const R4<float> a = n[0], b = n[1], z = n[2], c = n[3];
             const float tc = cut();
@@ -112,8 +124,10 @@ RM_HD bool bvh_walk(const BvhView& bv, const Vec3<float> o, const Vec3<float> d,
             }
         }
         const int code = ~cur, first = code >> 3, cnt = code & 7;
-        for (int k = 0; k < cnt; k++)
+        for (int k = 0; k < cnt; k++) {
+            RM_BVH_STAT(prims);
             if (leaf(bv.prims[first + k])) return true;
+        }
         if (sp == 0) return false;
         cur = stack[--sp];
     }

@@ -72,3 +72,10 @@ def bvh(scene):
     if rc != 0:
         raise RuntimeError("emu_bvh rc %d" % rc)
     return nodes[:n_nodes.value], prims[:n_prims.value], depth.value
+
+
+def walk_stats():
+    """(walks, node visits, primitive tests) of the hierarchy walks of the accel renders since the last call."""
+    out = (C.c_ulonglong * 3)()
+    lib().emu_walk_stats(out)
+    return tuple(int(x) for x in out)

@@ -5,6 +5,7 @@
 // can be studied in this GPU-less container before spending GPU minutes.  It is NOT a fallback:
 // librm_b200.so does not contain it and fails loudly without a GPU.  Differences to the device:
 // powf/sqrtf/division come from glibc instead of the CUDA math library.
+#define RM_EMU_STATS 1
 #include <atomic>
 #include <cstring>
 #include <thread>
@@ -95,6 +96,7 @@ int emu_render_impl(const RmFlatScene* fs, const RmParams* p, R* out_rgb, int32_
 
 }  // namespace
 
+static std::atomic<unsigned long long> g_walks{0}, g_walk_nodes{0}, g_walk_prims{0};   // hierarchy walks of all renders since the last reset
 static std::atomic<int> g_strip_bound{1};   // 0: walk every triangle in every strip (to prove the bound changes no pixel)
 
 // the FP32 production path (rm_fast.cuh): prepare_raster + fast_pixel, as the CUDA kernels run them
@@ -193,6 +195,9 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
                     }
                 }
             }
+            rm::BvhStats& bs = rm::bvh_stats();
+            g_walks += bs.walks; g_walk_nodes += bs.nodes; g_walk_prims += bs.prims;
+            bs = rm::BvhStats();
         });
     }
     for (auto& th : pool) th.join();
@@ -208,6 +213,10 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
 
 extern "C" {
 void emu_set_strip_bound(int on) { g_strip_bound.store(on); }
+// {walks, node visits, primitive tests} of the hierarchy walks since the last call (accel renders only)
+void emu_walk_stats(unsigned long long out[3]) {
+    out[0] = g_walks.exchange(0); out[1] = g_walk_nodes.exchange(0); out[2] = g_walk_prims.exchange(0);
+}
 int emu_render_fast(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
     // (the device keeps scenes with more than kBvhMaxLights lights on the brute-force kernel: launch_fast)
     return p->accel && fs->n_lights <= rm::kBvhMaxLights ? emu_render_fast_impl<true>(fs, p, out_rgb, prim, stats, n_threads)
