@@ -3,11 +3,11 @@
 # Usage: tools/gpu_cycle2.sh TAG N
 TAG=${1:-x}; N=${2:-2}
 nvidia-smi topo -m > gpurun_out/topo_$TAG.log 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_$TAG.log
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_${TAG}_n1.log 2> gpurun_out/bench_${TAG}_n1.err; echo "bench n1 rc=$?"
+timeout -s KILL 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_$TAG.log
+timeout -s KILL 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_${TAG}_n1.log 2> gpurun_out/bench_${TAG}_n1.err; echo "bench n1 rc=$?"
 for n in 2 4 8; do
   if [ $n -le $N ]; then
-    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/bench_${TAG}_n$n.log 2> gpurun_out/bench_${TAG}_n$n.err; echo "bench n$n rc=$?"
+    timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/bench_${TAG}_n$n.log 2> gpurun_out/bench_${TAG}_n$n.err; echo "bench n$n rc=$?"
     tail -3 gpurun_out/bench_${TAG}_n$n.err
   fi
 done

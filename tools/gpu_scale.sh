@@ -3,12 +3,12 @@
 # the compute-heavy stress workload, and the frame kernel's phase breakdown at N.   tools/gpu_scale.sh TAG N
 TAG=${1:-x}; N=${2:-8}
 nvidia-smi topo -m > gpurun_out/topo_$TAG.log 2>&1
-timeout 400 python -m pytest tests/test_gpu_parity.py -x -q -k "peer_exchange_across_gpus" > gpurun_out/pytest_$TAG.log 2>&1; echo "cross-GPU pytest rc=$?"; tail -2 gpurun_out/pytest_$TAG.log
+timeout -s KILL 400 python -m pytest tests/test_gpu_parity.py -x -q -k "peer_exchange_across_gpus" > gpurun_out/pytest_$TAG.log 2>&1; echo "cross-GPU pytest rc=$?"; tail -2 gpurun_out/pytest_$TAG.log
 run() {  # workload n extra-args
   if [ $2 -eq 1 ]; then
-    timeout 400 python bench.py --workload $1 --no-cpu-baseline $3 > gpurun_out/bench_${TAG}_$1_n$2.log 2> gpurun_out/bench_${TAG}_$1_n$2.err
+    timeout -s KILL 400 python bench.py --workload $1 --no-cpu-baseline $3 > gpurun_out/bench_${TAG}_$1_n$2.log 2> gpurun_out/bench_${TAG}_$1_n$2.err
   else
-    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 2951$2 bench.py --workload $1 --gpus $2 $3 > gpurun_out/bench_${TAG}_$1_n$2.log 2> gpurun_out/bench_${TAG}_$1_n$2.err
+    timeout -s KILL 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 2951$2 bench.py --workload $1 --gpus $2 $3 > gpurun_out/bench_${TAG}_$1_n$2.log 2> gpurun_out/bench_${TAG}_$1_n$2.err
   fi
   echo "bench $1 n$2 rc=$?"
 }
@@ -18,7 +18,7 @@ for n in 1 2 4 8; do
     run stress_4k $n "--steps 5 --warmup 3"
   fi
 done
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 tools/run_phases.py cornell_4k 8 > gpurun_out/phases_${TAG}_n$N.log 2>&1
+timeout -s KILL 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 tools/run_phases.py cornell_4k 8 > gpurun_out/phases_${TAG}_n$N.log 2>&1
 grep "frame 7" gpurun_out/phases_${TAG}_n$N.log
 python - <<PY
 import json,glob
