@@ -194,6 +194,17 @@ int rm_render(RmScene scene, const RmParams* params, float* out_rgb, int32_t* ou
 int rm_render_f64(RmScene scene, const RmParams* params, double* out_rgb, int32_t* out_prim_id,
                   uint8_t* out_rgb8, RmStats* stats);
 
+/* ---- extension mode: per-channel refractive indices (BASELINE.json configs[3]) ---------- *
+ * The reference has ONE scalar refractive index per material (shapes.rs:21-32, optics.rs:8-89); there is no reference
+ * behaviour for dispersion.  Defined here -- and identically in the oracle (oracle.render_dispersive) -- as three passes
+ * of the unchanged hot path: scenes[c] is the scene with every glass-like material at the index of channel c
+ * (c = 0, 1, 2 for R, G, B; the caller uploads the three variants, geometry and lights identical), and channel c of the
+ * frame is channel c of pass c.  out_prim_id: the primary ids (they do not depend on the index).  stats: timings,
+ * launches; max_value is not computed (FrameBuffer::normalize computes it from the frame, framebuffer.rs:58-69).
+ * RM_FP32, contiguous patch rows (patch_row_stride <= 1). */
+int rm_render_dispersive(const RmScene scenes[3], const RmParams* params, float* out_rgb, int32_t* out_prim_id,
+                         RmStats* stats);
+
 /* ---- the hot path, device buffers (no copies; for callers that keep frames in HBM) ----------- *
  * d_rgb: device float (RM_FP32) or double (RM_FP64) H*W*3; d_prim_id optional; d_max: device
  * scalar of the same type as d_rgb that receives max(previous value, tile max) -- zero it first.

@@ -72,6 +72,8 @@ def lib():
     L.orc_scene_add_obj_file.argtypes = [C.c_void_p, C.c_char_p, d3]
     L.orc_scene_add_mesh.argtypes = [C.c_void_p, d3, C.c_int, d3]
     L.orc_scene_add_light.argtypes = [C.c_void_p, d3, d3, C.c_double]
+    L.orc_scene_make_glass.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+    L.orc_scene_set_glass_index.argtypes = [C.c_void_p, C.c_double]
     L.orc_scene_num_shapes.argtypes = [C.c_void_p]
     L.orc_scene_num_prims.argtypes = [C.c_void_p]
     L.orc_scene_obj_triangles.argtypes = [C.c_void_p, C.c_int, d3, C.c_int]
@@ -167,6 +169,18 @@ class Scene:
     def add_light(self, position, color, intensity):
         lib().orc_scene_add_light(self._h, _d3(position), _d3(color), float(intensity))
 
+    # ---- extension mode (no reference counterpart) ----
+    def make_glass(self, shape, reflection=0.2, refractive_index=1.5, diffusion=1.):
+        """Every primitive of shape `shape` becomes glass-like (an OBJ mesh is opaque in the reference, obj.rs:125-138)."""
+        n = lib().orc_scene_make_glass(self._h, int(shape), float(reflection), float(refractive_index), float(diffusion))
+        if n < 0:
+            raise IndexError("oracle: no shape %d" % shape)
+        return n
+
+    def set_glass_index(self, refractive_index):
+        """Every glass-like material gets this refractive index (one pass of the per-channel dispersion)."""
+        return lib().orc_scene_set_glass_index(self._h, float(refractive_index))
+
     def add_default_lights(self):
         """engine/src/main.rs:293-315 (the same two lights as scene.rs:178-198)."""
         self.add_light((0., 0., 0.), (1., 1., 1.), 1.)
@@ -210,6 +224,29 @@ def render(scene, width, height, fov=1.5, max_depth=3, threads=None, patch_rows=
         raise ValueError("oracle: width must be a positive multiple of 32 (renderer.rs:107)")
     return {"rgb": rgb, "prim_id": ids, "fragile": frag, "counters": cnt.as_dict() if want_counters else None,
             "degenerate_hits": int(lib().orc_last_degenerate_hits())}
+
+
+def render_dispersive(scene, width, height, indices=(1.50, 1.52, 1.54), **kw):
+    """EXTENSION MODE (BASELINE.json configs[3]): per-channel refractive indices as three passes of
+    the unchanged restatement, pass c with every glass-like material at indices[c]; channel c of the frame is channel c
+    of pass c.  Primary ids are those of the first pass (the primary ray does not depend on the index), the fragile mask
+    is the union, the counters are summed.  No reference behaviour to compare with -- the oracle and the CUDA path are
+    extended identically.  The scene is left with indices[2]."""
+    out = None
+    for c, n in enumerate(indices):
+        scene.set_glass_index(n)
+        r = render(scene, width, height, **kw)
+        if out is None:
+            out = {"rgb": np.zeros_like(r["rgb"]), "prim_id": r["prim_id"], "fragile": r["fragile"],
+                   "counters": dict(r["counters"]) if r["counters"] else None, "degenerate_hits": r["degenerate_hits"]}
+        else:
+            if out["fragile"] is not None:
+                out["fragile"] = out["fragile"] | r["fragile"]
+            if out["counters"] is not None:
+                for k, v in r["counters"].items():
+                    out["counters"][k] += v
+        out["rgb"][..., c] = r["rgb"][..., c]
+    return out
 
 
 def normalize(rgb):

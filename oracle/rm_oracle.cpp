@@ -127,6 +127,8 @@ struct Shape {
     virtual bool intersect_probe(const V3& o, const V3& d, Hit& h, Probe* pr, bool anyhit) const = 0;
     virtual double max_abs() const = 0;
     virtual bool is_obj() const { return false; }
+    // materials of the shape's primitives, in primitive order (extension-mode helpers below; not used by the restatement)
+    virtual void materials(std::vector<Reflectance*>& out) = 0;
 };
 
 inline double max_abs3(V3 v) { return std::fmax(std::fabs(v.x), std::fmax(std::fabs(v.y), std::fabs(v.z))); }
@@ -136,6 +138,7 @@ struct Sphere : Shape {
     V3 center;
     double radius_square;
     Reflectance reflectance;
+    void materials(std::vector<Reflectance*>& out) override { out.push_back(&reflectance); }
     template <bool T>
     bool isect(const V3& o, const V3& d, Hit& h, Probe* pr) const {
         Trail<T> trail(pr);
@@ -249,6 +252,7 @@ struct Triangle {
 struct ConvexPolygon : Shape {
     std::vector<V3> vertices;
     Reflectance reflectance;
+    void materials(std::vector<Reflectance*>& out) override { out.push_back(&reflectance); }
     V3 plane_normal, plane_point;
     bool degenerate = false;
     static std::unique_ptr<ConvexPolygon> create(std::vector<V3> verts, const Reflectance& r) {  // polygon.rs:16-42
@@ -310,6 +314,7 @@ struct Obj : Shape {
     std::vector<Reflectance> reflectances;
     int n_prims() const override { return (int)triangles.size(); }
     bool is_obj() const override { return true; }
+    void materials(std::vector<Reflectance*>& out) override { for (auto& r : reflectances) out.push_back(&r); }
     void offset(V3 off) { for (auto& t : triangles) t.offset(off); }   // obj.rs:24-29
     void gradient_colours() {                                          // obj.rs:125-138
         size_t n = triangles.size();
@@ -748,6 +753,33 @@ int orc_scene_add_obj_file(OrcScene* s, const char* path, const double offset[3]
 
 void orc_scene_add_light(OrcScene* s, const double pos[3], const double color[3], double intensity) {
     s->lights.push_back(create_light(from3(pos), from3(color), intensity));
+}
+
+// ---- EXTENSION MODE (no reference counterpart: the reference has one scalar refractive index per
+// material, shapes.rs:21-32, and loads OBJ meshes opaque, obj.rs:125-138).  BASELINE.json configs[3] asks for a
+// refractive mesh with per-channel R/G/B indices; it is traced as three passes of the UNCHANGED restatement, one scalar
+// index each, and channel c of the frame is channel c of pass c.  These two setters only edit materials between passes.
+int orc_scene_make_glass(OrcScene* s, int shape, double reflection, double refractive_index, double diffusion) {
+    if (shape < 0 || shape >= (int)s->shapes.size()) return -1;
+    std::vector<Reflectance*> m;
+    s->shapes[shape]->materials(m);
+    for (Reflectance* r : m) {
+        r->is_glass_like = true;
+        r->reflection = reflection;
+        r->refractive_index = refractive_index;
+        r->diffusion = diffusion;
+    }
+    return (int)m.size();
+}
+int orc_scene_set_glass_index(OrcScene* s, double refractive_index) {
+    int n = 0;
+    for (auto& shape : s->shapes) {
+        std::vector<Reflectance*> m;
+        shape->materials(m);
+        for (Reflectance* r : m)
+            if (r->is_glass_like) { r->refractive_index = refractive_index; n++; }
+    }
+    return n;
 }
 
 int orc_scene_num_shapes(const OrcScene* s) { return (int)s->shapes.size(); }

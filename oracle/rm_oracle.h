@@ -70,6 +70,11 @@ int       orc_scene_add_obj_file(OrcScene*, const char* path, const double offse
 /* one Obj shape from raw triangles (f64 vertices, 9 per triangle), gradient colours as obj.rs:125-138 */
 int       orc_scene_add_mesh(OrcScene*, const double* tri_verts, int n_triangles, const double offset[3]);
 void      orc_scene_add_light(OrcScene*, const double pos[3], const double color[3], double intensity);
+/* Extension mode (no reference counterpart): every primitive of `shape` becomes glass-like with the
+ * given reflection / refractive index / diffusion (returns the number of materials changed, -1 for a bad index); and
+ * every glass-like material of the scene gets a new refractive index (one pass of the per-channel dispersion). */
+int       orc_scene_make_glass(OrcScene*, int shape, double reflection, double refractive_index, double diffusion);
+int       orc_scene_set_glass_index(OrcScene*, double refractive_index);
 int       orc_scene_num_shapes(const OrcScene*);
 int       orc_scene_num_prims(const OrcScene*);     /* flattened primitive count (prim_id space) */
 /* triangles of shape `shape` (0 if not an Obj); optionally copies 9 doubles per triangle */

@@ -108,6 +108,7 @@ struct Context {
     std::map<RmScene, SceneEntry> scenes;
     RmScene next_handle = 1;
     Scratch rgb, prim, rgb8, small;   // small: [0,8) max scalar, [64, 64+17*8) counters
+    Scratch mix;                      // rm_render_dispersive: the frame assembled from the three passes
     std::mutex mu;
 };
 Context g;
@@ -352,7 +353,7 @@ void rm_shutdown(void) {
     cudaDeviceSynchronize();
     for (auto& kv : g.scenes) { kv.second.f32.release(); kv.second.f64.release(); }
     g.scenes.clear();
-    g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release();
+    g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release(); g.mix.release();
     for (auto& ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ps : g.prof)
         for (auto& ev : ps.e) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
@@ -436,6 +437,56 @@ int rm_render(RmScene scene, const RmParams* params, float* out_rgb, int32_t* ou
 
 int rm_render_f64(RmScene scene, const RmParams* params, double* out_rgb, int32_t* out_prim_id, uint8_t* out_rgb8, RmStats* stats) {
     return render_host_impl<double>(scene, params, out_rgb, out_prim_id, out_rgb8, stats);
+}
+
+// Extension mode (include/rm_b200.h): three passes of the unchanged render kernels, channel c of pass c kept.  The merge
+// is three pitched device-to-device copies (one float of every pixel: width 4 bytes, pitch 12) -- no kernel of its own.
+int rm_render_dispersive(const RmScene scenes[3], const RmParams* params, float* out_rgb, int32_t* out_prim_id, RmStats* stats) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
+    int rc = check_params(params);
+    if (rc != RM_OK) return rc;
+    if (!scenes) return fail(RM_ERR_INVALID_ARGUMENT, "scenes is null");
+    if (params->precision != RM_FP32) return fail(RM_ERR_INVALID_ARGUMENT, "rm_render_dispersive computes in RM_FP32");
+    if (params->patch_row_stride > 1) return fail(RM_ERR_INVALID_ARGUMENT, "rm_render_dispersive renders contiguous patch rows (patch_row_stride <= 1)");
+    rm::FrameParams<float> fp = rm::make_frame_params<float>(*params);
+    const size_t rows = (size_t)fp.n_bands * 32;
+    const size_t n_px = rows * (size_t)fp.width;
+    if ((rc = g.rgb.ensure(std::max<size_t>(n_px * 12, 16))) != RM_OK) return rc;
+    if ((rc = g.mix.ensure(std::max<size_t>(n_px * 12, 16))) != RM_OK) return rc;
+    if (out_prim_id && (rc = g.prim.ensure(std::max<size_t>(n_px * sizeof(int), 16))) != RM_OK) return rc;
+    if ((rc = g.small.ensure(1024)) != RM_OK) return rc;
+    float* d_max = static_cast<float*>(g.small.p);
+    cudaStream_t s = g.stream;
+    CK(cudaEventRecord(g.ev[0], s));
+    int resident = 0, launches = 0;
+    for (int c = 0; c < 3; c++) {
+        CK(cudaMemsetAsync(g.small.p, 0, 1024, s));
+        // (the primary ray does not depend on the refractive index: the ids of the first pass are the frame's)
+        rc = render_device_impl<float>(scenes[c], params, static_cast<float*>(g.rgb.p), (out_prim_id && c == 0) ? static_cast<int*>(g.prim.p) : nullptr,
+                                       d_max, s, 1, nullptr, nullptr, &resident, &launches);
+        if (rc != RM_OK) return rc;
+        if (n_px)
+            CK(cudaMemcpy2DAsync(static_cast<char*>(g.mix.p) + 4 * c, 12, static_cast<const char*>(g.rgb.p) + 4 * c, 12, 4, n_px,
+                                 cudaMemcpyDeviceToDevice, s));
+    }
+    CK(cudaEventRecord(g.ev[2], s));
+    const size_t host_px = (size_t)fp.row_begin * fp.width;
+    if (out_rgb && n_px) CK(cudaMemcpyAsync(out_rgb + host_px * 3, g.mix.p, n_px * 12, cudaMemcpyDeviceToHost, s));
+    if (out_prim_id && n_px) CK(cudaMemcpyAsync(out_prim_id + host_px, g.prim.p, n_px * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(g.ev[3], s));
+    CK(cudaStreamSynchronize(s));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[2]));
+        stats->ms_render = ms;
+        CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[3]));
+        stats->ms_total = ms;
+        stats->kernel_launches = launches;
+        stats->resident_prims = resident;
+    }
+    return RM_OK;
 }
 
 int rm_render_device(RmScene scene, const RmParams* params, void* d_rgb, int32_t* d_prim_id, void* d_max, void* stream) {

@@ -66,6 +66,14 @@ class Obj(Shape):
         self.triangles[:, 12:15] += off                         # centre
         self.triangles[:, 0:9] += np.tile(off, 3)               # vertices; the normal is left alone
 
+    def make_glass(self, reflection=0.2, refractive_index=1.5, diffusion=1.):
+        """Extension mode: the reference loads meshes opaque (obj.rs:125-138); this turns every
+        triangle's material glass-like, the gradient colour stays."""
+        self.reflectances["is_glass_like"] = 1
+        self.reflectances["reflection"] = reflection
+        self.reflectances["refractive_index"] = refractive_index
+        self.reflectances["diffusion"] = diffusion
+
     def flatten(self, flat):
         flat.objs.append((flat.n_triangles, self.triangles.shape[0]))
         flat.triangle_chunks.append(self.triangles)

@@ -79,5 +79,41 @@ class Renderer:
         return message
 
 
+    def render_dispersive(self, frame, scene, indices=(1.50, 1.52, 1.54), prim_id=None, patch_rows=(0, -1)):
+        """EXTENSION MODE (no reference counterpart; BASELINE.json configs[3]): per-channel refractive
+        indices.  Three passes of the unchanged hot path -- pass c with every glass-like material of the scene at
+        indices[c] -- and channel c of the frame is channel c of pass c (rm_render_dispersive).  Fills frame.buffer like
+        render() and returns the same kind of status message."""
+        L = _abi.load()
+        _abi.init(_abi._initialised_device if _abi._initialised_device is not None else 0)
+        if self.precision != _abi.RM_FP32:
+            raise ValueError("render_dispersive computes in RM_FP32")
+        now = time.perf_counter()
+        p = self.params(frame, scene, patch_rows)
+        if frame.buffer.dtype != np.float32 or not frame.buffer.flags.c_contiguous:
+            frame.buffer = np.zeros((frame.height, frame.width, 3), dtype=np.float32)
+        handles = (C.c_int64 * 3)()
+        stats = _abi.RmStats()
+        try:
+            for c, n in enumerate(indices):
+                flat = scene.flatten()
+                flat.set_glass_index(float(n))
+                h = C.c_int64(0)
+                _abi.check(L.rm_scene_upload(C.byref(flat.c), C.byref(h)))
+                handles[c] = h.value
+            _abi.check(L.rm_render_dispersive(handles, C.byref(p), frame.buffer.ctypes.data,
+                                              prim_id.ctypes.data if prim_id is not None else None, C.byref(stats)))
+        finally:
+            for c in range(3):
+                if handles[c]:
+                    L.rm_scene_free(handles[c])
+        self.last_stats = stats
+        ms = int((time.perf_counter() - now) * 1000)
+        fps = 1000. / ms if ms > 0 else float("inf")
+        message = "Scene rendered in %d ms (%d fps, %.2f MP/s)" % (ms, int(min(fps, 2**32 - 1)), fps * frame.height * frame.width / 1e6)
+        print(message)
+        return message
+
+
 def create_renderer(fov, height, width):
     return Renderer(fov, height, width)

@@ -50,6 +50,24 @@ class _Flat:
         self.c = fs
         return self
 
+    def set_glass_index(self, refractive_index):
+        """Extension mode (rm_render_dispersive): every glass-like material of the flattened scene gets this refractive
+        index.  Returns the number of materials changed."""
+        n = 0
+        for i in range(self.c.n_spheres):
+            if self._spheres[i].reflectance.is_glass_like:
+                self._spheres[i].reflectance.refractive_index = refractive_index
+                n += 1
+        for i in range(self.c.n_polygons):
+            if self._polygons[i].reflectance.is_glass_like:
+                self._polygons[i].reflectance.refractive_index = refractive_index
+                n += 1
+        if self.n_triangles:
+            glass = self._refl["is_glass_like"] != 0
+            self._refl["refractive_index"][glass] = refractive_index
+            n += int(glass.sum())
+        return n
+
 
 class Scene:
     def __init__(self):                                         # Scene::new, scene.rs:16-23
@@ -135,7 +153,9 @@ class Scene:
     def _fp(self):
         def key(s):
             if isinstance(s, Obj):
-                return (id(s), s.triangles.shape[0], float(s.triangles[:, 12:15].sum()) if s.triangles.size else 0.)
+                return (id(s), s.triangles.shape[0], float(s.triangles[:, 12:15].sum()) if s.triangles.size else 0.,
+                        int(s.reflectances["is_glass_like"].sum()), float(s.reflectances["refractive_index"].sum()),
+                        float(s.reflectances["reflection"].sum()))
             if isinstance(s, sphere.Sphere):
                 return (id(s), tuple(s.center), s.radius_square, repr(s.reflectance))
             return (id(s), tuple(tuple(v) for v in s.vertices), repr(s.reflectance))

@@ -36,9 +36,11 @@ def lib():
     return _lib
 
 
-def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=True, threads=8, patch_rows=(0, -1), strip_bound=True, accel=False):
+def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=True, threads=8, patch_rows=(0, -1), strip_bound=True, accel=False, glass_index=None):
     lib().emu_set_strip_bound(int(strip_bound))
     flat = scene.flatten()
+    if glass_index is not None:
+        flat.set_glass_index(float(glass_index))     # one pass of the per-channel dispersion (extension mode)
     p = _abi.RmParams()
     p.width, p.height, p.fov = width, height, fov
     p.camera[:] = list(scene.camera)
