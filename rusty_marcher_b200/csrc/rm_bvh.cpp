@@ -1,11 +1,15 @@
 // rm_bvh.cpp -- host-side builder of the hierarchy in rm_bvh.cuh: binned surface-area heuristic (16 bins, three
 // axes), leaves of at most kBvhLeafMax primitives, median splits when the heuristic cannot separate a range or
 // the tree gets deeper than 40 levels (so the traversal stack of kBvhStack entries always suffices).
-// Pure C++: runs once per scene at upload (~50 ms for 10^5 primitives), shared with the host emulation.
+// Pure C++: runs once per scene at upload (~0.1 s for 10^5 primitives on one core; scenes of 8192 primitives and more
+// build their subtrees on a thread pool), shared with the host emulation.
 #include <algorithm>
+#include <atomic>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <thread>
 
 #include "rm_scene.h"
 
@@ -50,13 +54,22 @@ float round_up(double v) {
     return f;
 }
 
+// A subtree handed to the thread pool: items [begin, end), found at `depth`.  Child codes below kDeferred + 2^20 mark
+// such a subtree in the part of the tree built up front (leaf codes stay above -2^30, see make_leaf).
+struct Task {
+    int begin, end, depth;
+};
+constexpr int kDeferred = INT_MIN;
+
 struct Builder {
-    std::vector<Item> items;
+    std::vector<Item>& items;          // shared; a builder only touches the ranges it is given
     std::vector<R4<float>>& nodes;
     std::vector<int>& prims;
     int max_depth = 0;
+    std::vector<Task>* defer = nullptr;   // when set: ranges of at most `grain` items become tasks instead of subtrees
+    int grain = 0;
 
-    Builder(std::vector<R4<float>>& n, std::vector<int>& p) : nodes(n), prims(p) {}
+    Builder(std::vector<Item>& i, std::vector<R4<float>>& n, std::vector<int>& p) : items(i), nodes(n), prims(p) {}
 
     int make_leaf(int begin, int end) {
         const int first = (int)prims.size();
@@ -79,6 +92,10 @@ struct Builder {
         }
         const int n = end - begin;
         if (n <= kBvhLeafMax) return make_leaf(begin, end);
+        if (defer && n <= grain) {
+            defer->push_back({begin, end, depth});
+            return kDeferred + (int)defer->size() - 1;
+        }
 
         int mid = -1;
         if (depth < 40) {
@@ -179,8 +196,8 @@ int build_bvh(const std::vector<BvhPrimBox>& in, std::vector<R4<float>>& nodes, 
         }
     const double pad = std::max(S, 1e-30) * (1.0 / 16384.0);
     const double big = 1e30;
-    Builder b(nodes, prims);
-    b.items.reserve(in.size());
+    std::vector<Item> items;
+    items.reserve(in.size());
     for (const BvhPrimBox& p : in) {
         Item it;
         for (int a = 0; a < 3; a++) {
@@ -193,22 +210,98 @@ int build_bvh(const std::vector<BvhPrimBox>& in, std::vector<R4<float>>& nodes, 
             it.c[a] = (float)(0.5 * (lo + hi));
         }
         it.code = p.code;
-        b.items.push_back(it);
+        items.push_back(it);
     }
-    const int n = (int)b.items.size();
+    Builder b(items, nodes, prims);
+    const int n = (int)items.size();
     if (n <= kBvhLeafMax) {
         // the root is always an inner node: one real leaf and one empty one behind the same box
         Box box;
         box.clear();
-        for (auto& it : b.items) box.grow(it.box);
+        for (auto& it : items) box.grow(it.box);
         nodes.resize(4);
         const int leaf = b.make_leaf(0, n);
         b.write_node(0, box, leaf, box, ~0);
         return 1;
     }
     Box root;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int n_threads = (int)std::min(16u, hw ? hw : 1u);
+    if (n < 8192 || n_threads < 2) {
+        b.build(0, n, 1, root);
+        return b.max_depth;
+    }
+    // Large scenes: the top of the tree here, the subtrees of at most n/64 items on a pool of threads, each into
+    // arrays of its own, appended in task order afterwards -- the same splits as the sequential build (a subtree is a
+    // function of its item range only), a numbering that does not depend on thread timing.
+    std::vector<Task> tasks;
+    b.defer = &tasks;
+    b.grain = std::max(n / 64, 1024);
     b.build(0, n, 1, root);
-    return b.max_depth;
+    struct Sub {
+        std::vector<R4<float>> nodes;
+        std::vector<int> prims;
+        int root = 0, depth = 0;
+    };
+    std::vector<Sub> subs(tasks.size());
+    std::atomic<int> next{0};
+    auto work = [&] {
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= (int)tasks.size()) break;
+            // arrays local to the worker while they grow (neighbouring Sub records share cache lines)
+            std::vector<R4<float>> ln;
+            std::vector<int> lp;
+            Builder sb(items, ln, lp);
+            Box box;
+            const int root = sb.build(tasks[k].begin, tasks[k].end, tasks[k].depth, box);
+            subs[k].nodes = std::move(ln);
+            subs[k].prims = std::move(lp);
+            subs[k].root = root;
+            subs[k].depth = sb.max_depth;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    int depth = b.max_depth;
+    const size_t n_top = nodes.size() / 4;
+    std::vector<int> mapped(tasks.size());
+    for (size_t k = 0; k < tasks.size(); k++) {
+        const int node_base = (int)(nodes.size() / 4), prim_base = (int)prims.size();
+        auto remap = [&](int c) {
+            if (c >= 0) return c + node_base;
+            const int code = ~c;
+            return ~((((code >> 3) + prim_base) << 3) | (code & 7));
+        };
+        for (size_t i = 0; i + 3 < subs[k].nodes.size(); i += 4) {
+            R4<float> links = subs[k].nodes[i + 3];
+            int c0, c1;
+            std::memcpy(&c0, &links.x, 4);
+            std::memcpy(&c1, &links.y, 4);
+            c0 = remap(c0);
+            c1 = remap(c1);
+            std::memcpy(&links.x, &c0, 4);
+            std::memcpy(&links.y, &c1, 4);
+            subs[k].nodes[i + 3] = links;
+        }
+        mapped[k] = remap(subs[k].root);
+        nodes.insert(nodes.end(), subs[k].nodes.begin(), subs[k].nodes.end());
+        prims.insert(prims.end(), subs[k].prims.begin(), subs[k].prims.end());
+        depth = std::max(depth, subs[k].depth);
+    }
+    for (size_t i = 0; i < n_top; i++) {
+        R4<float>& links = nodes[4 * i + 3];
+        int c[2];
+        std::memcpy(&c[0], &links.x, 4);
+        std::memcpy(&c[1], &links.y, 4);
+        for (int j = 0; j < 2; j++)
+            if (c[j] < kDeferred + (1 << 20)) c[j] = mapped[c[j] - kDeferred];
+        std::memcpy(&links.x, &c[0], 4);
+        std::memcpy(&links.y, &c[1], 4);
+    }
+    return depth;
 }
 
 }  // namespace rm

@@ -143,7 +143,8 @@ def test_hierarchy_with_more_lights(n_lights):
     assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["rgb"], b["rgb"])
 
 
-@pytest.mark.parametrize("name,kw", [("demo", {}), ("cornell_box", {}), ("stress", dict(n_spheres=512, grid=32))])
+@pytest.mark.parametrize("name,kw", [("demo", {}), ("cornell_box", {}), ("stress", dict(n_spheres=512, grid=32)),
+                                     ("stress", dict(n_spheres=1024, grid=64))])     # last: >= 8192 primitives, built on a thread pool
 def test_hierarchy_invariants(name, kw):
     """Builder (rm_bvh.cpp): every hittable primitive sits in exactly one leaf, leaves hold at most four, a child's box
     lies inside the box its parent records for it, and the depth fits the traversal stack."""
@@ -183,6 +184,8 @@ def test_hierarchy_invariants(name, kw):
                 seen[first:first + cnt] += 1
     assert np.all(seen == 1)
     assert deepest <= depth
+    nodes2, prims2, depth2 = emu.bvh(scene)                    # the build does not depend on thread timing
+    assert np.array_equal(nodes.view(np.uint32), nodes2.view(np.uint32)) and np.array_equal(prims, prims2) and depth == depth2
 
 
 def test_hierarchy_walk_cost():
