@@ -81,3 +81,18 @@ def walk_stats():
     out = (C.c_ulonglong * 3)()
     lib().emu_walk_stats(out)
     return tuple(int(x) for x in out)
+
+
+def render_costs(scene, width, height, max_depth=3, threads=8):
+    """Accel render that also returns the per-pixel walk cost (node visits + 0.7 x primitive tests) of stage A and of
+    the shading stage, (H, W, 2) float32 -- the input of tools/tail_model.py."""
+    cost = np.zeros((height, width, 2), dtype=np.float32)
+    L = lib()
+    L.emu_set_cost_buffer.argtypes = [C.c_void_p]
+    L.emu_set_cost_buffer(cost.ctypes.data)
+    try:
+        r = render(scene, width, height, "fast", max_depth=max_depth, accel=True, threads=threads)
+    finally:
+        L.emu_set_cost_buffer(None)
+    r["cost"] = cost
+    return r

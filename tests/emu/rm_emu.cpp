@@ -97,6 +97,7 @@ int emu_render_impl(const RmFlatScene* fs, const RmParams* p, R* out_rgb, int32_
 }  // namespace
 
 static std::atomic<unsigned long long> g_walks{0}, g_walk_nodes{0}, g_walk_prims{0};   // hierarchy walks of all renders since the last reset
+static std::atomic<float*> g_cost{nullptr};   // optional H x W x 2 floats: per-pixel walk cost of stage A / of shading (tools/tail_model.py)
 static std::atomic<int> g_strip_bound{1};   // 0: walk every triangle in every strip (to prove the bound changes no pixel)
 
 // the FP32 production path (rm_fast.cuh): prepare_raster + fast_pixel, as the CUDA kernels run them
@@ -177,16 +178,23 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
                         const int x = xs + (lane & 7) * 4, y = y0 + (lane >> 3);
                         rm::PrimaryState<4> ps;
                         rm::primary_begin<4>(ps, fp, x, y);
+                        float* const cost = g_cost.load();
+                        auto walk_cost = [] { const rm::BvhStats& b = rm::bvh_stats(); return (float)b.nodes + 0.7f * (float)b.prims; };
                         if constexpr (kBvh) {
+                            const float c0 = walk_cost();
                             rm::primary_bvh<4>(ps, fv, fp);
+                            if (cost)
+                                for (int k = 0; k < 4; k++) cost[2 * ((size_t)y * fp.width + x + k)] = 0.25f * (walk_cost() - c0);
                         } else {
                             for (int j : cand) rm::primary_tri<4>(ps, tri_r[4 * j], tri_r[4 * j + 1], tri_r[4 * j + 2], tri_r[4 * j + 3], fv.n_sph + j);
                             if (fv.n_sph + fv.n_poly > 0) rm::primary_rest<4>(ps, fv, fp);
                         }
                         for (int k = 0; k < 4; k++) {
+                            const float c1 = walk_cost();
                             rm::Vec3<float> c = ps.slot[k] >= 0 ? rm::fast_shade(fv, fp, x + k, y, ps.t[k], ps.slot[k], ps.id[k])
                                                                 : rm::Vec3<float>{0.f, 0.f, 0.f};
                             size_t px = (size_t)y * fp.width + x + k;
+                            if (cost && kBvh) cost[2 * px + 1] = walk_cost() - c1;
                             out_rgb[3 * px] = c.x; out_rgb[3 * px + 1] = c.y; out_rgb[3 * px + 2] = c.z;
                             if (prim) prim[px] = ps.id[k];
                             float m = fmaxf(fmaxf(c.x, c.y), c.z);
@@ -213,6 +221,7 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
 
 extern "C" {
 void emu_set_strip_bound(int on) { g_strip_bound.store(on); }
+void emu_set_cost_buffer(float* hw2) { g_cost.store(hw2); }
 // {walks, node visits, primitive tests} of the hierarchy walks since the last call (accel renders only)
 void emu_walk_stats(unsigned long long out[3]) {
     out[0] = g_walks.exchange(0); out[1] = g_walk_nodes.exchange(0); out[2] = g_walk_prims.exchange(0);
