@@ -1,6 +1,7 @@
 """Scene (engine/src/scene.rs:9-211): lights, shapes and the camera position, plus the flattening
 of the shape list into the RmFlatScene PODs the C ABI consumes."""
 import ctypes as C
+import zlib
 
 import numpy as np
 
@@ -76,6 +77,8 @@ class Scene:
         self.camera = Vec3f.zero()
         self._handle = None
         self._fingerprint = None
+        self._flat = None                 # flatten() of the fingerprint below, reused by device_handle()
+        self._flat_fingerprint = None
 
     @staticmethod
     def new():
@@ -150,15 +153,25 @@ class Scene:
             flat.lights.append(c)
         return flat.finish()
 
+    @staticmethod
+    def _checksum(a):
+        """Content key of an array: CRC of the bytes for small arrays (exact, about a microsecond), plain sums for large
+        ones (a mesh of 10^5 triangles is megabytes; the sum runs at memory speed)."""
+        if a.nbytes <= 65536:
+            return zlib.crc32(np.ascontiguousarray(a).view(np.uint8).reshape(-1))
+        v = a.view(np.float64) if a.dtype.fields is not None and a.dtype.itemsize % 8 == 0 else a
+        return float(v.sum())
+
     def _fp(self):
         def key(s):
             if isinstance(s, Obj):
-                return (id(s), s.triangles.shape[0], float(s.triangles[:, 12:15].sum()) if s.triangles.size else 0.,
-                        int(s.reflectances["is_glass_like"].sum()), float(s.reflectances["refractive_index"].sum()),
-                        float(s.reflectances["reflection"].sum()))
+                return (id(s), s.triangles.shape[0], self._checksum(s.triangles), self._checksum(s.reflectances))
+            r = s.reflectance
+            cx, cy, cz = r.diffuse_color                          # a Vec3f or any 3-sequence
+            rk = (r.diffusion, cx, cy, cz, r.specular, r.specular_exponent, r.is_glass_like, r.reflection, r.refractive_index)
             if isinstance(s, sphere.Sphere):
-                return (id(s), tuple(s.center), s.radius_square, repr(s.reflectance))
-            return (id(s), tuple(tuple(v) for v in s.vertices), repr(s.reflectance))
+                return (id(s), s.center.x, s.center.y, s.center.z, s.radius_square, rk)
+            return (id(s), tuple((v.x, v.y, v.z) for v in s.vertices), rk)
         return (tuple(key(s) for s in self.shapes),
                 tuple((tuple(l.position), tuple(l.color), l.intensity) for l in self.lights))
 
@@ -169,7 +182,11 @@ class Scene:
         if self._handle is not None and fp == self._fingerprint:
             return self._handle
         self.release()
-        flat = self.flatten()
+        # the flattened host arrays are kept with the fingerprint they were made from: a scene that has to be uploaded
+        # again unchanged (after release(), on another device) is not marshalled again
+        if self._flat is None or self._flat_fingerprint != fp:
+            self._flat, self._flat_fingerprint = self.flatten(), fp
+        flat = self._flat
         h = C.c_int64(0)
         _abi.check(L.rm_scene_upload(C.byref(flat.c), C.byref(h)))
         self._handle, self._fingerprint = h.value, fp

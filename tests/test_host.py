@@ -217,3 +217,54 @@ def test_rm_write_ppm_reproduces_the_reference_golden_file(tmp_path):
     assert len(data) == meta["size"] and hashlib.sha256(data).hexdigest() == meta["sha256"]
     assert _abi.load().rm_write_ppm(None, 800, 600, rgb8.ctypes.data) == -3
     assert _abi.load().rm_write_ppm(str(tmp_path / "no" / "dir.ppm").encode(), 8, 8, rgb8.ctypes.data) == -3
+
+
+def test_scene_fingerprint_and_flat_cache():
+    """Scene.device_handle() re-uploads when the scene changed and re-marshals (flatten) only then: the fingerprint must
+    see every kind of edit -- materials, vertices, offsets, lights -- and ignore the camera (a per-frame parameter)."""
+    import rusty_marcher_b200 as rm
+    s = workloads.scene("cornell_box")
+    seen = {s._fp()}
+
+    def changed():
+        fp = s._fp()
+        new = fp not in seen
+        seen.add(fp)
+        return new
+
+    s.offset_camera((1., 2., 3.))
+    assert not changed()
+    s.shapes[0].offset((0., 0., 1.))
+    assert changed()
+    s.shapes[1].reflectances["refractive_index"][0] = 1.3
+    assert changed()
+    s.shapes[2].triangles[0, 0] += 1e-9
+    assert changed()
+    s.shapes[3].make_glass()
+    assert changed()
+    s.lights[0].intensity = 0.5
+    assert changed()
+    d = workloads.scene("demo")
+    a = d._fp()
+    d.shapes[0].reflectance.diffuse_color.x = 0.123
+    b = d._fp()
+    d.shapes[0].reflectance.refractive_index = 1.7
+    assert len({a, b, d._fp()}) == 3
+    big = workloads.scene("stress", n_spheres=8, grid=40)      # > 64 KB of triangles: the sum path of the checksum
+    a = big._fp()
+    big.shapes[-1].triangles[5, 2] += 0.25
+    assert big._fp() != a
+    # flatten() always marshals afresh (callers may edit the result); device_handle() keeps one per fingerprint
+    assert s.flatten() is not s.flatten()
+    if not rm._abi.load().rm_init(0) == 0:                      # no GPU here: the upload fails after the marshalling
+        with pytest.raises(rm.RmError):
+            s.device_handle()
+        first = s._flat
+        assert first is not None
+        with pytest.raises(rm.RmError):
+            s.device_handle()
+        assert s._flat is first                                 # unchanged scene: not marshalled again
+        s.shapes[0].offset((0., 0., 1.))
+        with pytest.raises(rm.RmError):
+            s.device_handle()
+        assert s._flat is not first
