@@ -57,9 +57,8 @@ def workload_of(name):
 
 
 def n_prims_of(desc):
-    if desc.get("default"):
-        return 6
-    return len(desc["spheres"]) + sum(len(v) for _n, v, _o in desc["meshes"])
+    from rusty_marcher_b200 import workloads
+    return workloads.n_prims(desc)
 
 
 def config_of(args, extra=None):

@@ -48,10 +48,12 @@ template <typename R> struct DevicePack {
     void* tri_r = nullptr;
     void* bvh_nodes = nullptr;
     void* bvh_prims = nullptr;
+    void* sph64 = nullptr;
+    void* pln64 = nullptr;
     rm::DeviceScene<R> ds;
     void release() {
         cudaFree(blob); cudaFree(mat_a); cudaFree(mat_b); cudaFree(mat_f); cudaFree(tri_src); cudaFree(tri_r);
-        cudaFree(bvh_nodes); cudaFree(bvh_prims);
+        cudaFree(bvh_nodes); cudaFree(bvh_prims); cudaFree(sph64); cudaFree(pln64);
         for (int i = 0; i < 2; i++) { cudaFree(order[i]); cudaFree(order_shape[i]); }
         *this = DevicePack<R>();
     }
@@ -158,6 +160,10 @@ template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
         dp.ds.bvh.prims = static_cast<const int*>(dp.bvh_prims);
         dp.ds.bvh.n_nodes = (int)(ps.bvh_nodes.size() / 4);
         dp.ds.bvh.status = dp.ds.tile_order + order_cap;
+        if ((rc = upload_vec(ps.sph64, &dp.sph64)) != RM_OK) return rc;
+        if ((rc = upload_vec(ps.pln64, &dp.pln64)) != RM_OK) return rc;
+        dp.ds.sph64 = static_cast<const double*>(dp.sph64);
+        dp.ds.pln64 = static_cast<const double*>(dp.pln64);
     }
     dp.ds.blob = static_cast<const unsigned char*>(dp.blob);
     dp.ds.lay = ps.lay;

@@ -80,14 +80,40 @@ template <bool kBvh> struct FastViewT {
     const R4<float>* lgt_p;
     const R4<float>* lgt_c;
     int n_lgt;
-    // primary hit of this thread's pixel
-    bool prim_got;
-    HitRec<float> prim_hit;
     // hierarchy over the hittable primitives (kBvh only), and this thread's count of scene queries behind the primary
     // one (closest-hit calls of the recursion + shadow rays): the segment count of a frame too large to run through the
     // instrumented brute-force kernel (rm_scene_query_count)
     BvhView bvh;
     mutable unsigned n_queries = 0;
+    // f64 sources for the refinement of winning hits on glass paths (cast_glass below): spheres {c, r^2}, fast-path
+    // triangles (the prepare kernel's source records: n at [0..2], n.C at [3]), generic planes by slot {n, n.C}
+    const double* sph64 = nullptr;
+    const double* tri64 = nullptr;
+    const double* pln64 = nullptr;
+
+    // Hit point and normal of the primitive an FP32 query picked, for the f64 ray (o, d): the reference's own f64 formulas
+    // (sphere.rs:28-60, triangle.rs:62-69 / polygon.rs:71-78).  t32 is the FP32 ray parameter; for a sphere it selects
+    // the root the FP32 test took (sphere.rs:44-51: the near one unless it lies behind the origin).
+    RM_HD void refine(const int slot, const Vec3<double> o, const Vec3<double> d, const double t32, Vec3<double>& p,
+                      Vec3<double>& n) const {
+        if (slot < n_sph) {
+            const double* q = sph64 + 4 * (size_t)slot;
+            const Vec3<double> c = {q[0], q[1], q[2]};
+            const Vec3<double> line = c - o;
+            const double tca = dot(line, d);
+            const double d2 = dot(line, line) - tca * tca;
+            const double thc = sqrt(fmax(q[3] - d2, 0.));      // (a grazing hit FP32 accepted and f64 would not: the tangent point)
+            const double ta = tca - thc, tb = tca + thc;
+            const double t = fabs(ta - t32) <= fabs(tb - t32) ? ta : tb;
+            p = axpy(o, d, t);
+            n = normalized(p - c);
+        } else {
+            const double* q = slot < n_sph + n_tri ? tri64 + (size_t)kTriSrcDoubles * (slot - n_sph) : pln64 + 4 * (size_t)(slot - n_sph - n_tri);
+            n = {q[0], q[1], q[2]};
+            const double t = (q[3] - dot(o, n)) / dot(d, n);   // ((C - o).n) / (d.n)
+            p = axpy(o, d, t);
+        }
+    }
 
     static RM_HD int as_int(float f) {
 #if defined(__CUDA_ARCH__)
@@ -137,11 +163,8 @@ template <bool kBvh> struct FastViewT {
         }
     }
 
-    template <bool S> RM_HD bool closest(const Vec3<float> o, const Vec3<float> d, int level, HitRec<float>& h, Counters<S>& st) const {
-        if (level == 1) {
-            h = prim_hit;
-            return prim_got;
-        }
+    // (the primary query is stage A of the render kernel; this is renderer.rs:266 at level > 1)
+    template <bool S> RM_HD bool closest(const Vec3<float> o, const Vec3<float> d, int /*level*/, HitRec<float>& h, Counters<S>& st) const {
         bool hit = false;
         if constexpr (kBvh) {
             h.dist = INFINITY;
@@ -470,11 +493,13 @@ RM_HD void primary_tri(PrimaryState<kPx>& ps, const R4<float> r0, const R4<float
     }
 }
 
-// spheres / n-gons: the general routines from the camera.  One copy of the code: the loop over the kPx pixels is
-// not unrolled and the pixel state rotates through index 0, so every array index stays a compile-time constant
-// (a dynamic index would push the arrays to local memory).
+// spheres / n-gons: the general routines from the camera, one pixel of the thread after the other; the pixel state
+// rotates through index 0, so every array index is a compile-time constant.  The loop over the kPx pixels is FULLY
+// UNROLLED: as a rolled loop (`#pragma unroll 1`) it had the shape that went wrong in primary_bvh on the B200 -- a trip
+// counter ptxas keeps in a uniform register around per-lane divergent inner loops (here: the per-edge early exits of
+// plane_intersect), see the note at primary_bvh.  Unrolled there is no counter to share.
 template <int kPx, class FV> RM_HD void primary_rest(PrimaryState<kPx>& ps, const FV& fv, const FrameParams<float>& fp) {
-#pragma unroll 1
+#pragma unroll
     for (int r = 0; r < kPx; r++) {
         const float inv = fast_rsqrt(ps.len2[0]);
         const Vec3<float> d = {ps.X[0] * inv, ps.Y * inv, -inv};
@@ -595,21 +620,140 @@ template <int kPx> RM_HD void primary_bvh(PrimaryState<kPx>& ps, const FastViewB
     }
 }
 
-// Shading + recursion of one pixel whose primary ray hit (t in units of |D|, slot, id): renderer.rs:254-309 from level 1.
+// ---- the shading stage (stage B of the render kernel) -------------------------------------------------------------------
+// An OPAQUE primary hit spawns no ray (renderer.rs:277): its colour is background + direct lighting, pure FP32.
+// A GLASS-LIKE primary hit starts the reflect / refract recursion (renderer.rs:254-309).  Those paths are traced by
+// cast_glass with f64 RAY GEOMETRY: a curved glass surface magnifies a direction error by (distance to the next hit /
+// radius), so positions rounded to FP32 at scene scale (2^-24 * 128 against radii of ~1) grow to 1e-3 relative colour
+// errors two bounces later -- measured on BASELINE.json configs[4]'s scene: only 99.5 % of the pixels within the north
+// star's 1e-4 with FP32 geometry.  What stays FP32 is everything that is a search or a smooth function: which primitive
+// a ray hits (the O(n) / O(log n) part), the shadow rays, the lighting arithmetic.  What is f64: the ray (origin,
+// direction), the hit point and normal of the ONE primitive each query picked (FastViewT::refine) and the optics
+// (optics.rs:8-89) -- a few dozen FP64 operations per segment next to hundreds of FP32 primitive tests.
+#if defined(__CUDACC__)
+#define RM_GLASS_FN __host__ __device__ __noinline__
+#else
+#define RM_GLASS_FN
+#endif
+
+RM_HD Vec3<float> to_f32(const Vec3<double> v) { return {(float)v.x, (float)v.y, (float)v.z}; }
+
+// renderer.rs:254-309 from a glass-like primary hit of pixel (x, y); t1 = FP32 ray parameter of that hit (unit direction).
 template <class FV>
+RM_GLASS_FN Vec3<float> cast_glass(const FV& fv, const FrameParams<float>& fp, const int x, const int y, const float t1,
+                                   const int slot1, const int id1) {
+    struct Frame {
+        Vec3<float> c;
+        Vec3<double> ro, rd;
+        float k;
+        int state;   // bit0: a refracted ray is pending, bit1: the refracted ray is the one in flight
+    };
+    Frame fr[kMaxDepth];
+    int sp = 0;
+    const Vec3<float> bg = {fp.background, fp.background, fp.background};
+    // renderer.rs:128-135 in the reference's own arithmetic
+    Vec3<double> o = {fp.cam64[0], fp.cam64[1], fp.cam64[2]};
+    Vec3<double> d = normalized(Vec3<double>{2. * ((double)x / fp.w64 - 0.5) * fp.hf64 * fp.ratio64,
+                                             -2. * ((double)y / fp.h64 - 0.5) * fp.hf64, -1.});
+    Counters<false> st;
+    Vec3<float> v;
+    for (;;) {
+        const int level = sp + 1;                               // n_recursion
+        if (level > fp.max_depth) {
+            v = bg;                                             // renderer.rs:262-264
+        } else {
+            const Vec3<float> o32 = to_f32(o), d32 = to_f32(d);
+            HitRec<float> h;
+            bool got = true;
+            if (level == 1) {
+                h.dist = t1;
+                h.slot = slot1;
+                h.id = id1;
+            } else {
+                got = fv.template closest<false>(o32, d32, level, h, st);      // renderer.rs:266: the search, FP32
+            }
+            if (!got) {
+                v = bg;                                         // renderer.rs:300-306 (level > 1 here)
+            } else {
+                Vec3<double> p, n;
+                fv.refine(h.slot, o, d, (double)h.dist, p, n);
+                const R4<float> ma = fv.mat_a[h.id];
+                const R4<float> mb = fv.mat_b[h.id];
+                Vec3<float> c = bg + fv.template direct<false>(o32, d32, to_f32(p), to_f32(n), ma, mb, st);   // renderer.rs:272-275
+                bool pushed = false;
+                if (fv.mat_f[h.id] & 1) {                       // renderer.rs:277
+                    Vec3<double> ro1, rd1, ro2, rd2;
+                    const bool has_refl = reflect_ray<double>(d, p, n, (double)mb.w, ro1, rd1);   // renderer.rs:203-207
+                    const bool has_refr = refract_ray<double>(d, p, n, (double)mb.w, ro2, rd2);   // renderer.rs:235-239
+                    if (has_refl || has_refr) {
+                        Frame& f = fr[sp];
+                        f.c = c;
+                        f.k = mb.z;
+                        if (has_refl) {
+                            f.state = has_refr ? 1 : 0;
+                            f.ro = ro2;
+                            f.rd = rd2;
+                            o = ro1;
+                            d = rd1;
+                        } else {
+                            f.state = 2;
+                            o = ro2;
+                            d = rd2;
+                        }
+                        sp++;
+                        pushed = true;
+                    }
+                }
+                if (pushed) continue;
+                v = c;
+            }
+        }
+        for (;;) {                                              // return v to the callers on the stack
+            if (sp == 0) return v;
+            Frame& f = fr[sp - 1];
+            if (f.state & 2) {
+                f.c = f.c + scaled(v, 1.f - f.k);               // renderer.rs:249
+                v = f.c;
+                sp--;
+            } else {
+                f.c = f.c + scaled(v, f.k);                     // renderer.rs:219
+                if (f.state & 1) {
+                    o = f.ro;
+                    d = f.rd;
+                    f.state = 2;
+                    break;
+                }
+                v = f.c;
+                sp--;
+            }
+        }
+    }
+}
+
+// One pixel whose primary ray hit (t in units of |D|, slot, id): renderer.rs:254-309 from level 1.
+// kGlass = false: the scene has neither glass-like materials nor spheres (every OBJ scene of the reference: obj.rs:125-138
+// loads meshes opaque) -- the kernel instantiated for it carries no recursion, no f64 code and far fewer registers.
+template <bool kGlass = true, class FV>
 RM_HD Vec3<float> fast_shade(FV& fv, const FrameParams<float>& fp, const int x, const int y, const float t, const int slot,
                              const int id) {
     const float X = pixel_X(fp, x), Y = pixel_Y(fp, y);
     const float len2 = fmaf(X, X, fmaf(Y, Y, 1.f));
     const float inv = fast_rsqrt(len2);                            // geometry.rs:104-109: scale(1/norm)
+    const float dist = t * (len2 * inv);                           // stage A reports t in units of |D|
+    // (spheres, glass-like or not, take the f64 route too: near a silhouette the hit point of a far sphere of radius ~1
+    // moves by many ulps of the FP32 centre per ulp of the ray, and a specular exponent of 100 turns that into 1e-4)
+    if constexpr (kGlass)
+        if ((fv.mat_f[id] & 1) || slot < fv.n_sph) return cast_glass(fv, fp, x, y, dist, slot, id);
     const Vec3<float> d = {X * inv, Y * inv, -inv};
-    fv.prim_got = true;
-    fv.prim_hit.dist = t * (len2 * inv);                           // stage A reports t in units of |D|
-    fv.prim_hit.slot = slot;
-    fv.prim_hit.id = id;
+    HitRec<float> h;
+    h.dist = dist;
+    h.slot = slot;
+    h.id = id;
+    Vec3<float> normal;
+    fv.surface(h, fp.camera, d, normal);
     Counters<false> st;
-    int pid;
-    return cast_ray<float, false, FV>(fv, fp.camera, d, fp.background, fp.max_depth, pid, st);
+    const Vec3<float> bg = {fp.background, fp.background, fp.background};
+    return bg + fv.template direct<false>(fp.camera, d, h.p, normal, fv.mat_a[id], fv.mat_b[id], st);   // renderer.rs:272-275
 }
 
 }  // namespace rm

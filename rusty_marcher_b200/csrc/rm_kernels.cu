@@ -332,12 +332,15 @@ constexpr int kWarpQueue = kFastTile * 4 + 32;                  // one strip of 
 #ifdef RM_K1_MAXREG
 #define RM_K1_BOUNDS __maxnreg__(RM_K1_MAXREG)
 #else
-#define RM_K1_BOUNDS __launch_bounds__(kFastBlock, RM_K1_MIN_BLOCKS)
+#define RM_K1_BOUNDS __launch_bounds__(kFastBlock, kGlass ? RM_K1_MIN_BLOCKS : RM_K1_MIN_BLOCKS_OPAQUE)
+#endif
+#ifndef RM_K1_MIN_BLOCKS_OPAQUE
+#define RM_K1_MIN_BLOCKS_OPAQUE 3                               // the instantiation without recursion / f64 code (kGlass = false)
 #endif
 template <int kPx> struct PxTag { static constexpr int value = kPx; };
 // kBvh (RmParams.accel): scene queries walk the hierarchy of rm_bvh.cuh (read through the read-only path; the nodes near
 // the root stay in L1) instead of every primitive; stage A then handles a thread's pixels one after the other.
-template <bool kSmem, bool kBvh>
+template <bool kSmem, bool kBvh, bool kGlass>
 __global__ void RM_K1_BOUNDS
 render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
@@ -417,6 +420,9 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     fv.lgt_p = reinterpret_cast<const R4<float>*>(base + L.off_lgt_p);
     fv.lgt_c = reinterpret_cast<const R4<float>*>(base + L.off_lgt_c);
     fv.n_lgt = L.n_lgt;
+    fv.sph64 = ds.sph64;
+    fv.tri64 = ds.tri_src;
+    fv.pln64 = ds.pln64;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lane_lt = (1u << lane) - 1u;
@@ -431,7 +437,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     auto shade_entry = [&](const float4 e) {
         const unsigned xy = __float_as_uint(e.w);
         const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
-        const Vec3<float> c = fast_shade(fv, fp, x, y, e.x, __float_as_int(e.y), __float_as_int(e.z));
+        const Vec3<float> c = fast_shade<kGlass>(fv, fp, x, y, e.x, __float_as_int(e.y), __float_as_int(e.z));
         float* dst = rgb + 3 * ((size_t)(y - fp.buf_row0) * fp.width + x);
         dst[0] = c.x;
         dst[1] = c.y;
@@ -818,9 +824,10 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
         cudaFuncAttributes fa;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-        if ((e = cudaFuncGetAttributes(&fa, render_fast_kernel<true, false>)) != cudaSuccess) return e;
+        if ((e = cudaFuncGetAttributes(&fa, render_fast_kernel<true, false, true>)) != cudaSuccess) return e;
         dyn_limit = std::min(kSmemLimit, optin - (int)fa.sharedSizeBytes - 1024);
-        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     }
     const size_t smem_geo = (size_t)ds.lay.bytes + (size_t)ds.lay.n_tri * 64;
@@ -840,7 +847,11 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     const int cull_i = cull ? 1 : 0;
     const int* order2 = order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr;
     const bool use_smem = !bvh && smem <= (size_t)dyn_limit;
-    auto k = bvh ? render_fast_kernel<false, true> : use_smem ? render_fast_kernel<true, false> : render_fast_kernel<false, false>;
+    // the reflect / refract recursion and the f64 ray geometry (cast_glass) only where a frame can need them
+    const bool glass = ds.lay.any_glass != 0 || ds.lay.n_sph > 0;
+    auto k = bvh ? (glass ? render_fast_kernel<false, true, true> : render_fast_kernel<false, true, false>)
+             : use_smem ? (glass ? render_fast_kernel<true, false, true> : render_fast_kernel<true, false, false>)
+                        : (glass ? render_fast_kernel<false, false, true> : render_fast_kernel<false, false, false>);
     cfg.dynamicSmemBytes = use_smem ? smem : 0;
     int occ = 1;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kFastBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;

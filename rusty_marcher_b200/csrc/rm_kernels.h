@@ -22,6 +22,9 @@ template <typename R> struct DeviceScene {
     // camera-specialised raster records it writes (4 x R4<float> per triangle, rebuilt every frame)
     const double* tri_src = nullptr;
     R4<float>* tri_r = nullptr;
+    // FP32 pack: f64 {c, r^2} per sphere and {n, n.C} per plane slot, read by the f64 ray geometry of glass paths (cast_glass)
+    const double* sph64 = nullptr;
+    const double* pln64 = nullptr;
     // frame control block of the persistent render kernel, zero between frames (the last CTA to finish resets it):
     //   ctr[0] next busy tile   ctr[1] fully covered tiles   ctr[2] empty tiles   ctr[3] CTAs finished   ctr[5] partially covered tiles
     //   ctr[6..7] u64: scene queries behind the primary rays, accumulated by the hierarchy kernel (rm_scene_query_count)

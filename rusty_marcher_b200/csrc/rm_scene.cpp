@@ -286,6 +286,7 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
         }
     }
     out.n_prims = id;
+    for (int f : out.mat_f) out.lay.any_glass |= f & 1;
 
     // hittable planes first, then back-facing, then degenerate (stable: scene order inside each class)
     std::stable_sort(pln.begin(), pln.end(), [](const PlaneTmp& a, const PlaneTmp& b) { return a.cls < b.cls; });
@@ -352,6 +353,21 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
         b_pid[i] = p.id;
     }
     write_fast<R>(pln, L, b, out);
+    if (sizeof(R) == 4) {
+        // f64 sources for the refinement of winning hits on glass paths (cast_glass, rm_fast.cuh): spheres {c, r^2}
+        // (sphere.rs:6-11) and planes by slot {n, n.C} (triangle.rs:33-47 / polygon.rs:16-42: precomputed normal, plane point)
+        out.sph64.resize((size_t)L.n_sph * 4 + 4, 0.);
+        for (int i = 0; i < L.n_sph; i++) {
+            const RmSphere& sp = *sph[i].s;
+            const double q[4] = {sp.center[0], sp.center[1], sp.center[2], sp.radius_square};
+            std::memcpy(out.sph64.data() + 4 * (size_t)i, q, sizeof q);
+        }
+        out.pln64.resize((size_t)L.n_pln * 4 + 4, 0.);
+        for (int i = 0; i < L.n_pln; i++) {
+            const double q[4] = {pln[i].n[0], pln[i].n[1], pln[i].n[2], plane_dn(pln[i])};
+            std::memcpy(out.pln64.data() + 4 * (size_t)i, q, sizeof q);
+        }
+    }
     for (int l = 0; l < L.n_lgt; l++) {
         const RmLight& lg = fs.lights[l];
         b_lp[l] = mk4<R>(lg.position[0], lg.position[1], lg.position[2], lg.intensity);
@@ -411,6 +427,11 @@ template <typename R> FrameParams<R> make_frame_params(const RmParams& p) {
     fp.background = (R)p.background;
     fp.max_depth = p.max_depth < 0 ? 0 : (p.max_depth > kMaxDepth ? kMaxDepth : p.max_depth);
     fp.accel = p.accel != 0 ? 1 : 0;
+    for (int a = 0; a < 3; a++) fp.cam64[a] = p.camera[a];
+    fp.w64 = width;
+    fp.h64 = height;
+    fp.hf64 = half_fov;
+    fp.ratio64 = ratio;
     return fp;
 }
 

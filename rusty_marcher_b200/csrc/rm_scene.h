@@ -29,6 +29,7 @@ struct BlobLayout {
     int n_tri = 0, n_tri_live = 0, n_poly = 0, n_poly_live = 0;
     int off_tri_g = 0, off_poly_slot = 0;
     int bytes = 0;
+    int any_glass = 0;                // some material is glass-like (shapes.rs:29): the frame may need the reflect / refract recursion
 };
 
 struct alignas(32) BlobChunk { unsigned char b[32]; };
@@ -49,6 +50,7 @@ template <typename R> struct PackedScene {
     const unsigned char* blob_data() const { return reinterpret_cast<const unsigned char*>(blob.data()); }
     size_t blob_bytes() const { return blob.size() * sizeof(BlobChunk); }
     std::vector<double> tri_src;      // FP32 pack only: kTriSrcDoubles per fast-path triangle (prepare_raster input)
+    std::vector<double> sph64, pln64; // FP32 pack only: f64 {c, r^2} per sphere and {n, n.C} per plane slot (cast_glass)
     std::vector<R4<R>> mat_a, mat_b;
     std::vector<int> mat_f;
     // scene-order traversal lists: [0] = every primitive, [1] = after culling

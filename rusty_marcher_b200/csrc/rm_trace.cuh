@@ -497,6 +497,9 @@ template <typename R> struct FrameParams {
     R background;
     int max_depth;
     int accel;                    // RmParams.accel: scene queries through the hierarchy (FP32 production kernel)
+    // the reference's own f64 operands of backproject (renderer.rs:128-135) and the camera, whatever R is: the FP32
+    // production kernel traces the paths behind a glass-like primary hit with f64 ray geometry (cast_glass, rm_fast.cuh)
+    double cam64[3], w64, h64, hf64, ratio64;
 };
 
 // pixel row of the l-th rendered row of this call (l in [0, 32 * n_bands))

@@ -5,6 +5,8 @@ be instantiated on the GPU path (build_scene) and, in tests, on the oracle.
   cornell_box   test_data/cornell_box.obj, every model moved by (0,0,-500), default lights (main.rs:261-315)
   dodecahedron  test_data/dodecahedron.obj, same treatment
   stress        synthetic: 4096 random spheres + a 224x224 quad grid (100,352 triangles), seed 0x5EED
+  ngons         synthetic: convex n-gons (n = 4..8, engine/src/polygon.rs) of random tilt + spheres, seed 0x90A5 -- the
+                primitives the demo scene has only two of; exercises the n-gon routines of the production kernel
 
 The OBJ meshes are shipped as parsed vertex arrays (scenes/*.npz, made from the reference's
 test_data by tests/golden/make_fixtures.py) because the reference tree is not present on the GPU box.
@@ -13,7 +15,7 @@ import os
 
 import numpy as np
 
-from . import lights, sphere
+from . import lights, polygon, sphere
 from .geometry import Vec3f
 from .obj import Obj
 from .scene import Scene
@@ -46,8 +48,9 @@ def _splitmix64(seed):
     return nxt
 
 
-def describe(name, n_spheres=4096, grid=224, seed=0x5EED):
-    """A workload as plain data: {'default': bool, 'spheres': [...], 'meshes': [...], 'lights': [...]}"""
+def describe(name, n_spheres=4096, grid=224, seed=0x5EED, n_polygons=320):
+    """A workload as plain data: {'default': bool, 'spheres': [...], 'polygons': [...], 'meshes': [...], 'lights': [...]}
+    (shape order of the scene: spheres, polygons, meshes)"""
     if name == "demo":
         return {"name": name, "default": True}
     if name in ("cornell_box", "dodecahedron"):
@@ -79,7 +82,39 @@ def describe(name, n_spheres=4096, grid=224, seed=0x5EED):
         tris = tris.astype(np.float32).astype(np.float64)
         return {"name": name, "default": False, "spheres": spheres, "meshes": [("grid", tris, (0., 0., 0.))],
                 "lights": DEFAULT_LIGHTS}
+    if name == "ngons":
+        u = _splitmix64(0x90A5 if seed == 0x5EED else seed)
+
+        def refl():
+            glass = u() < 0.2
+            return dict(diffusion=0.1 if glass else 1., diffuse_color=(u(), u(), u()), specular=1.,
+                        specular_exponent=30. if u() < .5 else 100., is_glass_like=glass,
+                        reflection=0.2 + 0.3 * u() if glass else 0.95, refractive_index=1.5 if glass else 1.)
+        polygons = []
+        for k in range(n_polygons):
+            n = 4 + k % 5                                          # 4, 5, 6, 7, 8 vertices in turn
+            z = -15. - 45. * u()
+            cx, cy = (2. * u() - 1.) * 1.2 * -z, (2. * u() - 1.) * 0.7 * -z
+            rad, a, b = 0.4 + 2.6 * u(), 1.6 * u() - 0.8, 1.6 * u() - 0.8
+            ccw = u() < 0.9                                        # one in ten wound clockwise in XY: never hittable (polygon.rs:83-91)
+            ts = [2. * np.pi * (i + 0.6 * u()) / n for i in range(n)]
+            if not ccw:
+                ts = ts[::-1]
+            verts = [(cx + rad * np.cos(t), cy + rad * np.sin(t), z + rad * (a * np.cos(t) + b * np.sin(t))) for t in ts]
+            polygons.append((verts, refl()))
+        spheres = []
+        for _ in range(n_spheres if n_spheres != 4096 else 48):
+            z = -12. - 50. * u()
+            c = ((2. * u() - 1.) * 1.1 * -z, (2. * u() - 1.) * 0.65 * -z, z)
+            spheres.append((c, 0.3 + 1.7 * u(), refl()))
+        return {"name": name, "default": False, "spheres": spheres, "polygons": polygons, "meshes": [], "lights": DEFAULT_LIGHTS}
     raise KeyError(name)
+
+
+def n_prims(desc):
+    if desc.get("default"):
+        return 6
+    return len(desc["spheres"]) + len(desc.get("polygons", ())) + sum(len(v) for _n, v, _o in desc["meshes"])
 
 
 def build_scene(desc):
@@ -91,6 +126,10 @@ def build_scene(desc):
         refl = Reflectance(r["diffusion"], Vec3f(*r["diffuse_color"]), r["specular"], r["specular_exponent"],
                            r["is_glass_like"], r["reflection"], r["refractive_index"])
         s.shapes.append(sphere.create(Vec3f(*c), radius, refl))
+    for verts, r in desc.get("polygons", ()):
+        refl = Reflectance(r["diffusion"], Vec3f(*r["diffuse_color"]), r["specular"], r["specular_exponent"],
+                           r["is_glass_like"], r["reflection"], r["refractive_index"])
+        s.shapes.append(polygon.ConvexPolygon.create([Vec3f(*v) for v in verts], refl))
     for name, verts, offset in desc["meshes"]:
         o = Obj.from_vertices(verts, name)
         o.offset(offset)

@@ -138,6 +138,9 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
     fv0.lgt_p = reinterpret_cast<const rm::R4<float>*>(base + L.off_lgt_p);
     fv0.lgt_c = reinterpret_cast<const rm::R4<float>*>(base + L.off_lgt_c);
     fv0.n_lgt = L.n_lgt;
+    fv0.sph64 = ps.sph64.data();
+    fv0.tri64 = ps.tri_src.data();
+    fv0.pln64 = ps.pln64.data();
     const rm::FrameParams<float> fp = rm::make_frame_params<float>(*p);
     std::atomic<int> next{fp.row_begin};
     std::vector<float> tmax(n_threads, 0.f);

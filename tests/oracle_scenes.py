@@ -8,6 +8,8 @@ def build_oracle_scene(desc):
     s = O.Scene()
     for c, radius, r in desc["spheres"]:
         s.add_sphere(c, radius, O.make_reflectance(**r))
+    for verts, r in desc.get("polygons", ()):
+        s.add_polygon(verts, O.make_reflectance(**r))
     for _name, verts, offset in desc["meshes"]:
         s.add_mesh(verts, offset)
     for pos, col, inten in desc["lights"]:

@@ -180,10 +180,17 @@ def test_cornell_1080p_config2(rm_gpu):
 
 
 @pytest.mark.parametrize("name,w,h", [("cornell_box", 3840, 2160), ("dodecahedron", 3840, 2160), ("demo", 1600, 1280)])
-def test_full_size_properties(rm_gpu, name, w, h):
-    """Configs 1, 3, 4 at full size: properties that need no oracle pass."""
-    scene = workloads.scene(name)
+def test_full_size_against_the_oracle_and_properties(rm_gpu, name, w, h):
+    """Configs 1, 3, 4 at BASELINE.json's full sizes: the FP32 production frame against the ORACLE's frame of the same
+    size (north-star criteria, fragile mask and all; the oracle needs one to two seconds for a 4K frame), the FP64
+    validation kernel bit-exact against it, then the size-independent properties."""
+    desc = workloads.describe(name)
+    ref = O.render(build_oracle_scene(desc), w, h)
+    scene = workloads.build_scene(desc)
     whole = gpu_render(rm_gpu, scene, w, h, "f32")
+    rep = parity.check_fp32(whole, ref, (h // 32) * 32, whole["rgb8"])
+    print(name, w, h, rep)
+    assert abs(whole["max"] - ref["rgb"].max()) <= 1e-4 * ref["rgb"].max()
     # the instrumented launch uses the generic FP32 kernel (other roundings than the production one): counters only
     counted = gpu_render(rm_gpu, scene, w, h, "f32", counters=True)
     rows = (h // 32) * 32
@@ -210,8 +217,12 @@ def test_full_size_properties(rm_gpu, name, w, h):
     nocull = gpu_render(rm_gpu, scene, w, h, "f32", cull=False)
     assert np.array_equal(nocull["prim_id"], whole["prim_id"])
     assert np.array_equal(nocull["rgb"], whole["rgb"])
-    # FP32 against the device's own FP64 validation kernels (which the other tests pin to the oracle)
+    # the device's FP64 validation kernel at full size: bit-exact ids, counters equal to the oracle's (culling on: the
+    # control-flow counters), colours up to pow ulps -- and the FP32 frame against it
     g64 = gpu_render(rm_gpu, scene, w, h, "f64", counters=True)
+    parity.check_exact(g64, ref, rel=1e-13)
+    for k in ("pixels", "closest_segments", "anyhit_segments", "hits", "light_evals", "lit_lights", "glass_hits", "reflections", "refractions"):
+        assert g64["counters"][k] == ref["counters"][k], k
     mism = whole["prim_id"] != g64["prim_id"]
     assert mism.mean() < 2e-4
     rel = (np.abs(whole["rgb"][:rows].astype(np.float64) - g64["rgb"][:rows]) / np.maximum(np.abs(g64["rgb"][:rows]), 1e-12)).max(axis=2)
@@ -226,6 +237,64 @@ def test_full_size_properties(rm_gpu, name, w, h):
         assert abs(c32[k] - c64[k]) <= 2e-4 * max(c64[k], 1), k
     # rows below the last patch row are untouched, rgb8 there is zero
     assert np.all(whole["rgb"][rows:] == 0) and np.all(whole["rgb8"][rows:] == 0)
+
+
+STRESS_PARITY = dict(n_spheres=2048, grid=32)                   # 2048 spheres + 2048 triangles
+STRESS_PARITY_CAMERA = (-20., 8., -90.)                         # inside the cloud of spheres: a quarter of them glass
+
+
+def test_stress_scene_against_the_oracle(rm_gpu):
+    """The stress generator (BASELINE.json configs[4]) at a size that exercises what the full scene exercises -- glass
+    spheres recursing to depth 6 over thousands of primitives: 2048 spheres + a 32x32 quad grid (2048 triangles), 640x352,
+    camera inside the cloud of spheres, depth cap 6 (52,729 glass hits, 1.3 closest-hit segments per pixel) -- against the
+    oracle: brute force and the hierarchy, FP32 production kernels; FP64 validation kernel bit-exact with equal counters."""
+    w, h, depth = 640, 352, 6
+    desc = workloads.describe("stress", **STRESS_PARITY)
+    osc = build_oracle_scene(desc)
+    osc.offset_camera(STRESS_PARITY_CAMERA)
+    ref = O.render(osc, w, h, max_depth=depth)
+    assert ref["counters"]["glass_hits"] > 40000 and ref["counters"]["closest_segments"] > 1.25 * ref["counters"]["pixels"]
+    scene = workloads.build_scene(desc)
+    scene.offset_camera(STRESS_PARITY_CAMERA)
+    a = gpu_render(rm_gpu, scene, w, h, "f32", depth=depth)
+    print("stress brute force", parity.check_fp32(a, ref, h, a["rgb8"]))
+    b = gpu_render(rm_gpu, scene, w, h, "f32", depth=depth, accel=True)
+    print("stress hierarchy  ", parity.check_fp32(b, ref, h, b["rgb8"]))
+    assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["rgb"], b["rgb"]) and np.array_equal(a["rgb8"], b["rgb8"])
+    g64 = gpu_render(rm_gpu, scene, w, h, "f64", depth=depth, cull=False, counters=True)
+    parity.check_exact(g64, ref, rel=1e-12)
+    assert g64["counters"] == ref["counters"]
+
+
+@pytest.mark.parametrize("cull", [False, True])
+def test_many_ngons_against_the_oracle(rm_gpu, cull):
+    """320 convex n-gons (n = 4 ... 8, one in ten wound clockwise = never hittable, a fifth glass-like) + 48 spheres, depth
+    cap 4: the n-gon routines of the production kernel (stage A's primary_rest, plane_intersect in the shading stage)
+    on far more than the demo scene's two polygons -- against the oracle (polygon.rs:60-98), brute force and hierarchy;
+    the frame must also be reproducible run to run."""
+    w, h, depth = 640, 352, 4
+    desc = workloads.describe("ngons")
+    ref = O.render(build_oracle_scene(desc), w, h, max_depth=depth)
+    assert len(np.unique(ref["prim_id"])) > 250 and ref["counters"]["glass_hits"] > 10000
+    scene = workloads.build_scene(desc)
+    a = gpu_render(rm_gpu, scene, w, h, "f32", depth=depth, cull=cull)
+    print("ngons brute force", parity.check_fp32(a, ref, h, a["rgb8"]))
+    a2 = gpu_render(rm_gpu, scene, w, h, "f32", depth=depth, cull=cull)
+    assert np.array_equal(a["prim_id"], a2["prim_id"]) and np.array_equal(a["rgb"], a2["rgb"])
+    b = gpu_render(rm_gpu, scene, w, h, "f32", depth=depth, cull=cull, accel=True)
+    parity.check_fp32(b, ref, h, b["rgb8"])
+    assert np.array_equal(a["prim_id"], b["prim_id"]) and np.array_equal(a["rgb"], b["rgb"]) and np.array_equal(a["rgb8"], b["rgb8"])
+    g64 = gpu_render(rm_gpu, scene, w, h, "f64", depth=depth, cull=cull, counters=True)
+    parity.check_exact(g64, ref, rel=1e-12)
+    if not cull:
+        assert g64["counters"] == ref["counters"]
+    # a camera off the axis and a 4K-wide strip of the same scene (many strips per warp: the schedule's other regime)
+    scene.offset_camera((3., -2., 6.))
+    osc = build_oracle_scene(desc)
+    osc.offset_camera((3., -2., 6.))
+    ref2 = O.render(osc, 3840, 160, max_depth=depth)
+    c = gpu_render(rm_gpu, scene, 3840, 160, "f32", depth=depth, cull=cull)
+    parity.check_fp32(c, ref2, 160, c["rgb8"])
 
 
 def test_error_behaviour(rm_gpu):
