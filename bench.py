@@ -245,6 +245,150 @@ def run_reference(args):
     return 0
 
 
+VERIFY_CAMERAS = {"default": [(0., 0., 0.), (30., -20., 10.), (-45., 15., 0.)],
+                  "stress": [(0., 0., 0.), (7.5, -3.25, 20.), (-5., 2., -10.)]}
+
+
+def verify_frames(tr, backend, cameras, world, rank, dev):
+    """Driver-visible proof that the frame the ranks assemble is the single-GPU frame (the reference's
+    reassembly is engine/src/renderer.rs:92-108).  For each camera, back to back (consecutive frames alternate between
+    rank 0's two 8-bit buffers, and rank 0 clears the other ranks' bands of the NEXT buffer inside the kernel): one frame
+    through the product path at N ranks -- rm_render_frame, exchange inside the kernel -- then rank 0 renders the same
+    frame alone (rm_render_device over every patch row + rm_tonemap_device, no exchange) and compares (1) the assembled
+    RGB8 frame byte for byte and (2) the float rows of every rank, gathered once, bit for bit.  Outside every timed region.
+    Returns (ok, sha256 of the first assembled 8-bit frame, detail) on rank 0, (True, None, None) elsewhere."""
+    import ctypes as C
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from rusty_marcher_b200 import _abi
+    L = backend.L
+    h, w, n_patch = tr.height, tr.width, tr.n_patch_rows
+    rows = n_patch * 32
+    ok, sha, detail = True, None, []
+    frames8, floats = [], []
+    for cam in cameras:                                      # the product path, consecutive frames
+        tr.set_camera(cam)
+        f = tr.render()
+        if rank == 0:
+            frames8.append(f.clone())                        # stream-ordered: valid until the next frame is issued
+        mine = tr.rgb[:rows].view(n_patch, 32, w, 3)[rank::world].contiguous()
+        if world == 1:
+            floats.append(tr.rgb.clone())
+        elif rank == 0:
+            full = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+            fv = full[:rows].view(n_patch, 32, w, 3)
+            fv[0::world] = mine
+            for r in range(1, world):
+                n = len(range(r, n_patch, world))
+                if n:
+                    buf = torch.empty((n, 32, w, 3), dtype=torch.float32, device=dev)
+                    dist.recv(buf, src=r)
+                    fv[r::world] = buf
+            floats.append(full)
+        elif mine.shape[0]:
+            dist.send(mine, dst=0)
+    torch.cuda.synchronize()
+    if tr.peer is not None:
+        tr.peer.status()
+    if rank == 0:
+        ref = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+        ref8 = torch.zeros((h, w, 3), dtype=torch.uint8, device=dev)
+        smax = torch.zeros(1, dtype=torch.float32, device=dev)
+        p = backend.frame_params((0, n_patch))
+        stream = torch.cuda.current_stream().cuda_stream
+        for i, cam in enumerate(cameras):
+            p.camera[:] = [float(c) for c in cam]
+            ref.zero_()
+            ref8.zero_()
+            smax.zero_()
+            _abi.check(L.rm_render_device(backend.handle, C.byref(p), ref.data_ptr(), None, smax.data_ptr(), stream))
+            _abi.check(L.rm_tonemap_device(C.byref(p), ref.data_ptr(), smax.data_ptr(), 1, ref8.data_ptr(), stream))
+            torch.cuda.synchronize()
+            same8 = bool(torch.equal(frames8[i], ref8))
+            samef = bool(torch.equal(floats[i], ref))
+            lit = int((ref8 != 0).any(dim=2).sum())
+            detail.append({"camera": list(cam), "rgb8_equal": same8, "float_rows_equal": samef, "nonzero_pixels": lit})
+            ok = ok and same8 and samef and lit > 0
+            if i == 0:
+                sha = hashlib.sha256(frames8[i].cpu().numpy().tobytes()).hexdigest()
+    tr.set_camera(cameras[0])
+    if world > 1:
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.broadcast(flag, src=0)
+        ok = bool(flag.item())
+    return ok, sha, detail
+
+
+def timed_frames(tr, flush, steps, warmup, world, dev):
+    """`warmup` untimed frames, then `steps` frames each bracketed by CUDA events on the launching stream, the L2 flushed
+    before each (outside its events), barrier + synchronize on both sides; returns ms per step, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warmup):
+        flush.fill_(1)
+        tr.render()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for a, b in ev:
+        flush.fill_(0)
+        a.record()
+        tr.render()
+        b.record()
+    barrier()
+    if tr.peer is not None:
+        tr.peer.status()
+    total = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    return float(total[0]) / steps
+
+
+def heavy_leg(name, world, rank, dev, flush, steps=3, warmup=3):
+    """The workload that CAN scale (BASELINE.json configs[4] at full size, through the hierarchy) at the same N: a few
+    device-timed frames and the same frame check as the headline workload.  Extra key of the bench line; the headline
+    (cornell_4k, the metric's configuration) is unchanged."""
+    import ctypes as C
+    import torch
+    import rusty_marcher_b200 as rm
+    from rusty_marcher_b200 import _abi, tiled, workloads
+    scene_name, w, h, depth, kw, accel = workload_of(name)
+    desc = workloads.describe(scene_name, **kw)
+    scene = workloads.build_scene(desc)
+    r = rm.create_renderer(1.5, h, w)
+    r.max_depth, r.accel = depth, accel
+    backend = tiled.CudaBackend(scene, r, w, h, dev)
+    tr = tiled.TiledRenderer(backend, w, h, dev)
+    try:
+        L = backend.L
+        ms = timed_frames(tr, flush, steps, warmup, world, dev)
+        ok, sha, detail = verify_frames(tr, backend, VERIFY_CAMERAS["stress"][:2], world, rank, dev)
+        segs = None
+        if rank == 0:                                       # segments of the frame: pixels + the queries the kernel counted behind them
+            rows = (h // 32) * 32
+            q = C.c_uint64(0)
+            p = backend.frame_params((0, h // 32))
+            scratch = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+            smax = torch.zeros(1, dtype=torch.float32, device=dev)
+            _abi.check(L.rm_scene_query_count(backend.handle, C.byref(q), 1))
+            _abi.check(L.rm_render_device(backend.handle, C.byref(p), scratch.data_ptr(), None, smax.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            _abi.check(L.rm_scene_query_count(backend.handle, C.byref(q), 1))
+            segs = rows * w + int(q.value) if accel else None
+        return {"workload": name, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+                "segments_per_frame": segs, "value": segs / (ms * 1e-3) if segs else None, "unit": UNIT,
+                "n_prims": workloads.n_prims(desc), "frame_matches_n1": ok, "frame_sha256": sha, "frame_check": detail,
+                "timing": "CUDA events around each frame, L2 flushed before each, max over ranks"}
+    finally:
+        tr.close()
+        scene.release()
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -376,6 +520,15 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = segs / (ms_per_step * 1e-3)
 
+    # ---- the frame the ranks assemble against the single-GPU frame: three consecutive frames, the camera moving
+    cams = VERIFY_CAMERAS["stress" if scene_name == "stress" else "default"]
+    frame_ok, frame_sha, frame_detail = verify_frames(tr, backend, cams, world, rank, dev)
+
+    # ---- the workload that can scale, at the same N (extra key; the headline is unchanged)
+    heavy = None
+    if args.heavy and args.heavy != args.workload:
+        heavy = heavy_leg(args.heavy, world, rank, dev, flush)
+
     # ---- e2e: the public call a user makes -- Renderer.render(frame, scene) with HOST buffers: scene (re)upload H2D and the
     # float framebuffer D2H inside the timed region.  With N > 1 every rank delivers its own row tile to its pinned host buffer.
     frame = rm.create_frame_buffer(w, h)
@@ -389,7 +542,7 @@ def run_ours(args):
     flat_bytes = 0
     try:
         sys.stdout = devnull                   # Renderer.render prints the reference's status lines
-        for i in range(args.warmup + args.steps):
+        for i in range(args.warmup + args.steps if world == 1 else 0):
             flush.fill_(0)
             barrier()
             t0 = time.perf_counter()
@@ -408,7 +561,7 @@ def run_ours(args):
     e2e_t = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_t[0]) * 1e3 / args.steps
+    e2e_ms = float(e2e_t[0]) * 1e3 / args.steps if world == 1 else None
     # the same call when the caller only wants what main.rs shows or saves: render + normalize + to_vec, the 8-bit frame
     # (24.9 MB instead of 98.8 MB over PCIe); extra information next to the headline e2e figure (single GPU only)
     rgb8_ms = None
@@ -473,8 +626,11 @@ def run_ours(args):
                 "parallelism": "32-row bands dealt round-robin to %d rank%s" % (world, "" if world == 1 else "s"),
                 "l2": "flushed between steps (256 MiB fill, outside each step's CUDA events)"}),
             "ms_per_frame": ms_per_step,
+            "frame_matches_n1": frame_ok, "frame_sha256": frame_sha, "frame_check": frame_detail,
+            "heavy": heavy,
             "clocks": clocks,
-            "e2e": {"value": segs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_frame": e2e_ms,
+            # (N > 1: Renderer.render is a one-GPU call; a per-rank partial-band figure is not the deliverable of N = 1)
+            "e2e": None if e2e_ms is None else {"value": segs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_frame": e2e_ms,
                     "h2d_bytes_per_step": flat_bytes, "d2h_bytes_per_step": d2h,
                     "path": "Renderer.render(frame, scene) -> rm_scene_upload + rm_render, float32 framebuffer into pinned host memory"
                             + ("; each rank delivers its own row tile" if world > 1 else ""),
@@ -505,6 +661,9 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not frame_ok or (heavy is not None and not heavy["frame_matches_n1"]):
+        sys.stderr.write("bench.py: the frame assembled by %d rank(s) differs from the single-GPU frame\n" % world)
+        return 3
     return 0
 
 
@@ -517,6 +676,7 @@ def main():
     ap.add_argument("--workload", default="cornell_4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cull", action="store_true", help="trace every primitive like the reference's brute force")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--heavy", default="stress_8k_bvh", help="second, short leg on a workload that can scale ('' = none)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -72,7 +72,29 @@ struct SceneEntry {
     DevicePack<float> f32;
     DevicePack<double> f64;
     LastFrame last;
+    // A scene's pack holds per-frame mutable state (raster records, frame control block, tile schedule): renders of ONE
+    // scene are ordered even when the caller issues them on different streams -- on a change of stream the new stream waits
+    // for everything submitted to the previous one.
+    bool rendered = false;
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t order_ev = nullptr;
 };
+
+// Called under g.mu before a render of `se` is issued on `stream`.
+int order_scene_renders(SceneEntry& se, cudaStream_t stream) {
+    if (se.rendered && se.last_stream != stream) {
+        if (!se.order_ev) CK(cudaEventCreateWithFlags(&se.order_ev, cudaEventDisableTiming));
+        if (cudaEventRecord(se.order_ev, se.last_stream) == cudaSuccess) {
+            CK(cudaStreamWaitEvent(stream, se.order_ev, 0));
+        } else {                                                // the previous stream is gone: everything it held has been submitted
+            cudaGetLastError();
+            CK(cudaDeviceSynchronize());
+        }
+    }
+    se.rendered = true;
+    se.last_stream = stream;
+    return RM_OK;
+}
 
 struct Scratch {
     void* p = nullptr;
@@ -191,6 +213,10 @@ int check_params(const RmParams* p) {
     if (p->width % p->patch_size != 0)
         return fail(RM_ERR_DIMENSIONS, "Dimensions mismatch: width must be a multiple of 32 (renderer.rs:49-51,107)");
     if (p->max_depth < 0 || p->max_depth > rm::kMaxDepth) return fail(RM_ERR_INVALID_ARGUMENT, "max_depth must be in [0, 8]");
+    // the production kernel packs pixel coordinates as x | y << 16 in its hit queue and derives tile coordinates with a
+    // float reciprocal that is exact below 2^22 tiles
+    if (p->width > 65535 || p->height > 65535 || (long long)(p->width / 32) * (p->height / 32) >= (1ll << 22))
+        return fail(RM_ERR_DIMENSIONS, "width and height must be below 65536 (and the frame below 2^22 patches)");
     return RM_OK;
 }
 
@@ -212,6 +238,7 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
     if (it == g.scenes.end()) return fail(RM_ERR_INVALID_ARGUMENT, "unknown scene handle");
     DevicePack<R>& dp = pack_of<R>(it->second);
     if ((rc = ensure_pack<R>(it->second, dp)) != RM_OK) return rc;
+    if ((rc = order_scene_renders(it->second, stream)) != RM_OK) return rc;
     rm::FrameParams<R> fp = rm::make_frame_params<R>(*params);
     fp.buf_row0 = buf_row0_is_tile ? fp.row_begin : 0;
     if (out_fp) *out_fp = fp;
@@ -357,7 +384,11 @@ void rm_shutdown(void) {
     if (!g.ready) return;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
-    for (auto& kv : g.scenes) { kv.second.f32.release(); kv.second.f64.release(); }
+    for (auto& kv : g.scenes) {
+        kv.second.f32.release();
+        kv.second.f64.release();
+        if (kv.second.order_ev) cudaEventDestroy(kv.second.order_ev);
+    }
     g.scenes.clear();
     g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release(); g.mix.release();
     for (auto& ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
@@ -425,6 +456,7 @@ int rm_scene_free(RmScene handle) {
     cudaDeviceSynchronize();
     it->second.f32.release();
     it->second.f64.release();
+    if (it->second.order_ev) cudaEventDestroy(it->second.order_ev);
     g.scenes.erase(it);
     return RM_OK;
 }

@@ -18,6 +18,8 @@
 //  * Spheres and n-gons (n > 3) reuse the routines of rm_trace.cuh.
 #pragma once
 
+#include <type_traits>
+
 #include "rm_bvh.cuh"
 #include "rm_trace.cuh"
 
@@ -102,15 +104,15 @@ template <bool kBvh> struct FastViewT {
             const Vec3<double> line = c - o;
             const double tca = dot(line, d);
             const double d2 = dot(line, line) - tca * tca;
-            const double thc = sqrt(fmax(q[3] - d2, 0.));      // (a grazing hit FP32 accepted and f64 would not: the tangent point)
+            const double thc = Fast64::sqrt_(q[3] - d2);       // (0 for a grazing hit FP32 accepted and f64 would not: the tangent point)
             const double ta = tca - thc, tb = tca + thc;
             const double t = fabs(ta - t32) <= fabs(tb - t32) ? ta : tb;
             p = axpy(o, d, t);
-            n = normalized(p - c);
+            n = Fast64::normalized(p - c);
         } else {
             const double* q = slot < n_sph + n_tri ? tri64 + (size_t)kTriSrcDoubles * (slot - n_sph) : pln64 + 4 * (size_t)(slot - n_sph - n_tri);
             n = {q[0], q[1], q[2]};
-            const double t = (q[3] - dot(o, n)) / dot(d, n);   // ((C - o).n) / (d.n)
+            const double t = (q[3] - dot(o, n)) * Fast64::rcp_(dot(d, n));   // ((C - o).n) / (d.n)
             p = axpy(o, d, t);
         }
     }
@@ -622,14 +624,33 @@ template <int kPx> RM_HD void primary_bvh(PrimaryState<kPx>& ps, const FastViewB
 
 // ---- the shading stage (stage B of the render kernel) -------------------------------------------------------------------
 // An OPAQUE primary hit spawns no ray (renderer.rs:277): its colour is background + direct lighting, pure FP32.
-// A GLASS-LIKE primary hit starts the reflect / refract recursion (renderer.rs:254-309).  Those paths are traced by
-// cast_glass with f64 RAY GEOMETRY: a curved glass surface magnifies a direction error by (distance to the next hit /
-// radius), so positions rounded to FP32 at scene scale (2^-24 * 128 against radii of ~1) grow to 1e-3 relative colour
-// errors two bounces later -- measured on BASELINE.json configs[4]'s scene: only 99.5 % of the pixels within the north
-// star's 1e-4 with FP32 geometry.  What stays FP32 is everything that is a search or a smooth function: which primitive
-// a ray hits (the O(n) / O(log n) part), the shadow rays, the lighting arithmetic.  What is f64: the ray (origin,
-// direction), the hit point and normal of the ONE primitive each query picked (FastViewT::refine) and the optics
-// (optics.rs:8-89) -- a few dozen FP64 operations per segment next to hundreds of FP32 primitive tests.
+// A GLASS-LIKE primary hit starts the reflect / refract recursion (renderer.rs:254-309), traced by cast_glass<G> with the
+// ray geometry in G = float or G = double:
+//   * G = float: everything FP32 (scenes whose spheres are large against the scene's coordinates, planar glass).
+//   * G = double: a curved glass surface magnifies a direction error by (distance to the next hit / radius), so positions
+//     rounded to FP32 at scene scale (2^-24 * 128 against radii of ~1) grow to 1e-3 relative colour errors two bounces
+//     later -- measured on BASELINE.json configs[4]'s scene: only 99.5 % of the pixels within the north star's 1e-4 with
+//     FP32 geometry, 99.999 % with this.  What stays FP32 is everything that is a search or a smooth function: which
+//     primitive a ray hits (the O(n) / O(log n) part), the shadow rays, the lighting arithmetic.  What is f64: the ray
+//     (origin, direction), the hit point and normal of the ONE primitive each query picked (FastViewT::refine) and the
+//     optics (optics.rs:8-89) -- a few dozen FP64 operations per segment next to hundreds of FP32 primitive tests.
+//     Sphere hits, glass-like or not, take this route as well: near a silhouette the hit point of a far sphere moves by
+//     many ulps of the FP32 centre per ulp of the ray, and a specular exponent of 100 turns that into 1e-4.
+// Which of the two a frame gets is decided per launch from the scene and the camera (glass_mode below).
+enum GlassMode { GLASS_NONE = 0, GLASS_F32 = 1, GLASS_F64 = 2 };
+
+// f64 ray geometry when some sphere is small against the coordinates rays travel through: S > 64 r_min, with S the
+// largest coordinate magnitude of the scene's primitives and the camera.  (FP32 positions carry 2^-24 S; against a
+// radius of S / 64 that is a normal error of 4e-6, which the recursion's magnification keeps below the tolerance; the demo
+// scene of the reference -- S = 50, radii 2 to 4 -- sits at 25 and meets the north-star criteria in FP32 on 99.99 % of its
+// pixels, the stress scene -- S = 170, radii from 0.3 -- at 570 and does not.)
+inline int glass_mode(const bool any_glass, const int n_sph, const double coord_max, const double r_min, const double camera[3]) {
+    if (!any_glass && n_sph == 0) return GLASS_NONE;
+    if (n_sph == 0) return GLASS_F32;
+    const double S = fmax(fmax(coord_max, fabs(camera[0])), fmax(fabs(camera[1]), fabs(camera[2])));
+    return S > 64. * r_min ? GLASS_F64 : GLASS_F32;
+}
+
 #if defined(__CUDACC__)
 #define RM_GLASS_FN __host__ __device__ __noinline__
 #else
@@ -637,24 +658,32 @@ template <int kPx> RM_HD void primary_bvh(PrimaryState<kPx>& ps, const FastViewB
 #endif
 
 RM_HD Vec3<float> to_f32(const Vec3<double> v) { return {(float)v.x, (float)v.y, (float)v.z}; }
+RM_HD Vec3<float> to_f32(const Vec3<float> v) { return v; }
 
-// renderer.rs:254-309 from a glass-like primary hit of pixel (x, y); t1 = FP32 ray parameter of that hit (unit direction).
-template <class FV>
-RM_GLASS_FN Vec3<float> cast_glass(const FV& fv, const FrameParams<float>& fp, const int x, const int y, const float t1,
-                                   const int slot1, const int id1) {
+// renderer.rs:254-309 from the primary hit of pixel (x, y); t1 = FP32 ray parameter of that hit (unit direction).
+template <typename G, class FV>
+RM_HD Vec3<float> cast_glass_impl(const FV& fv, const FrameParams<float>& fp, const int x, const int y, const float t1,
+                                  const int slot1, const int id1) {
     struct Frame {
         Vec3<float> c;
-        Vec3<double> ro, rd;
+        Vec3<G> ro, rd;
         float k;
         int state;   // bit0: a refracted ray is pending, bit1: the refracted ray is the one in flight
     };
     Frame fr[kMaxDepth];
     int sp = 0;
     const Vec3<float> bg = {fp.background, fp.background, fp.background};
-    // renderer.rs:128-135 in the reference's own arithmetic
-    Vec3<double> o = {fp.cam64[0], fp.cam64[1], fp.cam64[2]};
-    Vec3<double> d = normalized(Vec3<double>{2. * ((double)x / fp.w64 - 0.5) * fp.hf64 * fp.ratio64,
-                                             -2. * ((double)y / fp.h64 - 0.5) * fp.hf64, -1.});
+    Vec3<G> o, d;
+    if constexpr (sizeof(G) == 8) {                             // renderer.rs:128-135 in the reference's own arithmetic
+        o = {fp.cam64[0], fp.cam64[1], fp.cam64[2]};
+        d = Fast64::normalized(Vec3<double>{2. * ((double)x * fp.inv_w64 - 0.5) * fp.hf64 * fp.ratio64,
+                                            -2. * ((double)y * fp.inv_h64 - 0.5) * fp.hf64, -1.});
+    } else {
+        const float X = pixel_X(fp, x), Y = pixel_Y(fp, y);
+        const float inv = fast_rsqrt(fmaf(X, X, fmaf(Y, Y, 1.f)));     // geometry.rs:104-109: scale(1/norm)
+        o = fp.camera;
+        d = {X * inv, Y * inv, -inv};
+    }
     Counters<false> st;
     Vec3<float> v;
     for (;;) {
@@ -675,16 +704,27 @@ RM_GLASS_FN Vec3<float> cast_glass(const FV& fv, const FrameParams<float>& fp, c
             if (!got) {
                 v = bg;                                         // renderer.rs:300-306 (level > 1 here)
             } else {
-                Vec3<double> p, n;
-                fv.refine(h.slot, o, d, (double)h.dist, p, n);
+                Vec3<G> p, n;
+                Vec3<float> p32, n32;
+                if constexpr (sizeof(G) == 8) {
+                    fv.refine(h.slot, o, d, (double)h.dist, p, n);
+                    p32 = to_f32(p);
+                    n32 = to_f32(n);
+                } else {
+                    fv.surface(h, o32, d32, n32);
+                    p32 = h.p;
+                    p = p32;
+                    n = n32;
+                }
                 const R4<float> ma = fv.mat_a[h.id];
                 const R4<float> mb = fv.mat_b[h.id];
-                Vec3<float> c = bg + fv.template direct<false>(o32, d32, to_f32(p), to_f32(n), ma, mb, st);   // renderer.rs:272-275
+                Vec3<float> c = bg + fv.template direct<false>(o32, d32, p32, n32, ma, mb, st);   // renderer.rs:272-275
                 bool pushed = false;
                 if (fv.mat_f[h.id] & 1) {                       // renderer.rs:277
-                    Vec3<double> ro1, rd1, ro2, rd2;
-                    const bool has_refl = reflect_ray<double>(d, p, n, (double)mb.w, ro1, rd1);   // renderer.rs:203-207
-                    const bool has_refr = refract_ray<double>(d, p, n, (double)mb.w, ro2, rd2);   // renderer.rs:235-239
+                    Vec3<G> ro1, rd1, ro2, rd2;
+                    using N = typename std::conditional<sizeof(G) == 8, Fast64, Exact<float>>::type;
+                    const bool has_refl = reflect_ray<G, N>(d, p, n, (G)mb.w, ro1, rd1);  // renderer.rs:203-207
+                    const bool has_refr = refract_ray<G, N>(d, p, n, (G)mb.w, ro2, rd2);  // renderer.rs:235-239
                     if (has_refl || has_refr) {
                         Frame& f = fr[sp];
                         f.c = c;
@@ -729,21 +769,28 @@ RM_GLASS_FN Vec3<float> cast_glass(const FV& fv, const FrameParams<float>& fp, c
         }
     }
 }
+// The f64 instantiation as a function of its own (registers of the caller's loop are not held across the f64 code).
+template <class FV>
+RM_GLASS_FN Vec3<float> cast_glass64(const FV& fv, const FrameParams<float>& fp, const int x, const int y, const float t1,
+                                     const int slot1, const int id1) {
+    return cast_glass_impl<double, FV>(fv, fp, x, y, t1, slot1, id1);
+}
 
 // One pixel whose primary ray hit (t in units of |D|, slot, id): renderer.rs:254-309 from level 1.
-// kGlass = false: the scene has neither glass-like materials nor spheres (every OBJ scene of the reference: obj.rs:125-138
-// loads meshes opaque) -- the kernel instantiated for it carries no recursion, no f64 code and far fewer registers.
-template <bool kGlass = true, class FV>
+// kGlass = GLASS_NONE: the scene has neither glass-like materials nor spheres (every OBJ scene of the reference: obj.rs:125-138
+// loads meshes opaque) -- the kernel instantiated for it carries no recursion, no f64 code and fewer registers.
+template <int kGlass = GLASS_F64, class FV>
 RM_HD Vec3<float> fast_shade(FV& fv, const FrameParams<float>& fp, const int x, const int y, const float t, const int slot,
                              const int id) {
     const float X = pixel_X(fp, x), Y = pixel_Y(fp, y);
     const float len2 = fmaf(X, X, fmaf(Y, Y, 1.f));
     const float inv = fast_rsqrt(len2);                            // geometry.rs:104-109: scale(1/norm)
     const float dist = t * (len2 * inv);                           // stage A reports t in units of |D|
-    // (spheres, glass-like or not, take the f64 route too: near a silhouette the hit point of a far sphere of radius ~1
-    // moves by many ulps of the FP32 centre per ulp of the ray, and a specular exponent of 100 turns that into 1e-4)
-    if constexpr (kGlass)
-        if ((fv.mat_f[id] & 1) || slot < fv.n_sph) return cast_glass(fv, fp, x, y, dist, slot, id);
+    if constexpr (kGlass == GLASS_F64) {
+        if ((fv.mat_f[id] & 1) || slot < fv.n_sph) return cast_glass64(fv, fp, x, y, dist, slot, id);
+    } else if constexpr (kGlass == GLASS_F32) {
+        if (fv.mat_f[id] & 1) return cast_glass_impl<float, FV>(fv, fp, x, y, dist, slot, id);
+    }
     const Vec3<float> d = {X * inv, Y * inv, -inv};
     HitRec<float> h;
     h.dist = dist;

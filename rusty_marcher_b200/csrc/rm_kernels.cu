@@ -19,6 +19,7 @@
 #include "rm_kernels.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace rm {
 
@@ -332,15 +333,15 @@ constexpr int kWarpQueue = kFastTile * 4 + 32;                  // one strip of 
 #ifdef RM_K1_MAXREG
 #define RM_K1_BOUNDS __maxnreg__(RM_K1_MAXREG)
 #else
-#define RM_K1_BOUNDS __launch_bounds__(kFastBlock, kGlass ? RM_K1_MIN_BLOCKS : RM_K1_MIN_BLOCKS_OPAQUE)
+#define RM_K1_BOUNDS __launch_bounds__(kFastBlock, kGlass != GLASS_NONE ? RM_K1_MIN_BLOCKS : RM_K1_MIN_BLOCKS_OPAQUE)
 #endif
 #ifndef RM_K1_MIN_BLOCKS_OPAQUE
-#define RM_K1_MIN_BLOCKS_OPAQUE 3                               // the instantiation without recursion / f64 code (kGlass = false)
+#define RM_K1_MIN_BLOCKS_OPAQUE 2                               // the instantiation without recursion / f64 code (kGlass = false)
 #endif
 template <int kPx> struct PxTag { static constexpr int value = kPx; };
 // kBvh (RmParams.accel): scene queries walk the hierarchy of rm_bvh.cuh (read through the read-only path; the nodes near
 // the root stay in L1) instead of every primitive; stage A then handles a thread's pixels one after the other.
-template <bool kSmem, bool kBvh, bool kGlass>
+template <bool kSmem, bool kBvh, int kGlass>
 __global__ void RM_K1_BOUNDS
 render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
@@ -824,10 +825,11 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
         cudaFuncAttributes fa;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-        if ((e = cudaFuncGetAttributes(&fa, render_fast_kernel<true, false, true>)) != cudaSuccess) return e;
+        if ((e = cudaFuncGetAttributes(&fa, render_fast_kernel<true, false, GLASS_F64>)) != cudaSuccess) return e;
         dyn_limit = std::min(kSmemLimit, optin - (int)fa.sharedSizeBytes - 1024);
-        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false, GLASS_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false, GLASS_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false, GLASS_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     }
     const size_t smem_geo = (size_t)ds.lay.bytes + (size_t)ds.lay.n_tri * 64;
@@ -836,7 +838,7 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     const size_t smem = smem_geo + (stage_mat ? smem_mat : 0);
     const float inv_tiles_x = 1.0f / (float)tiles_x;
     // launched with programmatic stream serialisation: the CTAs may become resident while K0 still runs (pdl_wait_primary)
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg = {};
@@ -844,21 +846,48 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     cfg.stream = stream;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    // The fused exchange + K4 phase waits inside the kernel for a word that is published only when EVERY CTA of the grid
+    // has retired from rendering: all CTAs must be resident together.  The grid is sized from the occupancy API, which
+    // makes that true on an otherwise idle GPU; a cooperative launch makes the driver guarantee it (the launch waits
+    // until the whole grid fits, whatever else runs on the device).  RM_B200_COOPERATIVE=0 switches the attribute off;
+    // a driver that refuses it together with the programmatic launch edge switches it off for the process.
+    static int coop = -1;
+    if (coop < 0) {
+        const char* env = getenv("RM_B200_COOPERATIVE");
+        coop = (env && env[0] == '0') ? 0 : 1;
+    }
+    const bool want_coop = coop == 1 && link.world > 0 && rgb8_out != nullptr;
+    if (want_coop) {
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.numAttrs = 2;
+    }
     const int cull_i = cull ? 1 : 0;
     const int* order2 = order ? ds.tile_order + ds.tile_order_cap / 2 : nullptr;
     const bool use_smem = !bvh && smem <= (size_t)dyn_limit;
-    // the reflect / refract recursion and the f64 ray geometry (cast_glass) only where a frame can need them
-    const bool glass = ds.lay.any_glass != 0 || ds.lay.n_sph > 0;
-    auto k = bvh ? (glass ? render_fast_kernel<false, true, true> : render_fast_kernel<false, true, false>)
-             : use_smem ? (glass ? render_fast_kernel<true, false, true> : render_fast_kernel<true, false, false>)
-                        : (glass ? render_fast_kernel<false, false, true> : render_fast_kernel<false, false, false>);
+    // the reflect / refract recursion only where a frame can need it, its f64 ray geometry only where FP32 would not do
+    const int glass = glass_mode(ds.lay.any_glass != 0, ds.lay.n_sph, ds.lay.coord_max, ds.lay.r_min, camera);
+    if (ex) ex->glass_mode = glass;
+    using K1 = decltype(&render_fast_kernel<true, false, GLASS_NONE>);
+    static const K1 table[3][3] = {
+        {render_fast_kernel<true, false, GLASS_NONE>, render_fast_kernel<true, false, GLASS_F32>, render_fast_kernel<true, false, GLASS_F64>},
+        {render_fast_kernel<false, false, GLASS_NONE>, render_fast_kernel<false, false, GLASS_F32>, render_fast_kernel<false, false, GLASS_F64>},
+        {render_fast_kernel<false, true, GLASS_NONE>, render_fast_kernel<false, true, GLASS_F32>, render_fast_kernel<false, true, GLASS_F64>}};
+    const K1 k = table[bvh ? 2 : use_smem ? 0 : 1][glass];
     cfg.dynamicSmemBytes = use_smem ? smem : 0;
     int occ = 1;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kFastBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;
     cfg.gridDim = dim3(std::min(n_tiles, sm_count * std::max(occ, 1)));
-    if ((e = cudaLaunchKernelEx(&cfg, k, ds, fp, cull_i, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order2, rgb8,
-                                link, rgb8_out, normalise, rgb8_next, stage_mat)) != cudaSuccess)
-        return e;
+    e = cudaLaunchKernelEx(&cfg, k, ds, fp, cull_i, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order2, rgb8,
+                           link, rgb8_out, normalise, rgb8_next, stage_mat);
+    if (e != cudaSuccess && want_coop) {                        // not available in this combination: the plain persistent launch
+        cudaGetLastError();
+        coop = 0;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, k, ds, fp, cull_i, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order2, rgb8,
+                               link, rgb8_out, normalise, rgb8_next, stage_mat);
+    }
+    if (e != cudaSuccess) return e;
     if (launches) (*launches)++;
     if (ex && ex->ev_rendered) cudaEventRecord(ex->ev_rendered, stream);
     return cudaGetLastError();
@@ -873,7 +902,12 @@ cudaError_t launch_render(const DeviceScene<R>& ds, const FrameParams<R>& fp, bo
                           RenderExtras* ex) {
     const int rows = fp.n_bands * 32;
     if (ex) ex->scheduled = false;
-    if (rows <= 0 || fp.width <= 0) return cudaSuccess;
+    if (rows <= 0 || fp.width <= 0) {                           // nothing to render: the profiling events still mark the (empty) frame
+        if (ex && ex->ev_begin) cudaEventRecord(ex->ev_begin, stream);
+        if (ex && ex->ev_prepared) cudaEventRecord(ex->ev_prepared, stream);
+        if (ex && ex->ev_rendered) cudaEventRecord(ex->ev_rendered, stream);
+        return cudaSuccess;
+    }
     const dim3 grid((fp.width + kTileW - 1) / kTileW, (rows + kTileH - 1) / kTileH);
     if (sizeof(R) == 4 && !counters && camera && ds.tri_r) return launch_fast(ds, fp, cull, rgb, prim_id, dmax, stream, camera, launches, ex);
     if (ex && ex->ev_begin) cudaEventRecord(ex->ev_begin, stream);

@@ -72,6 +72,8 @@ struct RenderExtras {
     cudaEvent_t ev_begin = nullptr, ev_prepared = nullptr, ev_rendered = nullptr;
     // out: the frame was rendered with a tile schedule (and rgb8_zero, if given, has been zero-filled)
     bool scheduled = false;
+    // out: GlassMode of the production kernel that was launched (rm_fast.cuh)
+    int glass_mode = 0;
 };
 
 // K0 + K1.  With counters == null and R = float this is the production path: prepare_raster_kernel

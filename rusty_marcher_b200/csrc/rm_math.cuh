@@ -117,6 +117,23 @@ template <> struct Num<float> {
     static RM_HD float rcp_(float a) { return 1.f / a; }
 };
 
+// f64 at FP32 cost where 1e-14 is as good as 1e-16 (the glass paths of the production kernel, cast_glass<double> in
+// rm_fast.cuh -- NOT the RM_FP64 validation kernels, which keep IEEE sqrt and division): an FP32 seed (MUFU) and one
+// Newton step in f64 -- five f64 operations instead of the thirty-odd of the IEEE sequences.  Arguments are squared
+// lengths, cosines and refractive indices: well inside the FP32 range.
+struct Fast64 {
+    static RM_HD double rsqrt_(double a) {
+        const double r = (double)fast_rsqrt((float)a);
+        return r * fma(-0.5 * a * r, r, 1.5);
+    }
+    static RM_HD double rcp_(double a) {
+        const double r = (double)fast_div(1.f, (float)a);
+        return r * fma(-a, r, 2.);
+    }
+    static RM_HD double sqrt_(double a) { return a > 0. ? a * rsqrt_(a) : 0.; }
+    static RM_HD Vec3<double> normalized(Vec3<double> a);
+};
+
 template <typename R> RM_HD Vec3<R> operator+(Vec3<R> a, Vec3<R> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 template <typename R> RM_HD Vec3<R> operator-(Vec3<R> a, Vec3<R> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 template <typename R> RM_HD Vec3<R> operator*(Vec3<R> a, Vec3<R> b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
@@ -153,6 +170,16 @@ template <> RM_HD Vec3<float> normalized<float>(Vec3<float> a) {
     if (s > 0.f) a = scaled(a, fast_rsqrt(s));
     return a;
 }
+
+RM_HD Vec3<double> Fast64::normalized(Vec3<double> a) {
+    const double s = a.x * a.x + a.y * a.y + a.z * a.z;
+    if (s > 0.) a = scaled(a, rsqrt_(s));
+    return a;
+}
+// numeric policies of the optics (rm_trace.cuh): Num<R> with the reference's normalisation, or Fast64
+template <typename R> struct Exact : Num<R> {
+    static RM_HD Vec3<R> normalized(Vec3<R> a) { return rm::normalized(a); }
+};
 
 // Keeps a value in its register across the code that follows: ptxas otherwise rematerialises cheap loop
 // invariants (selects, offsets, int->float conversions) inside inner loops when registers are tight.

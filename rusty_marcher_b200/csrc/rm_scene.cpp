@@ -287,6 +287,20 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
     }
     out.n_prims = id;
     for (int f : out.mat_f) out.lay.any_glass |= f & 1;
+    {
+        double cm = 0., rmin = INFINITY;
+        for (auto& sp : sph) {
+            const double r = std::sqrt(sp.s->radius_square);
+            for (int a = 0; a < 3; a++) cm = std::fmax(cm, std::fabs(sp.s->center[a]) + r);
+            rmin = std::fmin(rmin, r);
+        }
+        for (auto& pl : pln) {
+            for (double v : pl.vxy) cm = std::fmax(cm, std::fabs(v));
+            cm = std::fmax(cm, std::fabs(pl.c[2]));
+        }
+        out.lay.coord_max = cm;
+        out.lay.r_min = sph.empty() ? 0. : rmin;
+    }
 
     // hittable planes first, then back-facing, then degenerate (stable: scene order inside each class)
     std::stable_sort(pln.begin(), pln.end(), [](const PlaneTmp& a, const PlaneTmp& b) { return a.cls < b.cls; });
@@ -432,6 +446,8 @@ template <typename R> FrameParams<R> make_frame_params(const RmParams& p) {
     fp.h64 = height;
     fp.hf64 = half_fov;
     fp.ratio64 = ratio;
+    fp.inv_w64 = 1. / width;
+    fp.inv_h64 = 1. / height;
     return fp;
 }
 

@@ -30,6 +30,7 @@ struct BlobLayout {
     int off_tri_g = 0, off_poly_slot = 0;
     int bytes = 0;
     int any_glass = 0;                // some material is glass-like (shapes.rs:29): the frame may need the reflect / refract recursion
+    double coord_max = 0., r_min = 0.; // largest coordinate magnitude of the primitives, smallest sphere radius (glass_mode, rm_fast.cuh)
 };
 
 struct alignas(32) BlobChunk { unsigned char b[32]; };

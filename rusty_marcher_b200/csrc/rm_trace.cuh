@@ -325,11 +325,11 @@ template <typename R> RM_HD Vec3<R> reflect(Vec3<R> incident, Vec3<R> normal) {
 }
 
 // ---------------------------------------------------------------- optics.rs:8-48
-template <typename R>
+template <typename R, typename N = Exact<R>>
 RM_HD bool reflect_ray(Vec3<R> incident, Vec3<R> point, Vec3<R> hit_normal, R refractive_index, Vec3<R>& ro, Vec3<R>& rd) {
     Vec3<R> normal = hit_normal;
     R c = dot(normal, incident);
-    R r = (c < R(0)) ? refractive_index : Num<R>::rcp_(refractive_index);
+    R r = (c < R(0)) ? refractive_index : N::rcp_(refractive_index);
     if (c < R(0)) { c = -c; normal = -normal; }
     R cos_theta_2 = R(1) - r * r * (R(1) - c * c);
     if (cos_theta_2 > R(0)) return false;
@@ -340,15 +340,15 @@ RM_HD bool reflect_ray(Vec3<R> incident, Vec3<R> point, Vec3<R> hit_normal, R re
 }
 
 // ---------------------------------------------------------------- optics.rs:50-89
-template <typename R>
+template <typename R, typename N = Exact<R>>
 RM_HD bool refract_ray(Vec3<R> incident, Vec3<R> point, Vec3<R> hit_normal, R refractive_index, Vec3<R>& ro, Vec3<R>& rd) {
     Vec3<R> normal = hit_normal;
     R c = -dot(normal, incident);
-    R r = (c < R(0)) ? refractive_index : Num<R>::rcp_(refractive_index);
+    R r = (c < R(0)) ? refractive_index : N::rcp_(refractive_index);
     if (c < R(0)) { c = -c; normal = -normal; }
     R cos_theta_2 = R(1) - r * r * (R(1) - c * c);
     if (cos_theta_2 < R(0)) return false;
-    rd = normalized(scaled(incident, r) + scaled(normal, r * c - Num<R>::sqrt_(cos_theta_2)));
+    rd = N::normalized(scaled(incident, r) + scaled(normal, r * c - N::sqrt_(cos_theta_2)));
     if (dot(rd, normal) > R(0)) ro = axpy(point, normal, R(1e-4));
     else ro = axmy(point, normal, R(1e-4));
     return true;
@@ -499,7 +499,7 @@ template <typename R> struct FrameParams {
     int accel;                    // RmParams.accel: scene queries through the hierarchy (FP32 production kernel)
     // the reference's own f64 operands of backproject (renderer.rs:128-135) and the camera, whatever R is: the FP32
     // production kernel traces the paths behind a glass-like primary hit with f64 ray geometry (cast_glass, rm_fast.cuh)
-    double cam64[3], w64, h64, hf64, ratio64;
+    double cam64[3], w64, h64, hf64, ratio64, inv_w64, inv_h64;
 };
 
 // pixel row of the l-th rendered row of this call (l in [0, 32 * n_bands))

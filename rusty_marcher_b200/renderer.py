@@ -49,6 +49,15 @@ class Renderer:
         """Renderer::render (renderer.rs:36-126).  Fills frame.buffer rows [0, floor(H/32)*32) and
         returns the reference's status message.  Optional outputs: prim_id (H, W) int32 array,
         rgb8 (H, W, 3) uint8 array (normalize + to_vec done on device)."""
+        # the reference projects with the Renderer's own width / height / ratio (renderer.rs:128-135) and indexes the
+        # frame with the frame's (renderer.rs:46-108); they are the same numbers in main.rs:364-371 and must be here
+        if int(self.width) != frame.width or int(self.height) != frame.height:
+            raise ValueError("renderer was created for %dx%d, the frame is %dx%d" % (int(self.width), int(self.height), frame.width, frame.height))
+        for name, a, dtype, shape in (("prim_id", prim_id, np.int32, (frame.height, frame.width)),
+                                      ("rgb8", rgb8, np.uint8, (frame.height, frame.width, 3))):
+            if a is not None and (not isinstance(a, np.ndarray) or a.dtype != dtype or a.shape != shape or not a.flags.c_contiguous
+                                  or not a.flags.writeable):
+                raise ValueError("%s must be a writeable C-contiguous %s array of shape %s" % (name, np.dtype(dtype).name, shape))
         L = _abi.load()
         _abi.init(_abi._initialised_device if _abi._initialised_device is not None else 0)
         now = time.perf_counter()
@@ -84,10 +93,15 @@ class Renderer:
         indices.  Three passes of the unchanged hot path -- pass c with every glass-like material of the scene at
         indices[c] -- and channel c of the frame is channel c of pass c (rm_render_dispersive).  Fills frame.buffer like
         render() and returns the same kind of status message."""
-        L = _abi.load()
-        _abi.init(_abi._initialised_device if _abi._initialised_device is not None else 0)
         if self.precision != _abi.RM_FP32:
             raise ValueError("render_dispersive computes in RM_FP32")
+        if int(self.width) != frame.width or int(self.height) != frame.height:
+            raise ValueError("renderer was created for %dx%d, the frame is %dx%d" % (int(self.width), int(self.height), frame.width, frame.height))
+        if prim_id is not None and (not isinstance(prim_id, np.ndarray) or prim_id.dtype != np.int32 or prim_id.shape != (frame.height, frame.width)
+                                    or not prim_id.flags.c_contiguous):
+            raise ValueError("prim_id must be a C-contiguous int32 array of shape (height, width)")
+        L = _abi.load()
+        _abi.init(_abi._initialised_device if _abi._initialised_device is not None else 0)
         now = time.perf_counter()
         p = self.params(frame, scene, patch_rows)
         if frame.buffer.dtype != np.float32 or not frame.buffer.flags.c_contiguous:

@@ -36,8 +36,12 @@ def lib():
     return _lib
 
 
-def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=True, threads=8, patch_rows=(0, -1), strip_bound=True, accel=False, glass_index=None):
+def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=True, threads=8, patch_rows=(0, -1), strip_bound=True, accel=False, glass_index=None,
+           glass_mode=None):
+    """glass_mode (fast path): None = as the device decides per scene and camera (rm::glass_mode), 1 = FP32 ray geometry on
+    glass paths, 2 = f64 ray geometry."""
     lib().emu_set_strip_bound(int(strip_bound))
+    lib().emu_set_glass_mode(-1 if glass_mode is None else int(glass_mode))
     flat = scene.flatten()
     if glass_index is not None:
         flat.set_glass_index(float(glass_index))     # one pass of the per-channel dispersion (extension mode)
@@ -56,7 +60,8 @@ def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=Tru
     rc = fn(C.byref(flat.c), C.byref(p), rgb.ctypes.data, ids.ctypes.data, C.byref(st), threads)
     if rc != 0:
         raise RuntimeError("emu rc %d" % rc)
-    return {"rgb": rgb, "prim_id": ids, "counters": st.counters(), "max": st.max_value, "resident": st.resident_prims}
+    return {"rgb": rgb, "prim_id": ids, "counters": st.counters(), "max": st.max_value, "resident": st.resident_prims,
+            "glass_mode": lib().emu_last_glass_mode() if precision == "fast" else None}
 
 
 def bvh(scene):

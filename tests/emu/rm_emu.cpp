@@ -98,6 +98,7 @@ int emu_render_impl(const RmFlatScene* fs, const RmParams* p, R* out_rgb, int32_
 
 static std::atomic<unsigned long long> g_walks{0}, g_walk_nodes{0}, g_walk_prims{0};   // hierarchy walks of all renders since the last reset
 static std::atomic<float*> g_cost{nullptr};   // optional H x W x 2 floats: per-pixel walk cost of stage A / of shading (tools/tail_model.py)
+static std::atomic<int> g_glass_mode{-1}, g_last_glass_mode{-1};   // -1: as launch_fast decides (rm::glass_mode); 1 / 2 force GLASS_F32 / GLASS_F64
 static std::atomic<int> g_strip_bound{1};   // 0: walk every triangle in every strip (to prove the bound changes no pixel)
 
 // the FP32 production path (rm_fast.cuh): prepare_raster + fast_pixel, as the CUDA kernels run them
@@ -142,6 +143,8 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
     fv0.tri64 = ps.tri_src.data();
     fv0.pln64 = ps.pln64.data();
     const rm::FrameParams<float> fp = rm::make_frame_params<float>(*p);
+    const int gm = g_glass_mode.load() >= 0 ? g_glass_mode.load() : rm::glass_mode(L.any_glass != 0, L.n_sph, L.coord_max, L.r_min, p->camera);
+    g_last_glass_mode.store(gm);
     std::atomic<int> next{fp.row_begin};
     std::vector<float> tmax(n_threads, 0.f);
     std::vector<std::thread> pool;
@@ -194,8 +197,11 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
                         }
                         for (int k = 0; k < 4; k++) {
                             const float c1 = walk_cost();
-                            rm::Vec3<float> c = ps.slot[k] >= 0 ? rm::fast_shade(fv, fp, x + k, y, ps.t[k], ps.slot[k], ps.id[k])
-                                                                : rm::Vec3<float>{0.f, 0.f, 0.f};
+                            rm::Vec3<float> c = {0.f, 0.f, 0.f};
+                            if (ps.slot[k] >= 0)            // the instantiation launch_fast picks for this scene and camera
+                                c = gm == rm::GLASS_NONE  ? rm::fast_shade<rm::GLASS_NONE>(fv, fp, x + k, y, ps.t[k], ps.slot[k], ps.id[k])
+                                    : gm == rm::GLASS_F32 ? rm::fast_shade<rm::GLASS_F32>(fv, fp, x + k, y, ps.t[k], ps.slot[k], ps.id[k])
+                                                          : rm::fast_shade<rm::GLASS_F64>(fv, fp, x + k, y, ps.t[k], ps.slot[k], ps.id[k]);
                             size_t px = (size_t)y * fp.width + x + k;
                             if (cost && kBvh) cost[2 * px + 1] = walk_cost() - c1;
                             out_rgb[3 * px] = c.x; out_rgb[3 * px + 1] = c.y; out_rgb[3 * px + 2] = c.z;
@@ -224,6 +230,8 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
 
 extern "C" {
 void emu_set_strip_bound(int on) { g_strip_bound.store(on); }
+void emu_set_glass_mode(int mode) { g_glass_mode.store(mode); }
+int emu_last_glass_mode(void) { return g_last_glass_mode.load(); }
 void emu_set_cost_buffer(float* hw2) { g_cost.store(hw2); }
 // {walks, node visits, primitive tests} of the hierarchy walks since the last call (accel renders only)
 void emu_walk_stats(unsigned long long out[3]) {

@@ -250,10 +250,20 @@ def test_scene_fingerprint_and_flat_cache():
     b = d._fp()
     d.shapes[0].reflectance.refractive_index = 1.7
     assert len({a, b, d._fp()}) == 3
-    big = workloads.scene("stress", n_spheres=8, grid=40)      # > 64 KB of triangles: the sum path of the checksum
-    a = big._fp()
-    big.shapes[-1].triangles[5, 2] += 0.25
-    assert big._fp() != a
+    big = workloads.scene("stress", n_spheres=8, grid=50)      # 5000 triangles, 600 KB: a large array
+    keys = {big._fp()}
+    mesh = big.shapes[-1]
+    mesh.triangles[5, 2] += 0.25
+    keys.add(big._fp())
+    mesh.reflectances["is_glass_like"] = 1                      # an int32 field (a float sum of an f64 view sees a denormal: nothing)
+    keys.add(big._fp())
+    mesh.triangles[:] = mesh.triangles[::-1].copy()             # same triangles, other order: other colour gradient, other tie-breaks
+    mesh.reflectances[:] = mesh.reflectances[::-1].copy()
+    keys.add(big._fp())
+    mesh.triangles[7, 0] += 1.                                  # a sum-preserving edit
+    mesh.triangles[8, 0] -= 1.
+    keys.add(big._fp())
+    assert len(keys) == 5
     # flatten() always marshals afresh (callers may edit the result); device_handle() keeps one per fingerprint
     assert s.flatten() is not s.flatten()
     if not rm._abi.load().rm_init(0) == 0:                      # no GPU here: the upload fails after the marshalling
@@ -268,3 +278,21 @@ def test_scene_fingerprint_and_flat_cache():
         with pytest.raises(rm.RmError):
             s.device_handle()
         assert s._flat is not first
+
+
+def test_renderer_rejects_buffers_it_would_overrun():
+    """Renderer.render hands raw pointers to the C ABI: arrays of the wrong dtype / shape / layout, or a frame of another
+    size than the renderer was created for (renderer.rs:25-33 vs 46-108), are refused before anything is rendered."""
+    import rusty_marcher_b200 as rm
+    sc = workloads.scene("demo")
+    r = rm.create_renderer(1.5, 64, 96)
+    fb = rm.create_frame_buffer(96, 64)
+    for bad in (dict(prim_id=np.zeros((64, 96), dtype=np.int64)), dict(prim_id=np.zeros((64, 64), dtype=np.int32)),
+                dict(prim_id=np.zeros((64, 192), dtype=np.int32)[:, ::2]), dict(rgb8=np.zeros((64, 96, 3), dtype=np.int8)),
+                dict(rgb8=np.zeros((64, 96), dtype=np.uint8))):
+        with pytest.raises(ValueError):
+            r.render(fb, sc, **bad)
+    with pytest.raises(ValueError):
+        r.render(rm.create_frame_buffer(128, 64), sc)
+    with pytest.raises(ValueError):
+        r.render_dispersive(rm.create_frame_buffer(128, 64), sc)
