@@ -405,6 +405,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if world > 1:                           # the library's host threads (delivery of frames): share the box's cores between the ranks
+        os.environ.setdefault("RM_B200_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     rm.init(local_rank)
     L = _abi.load()
 
@@ -530,40 +532,91 @@ def run_ours(args):
         heavy = heavy_leg(args.heavy, world, rank, dev, flush)
 
     # ---- e2e: the public call a user makes -- Renderer.render(frame, scene) with HOST buffers: scene (re)upload H2D and the
-    # float framebuffer D2H inside the timed region.  With N > 1 every rank delivers its own row tile to its pinned host buffer.
-    frame = rm.create_frame_buffer(w, h)
-    nbytes = frame.buffer.nbytes
-    pinned = L.rm_host_alloc(nbytes)
-    if pinned:
-        frame.buffer = np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_float)), shape=(h, w, 3))
+    # float frame delivered to host memory inside the timed region.  N = 1: a pinned frame of this process.  N > 1: ONE frame
+    # in host memory shared by the ranks (a file in /dev/shm mapped by every process); every rank uploads the scene, renders
+    # its bands and delivers them into that frame, timed from a common barrier to the barrier after the last delivery.
+    import mmap
+    frame = rm.create_frame_buffer(32, 32)
+    frame.width, frame.height = w, h
+    nbytes = h * w * 12
+    pinned, shm_path, shm_map = None, None, None
+    if world == 1:
+        pinned = L.rm_host_alloc(nbytes)
+        frame.buffer = (np.ctypeslib.as_array(C.cast(pinned, C.POINTER(C.c_float)), shape=(h, w, 3)) if pinned
+                        else np.zeros((h, w, 3), dtype=np.float32))
+    else:
+        name = [None]
+        if rank == 0:
+            name[0] = "/dev/shm/rm_b200_bench_%d" % os.getpid()
+            with open(name[0], "wb") as f:
+                f.truncate(nbytes)
+        dist.broadcast_object_list(name, src=0)
+        shm_path = name[0]
+        fd = os.open(shm_path, os.O_RDWR)
+        shm_map = mmap.mmap(fd, nbytes)
+        os.close(fd)
+        frame.buffer = np.frombuffer(shm_map, dtype=np.float32).reshape(h, w, 3)
+        if rank == 0:
+            frame.buffer[:] = 7.                 # poisoned: every rendered row must be written by some rank
+        barrier()
     devnull = open(os.devnull, "w")
     stdout = sys.stdout
-    e2e_times = []
-    flat_bytes = 0
-    try:
-        sys.stdout = devnull                   # Renderer.render prints the reference's status lines
-        for i in range(args.warmup + args.steps if world == 1 else 0):
+
+    def e2e_loop(fb, n, warm, reupload=True):
+        times, d2h_b = [], 0
+        for i in range(warm + n):
             flush.fill_(0)
             barrier()
             t0 = time.perf_counter()
-            scene.release()                    # force the H2D re-upload of the scene every step
-            renderer.render(frame, scene, patch_rows=tr.rows)
+            if reupload:
+                scene.release()                # force the H2D re-upload of the scene every step
+            renderer.render(fb, scene, patch_rows=tr.rows)
+            if world > 1:
+                dist.barrier()                 # the frame is complete when the last rank has delivered its bands
             dt = time.perf_counter() - t0
-            if i >= args.warmup:
-                e2e_times.append(dt)
+            if i >= warm:
+                times.append(dt)
+                d2h_b = int(renderer.last_stats.d2h_bytes)
+        t = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) * 1e3 / n, d2h_b
+
+    e2e_extra = {}
+    try:
+        sys.stdout = devnull                   # Renderer.render prints the reference's status lines
+        renderer.retained = False
+        e2e_ms, d2h = e2e_loop(frame, args.steps, args.warmup)
+        n_var = min(args.steps, 50)
+        # ... and what a re-render loop that keeps its FrameBuffer pays (main.rs:329-351; RM_ROWS_RETAINED)
+        renderer.retained = True
+        e2e_extra["retained_ms_per_frame"], e2e_extra["retained_d2h_bytes_per_step"] = e2e_loop(frame, n_var, 5)
+        renderer.retained = False
+        if world == 1:
+            # the reference's own frame type: f64 rows (framebuffer.rs:6-10), pageable memory like a Vec's
+            fb64 = rm.create_frame_buffer(w, h, dtype=np.float64)
+            e2e_extra["f64_rows_ms_per_frame"], _ = e2e_loop(fb64, n_var, 5)
+            renderer.retained = True
+            e2e_extra["f64_rows_retained_ms_per_frame"], _ = e2e_loop(fb64, n_var, 5)
+            renderer.retained = False
+            del fb64
     finally:
         sys.stdout = stdout
     clocks = sampler.stop() if rank == 0 else None
+    # the assembled host frame against the frame one GPU delivers (outside the timed region)
+    e2e_ok = True
+    if rank == 0:
+        check = np.zeros((h, w, 3), dtype=np.float32)
+        st1 = _abi.RmStats()
+        _abi.check(L.rm_render(scene.device_handle(), C.byref(p_all), check.ctypes.data, None, None, C.byref(st1)))
+        e2e_ok = bool(np.array_equal(check[:rows], frame.buffer[:rows]))
+        del check
     flat = scene.flatten()
     flat_bytes = (C.sizeof(_abi.RmSphere) * flat.c.n_spheres + C.sizeof(_abi.RmPolygon) * flat.c.n_polygons
                   + 24 * flat.c.n_polygon_vertices + (C.sizeof(_abi.RmTriangle) + C.sizeof(_abi.RmReflectance)) * flat.c.n_triangles
                   + C.sizeof(_abi.RmLight) * flat.c.n_lights + C.sizeof(_abi.RmParams))
-    e2e_t = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_t[0]) * 1e3 / args.steps if world == 1 else None
     # the same call when the caller only wants what main.rs shows or saves: render + normalize + to_vec, the 8-bit frame
-    # (24.9 MB instead of 98.8 MB over PCIe); extra information next to the headline e2e figure (single GPU only)
+    # (24.9 MB over PCIe); extra information next to the headline e2e figure (single GPU only)
     rgb8_ms = None
     if world == 1:
         nb8 = h * w * 3
@@ -580,8 +633,10 @@ def run_ours(args):
                     t8.append(time.perf_counter() - t0)
             rgb8_ms = 1e3 * sum(t8) / len(t8)
             L.rm_host_free(pin8)
-    tile_rows = len(range(*tr.rows)) * 32
-    d2h = tile_rows * w * 12
+    d2h_t = torch.tensor([d2h], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(d2h_t, op=dist.ReduceOp.SUM)
+    d2h = int(d2h_t[0])
 
     line = None
     if rank == 0:
@@ -629,13 +684,17 @@ def run_ours(args):
             "frame_matches_n1": frame_ok, "frame_sha256": frame_sha, "frame_check": frame_detail,
             "heavy": heavy,
             "clocks": clocks,
-            # (N > 1: Renderer.render is a one-GPU call; a per-rank partial-band figure is not the deliverable of N = 1)
-            "e2e": None if e2e_ms is None else {"value": segs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_frame": e2e_ms,
-                    "h2d_bytes_per_step": flat_bytes, "d2h_bytes_per_step": d2h,
-                    "path": "Renderer.render(frame, scene) -> rm_scene_upload + rm_render, float32 framebuffer into pinned host memory"
-                            + ("; each rank delivers its own row tile" if world > 1 else ""),
+            "e2e": {"value": segs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_frame": e2e_ms,
+                    "h2d_bytes_per_step": flat_bytes * world, "d2h_bytes_per_step": d2h,
+                    "path": ("Renderer.render(frame, scene) -> rm_scene_upload + rm_render: float32 frame delivered into pinned host memory -- "
+                             "busy tiles packed on the device, one device-to-host copy, host threads clear the black tiles and scatter"
+                             if world == 1 else
+                             "every rank: Renderer.render(frame, scene, patch_rows = its bands) -> rm_scene_upload + rm_render into ONE float32 "
+                             "frame in host memory shared by the ranks (/dev/shm); timed barrier to barrier, max over ranks"),
+                    "frame_matches_n1": e2e_ok,
                     "pcie_gbs": d2h / (e2e_ms * 1e-3) / 1e9,
-                    "rgb8_only_ms_per_frame": rgb8_ms},
+                    "host_threads_per_rank": int(os.environ.get("RM_B200_HOST_THREADS", "0")) or os.cpu_count(),
+                    "rgb8_only_ms_per_frame": rgb8_ms, **e2e_extra},
             "gpu_launches": tr.launches_per_frame() * args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak_t.value, "unit": "TFLOP/s",
                          "frac": ach_tflops / peak_t.value if ach_tflops is not None else None, "traffic": traffic, "traffic_source": traffic_src,
@@ -654,14 +713,23 @@ def run_ours(args):
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
+    frame.buffer = None
     if pinned:
-        frame.buffer = None
         L.rm_host_free(pinned)
+    if shm_map is not None:
+        try:
+            shm_map.close()
+        except BufferError:
+            pass
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            os.unlink(shm_path)
     tr.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if not frame_ok or (heavy is not None and not heavy["frame_matches_n1"]):
+    if not frame_ok or not e2e_ok or (heavy is not None and not heavy["frame_matches_n1"]):
         sys.stderr.write("bench.py: the frame assembled by %d rank(s) differs from the single-GPU frame\n" % world)
         return 3
     return 0

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RM_ABI_VERSION 4
+#define RM_ABI_VERSION 5
 
 typedef enum RmStatus {
     RM_OK = 0,
@@ -160,6 +160,7 @@ typedef struct RmStats {
     double   ms_total;        /* device time of the whole call incl. copies                             */
     int32_t  kernel_launches; /* kernels launched by this call                                          */
     int32_t  resident_prims;  /* primitives actually traced (after culling)                             */
+    uint64_t d2h_bytes;       /* bytes this call copied from device to host memory                      */
 } RmStats;
 
 typedef int64_t RmScene;   /* opaque handle, > 0 */
@@ -190,9 +191,26 @@ int rm_scene_num_prims(RmScene handle);
  * Host buffers may be pageable; pinned ones (rm_host_alloc / rm_host_register) copy faster. */
 int rm_render(RmScene scene, const RmParams* params, float* out_rgb, int32_t* out_prim_id,
               uint8_t* out_rgb8, RmStats* stats);
+/* rm_render with only out_rgb given (the float frame, what Renderer::render returns) delivers through the packed path
+ * described at rm_render_rows_f64 below; the rows it writes are bit-identical. */
 /* Same with RM_FP64 arithmetic and a double framebuffer (validation mode). */
 int rm_render_f64(RmScene scene, const RmParams* params, double* out_rgb, int32_t* out_prim_id,
                   uint8_t* out_rgb8, RmStats* stats);
+
+/* ---- the hot path into the reference's own frame type ------------------------------------------------------------------ *
+ * FrameBuffer.buffer is a Vec<Vec<Vec3f>> (engine/src/framebuffer.rs:6-10): one heap allocation per pixel row, f64
+ * channels.  rows[y] (y < params->height) points to row y: width * 3 doubles (rm_render_rows_f64; the FP32 results widened,
+ * exactly) or floats (rm_render_rows_f32).  Only rows of the call's bands are touched, like renderer.rs:92-108.
+ * Delivery: when the frame has a tile schedule (triangle-only scenes) the busy tiles are packed on the device and cross
+ * PCIe in one copy; the library's host threads (RM_B200_HOST_THREADS, default: all) zero-fill the provably black tiles
+ * while it runs and then scatter / widen the busy ones.
+ * flags: RM_ROWS_RETAINED -- the caller has not touched the frame since the library's previous delivery into it (the
+ * re-render loop of engine/src/main.rs:329-351 keeps one FrameBuffer): only tiles that held something then and are black
+ * now are cleared.  The first delivery into a frame clears every black tile regardless.  stats: timings, max_value.
+ * RM_FP32 only. */
+#define RM_ROWS_RETAINED 1
+int rm_render_rows_f64(RmScene scene, const RmParams* params, double* const* rows, int flags, RmStats* stats);
+int rm_render_rows_f32(RmScene scene, const RmParams* params, float* const* rows, int flags, RmStats* stats);
 
 /* ---- extension mode: per-channel refractive indices (BASELINE.json configs[3]) ---------- *
  * The reference has ONE scalar refractive index per material (shapes.rs:21-32, optics.rs:8-89); there is no reference

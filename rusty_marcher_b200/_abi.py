@@ -68,7 +68,7 @@ COUNTER_FIELDS = ["pixels", "closest_segments", "anyhit_segments", "sphere_tests
 class RmStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in COUNTER_FIELDS] + [
         ("max_value", C.c_double), ("ms_render", C.c_double), ("ms_total", C.c_double),
-        ("kernel_launches", C.c_int32), ("resident_prims", C.c_int32)]
+        ("kernel_launches", C.c_int32), ("resident_prims", C.c_int32), ("d2h_bytes", C.c_uint64)]
 
     def counters(self):
         return {n: int(getattr(self, n)) for n in COUNTER_FIELDS}
@@ -82,6 +82,7 @@ class RmExchange(C.Structure):
 
 
 RM_FP32, RM_FP64 = 0, 1
+RM_ROWS_RETAINED = 1
 RM_OK = 0
 STATUS_NAMES = {0: "RM_OK", -1: "RM_ERR_NO_DEVICE", -2: "RM_ERR_NOT_INITIALISED", -3: "RM_ERR_INVALID_ARGUMENT",
                 -4: "RM_ERR_DIMENSIONS", -5: "RM_ERR_SCENE", -6: "RM_ERR_CUDA", -7: "RM_ERR_OUT_OF_MEMORY", -8: "RM_ERR_PEER"}
@@ -101,6 +102,8 @@ SYMBOLS = {
     "rm_scene_num_prims": (C.c_int, [C.c_int64]),
     "rm_render": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_void_p, _P(RmStats)]),
     "rm_render_f64": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_void_p, _P(RmStats)]),
+    "rm_render_rows_f64": (C.c_int, [C.c_int64, _P(RmParams), _P(C.c_void_p), C.c_int, _P(RmStats)]),
+    "rm_render_rows_f32": (C.c_int, [C.c_int64, _P(RmParams), _P(C.c_void_p), C.c_int, _P(RmStats)]),
     "rm_render_device": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rm_render_device_stats": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _P(RmStats)]),
     "rm_render_device_rgb8": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

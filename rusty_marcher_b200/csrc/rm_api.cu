@@ -9,14 +9,17 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/rm_b200.h"
 #include "rm_kernels.h"
+#include "rm_pool.h"
 
 namespace {
 
@@ -61,6 +64,7 @@ template <typename R> struct DevicePack {
 
 // What the last FP32 render of a scene left behind, for rm_tonemap_device_busy().
 struct LastFrame {
+    bool classified = false;      // rendered with a tile schedule (K0 classified the tiles: busy ones listed, the rest provably black)
     bool scheduled = false;       // rendered with a tile schedule and the 8-bit frame zero-filled by the render kernel
     int width = 0, height = 0, row_begin = 0, row_step = 0, n_bands = 0, buf_row0 = 0;
     const void* rgb8 = nullptr;
@@ -118,6 +122,31 @@ struct ProfSlot {
     bool split = true;                                          // e[1] was recorded between K0 and K1
 };
 
+// Pinned host memory owned by the library (staging of the host-delivery path).
+struct Pinned {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return RM_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+        cap = bytes;
+        return RM_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// What the library last delivered into a caller's frame (rm_render_rows_*, RM_ROWS_RETAINED): which 32x32 tiles hold
+// anything but zeros.  Keyed by the address of the frame's first row.
+struct Delivered {
+    const void* key = nullptr;
+    int width = 0, height = 0, elem = 0;
+    std::vector<unsigned char> busy;      // per tile of the whole frame: tiles_x * floor(H / 32)
+    std::vector<unsigned char> known;     // per 32-row band: the library has delivered it before (its black tiles are black)
+};
+
 struct Context {
     bool ready = false;
     int device = -1;
@@ -133,6 +162,10 @@ struct Context {
     RmScene next_handle = 1;
     Scratch rgb, prim, rgb8, small;   // small: [0,8) max scalar, [64, 64+17*8) counters
     Scratch mix;                      // rm_render_dispersive: the frame assembled from the three passes
+    Scratch pack;                     // host delivery: the busy tiles of a frame, packed in schedule order
+    Pinned h_stage, h_order;          // host delivery: pinned staging of the packed tiles / of the tile schedule + counters
+    std::unique_ptr<rm::HostPool> pool;
+    std::vector<Delivered> delivered; // a handful of frames (RM_ROWS_RETAINED)
     std::mutex mu;
 };
 Context g;
@@ -265,7 +298,8 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
     }
     CK(rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, stream, params->camera, launches, &ex));
     LastFrame& lf = it->second.last;
-    lf.scheduled = sizeof(R) == 4 && ex.scheduled && d_rgb8_zero != nullptr;
+    lf.classified = sizeof(R) == 4 && ex.scheduled;
+    lf.scheduled = lf.classified && d_rgb8_zero != nullptr;
     lf.width = fp.width; lf.height = fp.height; lf.row_begin = fp.row_begin; lf.row_step = fp.row_step;
     lf.n_bands = fp.n_bands; lf.buf_row0 = fp.buf_row0; lf.rgb8 = d_rgb8_zero;
     if (scheduled) *scheduled = lf.scheduled;
@@ -340,6 +374,188 @@ int render_host_impl(RmScene scene, const RmParams* params, R* out_rgb, int32_t*
         stats->ms_total = ms;
         stats->kernel_launches = launches;
         stats->resident_prims = resident;
+        stats->d2h_bytes = (uint64_t)n_copies * band_px * ((out_rgb ? 3 * sizeof(R) : 0) + (out_prim ? 4 : 0) + (out_rgb8 ? 3 : 0));
+    }
+    return RM_OK;
+}
+
+// ---- host delivery of a frame: what Renderer::render hands back (engine/src/renderer.rs:92-108, framebuffer.rs:6-10) ----
+// The caller's frame as row pointers (Vec<Vec<Vec3f>>: one allocation per row) or as one contiguous block.
+struct RowSink {
+    void* const* rows = nullptr;
+    char* base = nullptr;
+    size_t row_bytes = 0;
+    int elem = 4;                                               // bytes per channel value: 4 (f32) or 8 (f64, the reference's type)
+    char* row(int y) const { return rows ? static_cast<char*>(rows[y]) : base + (size_t)y * row_bytes; }
+};
+
+inline void put_values(char* dst, const float* src, int n, int elem) {
+    if (elem == 4) {
+        std::memcpy(dst, src, (size_t)n * 4);
+    } else {
+        double* d = reinterpret_cast<double*>(dst);
+        for (int i = 0; i < n; i++) d[i] = (double)src[i];      // exact: the f64 frame holds the FP32 results
+    }
+}
+
+rm::HostPool& host_pool() {
+    if (!g.pool) {
+        int n = (int)std::thread::hardware_concurrency();
+        if (const char* env = getenv("RM_B200_HOST_THREADS")) n = atoi(env);
+        g.pool.reset(new rm::HostPool(std::max(1, std::min(n, 64))));
+    }
+    return *g.pool;
+}
+
+// FP32 render of the call's bands + delivery into `sink`.  Tile-scheduled frames (triangle-only scenes): the busy tiles
+// are packed on the device and cross PCIe in ONE copy (15 MB of the 99 MB cornell frame), the host threads zero-fill the
+// provably black tiles while that copy runs and then scatter the busy ones -- with RM_ROWS_RETAINED only the tiles that
+// held something in the previous delivery into the same frame and are black now are cleared.  Other scenes: every row
+// through the pinned staging buffer (or straight into a contiguous f32 frame).
+int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink, int flags, RmStats* stats) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
+    int rc = check_params(params);
+    if (rc != RM_OK) return rc;
+    if (params->precision != RM_FP32) return fail(RM_ERR_INVALID_ARGUMENT, "host delivery of rows computes in RM_FP32 (rm_render_f64 is the RM_FP64 validation call)");
+    rm::FrameParams<float> fp = rm::make_frame_params<float>(*params);
+    if ((rc = g.small.ensure(1024)) != RM_OK) return rc;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (fp.n_bands <= 0) return RM_OK;
+    const int W = fp.width, tiles_x = W / 32, n_tiles = tiles_x * fp.n_bands;
+    const size_t span_rows = (size_t)(fp.n_bands - 1) * fp.row_step + 32;
+    const size_t n_px = span_rows * (size_t)W;
+    if ((rc = g.rgb.ensure(n_px * 12)) != RM_OK) return rc;
+    float* d_max = static_cast<float*>(g.small.p);
+    cudaStream_t s = g.stream;
+    CK(cudaEventRecord(g.ev[0], s));
+    CK(cudaMemsetAsync(g.small.p, 0, 64, s));
+    CK(cudaEventRecord(g.ev[1], s));
+    int resident = 0, launches = 0;
+    rc = render_device_impl<float>(scene, params, static_cast<float*>(g.rgb.p), nullptr, d_max, s, 1, nullptr, &fp, &resident, &launches);
+    if (rc != RM_OK) return rc;
+    CK(cudaEventRecord(g.ev[2], s));
+    SceneEntry& se = g.scenes.find(scene)->second;
+    const bool classified = se.last.classified;
+    rm::HostPool& pool = host_pool();
+    const int elem = sink.elem;
+    const size_t px_bytes = 3 * (size_t)elem;
+    float h_max = 0.f;
+    uint64_t d2h = 0;
+
+    // the previous delivery into this frame (RM_ROWS_RETAINED)
+    const int P = fp.height / 32;
+    const void* key = sink.row(fp.row_begin);
+    Delivered* prev = nullptr;
+    for (auto& d : g.delivered)
+        if (d.key == key && d.width == W && d.height == fp.height && d.elem == elem) prev = &d;
+    const bool retained = (flags & RM_ROWS_RETAINED) && prev != nullptr;
+    if (!prev) {
+        if (g.delivered.size() >= 8) g.delivered.erase(g.delivered.begin());
+        g.delivered.emplace_back();
+        prev = &g.delivered.back();
+        prev->key = key; prev->width = W; prev->height = fp.height; prev->elem = elem;
+        prev->busy.assign((size_t)tiles_x * P, 0);
+        prev->known.assign((size_t)P, 0);
+    }
+
+    if (classified) {
+        if ((rc = g.pack.ensure((size_t)n_tiles * 12288)) != RM_OK) return rc;
+        const size_t order_bytes = (size_t)n_tiles * sizeof(int);
+        if ((rc = g.h_order.ensure(2 * order_bytes + 64)) != RM_OK) return rc;
+        CK(rm::launch_pack_busy(se.f32.ds, fp, static_cast<const float*>(g.rgb.p), static_cast<float*>(g.pack.p), s));
+        launches++;
+        int* h_cnt = reinterpret_cast<int*>(static_cast<char*>(g.h_order.p) + 2 * order_bytes);
+        int* h_order = static_cast<int*>(g.h_order.p);
+        CK(cudaMemcpyAsync(h_cnt, se.f32.ds.ctr + 8, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_cnt + 4, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_order, se.f32.ds.tile_order, order_bytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_order + n_tiles, se.f32.ds.tile_order + se.f32.ds.tile_order_cap / 2, order_bytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const int n_full = h_cnt[0], n_part = h_cnt[1], n_busy = n_full + n_part;
+        std::memcpy(&h_max, h_cnt + 4, 4);
+        if (n_full < 0 || n_part < 0 || n_busy > n_tiles) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
+        if ((rc = g.h_stage.ensure(std::max<size_t>((size_t)n_busy * 12288, 64))) != RM_OK) return rc;
+        if (n_busy) CK(cudaMemcpyAsync(g.h_stage.p, g.pack.p, (size_t)n_busy * 12288, cudaMemcpyDeviceToHost, s));   // the one big copy
+        d2h = (uint64_t)n_busy * 12288 + 2 * order_bytes + 12;
+        CK(cudaEventRecord(g.ev[3], s));
+        // while it runs: which tiles are busy now, and the black ones cleared
+        std::vector<unsigned char> now((size_t)n_tiles, 0);
+        auto tile_of = [&](int t) { return t < n_full ? h_order[t] : h_order[n_tiles + (t - n_full)]; };
+        for (int t = 0; t < n_busy; t++) {
+            const int tile = tile_of(t);
+            if (tile < 0 || tile >= n_tiles) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
+            now[tile] = 1;
+        }
+        const int band0 = fp.row_begin / 32, band_step = fp.row_step / 32;
+        unsigned char* pb = prev->busy.data();
+        // per pixel row of the call's bands: a band the library has not delivered into this frame before (or any band
+        // without RM_ROWS_RETAINED) gets every black tile cleared, runs of black tiles in one memset; a known band only
+        // the tiles that held something in the previous delivery and are black now
+        pool.run(fp.n_bands * 32, [&](int item) {
+            const int b = item >> 5, r = item & 31, band = band0 + b * band_step;
+            char* row = sink.row(fp.row_begin + b * fp.row_step + r);
+            const unsigned char* nb = now.data() + (size_t)b * tiles_x;
+            const unsigned char* ob = pb + (size_t)band * tiles_x;
+            const bool delta = retained && prev->known[band];
+            for (int tx = 0; tx < tiles_x;) {
+                if (nb[tx] || (delta && !ob[tx])) { tx++; continue; }
+                int e = tx + 1;
+                while (e < tiles_x && !nb[e] && !(delta && !ob[e])) e++;
+                std::memset(row + (size_t)tx * 32 * px_bytes, 0, (size_t)(e - tx) * 32 * px_bytes);
+                tx = e;
+            }
+        });
+        for (int b = 0; b < fp.n_bands; b++) prev->known[band0 + b * band_step] = 1;
+        for (int b = 0; b < fp.n_bands; b++)
+            std::memcpy(pb + (size_t)(band0 + b * band_step) * tiles_x, now.data() + (size_t)b * tiles_x, tiles_x);
+        CK(cudaStreamSynchronize(s));
+        const float* stage = static_cast<const float*>(g.h_stage.p);
+        pool.run(n_busy, [&](int t) {
+            const int tile = tile_of(t), ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const float* src = stage + (size_t)t * 3072;
+            for (int r = 0; r < 32; r++)
+                put_values(sink.row(fp.row_begin + ty * fp.row_step + r) + (size_t)tx * 32 * px_bytes, src + r * 96, 96, elem);
+        });
+    } else {
+        // no schedule (spheres, n-gons, hierarchy): every rendered row holds something
+        const bool direct = elem == 4 && !sink.rows && sink.row_bytes == (size_t)W * 12;
+        const size_t band_bytes = (size_t)32 * W * 12;
+        if (!direct && (rc = g.h_stage.ensure((size_t)fp.n_bands * band_bytes)) != RM_OK) return rc;
+        for (int b = 0; b < fp.n_bands; b++) {
+            const char* src = static_cast<const char*>(g.rgb.p) + (size_t)b * fp.row_step * W * 12;
+            char* dst = direct ? sink.row(fp.row_begin + b * fp.row_step) : static_cast<char*>(g.h_stage.p) + (size_t)b * band_bytes;
+            const size_t n = (direct && fp.row_step == 32) ? band_bytes * fp.n_bands : band_bytes;
+            CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, s));
+            d2h += n;
+            if (direct && fp.row_step == 32) break;
+        }
+        CK(cudaMemcpyAsync(&h_max, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(g.ev[3], s));
+        CK(cudaStreamSynchronize(s));
+        if (!direct) {
+            const float* stage = static_cast<const float*>(g.h_stage.p);
+            pool.run(fp.n_bands * 32, [&](int item) {
+                const int b = item >> 5, r = item & 31;
+                put_values(sink.row(fp.row_begin + b * fp.row_step + r), stage + ((size_t)b * 32 + r) * W * 3, W * 3, elem);
+            });
+        }
+        const int band0 = fp.row_begin / 32, band_step = fp.row_step / 32;
+        for (int b = 0; b < fp.n_bands; b++) {
+            std::memset(prev->busy.data() + (size_t)(band0 + b * band_step) * tiles_x, 1, tiles_x);
+            prev->known[band0 + b * band_step] = 1;
+        }
+    }
+    if (stats) {
+        stats->max_value = (double)h_max;
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]));
+        stats->ms_render = ms;
+        CK(cudaEventElapsedTime(&ms, g.ev[0], g.ev[3]));
+        stats->ms_total = ms;
+        stats->kernel_launches = launches;
+        stats->resident_prims = resident;
+        stats->d2h_bytes = d2h;
     }
     return RM_OK;
 }
@@ -390,7 +606,10 @@ void rm_shutdown(void) {
         if (kv.second.order_ev) cudaEventDestroy(kv.second.order_ev);
     }
     g.scenes.clear();
-    g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release(); g.mix.release();
+    g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release(); g.mix.release(); g.pack.release();
+    g.h_stage.release(); g.h_order.release();
+    g.pool.reset();
+    g.delivered.clear();
     for (auto& ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ps : g.prof)
         for (auto& ev : ps.e) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
@@ -470,7 +689,31 @@ int rm_scene_num_prims(RmScene handle) {
 
 int rm_render(RmScene scene, const RmParams* params, float* out_rgb, int32_t* out_prim_id, uint8_t* out_rgb8, RmStats* stats) {
     if (params && params->precision != RM_FP32) return fail(RM_ERR_INVALID_ARGUMENT, "rm_render computes in RM_FP32; use rm_render_f64 for RM_FP64");
+    if (out_rgb && !out_prim_id && !out_rgb8 && params && !(stats && stats->pixels == 1)) {
+        // the float frame only -- what Renderer::render returns: the packed host delivery (bit-identical rows)
+        RowSink sink;
+        sink.base = reinterpret_cast<char*>(out_rgb);
+        sink.row_bytes = (size_t)std::max(params->width, 0) * 12;
+        sink.elem = 4;
+        return render_rows_impl(scene, params, sink, 0, stats);
+    }
     return render_host_impl<float>(scene, params, out_rgb, out_prim_id, out_rgb8, stats);
+}
+
+int rm_render_rows_f32(RmScene scene, const RmParams* params, float* const* rows, int flags, RmStats* stats) {
+    if (!rows) return fail(RM_ERR_INVALID_ARGUMENT, "rows is null");
+    RowSink sink;
+    sink.rows = reinterpret_cast<void* const*>(rows);
+    sink.elem = 4;
+    return render_rows_impl(scene, params, sink, flags, stats);
+}
+
+int rm_render_rows_f64(RmScene scene, const RmParams* params, double* const* rows, int flags, RmStats* stats) {
+    if (!rows) return fail(RM_ERR_INVALID_ARGUMENT, "rows is null");
+    RowSink sink;
+    sink.rows = reinterpret_cast<void* const*>(rows);
+    sink.elem = 8;
+    return render_rows_impl(scene, params, sink, flags, stats);
 }
 
 int rm_render_f64(RmScene scene, const RmParams* params, double* out_rgb, int32_t* out_prim_id, uint8_t* out_rgb8, RmStats* stats) {

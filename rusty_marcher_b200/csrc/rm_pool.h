@@ -1,0 +1,99 @@
+// rm_pool.h -- the library's host threads (pure C++).
+//
+// The reference reassembles a frame single-threaded (engine/src/renderer.rs:92-108: one copy per pixel into
+// frame.buffer[y][x]).  Behind the C ABI the same step -- busy tiles from the pinned staging buffer into the caller's
+// rows, black pixels zero-filled, optionally widened to the reference's f64 -- is memory-bound host work that is spread
+// over a persistent pool: workers sleep on a condition variable between frames, a frame wakes them once, items are
+// handed out from an atomic counter (the same scheme the reference's Rayon loop uses for its patches).
+#pragma once
+
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace rm {
+
+class HostPool {
+public:
+    explicit HostPool(int n_threads) {
+        const int n = n_threads < 1 ? 1 : n_threads;
+        for (int i = 0; i + 1 < n; i++) workers_.emplace_back([this] { loop(); });   // the caller is the n-th thread
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            stop_ = true;
+            epoch_++;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    int threads() const { return (int)workers_.size() + 1; }
+
+    // fn(i) for every i in [0, n), on all threads including the caller's; returns when every item is done.
+    // Not re-entrant (one frame at a time: callers hold the library mutex).
+    void run(int n, const std::function<void(int)>& fn) {
+        if (n <= 0) return;
+        if (workers_.empty() || n == 1) {
+            for (int i = 0; i < n; i++) fn(i);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            fn_ = &fn;
+            n_ = n;
+            next_.store(0, std::memory_order_relaxed);
+            pending_.store((int)workers_.size(), std::memory_order_relaxed);
+            epoch_++;
+        }
+        cv_.notify_all();
+        work();
+        // the workers that woke up are few microseconds behind at most: spin, then sleep
+        for (int spins = 0; pending_.load(std::memory_order_acquire) != 0; spins++) {
+            if (spins > 2000) {
+                std::unique_lock<std::mutex> l(mu_);
+                done_cv_.wait(l, [this] { return pending_.load(std::memory_order_acquire) == 0; });
+                break;
+            }
+        }
+    }
+
+private:
+    void work() {
+        for (;;) {
+            const int i = next_.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n_) break;
+            (*fn_)(i);
+        }
+    }
+    void loop() {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (stop_) return;
+            }
+            work();
+            if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+                std::lock_guard<std::mutex> l(mu_);
+                done_cv_.notify_one();
+            }
+        }
+    }
+
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int n_ = 0;
+    std::atomic<int> next_{0}, pending_{0};
+    unsigned long long epoch_ = 0;
+    bool stop_ = false;
+};
+
+}  // namespace rm

@@ -26,6 +26,9 @@ class Renderer:
         # ACCEL_AUTO_PRIMS primitives.  The FP32 frame is bit-identical either way.
         self.accel = False
         self.precision = _abi.RM_FP32
+        # re-render loops that keep one FrameBuffer (main.rs:329-351): the frame has not been touched since this renderer's
+        # previous render into it, so only tiles that held something then and are black now need clearing (RM_ROWS_RETAINED)
+        self.retained = False
         self.last_stats = None
 
     def params(self, frame, scene, patch_rows=(0, -1)):
@@ -71,13 +74,21 @@ class Renderer:
         stats = _abi.RmStats()
         stats.pixels = 1 if counters else 0
         want64 = self.precision == _abi.RM_FP64
-        want_dtype = np.float64 if want64 else np.float32
-        if frame.buffer.dtype != want_dtype or not frame.buffer.flags.c_contiguous:
-            frame.buffer = np.zeros((frame.height, frame.width, 3), dtype=want_dtype)
-        fn = L.rm_render_f64 if want64 else L.rm_render
-        _abi.check(fn(handle, C.byref(p), frame.buffer.ctypes.data,
-                      prim_id.ctypes.data if prim_id is not None else None,
-                      rgb8.ctypes.data if rgb8 is not None else None, C.byref(stats)))
+        # the frame's own type decides the delivery: float64 rows are the reference's FrameBuffer (framebuffer.rs:6-10),
+        # filled from the FP32 kernels through rm_render_rows_f64; float32 is the lean form
+        rows_api = not want64 and prim_id is None and rgb8 is None and not counters and (
+            frame.buffer.dtype == np.float64 or self.retained) and frame.buffer.flags.c_contiguous and frame.buffer.dtype in (np.float32, np.float64)
+        if rows_api:
+            fn = L.rm_render_rows_f64 if frame.buffer.dtype == np.float64 else L.rm_render_rows_f32
+            _abi.check(fn(handle, C.byref(p), self._row_pointers(frame), _abi.RM_ROWS_RETAINED if self.retained else 0, C.byref(stats)))
+        else:
+            want_dtype = np.float64 if want64 else np.float32
+            if frame.buffer.dtype != want_dtype or not frame.buffer.flags.c_contiguous:
+                frame.buffer = np.zeros((frame.height, frame.width, 3), dtype=want_dtype)
+            fn = L.rm_render_f64 if want64 else L.rm_render
+            _abi.check(fn(handle, C.byref(p), frame.buffer.ctypes.data,
+                          prim_id.ctypes.data if prim_id is not None else None,
+                          rgb8.ctypes.data if rgb8 is not None else None, C.byref(stats)))
         self.last_stats = stats
         ms_render_time = int((time.perf_counter() - now) * 1000)
         fps = 1000. / ms_render_time if ms_render_time > 0 else float("inf")
@@ -87,6 +98,17 @@ class Renderer:
         print(message)
         return message
 
+
+    @staticmethod
+    def _row_pointers(frame):
+        """frame.buffer as the reference holds it: one pointer per pixel row (Vec<Vec<Vec3f>>), cached on the frame."""
+        b = frame.buffer
+        key = (b.ctypes.data, b.shape, b.dtype.str)
+        cached = getattr(frame, "_rows", None)
+        if cached is None or cached[0] != key:
+            ptrs = (C.c_void_p * frame.height)(*[b.ctypes.data + y * b.strides[0] for y in range(frame.height)])
+            frame._rows = cached = (key, ptrs)
+        return cached[1]
 
     def render_dispersive(self, frame, scene, indices=(1.50, 1.52, 1.54), prim_id=None, patch_rows=(0, -1)):
         """EXTENSION MODE (no reference counterpart; BASELINE.json configs[3]): per-channel refractive

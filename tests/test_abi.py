@@ -30,7 +30,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in decl:
         assert hasattr(L, name), "librm_b200.so does not export %s" % name
     assert sorted(_abi.SYMBOLS) == decl, "ctypes table and headers disagree"
-    assert L.rm_abi_version() == 4
+    assert L.rm_abi_version() == 5
 
 
 def test_struct_layouts_match_the_header(tmp_path):

@@ -418,6 +418,68 @@ def test_host_api_interleaved_bands(rm_gpu):
     assert np.array_equal(acc_rgb, whole["rgb"]) and np.array_equal(acc_id, whole["prim_id"])
 
 
+@pytest.mark.parametrize("name,w,h,depth", [("cornell_box", 1920, 1080, 3), ("dodecahedron", 640, 480, 3), ("demo", 800, 600, 3)])
+def test_host_delivery_of_rows(rm_gpu, name, w, h, depth):
+    """What Renderer::render hands back (renderer.rs:92-108): the float frame in HOST memory.  The packed delivery (busy
+    tiles in one copy, host threads clear the black tiles and scatter) against the plain copy of every row: float32 frame,
+    the reference's f64 rows (contiguous and one allocation per row, framebuffer.rs:6-10), the retained mode over a moving
+    camera, interleaved bands of several 'ranks' into one frame -- all bit-identical, on poisoned buffers."""
+    rm = rm_gpu
+    L = _abi.load()
+    cams = [(0., 0., 0.), (30., -20., 10.), (-45., 15., 0.), (0., 0., 0.)]
+    if name == "demo":
+        cams = [(0., 0., 0.), (3., -2., 1.), (-4., 1.5, 0.), (0., 0., 0.)]
+    rows = (h // 32) * 32
+    want = []
+    for cam in cams:                                           # the plain path: every row copied (prim_id requested)
+        scene = workloads.scene(name)
+        scene.offset_camera(cam)
+        want.append(gpu_render(rm, scene, w, h, "f32", depth)["rgb"])
+    assert not np.array_equal(want[0], want[1])
+    scene = workloads.scene(name)
+    r = rm.create_renderer(1.5, h, w)
+    r.max_depth = depth
+    # float32 frame, not retained: poisoned before every call
+    fb = rm.create_frame_buffer(w, h, dtype=np.float32)
+    for cam, ref in zip(cams, want):
+        scene.camera = type(scene.camera)(*cam)
+        fb.buffer[:] = 7.
+        r.render(fb, scene)
+        assert np.array_equal(fb.buffer[:rows], ref[:rows]) and np.all(fb.buffer[rows:] == 7.)
+        assert r.last_stats.max_value == float(ref.max())
+    # the reference's frame: f64 rows; poisoned once, then retained over the moving camera
+    fb64 = rm.create_frame_buffer(w, h, dtype=np.float64)
+    fb64.buffer[:] = 7.
+    r.retained = True
+    for cam, ref in zip(cams, want):
+        scene.camera = type(scene.camera)(*cam)
+        r.render(fb64, scene)
+        assert fb64.buffer.dtype == np.float64
+        assert np.array_equal(fb64.buffer[:rows], ref[:rows].astype(np.float64)) and np.all(fb64.buffer[rows:] == 7.)
+    # retained float32, and a caller that scribbles in between without saying so gets what it asked for only when it says so
+    fb32 = rm.create_frame_buffer(w, h, dtype=np.float32)
+    fb32.buffer[:] = 7.
+    for cam, ref in zip(cams, want):
+        scene.camera = type(scene.camera)(*cam)
+        r.render(fb32, scene)
+        assert np.array_equal(fb32.buffer[:rows], ref[:rows])
+    r.retained = False
+    fb32.buffer[:] = 3.
+    r.render(fb32, scene)
+    assert np.array_equal(fb32.buffer[:rows], want[-1][:rows])
+    # one allocation per row (Vec<Vec<Vec3f>>), bands of three 'ranks' into the same frame
+    row_arrays = [np.full((w, 3), 7., dtype=np.float64) for _ in range(h)]
+    ptrs = (C.c_void_p * h)(*[a.ctypes.data for a in row_arrays])
+    scene.camera = type(scene.camera)(*cams[1])
+    for k in range(3):
+        p = r.params(fb, scene, (k, -1, 3))
+        st = _abi.RmStats()
+        _abi.check(L.rm_render_rows_f64(scene.device_handle(), C.byref(p), ptrs, 0, C.byref(st)))
+    got = np.stack(row_arrays)
+    assert np.array_equal(got[:rows], want[1][:rows].astype(np.float64)) and np.all(got[rows:] == 7.)
+    assert L.rm_render_rows_f64(scene.device_handle(), C.byref(p), None, 0, None) == -3
+
+
 def test_kernel_profiling_events(rm_gpu):
     import torch
     from rusty_marcher_b200 import tiled
