@@ -286,6 +286,15 @@ int rm_peer_alloc(size_t bytes, void** d_ptr, unsigned char handle[RM_IPC_HANDLE
 int rm_peer_open(const unsigned char handle[RM_IPC_HANDLE_BYTES], void** d_ptr);
 int rm_peer_close(void* d_ptr);                                                           /* of rm_peer_open  */
 int rm_peer_free(void* d_ptr);                                                            /* of rm_peer_alloc */
+/* Sharing the device.  K1 is a persistent kernel whose last phase waits, inside the kernel, until all of its CTAs have
+ * finished rendering: every CTA of the grid must be resident.  The grid is sized for that on a GPU the calling process has
+ * to itself.  If other work occupies SMs for long (another process under MPS, a long kernel of the caller on a second
+ * stream), set RM_B200_COOPERATIVE=1: the launch then carries the cooperative attribute and the driver guarantees
+ * co-residency (+2 to 3 us per frame).  A wait that is not answered within 2 s gives up, the frame is NOT valid and
+ * rm_peer_status() reports RM_ERR_PEER -- check it after synchronising when frames matter.
+ * One scene, one frame at a time: a scene's device pack holds the per-frame schedule and raster records, so renders of the
+ * same scene are ordered by the library even across streams (a render issued on another stream waits for the previous one);
+ * different scenes render concurrently. */
 /* One frame (FP32).  d_rgb: this rank's float frame (H*W*3, rows of other ranks are not touched); d_max: device float,
  * receives this rank's maximum; seq >= 1 and equal on all ranks, incremented by one per frame.  Asynchronous on
  * `stream`.  After a synchronisation rm_peer_status() tells whether any wait on this GPU timed out (RM_ERR_PEER). */

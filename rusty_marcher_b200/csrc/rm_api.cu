@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,27 +40,17 @@ int fail_cuda(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return fail_cuda(e__, #call);      \
     } while (0)
 
+// A scene's device memory: ONE allocation (recycled through a small cache: cudaMalloc / cudaFree cost tens of microseconds
+// each and cudaFree synchronises the device -- a caller that uploads its scene for every frame, like the reference's
+// render() borrowing &Scene, must not pay a dozen of them per frame) filled by ONE host-to-device copy from pinned staging.
+struct Arena {
+    void* p = nullptr;
+    size_t cap = 0;
+};
 template <typename R> struct DevicePack {
     bool ready = false;
-    void* blob = nullptr;
-    void* mat_a = nullptr;
-    void* mat_b = nullptr;
-    int* mat_f = nullptr;
-    int* order[2] = {nullptr, nullptr};
-    int* order_shape[2] = {nullptr, nullptr};
-    void* tri_src = nullptr;
-    void* tri_r = nullptr;
-    void* bvh_nodes = nullptr;
-    void* bvh_prims = nullptr;
-    void* sph64 = nullptr;
-    void* pln64 = nullptr;
+    Arena arena;
     rm::DeviceScene<R> ds;
-    void release() {
-        cudaFree(blob); cudaFree(mat_a); cudaFree(mat_b); cudaFree(mat_f); cudaFree(tri_src); cudaFree(tri_r);
-        cudaFree(bvh_nodes); cudaFree(bvh_prims); cudaFree(sph64); cudaFree(pln64);
-        for (int i = 0; i < 2; i++) { cudaFree(order[i]); cudaFree(order_shape[i]); }
-        *this = DevicePack<R>();
-    }
 };
 
 // What the last FP32 render of a scene left behind, for rm_tonemap_device_busy().
@@ -82,23 +73,10 @@ struct SceneEntry {
     bool rendered = false;
     cudaStream_t last_stream = nullptr;
     cudaEvent_t order_ev = nullptr;
+    // uploads are asynchronous on the library's stream: the first render after one waits for this event on its own stream
+    cudaEvent_t upload_ev = nullptr;
+    bool upload_dirty = false;
 };
-
-// Called under g.mu before a render of `se` is issued on `stream`.
-int order_scene_renders(SceneEntry& se, cudaStream_t stream) {
-    if (se.rendered && se.last_stream != stream) {
-        if (!se.order_ev) CK(cudaEventCreateWithFlags(&se.order_ev, cudaEventDisableTiming));
-        if (cudaEventRecord(se.order_ev, se.last_stream) == cudaSuccess) {
-            CK(cudaStreamWaitEvent(stream, se.order_ev, 0));
-        } else {                                                // the previous stream is gone: everything it held has been submitted
-            cudaGetLastError();
-            CK(cudaDeviceSynchronize());
-        }
-    }
-    se.rendered = true;
-    se.last_stream = stream;
-    return RM_OK;
-}
 
 struct Scratch {
     void* p = nullptr;
@@ -163,6 +141,8 @@ struct Context {
     Scratch rgb, prim, rgb8, small;   // small: [0,8) max scalar, [64, 64+17*8) counters
     Scratch mix;                      // rm_render_dispersive: the frame assembled from the three passes
     Scratch pack;                     // host delivery: the busy tiles of a frame, packed in schedule order
+    std::vector<Arena> arena_cache;   // device allocations of freed scenes, for the next upload
+    Pinned h_upload;                  // pinned staging of a scene upload
     Pinned h_stage, h_order;          // host delivery: pinned staging of the packed tiles / of the tile schedule + counters
     std::unique_ptr<rm::HostPool> pool;
     std::vector<Delivered> delivered; // a handful of frames (RM_ROWS_RETAINED)
@@ -170,11 +150,74 @@ struct Context {
 };
 Context g;
 
-template <typename T> int upload_vec(const std::vector<T>& v, void** out) {
-    *out = nullptr;
-    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
-    CK(cudaMalloc(out, bytes));
-    if (!v.empty()) CK(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int arena_get(size_t bytes, Arena& out) {
+    int best = -1;
+    for (int i = 0; i < (int)g.arena_cache.size(); i++) {
+        const size_t c = g.arena_cache[i].cap;
+        if (c >= bytes && c <= 2 * bytes + (1u << 20) && (best < 0 || c < g.arena_cache[best].cap)) best = i;
+    }
+    if (best >= 0) {
+        out = g.arena_cache[best];
+        g.arena_cache.erase(g.arena_cache.begin() + best);
+        return RM_OK;
+    }
+    out = Arena();
+    const size_t cap = (bytes + 65535) & ~(size_t)65535;
+    CK(cudaMalloc(&out.p, cap));
+    out.cap = cap;
+    return RM_OK;
+}
+void arena_put(Arena& a) {
+    if (!a.p) return;
+    if (g.arena_cache.size() >= 8) {
+        cudaFree(g.arena_cache.front().p);
+        g.arena_cache.erase(g.arena_cache.begin());
+    }
+    g.arena_cache.push_back(a);
+    a = Arena();
+}
+template <typename R> void release_pack(DevicePack<R>& dp) {
+    arena_put(dp.arena);
+    dp = DevicePack<R>();
+}
+// Everything in flight that may read the scene's device memory has finished (before its memory is recycled).
+void quiesce_scene(SceneEntry& se) {
+    cudaError_t e = cudaSuccess;
+    if (se.upload_dirty) e = cudaStreamSynchronize(g.stream);
+    if (e == cudaSuccess && se.rendered) e = cudaStreamSynchronize(se.last_stream);
+    if (e != cudaSuccess) {                                     // (a caller's stream that no longer exists)
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+    }
+}
+void destroy_scene(SceneEntry& se) {
+    quiesce_scene(se);
+    release_pack(se.f32);
+    release_pack(se.f64);
+    if (se.order_ev) cudaEventDestroy(se.order_ev);
+    if (se.upload_ev) cudaEventDestroy(se.upload_ev);
+    se.order_ev = se.upload_ev = nullptr;
+}
+
+// Called under g.mu before a render of `se` is issued on `stream`.
+int order_scene_renders(SceneEntry& se, cudaStream_t stream) {
+    if (se.upload_dirty) {
+        if (stream != g.stream) CK(cudaStreamWaitEvent(stream, se.upload_ev, 0));
+        se.upload_dirty = false;
+    }
+    if (se.rendered && se.last_stream != stream) {
+        if (!se.order_ev) CK(cudaEventCreateWithFlags(&se.order_ev, cudaEventDisableTiming));
+        if (cudaEventRecord(se.order_ev, se.last_stream) == cudaSuccess) {
+            CK(cudaStreamWaitEvent(stream, se.order_ev, 0));
+        } else {                                                // the previous stream is gone: everything it held has been submitted
+            cudaGetLastError();
+            CK(cudaDeviceSynchronize());
+        }
+    }
+    se.rendered = true;
+    se.last_stream = stream;
     return RM_OK;
 }
 
@@ -185,52 +228,77 @@ template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
     RmFlatScene fs = se.flat.view();
     int rc = rm::pack_scene<R>(fs, ps, err);
     if (rc != RM_OK) return fail(rc, err);
-    if ((rc = upload_vec(ps.blob, &dp.blob)) != RM_OK) return rc;   // BlobChunk = 32 bytes each
-    if ((rc = upload_vec(ps.mat_a, &dp.mat_a)) != RM_OK) return rc;
-    if ((rc = upload_vec(ps.mat_b, &dp.mat_b)) != RM_OK) return rc;
-    if ((rc = upload_vec(ps.mat_f, (void**)&dp.mat_f)) != RM_OK) return rc;
+    // layout of the arena: every array at a 256-byte aligned offset, the zero-initialised frame state at the end
+    struct Piece { const void* src; size_t bytes, off; };
+    std::vector<Piece> pieces;
+    size_t total = 0;
+    auto add = [&](const void* src, size_t bytes) {
+        const size_t off = total;
+        pieces.push_back({src, bytes, off});
+        total = align256(total + std::max<size_t>(bytes, 16));
+        return off;
+    };
+    auto addv = [&](const auto& v) { return add(v.data(), v.size() * sizeof(v[0])); };
+    const size_t o_blob = addv(ps.blob), o_ma = addv(ps.mat_a), o_mb = addv(ps.mat_b), o_mf = addv(ps.mat_f);
+    size_t o_ord[2], o_ords[2];
     for (int i = 0; i < 2; i++) {
-        if ((rc = upload_vec(ps.order[i], (void**)&dp.order[i])) != RM_OK) return rc;
-        if ((rc = upload_vec(ps.order_shape[i], (void**)&dp.order_shape[i])) != RM_OK) return rc;
-        dp.ds.order[i] = dp.order[i];
-        dp.ds.order_shape[i] = dp.order_shape[i];
+        o_ord[i] = addv(ps.order[i]);
+        o_ords[i] = addv(ps.order_shape[i]);
+    }
+    size_t o_tsrc = 0, o_nodes = 0, o_prims = 0, o_s64 = 0, o_p64 = 0;
+    if (sizeof(R) == 4) {
+        o_tsrc = addv(ps.tri_src);
+        o_nodes = addv(ps.bvh_nodes);
+        o_prims = addv(ps.bvh_prims);
+        o_s64 = addv(ps.sph64);
+        o_p64 = addv(ps.pln64);
+    }
+    const size_t copy_bytes = total;
+    // FP32 pack: raster records | frame control block | tile schedule | status words of the hierarchy walk, all zero
+    const size_t rec_bytes = (size_t)ps.lay.n_tri * 64 + 64;
+    const int order_cap = 1 << 16;                              // tiles of a frame up to 8192 x 8192
+    const size_t zero_bytes = sizeof(R) == 4 ? rec_bytes + 64 + (size_t)order_cap * sizeof(int) + 64 : 0;
+    total = align256(total + zero_bytes);
+    if ((rc = arena_get(total, dp.arena)) != RM_OK) return rc;
+    // the staging buffer may still feed the previous upload's copy
+    CK(cudaStreamSynchronize(g.stream));
+    if ((rc = g.h_upload.ensure(copy_bytes)) != RM_OK) return rc;
+    char* st = static_cast<char*>(g.h_upload.p);
+    for (const Piece& pc : pieces)
+        if (pc.bytes) std::memcpy(st + pc.off, pc.src, pc.bytes);
+    char* base = static_cast<char*>(dp.arena.p);
+    CK(cudaMemcpyAsync(base, st, copy_bytes, cudaMemcpyHostToDevice, g.stream));
+    if (zero_bytes) CK(cudaMemsetAsync(base + copy_bytes, 0, zero_bytes, g.stream));
+    if (!se.upload_ev) CK(cudaEventCreateWithFlags(&se.upload_ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(se.upload_ev, g.stream));
+    se.upload_dirty = true;
+
+    for (int i = 0; i < 2; i++) {
+        dp.ds.order[i] = reinterpret_cast<const int*>(base + o_ord[i]);
+        dp.ds.order_shape[i] = reinterpret_cast<const int*>(base + o_ords[i]);
         dp.ds.n_order[i] = (int)ps.order[i].size();
     }
     if (sizeof(R) == 4) {
-        if ((rc = upload_vec(ps.tri_src, &dp.tri_src)) != RM_OK) return rc;
-        // raster records | frame control block | tile schedule
-        // raster records | frame control block | tile schedule | status words of the hierarchy walk
-        const size_t rec_bytes = (size_t)ps.lay.n_tri * 64 + 64;
-        const int order_cap = 1 << 16;                          // tiles of a frame up to 8192 x 8192
-        CK(cudaMalloc(&dp.tri_r, rec_bytes + 64 + (size_t)order_cap * sizeof(int) + 64));
-        CK(cudaMemset(dp.tri_r, 0, rec_bytes + 64 + (size_t)order_cap * sizeof(int) + 64));
-        dp.ds.tri_src = static_cast<const double*>(dp.tri_src);
-        dp.ds.tri_r = static_cast<rm::R4<float>*>(dp.tri_r);
-        dp.ds.ctr = reinterpret_cast<int*>(static_cast<char*>(dp.tri_r) + rec_bytes);
+        char* z = base + copy_bytes;
+        dp.ds.tri_src = reinterpret_cast<const double*>(base + o_tsrc);
+        dp.ds.tri_r = reinterpret_cast<rm::R4<float>*>(z);
+        dp.ds.ctr = reinterpret_cast<int*>(z + rec_bytes);
         dp.ds.tile_order = dp.ds.ctr + 16;
         dp.ds.tile_order_cap = order_cap;
-        if ((rc = upload_vec(ps.bvh_nodes, &dp.bvh_nodes)) != RM_OK) return rc;
-        if ((rc = upload_vec(ps.bvh_prims, &dp.bvh_prims)) != RM_OK) return rc;
-        dp.ds.bvh.nodes = static_cast<const rm::R4<float>*>(dp.bvh_nodes);
-        dp.ds.bvh.prims = static_cast<const int*>(dp.bvh_prims);
+        dp.ds.bvh.nodes = reinterpret_cast<const rm::R4<float>*>(base + o_nodes);
+        dp.ds.bvh.prims = reinterpret_cast<const int*>(base + o_prims);
         dp.ds.bvh.n_nodes = (int)(ps.bvh_nodes.size() / 4);
         dp.ds.bvh.status = dp.ds.tile_order + order_cap;
-        if ((rc = upload_vec(ps.sph64, &dp.sph64)) != RM_OK) return rc;
-        if ((rc = upload_vec(ps.pln64, &dp.pln64)) != RM_OK) return rc;
-        dp.ds.sph64 = static_cast<const double*>(dp.sph64);
-        dp.ds.pln64 = static_cast<const double*>(dp.pln64);
+        dp.ds.sph64 = reinterpret_cast<const double*>(base + o_s64);
+        dp.ds.pln64 = reinterpret_cast<const double*>(base + o_p64);
     }
-    dp.ds.blob = static_cast<const unsigned char*>(dp.blob);
+    dp.ds.blob = reinterpret_cast<const unsigned char*>(base + o_blob);
     dp.ds.lay = ps.lay;
-    dp.ds.mat_a = static_cast<const rm::R4<R>*>(dp.mat_a);
-    dp.ds.mat_b = static_cast<const rm::R4<R>*>(dp.mat_b);
-    dp.ds.mat_f = dp.mat_f;
+    dp.ds.mat_a = reinterpret_cast<const rm::R4<R>*>(base + o_ma);
+    dp.ds.mat_b = reinterpret_cast<const rm::R4<R>*>(base + o_mb);
+    dp.ds.mat_f = reinterpret_cast<const int*>(base + o_mf);
     dp.ds.n_mat = ps.n_prims;
     se.n_prims = ps.n_prims;
-    // The copies and the memset above ran on the legacy default stream, the kernels run on non-blocking streams that it
-    // does not order: a copy from pageable memory returns once the data is staged, a memset is asynchronous.  Everything
-    // must have landed before the first frame reads it.
-    CK(cudaDeviceSynchronize());
     dp.ready = true;
     return RM_OK;
 }
@@ -438,6 +506,11 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
     SceneEntry& se = g.scenes.find(scene)->second;
     const bool classified = se.last.classified;
     rm::HostPool& pool = host_pool();
+    // RM_B200_DELIVERY_TRACE=1: host-side phase times of every delivery on stderr (us since the call's launches were issued)
+    static const bool trace = getenv("RM_B200_DELIVERY_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto us_now = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_sched = 0, t_zero = 0, t_copy = 0, t_scatter = 0;
     const int elem = sink.elem;
     const size_t px_bytes = 3 * (size_t)elem;
     float h_max = 0.f;
@@ -474,6 +547,7 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
         CK(cudaStreamSynchronize(s));
         const int n_full = h_cnt[0], n_part = h_cnt[1], n_busy = n_full + n_part;
         std::memcpy(&h_max, h_cnt + 4, 4);
+        t_sched = us_now();
         if (n_full < 0 || n_part < 0 || n_busy > n_tiles) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
         if ((rc = g.h_stage.ensure(std::max<size_t>((size_t)n_busy * 12288, 64))) != RM_OK) return rc;
         if (n_busy) CK(cudaMemcpyAsync(g.h_stage.p, g.pack.p, (size_t)n_busy * 12288, cudaMemcpyDeviceToHost, s));   // the one big copy
@@ -507,9 +581,11 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
             }
         });
         for (int b = 0; b < fp.n_bands; b++) prev->known[band0 + b * band_step] = 1;
+        t_zero = us_now();
         for (int b = 0; b < fp.n_bands; b++)
             std::memcpy(pb + (size_t)(band0 + b * band_step) * tiles_x, now.data() + (size_t)b * tiles_x, tiles_x);
         CK(cudaStreamSynchronize(s));
+        t_copy = us_now();
         const float* stage = static_cast<const float*>(g.h_stage.p);
         pool.run(n_busy, [&](int t) {
             const int tile = tile_of(t), ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -517,6 +593,10 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
             for (int r = 0; r < 32; r++)
                 put_values(sink.row(fp.row_begin + ty * fp.row_step + r) + (size_t)tx * 32 * px_bytes, src + r * 96, 96, elem);
         });
+        t_scatter = us_now();
+        if (trace)
+            std::fprintf(stderr, "rm delivery: %d busy of %d tiles, %s: schedule on host %.0f us, black tiles cleared %.0f, copy done %.0f, scattered %.0f (%d threads)\n",
+                         n_busy, n_tiles, retained ? "retained" : "fresh", t_sched, t_zero, t_copy, t_scatter, pool.threads());
     } else {
         // no schedule (spheres, n-gons, hierarchy): every rendered row holds something
         const bool direct = elem == 4 && !sink.rows && sink.row_bytes == (size_t)W * 12;
@@ -600,14 +680,12 @@ void rm_shutdown(void) {
     if (!g.ready) return;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
-    for (auto& kv : g.scenes) {
-        kv.second.f32.release();
-        kv.second.f64.release();
-        if (kv.second.order_ev) cudaEventDestroy(kv.second.order_ev);
-    }
+    for (auto& kv : g.scenes) destroy_scene(kv.second);
     g.scenes.clear();
+    for (auto& a : g.arena_cache) cudaFree(a.p);
+    g.arena_cache.clear();
     g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release(); g.mix.release(); g.pack.release();
-    g.h_stage.release(); g.h_order.release();
+    g.h_stage.release(); g.h_order.release(); g.h_upload.release();
     g.pool.reset();
     g.delivered.clear();
     for (auto& ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
@@ -661,7 +739,7 @@ int rm_scene_upload(const RmFlatScene* scene, RmScene* out_handle) {
     if (rc != RM_OK) return fail(rc, err);
     SceneEntry se;
     se.flat.assign(*scene);
-    if ((rc = ensure_pack<float>(se, se.f32)) != RM_OK) { se.f32.release(); return rc; }
+    if ((rc = ensure_pack<float>(se, se.f32)) != RM_OK) { destroy_scene(se); return rc; }
     RmScene h = g.next_handle++;
     g.scenes.emplace(h, std::move(se));
     *out_handle = h;
@@ -672,10 +750,7 @@ int rm_scene_free(RmScene handle) {
     std::lock_guard<std::mutex> lock(g.mu);
     auto it = g.scenes.find(handle);
     if (it == g.scenes.end()) return fail(RM_ERR_INVALID_ARGUMENT, "unknown scene handle");
-    cudaDeviceSynchronize();
-    it->second.f32.release();
-    it->second.f64.release();
-    if (it->second.order_ev) cudaEventDestroy(it->second.order_ev);
+    destroy_scene(it->second);                                  // waits for the scene's renders, recycles its device memory
     g.scenes.erase(it);
     return RM_OK;
 }

@@ -870,13 +870,14 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     cfg.numAttrs = 1;
     // The fused exchange + K4 phase waits inside the kernel for a word that is published only when EVERY CTA of the grid
     // has retired from rendering: all CTAs must be resident together.  The grid is sized from the occupancy API, which
-    // makes that true on an otherwise idle GPU; a cooperative launch makes the driver guarantee it (the launch waits
-    // until the whole grid fits, whatever else runs on the device).  RM_B200_COOPERATIVE=0 switches the attribute off;
-    // a driver that refuses it together with the programmatic launch edge switches it off for the process.
+    // makes that true on a GPU this process has to itself (include/rm_b200.h, rm_render_frame: "sharing the device");
+    // a cooperative launch makes the driver guarantee it whatever else runs on the device, at the price of the launch
+    // overlap with K0 (measured: +2 to 3 us on a 70 us frame).  RM_B200_COOPERATIVE=1 asks for it; a driver that refuses
+    // the attribute together with the programmatic launch edge switches it off again for the process.
     static int coop = -1;
     if (coop < 0) {
         const char* env = getenv("RM_B200_COOPERATIVE");
-        coop = (env && env[0] == '0') ? 0 : 1;
+        coop = (env && env[0] == '1') ? 1 : 0;
     }
     const bool want_coop = coop == 1 && link.world > 0 && rgb8_out != nullptr;
     if (want_coop) {
