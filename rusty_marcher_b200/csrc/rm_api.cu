@@ -533,66 +533,98 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
     }
 
     if (classified) {
-        if ((rc = g.pack.ensure((size_t)n_tiles * 12288)) != RM_OK) return rc;
-        const size_t order_bytes = (size_t)n_tiles * sizeof(int);
-        if ((rc = g.h_order.ensure(2 * order_bytes + 64)) != RM_OK) return rc;
-        CK(rm::launch_pack_busy(se.f32.ds, fp, static_cast<const float*>(g.rgb.p), static_cast<float*>(g.pack.p), s));
-        launches++;
-        int* h_cnt = reinterpret_cast<int*>(static_cast<char*>(g.h_order.p) + 2 * order_bytes);
-        int* h_order = static_cast<int*>(g.h_order.p);
-        CK(cudaMemcpyAsync(h_cnt, se.f32.ds.ctr + 8, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(h_cnt + 4, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(h_order, se.f32.ds.tile_order, order_bytes, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(h_order + n_tiles, se.f32.ds.tile_order + se.f32.ds.tile_order_cap / 2, order_bytes, cudaMemcpyDeviceToHost, s));
+        // device: [sorted list: n_tiles + 1 ints][packed tiles]; host (pinned): the same list, then the tiles
+        const size_t list_bytes = align256((size_t)(n_tiles + 1) * sizeof(int));
+        if ((rc = g.pack.ensure(list_bytes + (size_t)n_tiles * 12288)) != RM_OK) return rc;
+        if ((rc = g.h_order.ensure(list_bytes + 64)) != RM_OK) return rc;
+        int* d_sorted = static_cast<int*>(g.pack.p);
+        float* d_packed = reinterpret_cast<float*>(static_cast<char*>(g.pack.p) + list_bytes);
+        CK(rm::launch_pack_busy(se.f32.ds, fp, static_cast<const float*>(g.rgb.p), d_sorted, d_packed, s));
+        launches += 2;
+        int* h_sorted = static_cast<int*>(g.h_order.p);
+        float* h_maxp = reinterpret_cast<float*>(static_cast<char*>(g.h_order.p) + list_bytes);
+        CK(cudaMemcpyAsync(h_sorted, d_sorted, (size_t)(n_tiles + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_maxp, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        const int n_full = h_cnt[0], n_part = h_cnt[1], n_busy = n_full + n_part;
-        std::memcpy(&h_max, h_cnt + 4, 4);
+        const int n_busy = h_sorted[0];
+        const int* tiles = h_sorted + 1;
+        h_max = *h_maxp;
         t_sched = us_now();
-        if (n_full < 0 || n_part < 0 || n_busy > n_tiles) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
+        if (n_busy < 0 || n_busy > n_tiles) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
         if ((rc = g.h_stage.ensure(std::max<size_t>((size_t)n_busy * 12288, 64))) != RM_OK) return rc;
-        if (n_busy) CK(cudaMemcpyAsync(g.h_stage.p, g.pack.p, (size_t)n_busy * 12288, cudaMemcpyDeviceToHost, s));   // the one big copy
-        d2h = (uint64_t)n_busy * 12288 + 2 * order_bytes + 12;
+        // the busy tiles cross PCIe in a few chunks, each followed by an event: the host scatters chunk k while chunk
+        // k + 1 is still on its way (one cudaMemcpyAsync per chunk)
+        constexpr int kChunks = 6;
+        static cudaEvent_t chunk_ev[kChunks] = {};
+        int chunk_end[kChunks];
+        int n_chunks = 0;
+        for (int k = 0; k < kChunks && n_busy > 0; k++) {
+            const int a0 = (int)((long long)n_busy * k / kChunks), a1 = (int)((long long)n_busy * (k + 1) / kChunks);
+            if (a1 <= a0) continue;
+            if (!chunk_ev[n_chunks]) CK(cudaEventCreateWithFlags(&chunk_ev[n_chunks], cudaEventDisableTiming));
+            CK(cudaMemcpyAsync(static_cast<char*>(g.h_stage.p) + (size_t)a0 * 12288, reinterpret_cast<const char*>(d_packed) + (size_t)a0 * 12288,
+                               (size_t)(a1 - a0) * 12288, cudaMemcpyDeviceToHost, s));
+            CK(cudaEventRecord(chunk_ev[n_chunks], s));
+            chunk_end[n_chunks++] = a1;
+        }
         CK(cudaEventRecord(g.ev[3], s));
-        // while it runs: which tiles are busy now, and the black ones cleared
+        d2h = (uint64_t)n_busy * 12288 + (uint64_t)(n_tiles + 1) * sizeof(int) + 4;
+        // while they travel: which tiles are busy now, and the black ones cleared
         std::vector<unsigned char> now((size_t)n_tiles, 0);
-        auto tile_of = [&](int t) { return t < n_full ? h_order[t] : h_order[n_tiles + (t - n_full)]; };
         for (int t = 0; t < n_busy; t++) {
-            const int tile = tile_of(t);
-            if (tile < 0 || tile >= n_tiles) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
-            now[tile] = 1;
+            if (tiles[t] < 0 || tiles[t] >= n_tiles || (t && tiles[t] <= tiles[t - 1])) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
+            now[tiles[t]] = 1;
         }
         const int band0 = fp.row_begin / 32, band_step = fp.row_step / 32;
         unsigned char* pb = prev->busy.data();
         // per pixel row of the call's bands: a band the library has not delivered into this frame before (or any band
         // without RM_ROWS_RETAINED) gets every black tile cleared, runs of black tiles in one memset; a known band only
         // the tiles that held something in the previous delivery and are black now
-        pool.run(fp.n_bands * 32, [&](int item) {
-            const int b = item >> 5, r = item & 31, band = band0 + b * band_step;
-            char* row = sink.row(fp.row_begin + b * fp.row_step + r);
-            const unsigned char* nb = now.data() + (size_t)b * tiles_x;
-            const unsigned char* ob = pb + (size_t)band * tiles_x;
-            const bool delta = retained && prev->known[band];
-            for (int tx = 0; tx < tiles_x;) {
-                if (nb[tx] || (delta && !ob[tx])) { tx++; continue; }
-                int e = tx + 1;
-                while (e < tiles_x && !nb[e] && !(delta && !ob[e])) e++;
-                std::memset(row + (size_t)tx * 32 * px_bytes, 0, (size_t)(e - tx) * 32 * px_bytes);
-                tx = e;
-            }
-        });
-        for (int b = 0; b < fp.n_bands; b++) prev->known[band0 + b * band_step] = 1;
-        t_zero = us_now();
-        for (int b = 0; b < fp.n_bands; b++)
+        bool any_clear = !retained;
+        for (int b = 0; b < fp.n_bands && !any_clear; b++) {
+            const int band = band0 + b * band_step;
+            if (!prev->known[band]) any_clear = true;
+            for (int tx = 0; tx < tiles_x && !any_clear; tx++) any_clear = pb[(size_t)band * tiles_x + tx] && !now[(size_t)b * tiles_x + tx];
+        }
+        if (any_clear)
+            pool.run(fp.n_bands * 32, [&](int item) {
+                const int b = item >> 5, r = item & 31, band = band0 + b * band_step;
+                char* row = sink.row(fp.row_begin + b * fp.row_step + r);
+                const unsigned char* nb = now.data() + (size_t)b * tiles_x;
+                const unsigned char* ob = pb + (size_t)band * tiles_x;
+                const bool delta = retained && prev->known[band];
+                for (int tx = 0; tx < tiles_x;) {
+                    if (nb[tx] || (delta && !ob[tx])) { tx++; continue; }
+                    int e = tx + 1;
+                    while (e < tiles_x && !nb[e] && !(delta && !ob[e])) e++;
+                    std::memset(row + (size_t)tx * 32 * px_bytes, 0, (size_t)(e - tx) * 32 * px_bytes);
+                    tx = e;
+                }
+            });
+        for (int b = 0; b < fp.n_bands; b++) {
+            prev->known[band0 + b * band_step] = 1;
             std::memcpy(pb + (size_t)(band0 + b * band_step) * tiles_x, now.data() + (size_t)b * tiles_x, tiles_x);
-        CK(cudaStreamSynchronize(s));
-        t_copy = us_now();
+        }
+        t_zero = us_now();
+        // scatter, chunk by chunk; an item is a run of up to 8 tiles in frame order -- neighbours in a band share the pages
+        // of their 32 pixel rows, so a thread walks row by row over the run
         const float* stage = static_cast<const float*>(g.h_stage.p);
-        pool.run(n_busy, [&](int t) {
-            const int tile = tile_of(t), ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const float* src = stage + (size_t)t * 3072;
-            for (int r = 0; r < 32; r++)
-                put_values(sink.row(fp.row_begin + ty * fp.row_step + r) + (size_t)tx * 32 * px_bytes, src + r * 96, 96, elem);
-        });
+        int done = 0;
+        for (int k = 0; k < n_chunks; k++) {
+            CK(cudaEventSynchronize(chunk_ev[k]));
+            if (k == n_chunks - 1) t_copy = us_now();
+            const int c0 = done, c1 = chunk_end[k];
+            pool.run((c1 - c0 + 7) / 8, [&](int item) {
+                const int t0 = c0 + item * 8, t1 = std::min(t0 + 8, c1);
+                for (int r = 0; r < 32; r++)
+                    for (int t = t0; t < t1; t++) {
+                        const int tile = tiles[t], ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                        put_values(sink.row(fp.row_begin + ty * fp.row_step + r) + (size_t)tx * 32 * px_bytes,
+                                   stage + (size_t)t * 3072 + r * 96, 96, elem);
+                    }
+            });
+            done = c1;
+        }
         t_scatter = us_now();
         if (trace)
             std::fprintf(stderr, "rm delivery: %d busy of %d tiles, %s: schedule on host %.0f us, black tiles cleared %.0f, copy done %.0f, scattered %.0f (%d threads)\n",

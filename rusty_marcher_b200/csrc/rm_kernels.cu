@@ -765,16 +765,58 @@ tonemap_busy_kernel(const float* __restrict__ rgb, const float* __restrict__ dma
     }
 }
 
-// Host delivery of a tile-scheduled frame (rm_render / rm_render_rows_*): the busy tiles of the frame rendered last, packed
-// in schedule order into a contiguous staging buffer -- tile t of the schedule at floats [3072 t, 3072 (t + 1)), rows of
-// 32 pixels -- so that ONE device-to-host copy moves everything that is not black (15 % of the cornell frame).  Same
-// addressing as tonemap_busy_kernel; 384-byte runs in, 12 KB contiguous out.
-__global__ void __launch_bounds__(256)
-pack_busy_kernel(const float* __restrict__ rgb, const FrameParams<float> fp, const int tiles_x, const int* __restrict__ order,
-                 const int* __restrict__ order2, const int* __restrict__ ctr, float* __restrict__ packed) {
-    const int n_full = ctr[8], n_busy = n_full + ctr[9];
-    for (int t = blockIdx.x; t < n_busy; t += gridDim.x) {
+// Host delivery of a tile-scheduled frame (rm_render / rm_render_rows_*), two small kernels after K1.
+// (1) The schedule lists the busy tiles in the order K0's atomics happened to hand out; the host wants them in frame order
+// (tile index = band * tiles_x + column), so that tiles it scatters one after the other are neighbours in the caller's
+// frame.  One CTA: bitmap of the busy tiles in shared memory, prefix sum of the words' popcounts, every word writes its
+// tiles at its offset.  sorted[0] = number of busy tiles, sorted[1 + k] = k-th busy tile in frame order.
+constexpr int kSortMaxWords = 1024;                             // 32768 tiles: the classify kernel's own limit
+__global__ void __launch_bounds__(1024)
+sort_busy_kernel(const int* __restrict__ order, const int* __restrict__ order2, const int* __restrict__ ctr, int* __restrict__ sorted) {
+    __shared__ unsigned bm[kSortMaxWords];
+    __shared__ int off[kSortMaxWords];
+    __shared__ int warp_sum[32];
+    const int n_full = ctr[8], n_busy = n_full + ctr[9], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bm[tid] = 0u;
+    __syncthreads();
+    for (int t = tid; t < n_busy; t += 1024) {
         const int tile = t < n_full ? order[t] : order2[t - n_full];
+        atomicOr(&bm[tile >> 5], 1u << (tile & 31));
+    }
+    __syncthreads();
+    const int c = __popc(bm[tid]);
+    int inc = c;                                                // inclusive scan over the 1024 words
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+    }
+    if (lane == 31) warp_sum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += v;
+        }
+        warp_sum[lane] = w;
+    }
+    __syncthreads();
+    off[tid] = inc - c + (warp ? warp_sum[warp - 1] : 0);
+    if (tid == 0) sorted[0] = n_busy;
+    int k = off[tid];
+    for (unsigned bits = bm[tid]; bits; bits &= bits - 1) sorted[1 + k++] = tid * 32 + __ffs(bits) - 1;
+}
+// (2) The busy tiles packed in that order into a contiguous staging buffer -- tile k at floats [3072 k, 3072 (k + 1)),
+// rows of 32 pixels -- so that the device-to-host copies move only what is not black (15 % of the cornell frame) and the
+// host can scatter a chunk while the next one is still crossing PCIe.  384-byte runs in, 12 KB contiguous out.
+__global__ void __launch_bounds__(256)
+pack_busy_kernel(const float* __restrict__ rgb, const FrameParams<float> fp, const int tiles_x, const int* __restrict__ sorted,
+                 float* __restrict__ packed) {
+    const int n_busy = sorted[0];
+    for (int t = blockIdx.x; t < n_busy; t += gridDim.x) {
+        const int tile = sorted[1 + t];
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const size_t p0 = (size_t)(fp.row_begin + ty * fp.row_step - fp.buf_row0) * fp.width + tx * 32;
         float4* dst = reinterpret_cast<float4*>(packed + (size_t)t * 3072);
@@ -962,12 +1004,13 @@ cudaError_t launch_tonemap_busy(const DeviceScene<float>& ds, const FrameParams<
     return cudaGetLastError();
 }
 
-cudaError_t launch_pack_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, float* packed,
+cudaError_t launch_pack_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, int* sorted, float* packed,
                              cudaStream_t stream) {
     const int tiles_x = fp.width / kFastTile, n_tiles = tiles_x * fp.n_bands;
     if (n_tiles <= 0) return cudaSuccess;
-    pack_busy_kernel<<<std::min(n_tiles, 148 * 8), 256, 0, stream>>>(rgb, fp, tiles_x, ds.tile_order, ds.tile_order + ds.tile_order_cap / 2,
-                                                                     ds.ctr, packed);
+    if (n_tiles > kSortMaxWords * 32) return cudaErrorInvalidValue;
+    sort_busy_kernel<<<1, 1024, 0, stream>>>(ds.tile_order, ds.tile_order + ds.tile_order_cap / 2, ds.ctr, sorted);
+    pack_busy_kernel<<<std::min(n_tiles, 148 * 8), 256, 0, stream>>>(rgb, fp, tiles_x, sorted, packed);
     return cudaGetLastError();
 }
 

@@ -93,8 +93,9 @@ cudaError_t launch_tonemap(const FrameParams<R>& fp, const R* rgb, const R* dmax
 // K4 over the busy tiles of the frame `ds` rendered last with a schedule and RenderExtras::rgb8_zero (same fp).
 cudaError_t launch_tonemap_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, const float* dmax,
                                 bool normalise, unsigned char* rgb8, cudaStream_t stream);
-// The busy tiles of the frame `ds` rendered last with a schedule (same fp), packed in schedule order: 3072 floats per tile.
-cudaError_t launch_pack_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, float* packed,
+// The busy tiles of the frame `ds` rendered last with a schedule (same fp): sorted[0] = their number, sorted[1 + k] = the
+// k-th in frame order (n_tiles + 1 ints), packed[3072 k ...] = its 32 x 32 x 3 floats.  Two launches.
+cudaError_t launch_pack_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, int* sorted, float* packed,
                              cudaStream_t stream);
 // launch_tonemap<float> that takes the frame maximum from this rank's mailbox (waiting for every rank's word of frame
 // link.seq) and signals rank 0 when its bytes are stored -- the exchange of a rank that has no rows to render (its render

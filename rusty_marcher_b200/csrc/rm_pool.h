@@ -8,6 +8,7 @@
 #pragma once
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -27,6 +28,7 @@ public:
             std::lock_guard<std::mutex> l(mu_);
             stop_ = true;
             epoch_++;
+            hot_.store(epoch_, std::memory_order_release);
         }
         cv_.notify_all();
         for (auto& t : workers_) t.join();
@@ -48,6 +50,7 @@ public:
             next_.store(0, std::memory_order_relaxed);
             pending_.store((int)workers_.size(), std::memory_order_relaxed);
             epoch_++;
+            hot_.store(epoch_, std::memory_order_release);
         }
         cv_.notify_all();
         work();
@@ -72,6 +75,15 @@ private:
     void loop() {
         unsigned long long seen = 0;
         for (;;) {
+            // A frame hands the pool several jobs microseconds apart (clear, then scatter chunk by chunk): stay awake for a
+            // while after a job -- a sleeping thread takes tens of microseconds to come back -- then sleep until the next frame.
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int spins = 0; hot_.load(std::memory_order_acquire) == seen; spins++) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+                if ((spins & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+            }
             {
                 std::unique_lock<std::mutex> l(mu_);
                 cv_.wait(l, [&] { return epoch_ != seen; });
@@ -92,6 +104,7 @@ private:
     const std::function<void(int)>* fn_ = nullptr;
     int n_ = 0;
     std::atomic<int> next_{0}, pending_{0};
+    std::atomic<unsigned long long> hot_{0};   // copy of epoch_ the workers poll without the mutex
     unsigned long long epoch_ = 0;
     bool stop_ = false;
 };
