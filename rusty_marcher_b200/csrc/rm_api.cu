@@ -481,6 +481,7 @@ rm::HostPool& host_pool() {
 // held something in the previous delivery into the same frame and are black now are cleared.  Other scenes: every row
 // through the pinned staging buffer (or straight into a contiguous f32 frame).
 int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink, int flags, RmStats* stats) {
+    const auto t_entry = std::chrono::steady_clock::now();
     std::lock_guard<std::mutex> lock(g.mu);
     if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
     int rc = check_params(params);
@@ -554,7 +555,7 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
         if ((rc = g.h_stage.ensure(std::max<size_t>((size_t)n_busy * 12288, 64))) != RM_OK) return rc;
         // the busy tiles cross PCIe in a few chunks, each followed by an event: the host scatters chunk k while chunk
         // k + 1 is still on its way (one cudaMemcpyAsync per chunk)
-        constexpr int kChunks = 6;
+        constexpr int kChunks = 4;
         static cudaEvent_t chunk_ev[kChunks] = {};
         int chunk_end[kChunks];
         int n_chunks = 0;
@@ -627,8 +628,9 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
         }
         t_scatter = us_now();
         if (trace)
-            std::fprintf(stderr, "rm delivery: %d busy of %d tiles, %s: schedule on host %.0f us, black tiles cleared %.0f, copy done %.0f, scattered %.0f (%d threads)\n",
-                         n_busy, n_tiles, retained ? "retained" : "fresh", t_sched, t_zero, t_copy, t_scatter, pool.threads());
+            std::fprintf(stderr, "rm delivery: %d busy of %d tiles, %s: launches issued %.0f us after entry; from there: schedule on host %.0f us, black tiles cleared %.0f, copy done %.0f, scattered %.0f (%d threads)\n",
+                         n_busy, n_tiles, retained ? "retained" : "fresh", std::chrono::duration<double, std::micro>(t_begin - t_entry).count(),
+                         t_sched, t_zero, t_copy, t_scatter, pool.threads());
     } else {
         // no schedule (spheres, n-gons, hierarchy): every rendered row holds something
         const bool direct = elem == 4 && !sink.rows && sink.row_bytes == (size_t)W * 12;

@@ -54,9 +54,14 @@ public:
         }
         cv_.notify_all();
         work();
-        // the workers that woke up are few microseconds behind at most: spin, then sleep
+        // the workers are at most one item behind (tens of microseconds): spin -- going to sleep here costs more than that
+        // to wake up from -- and only sleep if something holds a worker up for milliseconds
+        const auto t0 = std::chrono::steady_clock::now();
         for (int spins = 0; pending_.load(std::memory_order_acquire) != 0; spins++) {
-            if (spins > 2000) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+            if ((spins & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(5)) {
                 std::unique_lock<std::mutex> l(mu_);
                 done_cv_.wait(l, [this] { return pending_.load(std::memory_order_acquire) == 0; });
                 break;
