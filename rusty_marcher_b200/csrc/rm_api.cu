@@ -76,6 +76,10 @@ struct SceneEntry {
     // uploads are asynchronous on the library's stream: the first render after one waits for this event on its own stream
     cudaEvent_t upload_ev = nullptr;
     bool upload_dirty = false;
+    // the frame-level call as a CUDA graph (K0 -> K1 with their programmatic launch edge): re-captured per frame -- camera,
+    // sequence number and buffers are kernel parameters -- and pushed into the instantiated graph with cudaGraphExecUpdate
+    cudaGraphExec_t graph_exec = nullptr;
+    long long frames = 0;
 };
 
 struct Scratch {
@@ -198,7 +202,9 @@ void destroy_scene(SceneEntry& se) {
     release_pack(se.f64);
     if (se.order_ev) cudaEventDestroy(se.order_ev);
     if (se.upload_ev) cudaEventDestroy(se.upload_ev);
+    if (se.graph_exec) cudaGraphExecDestroy(se.graph_exec);
     se.order_ev = se.upload_ev = nullptr;
+    se.graph_exec = nullptr;
 }
 
 // Called under g.mu before a render of `se` is issued on `stream`.
@@ -331,7 +337,7 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
                        int buf_row0_is_tile, unsigned long long* d_counters, rm::FrameParams<R>* out_fp, int* resident,
                        int* launches = nullptr, unsigned char* d_rgb8_zero = nullptr, bool* scheduled = nullptr,
                        const rm::PeerLink* link = nullptr, unsigned char* d_rgb8_out = nullptr, bool normalise = true,
-                       unsigned char* d_rgb8_next = nullptr) {
+                       unsigned char* d_rgb8_next = nullptr, bool as_graph = false) {
     if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
     int rc = check_params(params);
     if (rc != RM_OK) return rc;
@@ -364,7 +370,53 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
         ex.ev_prepared = ps.split ? ps.e[1] : nullptr;
         ex.ev_rendered = ps.e[2];
     }
-    CK(rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, stream, params->camera, launches, &ex));
+    SceneEntry& se = it->second;
+    // RM_B200_GRAPH (default on): frame-level calls go to the GPU as ONE graph launch from the scene's second frame on
+    // (the first one runs the launchers' one-time set-up).  A driver that cannot capture the launch pair switches it off.
+    static int graph_mode = -1;
+    if (graph_mode < 0) {
+        const char* env = getenv("RM_B200_GRAPH");
+        graph_mode = (env && env[0] == '0') ? 0 : 1;
+    }
+    bool launched = false;
+    if (as_graph && graph_mode == 1 && se.frames > 0 && fp.n_bands > 0) {
+        cudaEvent_t ev_begin = ex.ev_begin, ev_rendered = ex.ev_rendered;
+        ex.ev_begin = ex.ev_prepared = ex.ev_rendered = nullptr;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed);
+        if (e == cudaSuccess) {
+            const cudaError_t el = rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, stream, params->camera, launches, &ex);
+            e = cudaStreamEndCapture(stream, &graph);
+            if (el != cudaSuccess) e = el;
+        }
+        if (e == cudaSuccess && se.graph_exec) {
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(se.graph_exec, graph, &info) != cudaSuccess) {     // another kernel instantiation (glass mode, layout)
+                cudaGetLastError();
+                cudaGraphExecDestroy(se.graph_exec);
+                se.graph_exec = nullptr;
+            }
+        }
+        if (e == cudaSuccess && !se.graph_exec) e = cudaGraphInstantiate(&se.graph_exec, graph, 0);
+        if (e == cudaSuccess) {
+            if (ev_begin) cudaEventRecord(ev_begin, stream);
+            e = cudaGraphLaunch(se.graph_exec, stream);
+            if (ev_rendered) cudaEventRecord(ev_rendered, stream);
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (e == cudaSuccess) {
+            launched = true;
+        } else {                                                // not on this driver: plain launches from now on
+            cudaGetLastError();
+            graph_mode = 0;
+            if (se.graph_exec) cudaGraphExecDestroy(se.graph_exec);
+            se.graph_exec = nullptr;
+            ex.ev_begin = ev_begin;
+            ex.ev_rendered = ev_rendered;
+        }
+    }
+    if (!launched) CK(rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, stream, params->camera, launches, &ex));
+    se.frames++;
     LastFrame& lf = it->second.last;
     lf.classified = sizeof(R) == 4 && ex.scheduled;
     lf.scheduled = lf.classified && d_rgb8_zero != nullptr;
@@ -1059,7 +1111,7 @@ int rm_render_frame(RmScene scene, const RmParams* params, void* d_rgb, int32_t*
     // zeros never travel over NVLink.
     int rc = render_device_impl<float>(scene, params, static_cast<float*>(d_rgb), d_prim_id, static_cast<float*>(d_max), s, 0,
                                        nullptr, &fp, nullptr, nullptr, x->rank == 0 ? frame8 : nullptr, nullptr, &link, frame8,
-                                       normalise != 0, frame8_next);
+                                       normalise != 0, frame8_next, true);
     if (rc != RM_OK) return rc;
     auto it = g.scenes.find(scene);
     const rm::DeviceScene<float>& ds = it->second.f32.ds;
