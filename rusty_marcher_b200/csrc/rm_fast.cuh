@@ -651,10 +651,15 @@ inline int glass_mode(const bool any_glass, const int n_sph, const double coord_
     return S > 64. * r_min ? GLASS_F64 : GLASS_F32;
 }
 
-#if defined(__CUDACC__)
+// (inlined: as a function of its own -- __noinline__, so that the caller's loop state is not held in registers across the
+// f64 code -- the view and the frame parameters are passed through local memory and the call costs more than the spills
+// it avoids: stress_8k through the hierarchy 18.3 ms against 15.6 ms inlined, profiles/r4h_glass64_inline_ab.txt)
+#if defined(__CUDACC__) && !defined(RM_GLASS64_NOINLINE)
+#define RM_GLASS_FN __host__ __device__ __forceinline__
+#elif defined(__CUDACC__)
 #define RM_GLASS_FN __host__ __device__ __noinline__
 #else
-#define RM_GLASS_FN
+#define RM_GLASS_FN inline
 #endif
 
 RM_HD Vec3<float> to_f32(const Vec3<double> v) { return {(float)v.x, (float)v.y, (float)v.z}; }
@@ -769,7 +774,6 @@ RM_HD Vec3<float> cast_glass_impl(const FV& fv, const FrameParams<float>& fp, co
         }
     }
 }
-// The f64 instantiation as a function of its own (registers of the caller's loop are not held across the f64 code).
 template <class FV>
 RM_GLASS_FN Vec3<float> cast_glass64(const FV& fv, const FrameParams<float>& fp, const int x, const int y, const float t1,
                                      const int slot1, const int id1) {

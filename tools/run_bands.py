@@ -28,10 +28,11 @@ rgb8 = torch.zeros((h, w, 3), dtype=torch.uint8, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 _abi.check(L.rm_set_profiling(1))
 P = h // 32
-for stride in (1, 2, 4, 8):
-    for first in range(min(stride, 2)):
+strides = [int(x) for x in os.environ.get("BANDS_STRIDES", "1,2,4,8").split(",")]
+for stride in strides:
+    for first in range(stride if os.environ.get("BANDS_ALL") else min(stride, 2)):
         rows = (first, P, stride)
-        for flushed in (False, True):
+        for flushed in ((True,) if os.environ.get("BANDS_ALL") else (False, True)):
             for i in range(reps):
                 if flushed:
                     flush.fill_(0)
