@@ -465,6 +465,26 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize()
             brute_ms = e0.elapsed_time(e1)
+    walk = None
+    if accel:
+        # the work the hierarchy kernel itself does for this frame: node visits and leaf tests, counted by its counting
+        # instantiation (RmParams.accel = 2) once, outside the timed region -- the roofline numerator of accel workloads
+        p_cnt = renderer.params(fb, scene, (0, -1))
+        p_cnt.accel = 2
+        ws = (C.c_uint64 * 3)()
+        _abi.check(L.rm_scene_walk_stats(backend.handle, ws, 1))
+        smax.zero_()
+        _abi.check(L.rm_render_device(backend.handle, C.byref(p_cnt), scratch.data_ptr(), None, smax.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream))
+        _abi.check(L.rm_scene_walk_stats(backend.handle, ws, 1))
+        walk = {"node_visits": int(ws[0]), "sphere_tests": int(ws[1]), "plane_tests": int(ws[2])}
+        # per node visit: two slab tests = 2 x (6 sub + 6 mul + 5 min/max + ordering) ~ 50 flop, 64 bytes; leaf tests with
+        # SURVEY.md 8d's reject-stage weights (sphere 15, plane 5 + 9 + 6: d.n, distance, point; edge terms not counted);
+        # primary ray generation 22 per pixel.  Shading arithmetic is NOT included: a lower bound of the frame's work.
+        walk["flops"] = 50 * walk["node_visits"] + 15 * walk["sphere_tests"] + 20 * walk["plane_tests"] + 22 * rows * w
+        walk["node_bytes"] = 64 * walk["node_visits"]
+        walk["definition"] = ("50 flop + 64 B per node visit (two slab tests), 15 per sphere test, 20 per plane test (SURVEY.md 8d reject-stage "
+                              "weights), 22 per primary ray; shading not counted -- a lower bound")
     del scratch
 
     # ---- FP32 FMA peak, measured live (roofline denominator)
@@ -646,6 +666,14 @@ def run_ours(args):
         # frame is, not how busy the FP32 pipes are; null when the frame is too large for the instrumented kernel)
         ach_tflops = flops / world / (k1_ms_avg * 1e-3) / 1e12 if flops is not None else None
         issue_frac = (slots / world / (k1_ms_avg * 1e-3)) / (peak_t.value * 1e12 / 2.0) if slots is not None else None
+        brute_frac = ach_tflops / peak_t.value if ach_tflops is not None else None
+        if walk is not None:
+            # accel workloads: the fraction is quoted on the work the hierarchy kernel executes (its own counters), not on
+            # the brute-force traversal it replaces (kept as brute_force_equivalent_frac: how far beyond a perfect
+            # brute-force kernel the frame is)
+            ach_tflops = walk["flops"] / world / (k1_ms_avg * 1e-3) / 1e12
+            walk["node_gbs"] = walk["node_bytes"] / world / (k1_ms_avg * 1e-3) / 1e9
+            issue_frac = None
         # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture of the same workload
         traffic, traffic_src = None, None
         try:
@@ -698,8 +726,9 @@ def run_ours(args):
             "gpu_launches": tr.launches_per_frame() * args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak_t.value, "unit": "TFLOP/s",
                          "frac": ach_tflops / peak_t.value if ach_tflops is not None else None, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "render_fast_kernel<false, true> (hierarchy walk)" if accel else "render_fast_kernel<true, false>", "kernel_ms": k1_ms_avg,
-                         "work_definition": ("reference brute-force traversal (SURVEY.md 8d); the hierarchy skips most of it, so frac is a speed-up over a perfect brute-force kernel, not pipe utilisation" if accel else "reference traversal, resident primitives (SURVEY.md 8d)"),
+                         "kernel": "render_fast_kernel<false, 1, *> (hierarchy walk)" if accel else "render_fast_kernel<true, 0, *>", "kernel_ms": k1_ms_avg,
+                         "work_definition": (walk["definition"] if walk is not None else "reference traversal, resident primitives (SURVEY.md 8d)"),
+                         "walk": walk, "brute_force_equivalent_frac": brute_frac if accel else None,
                          "brute_force_ms_same_frame": brute_ms,
                          "prepare_kernel_ms": k0_ms_avg,
                          "kernel_includes": "K0 (prepare) + K1: render + exchange wait + fused K4, CUDA events around both launches" if tr.exchange == "peer" else "render only",

@@ -145,7 +145,9 @@ typedef struct RmParams {
                                  volume hierarchy over the hittable primitives (the bounding boxes the
                                  reference carries but never uses, shapes.rs:34-38,63-86).  Same tests per
                                  (ray, primitive), same winner: the FP32 frame is bit-identical, the work per
-                                 segment drops from O(n) to O(log n).  RM_FP32 production kernel only       */
+                                 segment drops from O(n) to O(log n).  RM_FP32 production kernel only.
+                                 2 = the same through the instantiation that also counts its work (node visits,
+                                 leaf tests: rm_scene_walk_stats) -- for measurement, a few percent slower       */
 } RmParams;
 
 /* Event counters (same definitions as SURVEY.md 8d) + timings of one call. */
@@ -322,6 +324,11 @@ int rm_kernel_times(int back, double* ms_prepare, double* ms_render, double* ms_
  * Ray segments of a frame = rendered pixels + this count: the figure the instrumented brute-force kernel (RmStats)
  * gives for scenes small enough to run through it.  Synchronises the device. */
 int rm_scene_query_count(RmScene scene, uint64_t* out_queries, int reset);
+/* Work of the accel = 2 renders of `scene` since the last reset: out[0] node visits (one visit = the boxes of both
+ * children: 64 bytes, two slab tests), out[1] sphere tests, out[2] plane tests (triangles and n-gons) at the leaves --
+ * the algorithmic work of a frame rendered through the hierarchy (bench.py's roofline for accel workloads).
+ * Synchronises the device. */
+int rm_scene_walk_stats(RmScene scene, uint64_t out[3], int reset);
 /* A walk of the hierarchy visits every node at most once; one that exceeds that budget (possible only with corrupt
  * hierarchy memory) gives up instead of hanging the GPU and raises a sticky flag.  Returns RM_OK while the flag is down,
  * RM_ERR_CUDA once it is up; out_words (optional): [0] flag, [1..6] origin and direction of the first such ray (float

@@ -226,6 +226,7 @@ extern "C" {
     pub fn rm_last_kernel_times(ms_prepare: *mut f64, ms_render: *mut f64) -> c_int;
     pub fn rm_kernel_times(back: c_int, ms_prepare: *mut f64, ms_render: *mut f64, ms_tonemap: *mut f64) -> c_int;
     pub fn rm_scene_query_count(scene: RmScene, out_queries: *mut u64, reset: c_int) -> c_int;
+    pub fn rm_scene_walk_stats(scene: RmScene, out: *mut u64, reset: c_int) -> c_int;
     pub fn rm_scene_accel_status(scene: RmScene, out_words: *mut i32) -> c_int;
     pub fn rm_measure_fp32_peak(out_tflops: *mut f64, out_ms: *mut f64) -> c_int;
 }

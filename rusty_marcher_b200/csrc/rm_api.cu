@@ -146,6 +146,15 @@ struct Context {
     Scratch mix;                      // rm_render_dispersive: the frame assembled from the three passes
     Scratch pack;                     // host delivery: the busy tiles of a frame, packed in schedule order
     std::vector<Arena> arena_cache;   // device allocations of freed scenes, for the next upload
+    // Host packs of the last few scenes by content (ingest): a caller that hands over the same scene
+    // again -- the reference's render() borrows &Scene for every frame -- gets its pack (sorted primitive classes, raster
+    // sources, the hierarchy: 0.1 to 0.2 s for 10^5 primitives) from here and only pays the hash and the upload.
+    struct PackEntry {
+        uint64_t hash = 0;
+        size_t bytes = 0;
+        std::shared_ptr<rm::PackedScene<float>> pack;
+    };
+    std::vector<PackEntry> pack_cache;
     Pinned h_upload;                  // pinned staging of a scene upload
     Pinned h_stage, h_order;          // host delivery: pinned staging of the packed tiles / of the tile schedule + counters
     std::unique_ptr<rm::HostPool> pool;
@@ -227,13 +236,74 @@ int order_scene_renders(SceneEntry& se, cudaStream_t stream) {
     return RM_OK;
 }
 
-template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
-    if (dp.ready) return RM_OK;
-    rm::PackedScene<R> ps;
+// 64-bit content hash of a byte range: four independent multiply-rotate lanes over 32-byte blocks (memory speed).
+uint64_t hash_bytes(const void* data, size_t n, uint64_t seed) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    uint64_t h[4] = {seed ^ 0x9E3779B97F4A7C15ull, seed ^ 0xC2B2AE3D27D4EB4Full, seed ^ 0x165667B19E3779F9ull, seed ^ 0x27D4EB2F165667C5ull};
+    auto mix = [](uint64_t a, uint64_t w) {
+        a ^= w * 0x9FB21C651E98DF25ull;
+        a = (a << 29) | (a >> 35);
+        return a * 0xD6E8FEB86659FD93ull;
+    };
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        uint64_t w[4];
+        std::memcpy(w, p + i, 32);
+        for (int k = 0; k < 4; k++) h[k] = mix(h[k], w[k]);
+    }
+    uint64_t tail[4] = {0, 0, 0, 0};
+    std::memcpy(tail, p + i, n - i);
+    for (int k = 0; k < 4; k++) h[k] = mix(h[k], tail[k] ^ (uint64_t)n);
+    uint64_t r = h[0] ^ (h[1] << 1 | h[1] >> 63) ^ (h[2] << 2 | h[2] >> 62) ^ (h[3] << 3 | h[3] >> 61);
+    r ^= r >> 32;
+    return r * 0x9FB21C651E98DF25ull;
+}
+uint64_t hash_scene(const rm::OwnedFlatScene& f, size_t& bytes) {
+    uint64_t h = 0x243F6A8885A308D3ull;
+    bytes = 0;
+    auto add = [&](const auto& v) {
+        const size_t n = v.size() * sizeof(v[0]);
+        h = hash_bytes(v.data(), n, h + v.size());
+        bytes += n;
+    };
+    add(f.shapes); add(f.spheres); add(f.polygons); add(f.polygon_vertices); add(f.objs); add(f.triangles);
+    add(f.triangle_reflectances); add(f.lights);
+    return h;
+}
+
+template <typename R> int pack_for(SceneEntry& se, std::shared_ptr<rm::PackedScene<R>>& out);
+template <> int pack_for<double>(SceneEntry& se, std::shared_ptr<rm::PackedScene<double>>& out) {
+    out = std::make_shared<rm::PackedScene<double>>();
     std::string err;
     RmFlatScene fs = se.flat.view();
-    int rc = rm::pack_scene<R>(fs, ps, err);
+    const int rc = rm::pack_scene<double>(fs, *out, err);
+    return rc == RM_OK ? RM_OK : fail(rc, err);
+}
+template <> int pack_for<float>(SceneEntry& se, std::shared_ptr<rm::PackedScene<float>>& out) {
+    size_t bytes = 0;
+    const uint64_t h = hash_scene(se.flat, bytes);
+    for (size_t i = 0; i < g.pack_cache.size(); i++)
+        if (g.pack_cache[i].hash == h && g.pack_cache[i].bytes == bytes) {
+            out = g.pack_cache[i].pack;
+            std::rotate(g.pack_cache.begin() + i, g.pack_cache.begin() + i + 1, g.pack_cache.end());   // most recent last
+            return RM_OK;
+        }
+    out = std::make_shared<rm::PackedScene<float>>();
+    std::string err;
+    RmFlatScene fs = se.flat.view();
+    const int rc = rm::pack_scene<float>(fs, *out, err);
     if (rc != RM_OK) return fail(rc, err);
+    if (g.pack_cache.size() >= 4) g.pack_cache.erase(g.pack_cache.begin());
+    g.pack_cache.push_back({h, bytes, out});
+    return RM_OK;
+}
+
+template <typename R> int ensure_pack(SceneEntry& se, DevicePack<R>& dp) {
+    if (dp.ready) return RM_OK;
+    std::shared_ptr<rm::PackedScene<R>> pack;
+    int rc = pack_for<R>(se, pack);
+    if (rc != RM_OK) return rc;
+    const rm::PackedScene<R>& ps = *pack;
     // layout of the arena: every array at a 256-byte aligned offset, the zero-initialised frame state at the end
     struct Piece { const void* src; size_t bytes, off; };
     std::vector<Piece> pieces;
@@ -770,6 +840,7 @@ void rm_shutdown(void) {
     g.scenes.clear();
     for (auto& a : g.arena_cache) cudaFree(a.p);
     g.arena_cache.clear();
+    g.pack_cache.clear();
     g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release(); g.mix.release(); g.pack.release();
     g.h_stage.release(); g.h_order.release(); g.h_upload.release();
     g.pool.reset();
@@ -1022,6 +1093,20 @@ int rm_scene_accel_status(RmScene scene, int32_t out_words[16]) {
     CK(cudaMemcpy(w, it->second.f32.ds.bvh.status, sizeof w, cudaMemcpyDeviceToHost));
     if (out_words) std::memcpy(out_words, w, sizeof w);
     if (w[0]) return fail(RM_ERR_CUDA, "a walk of the scene's hierarchy exceeded its node budget (corrupt hierarchy memory?): the frame is not valid");
+    return RM_OK;
+}
+
+int rm_scene_walk_stats(RmScene scene, uint64_t out[3], int reset) {
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");
+    auto it = g.scenes.find(scene);
+    if (it == g.scenes.end()) return fail(RM_ERR_INVALID_ARGUMENT, "unknown scene handle");
+    if (!it->second.f32.ready || !it->second.f32.ds.bvh.status) return fail(RM_ERR_INVALID_ARGUMENT, "scene has no FP32 pack");
+    CK(cudaDeviceSynchronize());
+    unsigned long long v[3] = {0, 0, 0};
+    CK(cudaMemcpy(v, it->second.f32.ds.bvh.status + 10, sizeof v, cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(it->second.f32.ds.bvh.status + 10, 0, sizeof v));
+    if (out) for (int i = 0; i < 3; i++) out[i] = v[i];
     return RM_OK;
 }
 

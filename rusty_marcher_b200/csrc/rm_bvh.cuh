@@ -78,10 +78,16 @@ RM_HD bool bvh_slab(const float lox, const float hix, const float loy, const flo
     return (t0 <= t1 * 1.000001f) & (t0 <= tcut);
 }
 
+// Work counters of the counting instantiation (RmParams.accel = 2): node visits (one visit = both children's boxes:
+// 64 bytes, two slab tests) and leaf entries tested, per thread.
+struct BvhCount {
+    unsigned nodes = 0, sph = 0, pln = 0;
+};
+
 // Depth-first walk, nearer child first.  `leaf(entry)` tests one primitive and returns true to end the walk
 // (any-hit); `cut()` is the current closest-hit cut-off (the walk skips boxes entered beyond it).
-template <class Leaf, class Cut>
-RM_HD bool bvh_walk(const BvhView& bv, const Vec3<float> o, const Vec3<float> d, Leaf&& leaf, Cut&& cut) {
+template <bool kCount = false, class Leaf, class Cut>
+RM_HD bool bvh_walk(const BvhView& bv, const Vec3<float> o, const Vec3<float> d, Leaf&& leaf, Cut&& cut, BvhCount* cnt = nullptr) {
     if (bv.n_nodes <= 0) return false;
     const BvhRay r = bvh_ray(o, d);
     int stack[kBvhStack];
@@ -103,6 +109,7 @@ RM_HD bool bvh_walk(const BvhView& bv, const Vec3<float> o, const Vec3<float> d,
                 return false;
             }
             RM_BVH_STAT(nodes);
+            if constexpr (kCount) cnt->nodes++;
             const R4<float>* n = bv.nodes + 4 * (size_t)cur;
             const R4<float> a = n[0], b = n[1], z = n[2], c = n[3];
             const float tc = cut();

@@ -58,7 +58,7 @@ RM_HD void prepare_raster(const double* __restrict__ src, const double cam[3], R
 
 // kBvh: scene queries walk the hierarchy of rm_bvh.cuh instead of every primitive (RmParams.accel).  The tests per
 // (ray, primitive) and the rule that picks the winner are the same code either way.
-template <bool kBvh> struct FastViewT {
+template <bool kBvh, bool kCount = false> struct FastViewT {
     // spheres
     const R4<float>* sph;
     const int* sph_id;
@@ -87,6 +87,7 @@ template <bool kBvh> struct FastViewT {
     // instrumented brute-force kernel (rm_scene_query_count)
     BvhView bvh;
     mutable unsigned n_queries = 0;
+    mutable BvhCount cnt;          // kCount: node visits and leaf tests of this thread's walks (rm_scene_walk_stats)
     // f64 sources for the refinement of winning hits on glass paths (cast_glass below): spheres {c, r^2}, fast-path
     // triangles (the prepare kernel's source records: n at [0..2], n.C at [3]), generic planes by slot {n, n.C}
     const double* sph64 = nullptr;
@@ -171,14 +172,14 @@ template <bool kBvh> struct FastViewT {
         if constexpr (kBvh) {
             h.dist = INFINITY;
             n_queries++;
-            bvh_walk(bvh, o, d,
-                     [&](const int e) {
-                         float t;
-                         int slot, id;
-                         if (leaf_hit(e, o, d, t, slot, id)) keep(h, hit, t, slot, id);
-                         return false;
-                     },
-                     [&]() { return h.dist * 1.00001f; });
+            bvh_walk<kCount>(bvh, o, d,
+                             [&](const int e) {
+                                 float t;
+                                 int slot, id;
+                                 if (leaf_hit(e, o, d, t, slot, id)) keep(h, hit, t, slot, id);
+                                 return false;
+                             },
+                             [&]() { return h.dist * 1.00001f; }, &cnt);
             return hit;
         }
         for (int i = 0; i < n_sph; i++) {
@@ -206,6 +207,7 @@ template <bool kBvh> struct FastViewT {
         const int i = e & 0x3fffffff;
         Counters<false> st;
         Cand<float> c;
+        if constexpr (kCount) (kind == BVH_SPHERE ? cnt.sph : cnt.pln)++;
         if (kind == BVH_TRI) {
             const R4<float>* g = tri_g + 4 * (size_t)i;
             if (!tri_hit(g, o, d, t)) return false;
@@ -227,13 +229,13 @@ template <bool kBvh> struct FastViewT {
     }
     RM_HD bool anyhit_bvh(const Vec3<float> o, const Vec3<float> d) const {
         n_queries++;
-        return bvh_walk(bvh, o, d,
-                        [&](const int e) {
-                            float t;
-                            int slot, id;
-                            return leaf_hit(e, o, d, t, slot, id);
-                        },
-                        []() { return INFINITY; });
+        return bvh_walk<kCount>(bvh, o, d,
+                                [&](const int e) {
+                                    float t;
+                                    int slot, id;
+                                    return leaf_hit(e, o, d, t, slot, id);
+                                },
+                                []() { return INFINITY; }, &cnt);
     }
 
     template <bool S> RM_HD bool anyhit(const Vec3<float> o, const Vec3<float> d, Counters<S>& st) const {
@@ -400,7 +402,6 @@ template <bool kBvh> struct FastViewT {
     }
 };
 using FastView = FastViewT<false>;
-using FastViewBvh = FastViewT<true>;
 
 // ---- primary visibility (stage A of the render kernel) ------------------------------------------
 // kPx horizontally adjacent pixels of one thread (the CUDA kernel uses 4; they share Y, so each affine
@@ -544,7 +545,8 @@ template <int kPx, class FV> RM_HD void primary_rest(PrimaryState<kPx>& ps, cons
 // triangle leaf runs primary_tri on the triangle's raster record, a sphere / n-gon leaf the general routine from the
 // camera, and the two partial winners are merged the way primary_rest merges them -- the same arithmetic per (pixel,
 // primitive) and the same (distance, id) order as the brute-force stage A, hence the same t / slot / id, bit for bit.
-template <int kPx> RM_HD void primary_bvh(PrimaryState<kPx>& ps, const FastViewBvh& fv, const FrameParams<float>& fp) {
+template <int kPx, bool kCount> RM_HD void primary_bvh(PrimaryState<kPx>& ps, const FastViewT<true, kCount>& fv, const FrameParams<float>& fp) {
+    using FastViewBvh = FastViewT<true, kCount>;
     const bool rest = fv.n_sph + fv.n_poly > 0;
     // One walk per pixel, the loop over the thread's pixels fully unrolled.  As a rolled loop (`#pragma unroll 1`, like
     // primary_rest) it went wrong on the B200 for scenes with deep hierarchies: ptxas keeps the trip counter of such a
@@ -570,11 +572,12 @@ template <int kPx> RM_HD void primary_bvh(PrimaryState<kPx>& ps, const FastViewB
         other.id = -1;
         bool hit_other = false;
         float tcut = INFINITY;
-        bvh_walk(fv.bvh, fp.camera, d,
+        bvh_walk<kCount>(fv.bvh, fp.camera, d,
                  [&](const int e) {
                      const unsigned kind = (unsigned)e >> 30;
                      const int i = e & 0x3fffffff;
                      if (kind == BVH_TRI) {
+                         if constexpr (kCount) fv.cnt.pln++;
                          const R4<float>* q = fv.tri_r + 4 * (size_t)i;
                          primary_tri<1>(p1, q[0], q[1], q[2], q[3], fv.n_sph + i);
                          if (p1.slot[0] >= 0) tcut = fminf(tcut, p1.t[0] * len);
@@ -588,7 +591,7 @@ template <int kPx> RM_HD void primary_bvh(PrimaryState<kPx>& ps, const FastViewB
                      }
                      return false;
                  },
-                 [&]() { return tcut * 1.00001f; });
+                 [&]() { return tcut * 1.00001f; }, &fv.cnt);
         float t_new = p1.t[0];
         int slot_new = p1.slot[0], id_new = p1.id[0];
         if (rest) {                                            // primary_rest's merge and its round trip through unit distances

@@ -341,13 +341,14 @@ constexpr int kWarpQueue = kFastTile * 4 + 32;                  // one strip of 
 template <int kPx> struct PxTag { static constexpr int value = kPx; };
 // kBvh (RmParams.accel): scene queries walk the hierarchy of rm_bvh.cuh (read through the read-only path; the nodes near
 // the root stay in L1) instead of every primitive; stage A then handles a thread's pixels one after the other.
-template <bool kSmem, bool kBvh, int kGlass>
+template <bool kSmem, int kBvhMode, int kGlass>
 __global__ void RM_K1_BOUNDS
 render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, const int cull, const int tiles_x,
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
                    float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order, const int* __restrict__ order2,
                    unsigned char* rgb8, const PeerLink link, unsigned char* rgb8_out, const int normalise,
                    unsigned char* rgb8_next, const int stage_mat) {
+    constexpr bool kBvh = kBvhMode != 0, kCount = kBvhMode == 2;    // 2: the counting instantiation (RmParams.accel = 2)
     const int zero_foreign = rgb8_next != nullptr;
     extern __shared__ __align__(32) unsigned char smem_raw[];
     __shared__ int cta_max;
@@ -395,7 +396,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         tri_r = reinterpret_cast<const R4<float>*>(smem_raw + L.bytes);
     }
     __syncthreads();
-    FastViewT<kBvh> fv;
+    FastViewT<kBvh, kCount> fv;
     fv.bvh = ds.bvh;
     fv.sph = reinterpret_cast<const R4<float>*>(base + L.off_sph);
     fv.sph_id = reinterpret_cast<const int*>(base + L.off_sph_id);
@@ -514,7 +515,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                 PrimaryState<kPx> ps;
                 primary_begin<kPx>(ps, fp, x0 + lx, ys + ly);
                 if constexpr (kBvh) {
-                    primary_bvh<kPx>(ps, fv, fp);
+                    primary_bvh<kPx, kCount>(ps, fv, fp);
                 } else {
                     // the strip: pixels [x0, x0 + 31] x [ys, ys + 3]
                     const float Xa = pixel_X(fp, x0), Xb = pixel_X(fp, x0 + kFastTile - 1);
@@ -598,6 +599,21 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     if constexpr (kBvh) {                                       // ctr[6..7]: u64 count of secondary + shadow queries, kept across frames
         const unsigned q = __reduce_add_sync(0xffffffffu, fv.n_queries);
         if (lane == 0 && q) atomicAdd(reinterpret_cast<unsigned long long*>(ctr + 6), (unsigned long long)q);
+    }
+    if constexpr (kCount) {                                     // status words [10..15]: three u64 (node visits, sphere tests, plane tests)
+        unsigned long long* w = reinterpret_cast<unsigned long long*>(ds.bvh.status + 10);
+        // (per-thread 32-bit counts summed in 64 bits: a lane of a heavy frame stays far below 2^32)
+        unsigned long long a = fv.cnt.nodes, b = fv.cnt.sph, c = fv.cnt.pln;
+        for (int off = 16; off > 0; off >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, off);
+            b += __shfl_xor_sync(0xffffffffu, b, off);
+            c += __shfl_xor_sync(0xffffffffu, c, off);
+        }
+        if (lane == 0) {
+            atomicAdd(w, a);
+            atomicAdd(w + 1, b);
+            atomicAdd(w + 2, c);
+        }
     }
     // values are >= 0, so the integer order of the bit patterns is the float order
     const int wm = __reduce_max_sync(0xffffffffu, __float_as_int(m));
@@ -889,11 +905,11 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
         cudaFuncAttributes fa;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
-        if ((e = cudaFuncGetAttributes(&fa, render_fast_kernel<true, false, GLASS_F64>)) != cudaSuccess) return e;
+        if ((e = cudaFuncGetAttributes(&fa, render_fast_kernel<true, 0, GLASS_F64>)) != cudaSuccess) return e;
         dyn_limit = std::min(kSmemLimit, optin - (int)fa.sharedSizeBytes - 1024);
-        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false, GLASS_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false, GLASS_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, false, GLASS_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, 0, GLASS_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, 0, GLASS_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(render_fast_kernel<true, 0, GLASS_F64>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     }
     const size_t smem_geo = (size_t)ds.lay.bytes + (size_t)ds.lay.n_tri * 64;
@@ -933,12 +949,13 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     // the reflect / refract recursion only where a frame can need it, its f64 ray geometry only where FP32 would not do
     const int glass = glass_mode(ds.lay.any_glass != 0, ds.lay.n_sph, ds.lay.coord_max, ds.lay.r_min, camera);
     if (ex) ex->glass_mode = glass;
-    using K1 = decltype(&render_fast_kernel<true, false, GLASS_NONE>);
-    static const K1 table[3][3] = {
-        {render_fast_kernel<true, false, GLASS_NONE>, render_fast_kernel<true, false, GLASS_F32>, render_fast_kernel<true, false, GLASS_F64>},
-        {render_fast_kernel<false, false, GLASS_NONE>, render_fast_kernel<false, false, GLASS_F32>, render_fast_kernel<false, false, GLASS_F64>},
-        {render_fast_kernel<false, true, GLASS_NONE>, render_fast_kernel<false, true, GLASS_F32>, render_fast_kernel<false, true, GLASS_F64>}};
-    const K1 k = table[bvh ? 2 : use_smem ? 0 : 1][glass];
+    using K1 = decltype(&render_fast_kernel<true, 0, GLASS_NONE>);
+    static const K1 table[4][3] = {
+        {render_fast_kernel<true, 0, GLASS_NONE>, render_fast_kernel<true, 0, GLASS_F32>, render_fast_kernel<true, 0, GLASS_F64>},
+        {render_fast_kernel<false, 0, GLASS_NONE>, render_fast_kernel<false, 0, GLASS_F32>, render_fast_kernel<false, 0, GLASS_F64>},
+        {render_fast_kernel<false, 1, GLASS_NONE>, render_fast_kernel<false, 1, GLASS_F32>, render_fast_kernel<false, 1, GLASS_F64>},
+        {render_fast_kernel<false, 2, GLASS_NONE>, render_fast_kernel<false, 2, GLASS_F32>, render_fast_kernel<false, 2, GLASS_F64>}};
+    const K1 k = table[bvh ? (fp.accel == 2 ? 3 : 2) : use_smem ? 0 : 1][glass];
     cfg.dynamicSmemBytes = use_smem ? smem : 0;
     int occ = 1;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kFastBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;

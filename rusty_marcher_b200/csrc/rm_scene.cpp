@@ -440,7 +440,7 @@ template <typename R> FrameParams<R> make_frame_params(const RmParams& p) {
     fp.camera = {(R)p.camera[0], (R)p.camera[1], (R)p.camera[2]};
     fp.background = (R)p.background;
     fp.max_depth = p.max_depth < 0 ? 0 : (p.max_depth > kMaxDepth ? kMaxDepth : p.max_depth);
-    fp.accel = p.accel != 0 ? 1 : 0;
+    fp.accel = p.accel == 2 ? 2 : (p.accel != 0 ? 1 : 0);     // 2: the hierarchy kernel that also counts its work
     for (int a = 0; a < 3; a++) fp.cam64[a] = p.camera[a];
     fp.w64 = width;
     fp.h64 = height;

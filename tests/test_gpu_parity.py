@@ -266,6 +266,36 @@ def test_stress_scene_against_the_oracle(rm_gpu):
     assert g64["counters"] == ref["counters"]
 
 
+def load_stress_golden():
+    """The oracle's frame of configs[4]'s full scene (tests/golden/make_stress_golden.py: 86 s of CPU here)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stress_full_384x224.npz"))
+    ref = {"rgb": z["rgb"].astype(np.float64), "prim_id": z["prim_id"], "fragile": z["fragile"],
+           "counters": dict(zip(O.COUNTER_FIELDS, (int(v) for v in z["counters"])))}
+    return ref, int(z["depth"]), float(z["rgb_max"])
+
+
+def test_full_stress_scene_against_the_oracles_golden_frame(rm_gpu):
+    """BASELINE.json configs[4]'s scene at FULL size -- 4096 spheres + 100,352 triangles, depth cap 6 -- through the hierarchy,
+    against the oracle's frame of the same scene (a committed fixture: the reference's brute force needs 10^5 primitive
+    tests per segment).  North-star criteria; the FP64 validation kernel (brute force, a few seconds on the GPU) must
+    reproduce the oracle's ids and counters exactly."""
+    ref, depth, ref_max = load_stress_golden()
+    h, w = ref["prim_id"].shape
+    assert ref["counters"]["glass_hits"] > 10000 and ref["counters"]["plane_tests"] > 1e10
+    scene = workloads.scene("stress")
+    assert scene.num_prims == 104448
+    got = gpu_render(rm_gpu, scene, w, h, "f32", depth=depth, accel=True)
+    rep = parity.check_fp32(got, ref, h)
+    print("full stress scene, hierarchy:", rep)
+    assert abs(got["max"] - ref_max) <= 1e-4 * ref_max
+    g64 = gpu_render(rm_gpu, scene, w, h, "f64", depth=depth, cull=False, counters=True)
+    assert np.array_equal(g64["prim_id"], ref["prim_id"])
+    assert g64["counters"] == ref["counters"]
+    err = np.abs(g64["rgb"] - ref["rgb"]) / np.maximum(np.abs(ref["rgb"]), 1e-30)
+    assert err.max() < 1e-6                                    # the fixture stores the oracle's colours as float32
+
+
 @pytest.mark.parametrize("cull", [False, True])
 def test_many_ngons_against_the_oracle(rm_gpu, cull):
     """320 convex n-gons (n = 4 ... 8, one in ten wound clockwise = never hittable, a fifth glass-like) + 48 spheres, depth
