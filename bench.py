@@ -5,10 +5,13 @@
 
 Workload (config.workload): the cornell_box mesh at 3840x2160, fov 1.5, camera origin, depth cap 3
 -- the configuration BASELINE.json's metric and north_star target are quoted on (configs[2]; the
-cornell_box2.obj it names does not exist in the reference).  A step is one frame:
-K1 render (float framebuffer + fused channel max) and K4 normalise+quantise to RGB8; with N > 1 GPUs
-the frame's 67 patch rows are split into contiguous row tiles, one process per GPU, with a one-float
-max all-reduce and an RGB8 gather to rank 0 over NCCL (scaling "strong": the frame is fixed).
+cornell_box2.obj it names does not exist in the reference).  A step is one frame
+through rm_render_frame: K0 (per-frame records + tile schedule) and K1 (render, channel max, the
+exchange over NVLink peer memory, fused normalise + quantise), one CUDA graph launch; with N > 1
+GPUs the frame's 67 patch rows are dealt round-robin, one process per GPU (scaling "strong").
+Every run also proves that the frame the ranks assemble IS the single-GPU frame (frame_matches_n1),
+times the end-to-end call through host buffers (e2e: at N > 1 into ONE frame shared by the ranks)
+and adds a short `heavy` leg on BASELINE.json's configs[4] at full size through the hierarchy.
 
 `--impl reference` times the reference's own CPU algorithm (the f64 oracle restatement of the Rayon
 patch loop -- the Rust original cannot be built here) on the host cores, same workload and metric.

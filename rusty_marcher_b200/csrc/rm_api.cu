@@ -6,6 +6,9 @@
 // nothing.  There is no CPU fallback anywhere in this file: every entry point either runs the
 // CUDA kernels or returns an error.
 #include <cuda_runtime.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <chrono>
@@ -579,6 +582,26 @@ struct RowSink {
     char* row(int y) const { return rows ? static_cast<char*>(rows[y]) : base + (size_t)y * row_bytes; }
 };
 
+// Zero-fill with non-temporal stores: the black part of a frame is written once and not read by these threads, and a
+// plain memset of a row segment below the C library's streaming threshold first reads every line it is about to overwrite
+// (read-for-ownership) -- twice the memory traffic on a pass that is bound by exactly that.
+inline void zero_stream(char* p, size_t n) {
+#if defined(__x86_64__)
+    while (n && (reinterpret_cast<uintptr_t>(p) & 15)) { *p++ = 0; n--; }
+    const __m128i z = _mm_setzero_si128();
+    for (; n >= 64; n -= 64, p += 64) {
+        _mm_stream_si128(reinterpret_cast<__m128i*>(p), z);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(p + 16), z);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(p + 32), z);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(p + 48), z);
+    }
+    for (; n >= 16; n -= 16, p += 16) _mm_stream_si128(reinterpret_cast<__m128i*>(p), z);
+    while (n) { *p++ = 0; n--; }
+#else
+    std::memset(p, 0, n);
+#endif
+}
+
 inline void put_values(char* dst, const float* src, int n, int elem) {
     if (elem == 4) {
         std::memcpy(dst, src, (size_t)n * 4);
@@ -720,9 +743,12 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
                     if (nb[tx] || (delta && !ob[tx])) { tx++; continue; }
                     int e = tx + 1;
                     while (e < tiles_x && !nb[e] && !(delta && !ob[e])) e++;
-                    std::memset(row + (size_t)tx * 32 * px_bytes, 0, (size_t)(e - tx) * 32 * px_bytes);
+                    zero_stream(row + (size_t)tx * 32 * px_bytes, (size_t)(e - tx) * 32 * px_bytes);
                     tx = e;
                 }
+#if defined(__x86_64__)
+                _mm_sfence();
+#endif
             });
         for (int b = 0; b < fp.n_bands; b++) {
             prev->known[band0 + b * band_step] = 1;
@@ -745,7 +771,7 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
                         put_values(sink.row(fp.row_begin + ty * fp.row_step + r) + (size_t)tx * 32 * px_bytes,
                                    stage + (size_t)t * 3072 + r * 96, 96, elem);
                     }
-            });
+            }, 8);
             done = c1;
         }
         t_scatter = us_now();
@@ -932,20 +958,36 @@ int rm_render(RmScene scene, const RmParams* params, float* out_rgb, int32_t* ou
     return render_host_impl<float>(scene, params, out_rgb, out_prim_id, out_rgb8, stats);
 }
 
+namespace {
+// Row pointers that turn out to be one contiguous block (a frame kept as one allocation) are treated as such: rows can
+// then be copied from the device straight into the caller's memory when nothing has to be widened or scattered.
+RowSink sink_of_rows(void* const* rows, const RmParams* params, int elem) {
+    RowSink sink;
+    sink.rows = rows;
+    sink.elem = elem;
+    if (params && params->width > 0 && params->height > 0) {
+        const size_t row_bytes = (size_t)params->width * 3 * elem;
+        bool contiguous = true;
+        for (int y = 1; y < params->height && contiguous; y++)
+            contiguous = static_cast<const char*>(rows[y]) == static_cast<const char*>(rows[y - 1]) + row_bytes;
+        if (contiguous) {
+            sink.rows = nullptr;
+            sink.base = static_cast<char*>(rows[0]);
+            sink.row_bytes = row_bytes;
+        }
+    }
+    return sink;
+}
+}  // namespace
+
 int rm_render_rows_f32(RmScene scene, const RmParams* params, float* const* rows, int flags, RmStats* stats) {
     if (!rows) return fail(RM_ERR_INVALID_ARGUMENT, "rows is null");
-    RowSink sink;
-    sink.rows = reinterpret_cast<void* const*>(rows);
-    sink.elem = 4;
-    return render_rows_impl(scene, params, sink, flags, stats);
+    return render_rows_impl(scene, params, sink_of_rows(reinterpret_cast<void* const*>(rows), params, 4), flags, stats);
 }
 
 int rm_render_rows_f64(RmScene scene, const RmParams* params, double* const* rows, int flags, RmStats* stats) {
     if (!rows) return fail(RM_ERR_INVALID_ARGUMENT, "rows is null");
-    RowSink sink;
-    sink.rows = reinterpret_cast<void* const*>(rows);
-    sink.elem = 8;
-    return render_rows_impl(scene, params, sink, flags, stats);
+    return render_rows_impl(scene, params, sink_of_rows(reinterpret_cast<void* const*>(rows), params, 8), flags, stats);
 }
 
 int rm_render_f64(RmScene scene, const RmParams* params, double* out_rgb, int32_t* out_prim_id, uint8_t* out_rgb8, RmStats* stats) {

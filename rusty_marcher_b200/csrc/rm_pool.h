@@ -21,7 +21,7 @@ class HostPool {
 public:
     explicit HostPool(int n_threads) {
         const int n = n_threads < 1 ? 1 : n_threads;
-        for (int i = 0; i + 1 < n; i++) workers_.emplace_back([this] { loop(); });   // the caller is the n-th thread
+        for (int i = 0; i + 1 < n; i++) workers_.emplace_back([this, i] { loop(i + 1); });   // the caller is thread 0
     }
     ~HostPool() {
         {
@@ -35,11 +35,14 @@ public:
     }
     int threads() const { return (int)workers_.size() + 1; }
 
-    // fn(i) for every i in [0, n), on all threads including the caller's; returns when every item is done.
+    // fn(i) for every i in [0, n), on the caller's thread and the workers (at most `limit` threads in all: a light job --
+    // scattering a few megabytes -- gains nothing beyond eight, and threads that are not needed should sleep: on a box
+    // whose every core spins, the caller's own next steps wait for a core); returns when every item is done.
     // Not re-entrant (one frame at a time: callers hold the library mutex).
-    void run(int n, const std::function<void(int)>& fn) {
+    void run(int n, const std::function<void(int)>& fn, int limit = 1 << 30) {
         if (n <= 0) return;
-        if (workers_.empty() || n == 1) {
+        limit_ = limit;
+        if (workers_.empty() || n == 1 || limit <= 1) {
             for (int i = 0; i < n; i++) fn(i);
             return;
         }
@@ -77,17 +80,21 @@ private:
             (*fn_)(i);
         }
     }
-    void loop() {
+    void loop(const int id) {
         unsigned long long seen = 0;
+        bool worked = false;
         for (;;) {
-            // A frame hands the pool several jobs microseconds apart (clear, then scatter chunk by chunk): stay awake for a
-            // while after a job -- a sleeping thread takes tens of microseconds to come back -- then sleep until the next frame.
-            const auto t0 = std::chrono::steady_clock::now();
-            for (int spins = 0; hot_.load(std::memory_order_acquire) == seen; spins++) {
+            // A frame hands the pool several jobs microseconds apart (clear, then scatter chunk by chunk): a thread that
+            // worked on the last one stays awake for a while -- a sleeping thread takes tens of microseconds to come back --
+            // then sleeps until the next frame.
+            if (worked) {
+                const auto t0 = std::chrono::steady_clock::now();
+                for (int spins = 0; hot_.load(std::memory_order_acquire) == seen; spins++) {
 #if defined(__x86_64__)
-                __builtin_ia32_pause();
+                    __builtin_ia32_pause();
 #endif
-                if ((spins & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+                    if ((spins & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+                }
             }
             {
                 std::unique_lock<std::mutex> l(mu_);
@@ -95,7 +102,8 @@ private:
                 seen = epoch_;
                 if (stop_) return;
             }
-            work();
+            worked = id < limit_;
+            if (worked) work();
             if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
                 std::lock_guard<std::mutex> l(mu_);
                 done_cv_.notify_one();
@@ -107,7 +115,7 @@ private:
     std::mutex mu_;
     std::condition_variable cv_, done_cv_;
     const std::function<void(int)>* fn_ = nullptr;
-    int n_ = 0;
+    int n_ = 0, limit_ = 1 << 30;
     std::atomic<int> next_{0}, pending_{0};
     std::atomic<unsigned long long> hot_{0};   // copy of epoch_ the workers poll without the mutex
     unsigned long long epoch_ = 0;

@@ -96,6 +96,37 @@ def test_hierarchy_changes_no_pixel(rm_gpu, case, cull):
     assert L.rm_scene_accel_status(scene.device_handle(), words) == 0 and words[0] == 0
 
 
+def test_hierarchy_walk_statistics(rm_gpu):
+    """RmParams.accel = 2: the counting instantiation renders the very same frame and reports the walks' work -- node
+    visits and leaf tests -- which must agree with the counts of the host emulation of the same kernel code."""
+    from tests.emu import emu
+    w, h, depth = 640, 352, 6
+    scene = workloads.build_scene(workloads.describe("stress", n_spheres=512, grid=32))
+    a = gpu_render(rm_gpu, scene, w, h, "f32", depth=depth, accel=True)
+    L = _abi.load()
+    ws = (C.c_uint64 * 3)()
+    _abi.check(L.rm_scene_walk_stats(scene.device_handle(), ws, 1))
+    r = rm_gpu.create_renderer(1.5, h, w)
+    r.max_depth, r.accel = depth, True
+    fb = rm_gpu.create_frame_buffer(w, h, dtype=np.float32)
+    ids = np.full((h, w), -1, dtype=np.int32)
+    p = r.params(fb, scene)
+    p.accel = 2
+    st = _abi.RmStats()
+    _abi.check(L.rm_render(scene.device_handle(), C.byref(p), fb.buffer.ctypes.data, ids.ctypes.data, None, C.byref(st)))
+    _abi.check(L.rm_scene_walk_stats(scene.device_handle(), ws, 1))
+    assert np.array_equal(fb.buffer, a["rgb"]) and np.array_equal(ids, a["prim_id"])
+    nodes, sph, pln = int(ws[0]), int(ws[1]), int(ws[2])
+    assert nodes > 10 * w * h and sph > 0 and pln > 0
+    emu.lib().emu_walk_stats((C.c_ulonglong * 3)())
+    emu.render(scene, w, h, "fast", max_depth=depth, accel=True)
+    ew = (C.c_ulonglong * 3)()
+    emu.lib().emu_walk_stats(ew)
+    assert abs(nodes - int(ew[1])) <= 0.01 * nodes and abs(sph + pln - int(ew[2])) <= 0.01 * (sph + pln), (nodes, sph, pln, list(ew))
+    _abi.check(L.rm_scene_walk_stats(scene.device_handle(), ws, 0))
+    assert int(ws[0]) == 0
+
+
 def test_hierarchy_on_the_stress_scene(rm_gpu):
     """The bench's stress scene (1024 spheres + 8192 triangles, depth cap 6) at 1280x704, camera off the origin: hierarchy
     against brute force bit for bit, whole frame and interleaved bands, host call and frame-level call."""

@@ -51,14 +51,31 @@ def both():
     render()
 
 
+import torch  # noqa: E402
+
+
+def upload_sync():
+    scene.release()
+    scene.device_handle()
+    torch.cuda.synchronize()
+
+
+def mark(msg):
+    sys.stderr.write("== %s\n" % msg)
+    sys.stderr.flush()
+
+
 p = r.params(fb, scene)
+print("upload + device synchronise           median %.3f  min %.3f ms" % timed(upload_sync))
 st = _abi.RmStats()
 print("upload (release + device_handle)      median %.3f  min %.3f ms" % timed(upload))
 print("render, scene resident, fresh         median %.3f  min %.3f ms" % timed(render))
 print("upload + render (bench e2e)           median %.3f  min %.3f ms" % timed(both))
 print("bare rm_render (ctypes), fresh        median %.3f  min %.3f ms" % timed(lambda: L.rm_render(scene.device_handle(), C.byref(p), fb.buffer.ctypes.data, None, None, C.byref(st))))
 r.retained = True
+mark("retained resident")
 print("render, scene resident, retained      median %.3f  min %.3f ms" % timed(render))
+mark("retained with upload")
 print("upload + render, retained             median %.3f  min %.3f ms" % timed(both))
 fb64 = rm.create_frame_buffer(w, h, dtype=np.float64)
 r.retained = False
@@ -70,6 +87,7 @@ def render64():
     sys.stdout = real
 
 
+mark("f64")
 print("f64 rows, fresh                       median %.3f  min %.3f ms" % timed(render64, 30))
 r.retained = True
 print("f64 rows, retained                    median %.3f  min %.3f ms" % timed(render64, 30))
