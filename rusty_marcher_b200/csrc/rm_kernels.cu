@@ -347,7 +347,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
                    float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order, const int* __restrict__ order2,
                    unsigned char* rgb8, const PeerLink link, unsigned char* rgb8_out, const int normalise,
-                   unsigned char* rgb8_next, const int stage_mat) {
+                   unsigned char* rgb8_next, const int stage_mat, GlassNode* __restrict__ tree) {
     constexpr bool kBvh = kBvhMode != 0, kCount = kBvhMode == 2;    // 2: the counting instantiation (RmParams.accel = 2)
     const int zero_foreign = rgb8_next != nullptr;
     extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -436,15 +436,99 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     int final_take = 0;
     float m = 0.f;
 
-    auto shade_entry = [&](const float4 e) {
+    auto shade_entry = [&](const float4 e) {                    // (opaque-only scenes; the glass modes shade in pooled rounds, below)
         const unsigned xy = __float_as_uint(e.w);
         const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
-        const Vec3<float> c = fast_shade<kGlass>(fv, fp, x, y, e.x, __float_as_int(e.y), __float_as_int(e.z));
+        const Vec3<float> c = fast_shade<GLASS_NONE>(fv, fp, x, y, e.x, __float_as_int(e.y), __float_as_int(e.z));
         float* dst = rgb + 3 * ((size_t)(y - fp.buf_row0) * fp.width + x);
         dst[0] = c.x;
         dst[1] = c.y;
         dst[2] = c.z;
         m = fmaxf(m, fmaxf(fmaxf(c.x, c.y), c.z));
+    };
+
+    // ---- stage B for the glass modes: a round's recursion trees processed NODE BY NODE by the whole warp.
+    // shade_entry would run a pixel's tree depth-first in its lane -- up to 63 closest-hit and 126 any-hit queries in a row
+    // while the lanes whose pixels are opaque (one node) wait: 19.6 of 32 lanes alive on the stress frame, and a chain of
+    // ~1 ms that no split of the frame over more GPUs shortens (and is not instantiated in these kernels any more).  Here a lane that spawns two children keeps one and puts
+    // the other into the warp's pool (shared memory; a private stack takes what does not fit); a lane without a task takes
+    // one from the pool.  Every iteration each lane with a task processes ONE node (glass_node: query, direct lighting,
+    // optics) and files the result under (pixel, heap index) in the warp's scratch (L1/L2-resident global memory); when
+    // nothing is left each pixel's owner folds its records in the recursion's order (glass_eval), so the pixel is
+    // bit-identical to the depth-first result however the nodes were dealt.
+    constexpr int kGlassPool = 32;
+    using GT = GlassTask<typename std::conditional<kGlass == GLASS_F64, double, float>::type>;
+    auto shade_round_pooled = [&](const float4* src, const int take) {
+        using G = typename std::conditional<kGlass == GLASS_F64, double, float>::type;
+        __shared__ GT gpool[kFastBlock / 32][kGlassPool];
+        GT* const mypool = gpool[warp];
+        GlassNode* const rec0 = tree + (size_t)(blockIdx.x * (kFastBlock / 32) + warp) * 32 * kTreeNodes;
+        const bool own = lane < take;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        int x = 0, y = 0;
+        float t1 = 0.f;
+        GT task, priv[kTreeDepth + 1];
+        int n_priv = 0;
+        bool have = false;
+        if (own) {
+            e = src[lane];
+            const unsigned xy = __float_as_uint(e.w);
+            x = (int)(xy & 0xffffu);
+            y = (int)(xy >> 16);
+            const float X = pixel_X(fp, x), Y = pixel_Y(fp, y);
+            const float len2 = fmaf(X, X, fmaf(Y, Y, 1.f));
+            t1 = e.x * (len2 * fast_rsqrt(len2));               // stage A reports t in units of |D|
+            glass_primary_ray<G>(fp, x, y, task.o, task.d);
+            task.pix = lane;
+            task.node = 1;
+            task.level = 1;
+            have = true;
+        }
+        int avail = 0;                                          // tasks in the pool (warp-uniform)
+        for (int it = 0; it < 32 * kTreeNodes + 8; it++) {     // (every iteration retires at least one node: a bound, not a schedule)
+            if (!have && n_priv > 0) {
+                task = priv[--n_priv];
+                have = true;
+            }
+            const unsigned need = __ballot_sync(0xffffffffu, !have);
+            if (avail > 0 && need) {
+                const int r = __popc(need & lane_lt);
+                if (!have && r < avail) {
+                    task = mypool[avail - 1 - r];
+                    have = true;
+                }
+                avail = max(avail - __popc(need), 0);
+            }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, have)) break;
+            int spawned = 0;
+            GT a, b;
+            if (have) {
+                GlassNode nd;
+                spawned = glass_node<G>(fv, fp, task, t1, __float_as_int(e.y), __float_as_int(e.z), nd, a, b);
+                rec0[task.pix * kTreeNodes + task.node] = nd;
+            }
+            const bool push = spawned == 3;
+            const unsigned pm = __ballot_sync(0xffffffffu, push);
+            if (push) {
+                const int r = avail + __popc(pm & lane_lt);
+                if (r < kGlassPool) mypool[r] = b;
+                else priv[n_priv++] = b;
+            }
+            avail = min(avail + __popc(pm), kGlassPool);
+            have = spawned != 0;
+            if (spawned & 1) task = a;
+            else if (spawned & 2) task = b;
+            __syncwarp();
+        }
+        if (own) {
+            const Vec3<float> c = glass_eval(rec0 + lane * kTreeNodes, fp.background, fp.max_depth);
+            float* dst = rgb + 3 * ((size_t)(y - fp.buf_row0) * fp.width + x);
+            dst[0] = c.x;
+            dst[1] = c.y;
+            dst[2] = c.z;
+            m = fmaxf(m, fmaxf(fmaxf(c.x, c.y), c.z));
+        }
     };
 
     // Zero-fill (renderer.rs:300-306: a primary miss is black) of a 32-pixel wide strip of kStripRows rows by one warp,
@@ -587,7 +671,11 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                 src = wq + qn;
                 take = 32;
             }
-            if (lane < take) shade_entry(src[lane]);
+            if constexpr (kGlass != GLASS_NONE) {
+                shade_round_pooled(src, take);
+            } else {
+                if (lane < take) shade_entry(src[lane]);
+            }
             if (phase == 3) break;
         }
         if (phase == 3) break;
@@ -960,14 +1048,21 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     int occ = 1;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kFastBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;
     cfg.gridDim = dim3(std::min(n_tiles, sm_count * std::max(occ, 1)));
+    // scratch of the pooled recursion: 32 pixels x kTreeNodes records per warp of the grid, every slot invalid between rounds
+    GlassNode* tree = nullptr;
+    if (glass != GLASS_NONE) {
+        if (!ex || !ex->tree || ex->tree_bytes < (size_t)cfg.gridDim.x * (kFastBlock / 32) * 32 * kTreeNodes * sizeof(GlassNode))
+            return cudaErrorInvalidValue;                       // (rm_api.cu provides it for every scene that can need it)
+        tree = static_cast<GlassNode*>(ex->tree);
+    }
     e = cudaLaunchKernelEx(&cfg, k, ds, fp, cull_i, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order2, rgb8,
-                           link, rgb8_out, normalise, rgb8_next, stage_mat);
+                           link, rgb8_out, normalise, rgb8_next, stage_mat, tree);
     if (e != cudaSuccess && want_coop) {                        // not available in this combination: the plain persistent launch
         cudaGetLastError();
         coop = 0;
         cfg.numAttrs = 1;
         e = cudaLaunchKernelEx(&cfg, k, ds, fp, cull_i, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order2, rgb8,
-                               link, rgb8_out, normalise, rgb8_next, stage_mat);
+                               link, rgb8_out, normalise, rgb8_next, stage_mat, tree);
     }
     if (e != cudaSuccess) return e;
     if (launches) (*launches)++;
@@ -991,7 +1086,9 @@ cudaError_t launch_render(const DeviceScene<R>& ds, const FrameParams<R>& fp, bo
         return cudaSuccess;
     }
     const dim3 grid((fp.width + kTileW - 1) / kTileW, (rows + kTileH - 1) / kTileH);
-    if (sizeof(R) == 4 && !counters && camera && ds.tri_r) return launch_fast(ds, fp, cull, rgb, prim_id, dmax, stream, camera, launches, ex);
+    // (a depth cap of 0 makes every pixel the background, hit or not -- renderer.rs:262-264 with n_recursion = 1: the generic
+    // kernel follows cast_ray literally, the production kernel assumes at least the primary level)
+    if (sizeof(R) == 4 && !counters && camera && ds.tri_r && fp.max_depth >= 1) return launch_fast(ds, fp, cull, rgb, prim_id, dmax, stream, camera, launches, ex);
     if (ex && ex->ev_begin) cudaEventRecord(ex->ev_begin, stream);
     if (ex && ex->ev_prepared) cudaEventRecord(ex->ev_prepared, stream);
     if (launches) (*launches)++;
