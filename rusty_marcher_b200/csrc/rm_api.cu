@@ -428,13 +428,10 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
     rm::RenderExtras ex;
     ex.rgb8_zero = d_rgb8_zero;
     if (sizeof(R) == 4 && (dp.ds.lay.any_glass || dp.ds.lay.n_sph > 0)) {
-        // node records of the pooled recursion: 388 MB on a B200 (148 SMs x 2 CTAs x 8 warps x 32 pixels x 256 slots x 20
-        // bytes), allocated when a scene first needs it; every slot starts invalid (flags = -1) and the kernel leaves it so
-        const size_t need = (size_t)g.prop.multiProcessorCount * 2 * 8 * 32 * rm::kTreeNodes * sizeof(rm::GlassNode);
-        if (g.tree.cap < need) {
-            if ((rc = g.tree.ensure(need)) != RM_OK) return rc;
-            CK(cudaMemsetAsync(g.tree.p, 0xFF, g.tree.cap, stream));
-        }
+        // node contributions of the pooled recursion: 310 MB on a B200 (148 SMs x 2 CTAs x 8 warps x 32 pixels x 256 slots
+        // x 16 bytes), allocated when a scene first needs it
+        const size_t need = (size_t)g.prop.multiProcessorCount * 2 * 8 * 32 * rm::kTreeNodes * sizeof(float4);
+        if ((rc = g.tree.ensure(need)) != RM_OK) return rc;
         ex.tree = g.tree.p;
         ex.tree_bytes = g.tree.cap;
     }

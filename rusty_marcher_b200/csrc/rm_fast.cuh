@@ -781,26 +781,31 @@ RM_HD Vec3<float> cast_glass_impl(const FV& fv, const FrameParams<float>& fp, co
 // cast_glass_impl walks a pixel's recursion depth-first in one lane: up to 2^depth - 1 scene queries one after the other,
 // while the 31 other lanes of the round wait for the longest chain.  The same recursion, cut into its nodes: one NODE =
 // one scene query (renderer.rs:266) + the direct lighting of its hit (renderer.rs:272-275) + the optics that spawn its
-// children (renderer.rs:277, optics.rs:8-89).  Nodes are independent given their ray, so any lane can process any node
-// (the render kernel pools a round's nodes over its warp, rm_kernels.cu); what a node computes goes into a record at its
-// heap index (root 1, reflected child 2 i, refracted child 2 i + 1), and glass_eval folds the records in the order the
-// recursion would have: value(i) = own(i) (+ value(2 i) * k) (+ value(2 i + 1) * (1 - k)) -- the very additions of
-// renderer.rs:219,249 in the very order, so the pixel is bit-identical to cast_glass_impl's whatever the order in which
-// the nodes were processed.  A pixel's records live in kTreeNodes slots (heap indices below 2^kMaxDepth); a slot is valid
-// while its flags are >= 0: a node's processor writes them, glass_eval invalidates every record it has folded, so between
-// pixels (between rounds, on the device) every slot is invalid and nothing needs clearing.
-constexpr int kTreeDepth = kMaxDepth, kTreeNodes = 1 << kTreeDepth;
+// children (renderer.rs:277, optics.rs:8-89).  Nodes are independent given their ray and their WEIGHT -- the product of
+// the factors k / (1 - k) of renderer.rs:219,249 along the path from the root -- so any lane can process any node (the
+// render kernel pools a round's nodes over its warp, rm_kernels.cu).  A node files weight * (bg + direct) (+ weight *
+// factor * bg for a child beyond the depth cap, renderer.rs:262-264) under its heap index (root 1, reflected child 2 i,
+// refracted child 2 i + 1), and the pixel is the sum of its nodes' contributions IN HEAP ORDER: the recursion's nested sums
+// multiplied out.  Same terms as renderer.rs:254-309, another association of the additions (differences of a few 1e-7
+// relative, far inside the tolerance) -- chosen because it makes every term independent: no value travels from child to
+// parent, so the fold is a handful of independent loads instead of a chain of dependent ones (the nested form was tried
+// first: 63 dependent L2 round trips per pixel at depth 6, slower than the depth-first routine it replaced).
+// The order of the sum is fixed, so the frame is bit-reproducible whatever the order in which the nodes were processed.
+constexpr int kTreeDepth = kMaxDepth, kTreeNodes = 1 << kTreeDepth, kTreeMaskWords = kTreeNodes / 32;
 
 template <typename G> struct GlassTask {
     Vec3<G> o, d;
+    float w;                      // weight of this node's value in the pixel
     int pix, node, level;         // owner pixel of the round (0..31), heap index, n_recursion
 };
-struct GlassNode {
-    float c[3];                   // bg + direct lighting of this node's hit (bg alone for a miss)
-    float k;                      // reflection weight of the material (renderer.rs:219,249)
-    int flags;                    // < 0: no record.  bit 0 / 1: a reflected / refracted child contributes; bit 2 / 3: that child is the
-                                  // depth cap (value bg, no query, no record)
-};
+
+RM_HD int low_bit(const unsigned v) {
+#if defined(__CUDA_ARCH__)
+    return __ffs(v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
 
 template <typename G> RM_HD void glass_primary_ray(const FrameParams<float>& fp, const int x, const int y, Vec3<G>& o, Vec3<G>& d) {
     if constexpr (sizeof(G) == 8) {                             // renderer.rs:128-135 in the reference's own arithmetic
@@ -815,12 +820,13 @@ template <typename G> RM_HD void glass_primary_ray(const FrameParams<float>& fp,
     }
 }
 
-// One node.  Level 1: the hit comes from stage A (t1: FP32 ray parameter of the unit direction, slot1, id1).  Returns
-// bit 0 / bit 1: a reflected / refracted child task was written to `refl` / `refr`.
+// One node.  Level 1: the hit comes from stage A (t1: FP32 ray parameter of the unit direction, slot1, id1).  `out`: the
+// node's contribution to its pixel.  Returns bit 0 / bit 1: a reflected / refracted child task was written to `refl` / `refr`.
 template <typename G, class FV>
 RM_HD int glass_node(const FV& fv, const FrameParams<float>& fp, const GlassTask<G>& t, const float t1, const int slot1, const int id1,
-                     GlassNode& out, GlassTask<G>& refl, GlassTask<G>& refr) {
+                     Vec3<float>& out, GlassTask<G>& refl, GlassTask<G>& refr) {
     const Vec3<float> o32 = to_f32(t.o), d32 = to_f32(t.d);
+    const Vec3<float> bg = {fp.background, fp.background, fp.background};
     Counters<false> st;
     HitRec<float> h;
     bool got = true;
@@ -831,10 +837,8 @@ RM_HD int glass_node(const FV& fv, const FrameParams<float>& fp, const GlassTask
     } else {
         got = fv.template closest<false>(o32, d32, t.level, h, st);            // renderer.rs:266: the search, FP32
     }
-    out.k = 0.f;
-    out.flags = 0;
     if (!got) {
-        out.c[0] = out.c[1] = out.c[2] = fp.background;         // renderer.rs:300-306 (level > 1 here)
+        out = scaled(bg, t.w);                                  // renderer.rs:300-306 (level > 1 here)
         return 0;
     }
     Vec3<G> p, n;
@@ -851,19 +855,17 @@ RM_HD int glass_node(const FV& fv, const FrameParams<float>& fp, const GlassTask
     }
     const R4<float> ma = fv.mat_a[h.id];
     const R4<float> mb = fv.mat_b[h.id];
-    const Vec3<float> bg = {fp.background, fp.background, fp.background};
-    const Vec3<float> c = bg + fv.template direct<false>(o32, d32, p32, n32, ma, mb, st);   // renderer.rs:272-275
-    out.c[0] = c.x;
-    out.c[1] = c.y;
-    out.c[2] = c.z;
-    out.k = mb.z;
+    out = scaled(bg + fv.template direct<false>(o32, d32, p32, n32, ma, mb, st), t.w);          // renderer.rs:272-275
     int spawned = 0;
     if (fv.mat_f[h.id] & 1) {                                   // renderer.rs:277
         using N = typename std::conditional<sizeof(G) == 8, Fast64, Exact<float>>::type;
         const bool cap = t.level + 1 > fp.max_depth;            // renderer.rs:262-264: the child returns the background
+        const float w_refl = t.w * mb.z, w_refr = t.w * (1.f - mb.z);              // renderer.rs:219,249
         if (reflect_ray<G, N>(t.d, p, n, (G)mb.w, refl.o, refl.d)) {              // renderer.rs:203-207
-            out.flags |= cap ? (1 | 4) : 1;
-            if (!cap) {
+            if (cap) {
+                out = out + scaled(bg, w_refl);
+            } else {
+                refl.w = w_refl;
                 refl.pix = t.pix;
                 refl.node = 2 * t.node;
                 refl.level = t.level + 1;
@@ -871,8 +873,10 @@ RM_HD int glass_node(const FV& fv, const FrameParams<float>& fp, const GlassTask
             }
         }
         if (refract_ray<G, N>(t.d, p, n, (G)mb.w, refr.o, refr.d)) {              // renderer.rs:235-239
-            out.flags |= cap ? (2 | 8) : 2;
-            if (!cap) {
+            if (cap) {
+                out = out + scaled(bg, w_refr);
+            } else {
+                refr.w = w_refr;
                 refr.pix = t.pix;
                 refr.node = 2 * t.node + 1;
                 refr.level = t.level + 1;
@@ -883,58 +887,27 @@ RM_HD int glass_node(const FV& fv, const FrameParams<float>& fp, const GlassTask
     return spawned;
 }
 
-// The pixel from its node records (rec[i], i = heap index < 2^max_depth): the recursion's additions in the recursion's
-// order, bottom up (children have larger indices than their parent).  Every record read is invalidated.
-RM_HD Vec3<float> glass_eval(GlassNode* rec, const float background, const int max_depth) {
-    const Vec3<float> bg = {background, background, background};
-    Vec3<float> c = bg;
-    for (int i = (1 << max_depth) - 1; i >= 1; i--) {
-        GlassNode& r = rec[i];
-        const int f = r.flags;
-        if (f < 0) continue;
-        c = {r.c[0], r.c[1], r.c[2]};
-        if (f & 1) {
-            Vec3<float> v = bg;
-            if (!(f & 4)) {
-                v = {rec[2 * i].c[0], rec[2 * i].c[1], rec[2 * i].c[2]};
-                rec[2 * i].flags = -1;
-            }
-            c = c + scaled(v, r.k);                             // renderer.rs:219
-        }
-        if (f & 2) {
-            Vec3<float> v = bg;
-            if (!(f & 8)) {
-                v = {rec[2 * i + 1].c[0], rec[2 * i + 1].c[1], rec[2 * i + 1].c[2]};
-                rec[2 * i + 1].flags = -1;
-            }
-            c = c + scaled(v, 1.f - r.k);                       // renderer.rs:249
-        }
-        r.c[0] = c.x;
-        r.c[1] = c.y;
-        r.c[2] = c.z;
-    }
-    rec[1].flags = -1;
-    return c;                                                   // the root is the last record folded
-}
-
-// Serial driver of the node form (one lane processes all nodes of its pixel, depth-first): what the host emulation runs,
-// and the reference the pooled device driver is tested against.
+// Serial driver of the node form (one lane processes all nodes of its pixel, depth-first, and sums their contributions in
+// heap order): what the host emulation runs, and the reference the pooled device driver must reproduce bit for bit.
 template <typename G, class FV>
 RM_HD Vec3<float> cast_glass_tree(const FV& fv, const FrameParams<float>& fp, const int x, const int y, const float t1,
                                   const int slot1, const int id1) {
-    GlassNode rec[kTreeNodes];
+    Vec3<float> contrib[kTreeNodes];
+    unsigned mask[kTreeMaskWords];
     GlassTask<G> stack[kTreeDepth + 1];
     int sp = 0;
     GlassTask<G> t;
     if (fp.max_depth < 1) return {fp.background, fp.background, fp.background};   // renderer.rs:262-264
-    for (int i = 0; i < (1 << fp.max_depth); i++) rec[i].flags = -1;
+    for (int i = 0; i < kTreeMaskWords; i++) mask[i] = 0u;
     glass_primary_ray<G>(fp, x, y, t.o, t.d);
+    t.w = 1.f;
     t.pix = 0;
     t.node = 1;
     t.level = 1;
     for (;;) {
         GlassTask<G> a, b;
-        const int spawned = glass_node<G, FV>(fv, fp, t, t1, slot1, id1, rec[t.node], a, b);
+        const int spawned = glass_node<G, FV>(fv, fp, t, t1, slot1, id1, contrib[t.node], a, b);
+        mask[t.node >> 5] |= 1u << (t.node & 31);
         if (spawned == 3) {
             stack[sp++] = b;
             t = a;
@@ -947,7 +920,13 @@ RM_HD Vec3<float> cast_glass_tree(const FV& fv, const FrameParams<float>& fp, co
             t = stack[--sp];
         }
     }
-    return glass_eval(rec, fp.background, fp.max_depth);
+    Vec3<float> c = {0.f, 0.f, 0.f};
+    for (int wd = 0; wd < kTreeMaskWords; wd++)
+        for (unsigned bits = mask[wd]; bits; bits &= bits - 1) {
+            const int i = wd * 32 + low_bit(bits);
+            c = c + contrib[i];
+        }
+    return c;
 }
 
 template <class FV>
@@ -977,8 +956,8 @@ RM_HD Vec3<float> fast_shade(FV& fv, const FrameParams<float>& fp, const int x, 
     // warp's 32 queue entries mix glass-like and opaque hits, and two routines would run the expensive part of both --
     // the shadow rays of direct() -- one after the other for the two groups of lanes (measured on the demo frame: 170
     // instead of 156 us).
-    // (the node form -- the same node arithmetic and the same fold the kernel's pooled rounds use; the depth-first routine is
-    // kept as the cross-check: bit-identical results, tests/test_kernel_emulation.py)
+    // (the node form -- the same node arithmetic and the same heap-order sum the kernel's pooled rounds use; the depth-first
+    // routine is kept as the cross-check: the same terms in the recursion's own association, tests/test_kernel_emulation.py)
     if constexpr (kGlass != GLASS_NONE) {
         using G = typename std::conditional<kGlass == GLASS_F64, double, float>::type;
         if (!glass_force_depth_first()) return cast_glass_tree<G, FV>(fv, fp, x, y, dist, slot, id);

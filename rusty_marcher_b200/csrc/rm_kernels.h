@@ -75,7 +75,7 @@ struct RenderExtras {
     // out: GlassMode of the production kernel that was launched (rm_fast.cuh)
     int glass_mode = 0;
     // in: device scratch of the pooled recursion of the glass modes (rm_kernels.cu, shade_round_pooled): at least
-    // grid warps x 32 x kTreeNodes GlassNode records; null = depth-first recursion per lane
+    // grid warps x 32 x kTreeNodes float4 (a node's contribution to its pixel); required for scenes with a glass mode
     void* tree = nullptr;
     size_t tree_bytes = 0;
 };
