@@ -148,7 +148,6 @@ struct Context {
     Scratch rgb, prim, rgb8, small;   // small: [0,8) max scalar, [64, 64+17*8) counters
     Scratch mix;                      // rm_render_dispersive: the frame assembled from the three passes
     Scratch pack;                     // host delivery: the busy tiles of a frame, packed in schedule order
-    Scratch tree;                     // node records of the pooled recursion of the glass modes (one block per warp of the grid)
     std::vector<Arena> arena_cache;   // device allocations of freed scenes, for the next upload
     // Host packs of the last few scenes by content (ingest): a caller that hands over the same scene
     // again -- the reference's render() borrows &Scene for every frame -- gets its pack (sorted primitive classes, raster
@@ -427,14 +426,6 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
     if (resident) *resident = dp.ds.lay.n_sph + rm::plane_count<R>(dp.ds.lay, cull);
     rm::RenderExtras ex;
     ex.rgb8_zero = d_rgb8_zero;
-    if (sizeof(R) == 4 && (dp.ds.lay.any_glass || dp.ds.lay.n_sph > 0)) {
-        // node contributions of the pooled recursion: 310 MB on a B200 (148 SMs x 2 CTAs x 8 warps x 32 pixels x 256 slots
-        // x 16 bytes), allocated when a scene first needs it
-        const size_t need = (size_t)g.prop.multiProcessorCount * 2 * 8 * 32 * rm::kTreeNodes * sizeof(float4);
-        if ((rc = g.tree.ensure(need)) != RM_OK) return rc;
-        ex.tree = g.tree.p;
-        ex.tree_bytes = g.tree.cap;
-    }
     if (link) {
         ex.link = *link;
         ex.zero_dmax = true;
@@ -876,7 +867,7 @@ void rm_shutdown(void) {
     for (auto& a : g.arena_cache) cudaFree(a.p);
     g.arena_cache.clear();
     g.pack_cache.clear();
-    g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release(); g.mix.release(); g.pack.release(); g.tree.release();
+    g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release(); g.mix.release(); g.pack.release();
     g.h_stage.release(); g.h_order.release(); g.h_upload.release();
     g.pool.reset();
     g.delivered.clear();

@@ -777,170 +777,11 @@ RM_HD Vec3<float> cast_glass_impl(const FV& fv, const FrameParams<float>& fp, co
         }
     }
 }
-// ---- the recursion as a TREE OF NODES ---------------------------------------------------------------------------------
-// cast_glass_impl walks a pixel's recursion depth-first in one lane: up to 2^depth - 1 scene queries one after the other,
-// while the 31 other lanes of the round wait for the longest chain.  The same recursion, cut into its nodes: one NODE =
-// one scene query (renderer.rs:266) + the direct lighting of its hit (renderer.rs:272-275) + the optics that spawn its
-// children (renderer.rs:277, optics.rs:8-89).  Nodes are independent given their ray and their WEIGHT -- the product of
-// the factors k / (1 - k) of renderer.rs:219,249 along the path from the root -- so any lane can process any node (the
-// render kernel pools a round's nodes over its warp, rm_kernels.cu).  A node files weight * (bg + direct) (+ weight *
-// factor * bg for a child beyond the depth cap, renderer.rs:262-264) under its heap index (root 1, reflected child 2 i,
-// refracted child 2 i + 1), and the pixel is the sum of its nodes' contributions IN HEAP ORDER: the recursion's nested sums
-// multiplied out.  Same terms as renderer.rs:254-309, another association of the additions (differences of a few 1e-7
-// relative, far inside the tolerance) -- chosen because it makes every term independent: no value travels from child to
-// parent, so the fold is a handful of independent loads instead of a chain of dependent ones (the nested form was tried
-// first: 63 dependent L2 round trips per pixel at depth 6, slower than the depth-first routine it replaced).
-// The order of the sum is fixed, so the frame is bit-reproducible whatever the order in which the nodes were processed.
-constexpr int kTreeDepth = kMaxDepth, kTreeNodes = 1 << kTreeDepth, kTreeMaskWords = kTreeNodes / 32;
-
-template <typename G> struct GlassTask {
-    Vec3<G> o, d;
-    float w;                      // weight of this node's value in the pixel
-    int pix, node, level;         // owner pixel of the round (0..31), heap index, n_recursion
-};
-
-RM_HD int low_bit(const unsigned v) {
-#if defined(__CUDA_ARCH__)
-    return __ffs(v) - 1;
-#else
-    return __builtin_ctz(v);
-#endif
-}
-
-template <typename G> RM_HD void glass_primary_ray(const FrameParams<float>& fp, const int x, const int y, Vec3<G>& o, Vec3<G>& d) {
-    if constexpr (sizeof(G) == 8) {                             // renderer.rs:128-135 in the reference's own arithmetic
-        o = {fp.cam64[0], fp.cam64[1], fp.cam64[2]};
-        d = Fast64::normalized(Vec3<double>{2. * ((double)x * fp.inv_w64 - 0.5) * fp.hf64 * fp.ratio64,
-                                            -2. * ((double)y * fp.inv_h64 - 0.5) * fp.hf64, -1.});
-    } else {
-        const float X = pixel_X(fp, x), Y = pixel_Y(fp, y);
-        const float inv = fast_rsqrt(fmaf(X, X, fmaf(Y, Y, 1.f)));     // geometry.rs:104-109: scale(1/norm)
-        o = fp.camera;
-        d = {X * inv, Y * inv, -inv};
-    }
-}
-
-// One node.  Level 1: the hit comes from stage A (t1: FP32 ray parameter of the unit direction, slot1, id1).  `out`: the
-// node's contribution to its pixel.  Returns bit 0 / bit 1: a reflected / refracted child task was written to `refl` / `refr`.
-template <typename G, class FV>
-RM_HD int glass_node(const FV& fv, const FrameParams<float>& fp, const GlassTask<G>& t, const float t1, const int slot1, const int id1,
-                     Vec3<float>& out, GlassTask<G>& refl, GlassTask<G>& refr) {
-    const Vec3<float> o32 = to_f32(t.o), d32 = to_f32(t.d);
-    const Vec3<float> bg = {fp.background, fp.background, fp.background};
-    Counters<false> st;
-    HitRec<float> h;
-    bool got = true;
-    if (t.level == 1) {
-        h.dist = t1;
-        h.slot = slot1;
-        h.id = id1;
-    } else {
-        got = fv.template closest<false>(o32, d32, t.level, h, st);            // renderer.rs:266: the search, FP32
-    }
-    if (!got) {
-        out = scaled(bg, t.w);                                  // renderer.rs:300-306 (level > 1 here)
-        return 0;
-    }
-    Vec3<G> p, n;
-    Vec3<float> p32, n32;
-    if constexpr (sizeof(G) == 8) {
-        fv.refine(h.slot, t.o, t.d, (double)h.dist, p, n);
-        p32 = to_f32(p);
-        n32 = to_f32(n);
-    } else {
-        fv.surface(h, o32, d32, n32);
-        p32 = h.p;
-        p = p32;
-        n = n32;
-    }
-    const R4<float> ma = fv.mat_a[h.id];
-    const R4<float> mb = fv.mat_b[h.id];
-    out = scaled(bg + fv.template direct<false>(o32, d32, p32, n32, ma, mb, st), t.w);          // renderer.rs:272-275
-    int spawned = 0;
-    if (fv.mat_f[h.id] & 1) {                                   // renderer.rs:277
-        using N = typename std::conditional<sizeof(G) == 8, Fast64, Exact<float>>::type;
-        const bool cap = t.level + 1 > fp.max_depth;            // renderer.rs:262-264: the child returns the background
-        const float w_refl = t.w * mb.z, w_refr = t.w * (1.f - mb.z);              // renderer.rs:219,249
-        if (reflect_ray<G, N>(t.d, p, n, (G)mb.w, refl.o, refl.d)) {              // renderer.rs:203-207
-            if (cap) {
-                out = out + scaled(bg, w_refl);
-            } else {
-                refl.w = w_refl;
-                refl.pix = t.pix;
-                refl.node = 2 * t.node;
-                refl.level = t.level + 1;
-                spawned |= 1;
-            }
-        }
-        if (refract_ray<G, N>(t.d, p, n, (G)mb.w, refr.o, refr.d)) {              // renderer.rs:235-239
-            if (cap) {
-                out = out + scaled(bg, w_refr);
-            } else {
-                refr.w = w_refr;
-                refr.pix = t.pix;
-                refr.node = 2 * t.node + 1;
-                refr.level = t.level + 1;
-                spawned |= 2;
-            }
-        }
-    }
-    return spawned;
-}
-
-// Serial driver of the node form (one lane processes all nodes of its pixel, depth-first, and sums their contributions in
-// heap order): what the host emulation runs, and the reference the pooled device driver must reproduce bit for bit.
-template <typename G, class FV>
-RM_HD Vec3<float> cast_glass_tree(const FV& fv, const FrameParams<float>& fp, const int x, const int y, const float t1,
-                                  const int slot1, const int id1) {
-    Vec3<float> contrib[kTreeNodes];
-    unsigned mask[kTreeMaskWords];
-    GlassTask<G> stack[kTreeDepth + 1];
-    int sp = 0;
-    GlassTask<G> t;
-    if (fp.max_depth < 1) return {fp.background, fp.background, fp.background};   // renderer.rs:262-264
-    for (int i = 0; i < kTreeMaskWords; i++) mask[i] = 0u;
-    glass_primary_ray<G>(fp, x, y, t.o, t.d);
-    t.w = 1.f;
-    t.pix = 0;
-    t.node = 1;
-    t.level = 1;
-    for (;;) {
-        GlassTask<G> a, b;
-        const int spawned = glass_node<G, FV>(fv, fp, t, t1, slot1, id1, contrib[t.node], a, b);
-        mask[t.node >> 5] |= 1u << (t.node & 31);
-        if (spawned == 3) {
-            stack[sp++] = b;
-            t = a;
-        } else if (spawned == 1) {
-            t = a;
-        } else if (spawned == 2) {
-            t = b;
-        } else {
-            if (sp == 0) break;
-            t = stack[--sp];
-        }
-    }
-    Vec3<float> c = {0.f, 0.f, 0.f};
-    for (int wd = 0; wd < kTreeMaskWords; wd++)
-        for (unsigned bits = mask[wd]; bits; bits &= bits - 1) {
-            const int i = wd * 32 + low_bit(bits);
-            c = c + contrib[i];
-        }
-    return c;
-}
-
 template <class FV>
 RM_GLASS_FN Vec3<float> cast_glass64(const FV& fv, const FrameParams<float>& fp, const int x, const int y, const float t1,
                                      const int slot1, const int id1) {
     return cast_glass_impl<double, FV>(fv, fp, x, y, t1, slot1, id1);
 }
-
-// (host emulation only: run the depth-first routine where the node form would be used -- to prove them bit-identical)
-#if defined(RM_EMU_STATS) && !defined(__CUDA_ARCH__)
-inline bool& glass_force_depth_first() { static bool v = false; return v; }
-#else
-RM_HD bool glass_force_depth_first() { return false; }
-#endif
 
 // One pixel whose primary ray hit (t in units of |D|, slot, id): renderer.rs:254-309 from level 1.
 // kGlass = GLASS_NONE: the scene has neither glass-like materials nor spheres (every OBJ scene of the reference: obj.rs:125-138
@@ -956,12 +797,6 @@ RM_HD Vec3<float> fast_shade(FV& fv, const FrameParams<float>& fp, const int x, 
     // warp's 32 queue entries mix glass-like and opaque hits, and two routines would run the expensive part of both --
     // the shadow rays of direct() -- one after the other for the two groups of lanes (measured on the demo frame: 170
     // instead of 156 us).
-    // (the node form -- the same node arithmetic and the same heap-order sum the kernel's pooled rounds use; the depth-first
-    // routine is kept as the cross-check: the same terms in the recursion's own association, tests/test_kernel_emulation.py)
-    if constexpr (kGlass != GLASS_NONE) {
-        using G = typename std::conditional<kGlass == GLASS_F64, double, float>::type;
-        if (!glass_force_depth_first()) return cast_glass_tree<G, FV>(fv, fp, x, y, dist, slot, id);
-    }
     if constexpr (kGlass == GLASS_F64) return cast_glass64(fv, fp, x, y, dist, slot, id);
     if constexpr (kGlass == GLASS_F32) return cast_glass_impl<float, FV>(fv, fp, x, y, dist, slot, id);
     const Vec3<float> d = {X * inv, Y * inv, -inv};

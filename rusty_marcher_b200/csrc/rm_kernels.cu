@@ -347,7 +347,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                    const int n_tiles, const float inv_tiles_x, float* __restrict__ rgb, int* __restrict__ prim_id,
                    float* __restrict__ dmax, int* __restrict__ ctr, const int* __restrict__ order, const int* __restrict__ order2,
                    unsigned char* rgb8, const PeerLink link, unsigned char* rgb8_out, const int normalise,
-                   unsigned char* rgb8_next, const int stage_mat, float4* __restrict__ tree) {
+                   unsigned char* rgb8_next, const int stage_mat) {
     constexpr bool kBvh = kBvhMode != 0, kCount = kBvhMode == 2;    // 2: the counting instantiation (RmParams.accel = 2)
     const int zero_foreign = rgb8_next != nullptr;
     extern __shared__ __align__(32) unsigned char smem_raw[];
@@ -357,14 +357,6 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     __shared__ int fill_off[96];                                // float offset of each 16-byte chunk of a strip (see fill_strip)
     __shared__ float4 pool[kFastBlock];                             // pooled leftovers of the eight warp queues (< 32 each)
     __shared__ float4 queue[kFastBlock / 32][kWarpQueue];           // {t, slot, id, x | y << 16}
-    // glass modes (shade_round_pooled below): the warps' task pools and, per pixel of a round, the mask of its nodes' heap
-    // indices -- zero between rounds (the owner clears what it reads)
-    constexpr int kGlassPool = 24, kGlassWarps = kGlass != GLASS_NONE ? kFastBlock / 32 : 1;
-    using GT = GlassTask<typename std::conditional<kGlass == GLASS_F64, double, float>::type>;
-    __shared__ GT gpool[kGlassWarps][kGlass != GLASS_NONE ? kGlassPool : 1];
-    __shared__ unsigned gmask[kGlassWarps][kGlass != GLASS_NONE ? 32 : 1][kTreeMaskWords];
-    if constexpr (kGlass != GLASS_NONE)
-        for (int i = threadIdx.x; i < kGlassWarps * 32 * kTreeMaskWords; i += kFastBlock) (&gmask[0][0][0])[i] = 0u;
     const BlobLayout& L = ds.lay;
     const int n_tri = tri_count(L, cull != 0);
 
@@ -444,118 +436,15 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     int final_take = 0;
     float m = 0.f;
 
-    auto shade_entry = [&](const float4 e) {                    // (opaque-only scenes; the glass modes shade in pooled rounds, below)
+    auto shade_entry = [&](const float4 e) {
         const unsigned xy = __float_as_uint(e.w);
         const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
-        const Vec3<float> c = fast_shade<GLASS_NONE>(fv, fp, x, y, e.x, __float_as_int(e.y), __float_as_int(e.z));
+        const Vec3<float> c = fast_shade<kGlass>(fv, fp, x, y, e.x, __float_as_int(e.y), __float_as_int(e.z));
         float* dst = rgb + 3 * ((size_t)(y - fp.buf_row0) * fp.width + x);
         dst[0] = c.x;
         dst[1] = c.y;
         dst[2] = c.z;
         m = fmaxf(m, fmaxf(fmaxf(c.x, c.y), c.z));
-    };
-
-    // ---- stage B for the glass modes: a round's recursion trees processed NODE BY NODE by the whole warp.
-    // Run depth-first in its lane, a pixel's tree is up to 63 closest-hit and 126 any-hit queries in a row while the lanes
-    // whose pixels are opaque (one node) wait: 19.6 of 32 lanes alive on the stress frame, and a chain of ~1 ms that no split
-    // of the frame over more GPUs shortens.  Here a lane that spawns two children keeps one and puts the other into the
-    // warp's pool (shared memory; a private stack takes what does not fit); a lane without a task takes one from the pool.
-    // Every iteration each lane with a task processes ONE node (glass_node: query, direct lighting, optics) and files its
-    // contribution under (pixel, heap index) in the warp's scratch (global memory, L2-resident) and a bit in the pixel's mask
-    // (shared memory); when nothing is left each pixel's owner sums its nodes' contributions in heap order -- independent
-    // loads, a fixed order: the pixel is bit-reproducible however the nodes were dealt (rm_fast.cuh, "tree of nodes").
-    auto shade_round_pooled = [&](const float4* src, const int take) {
-        using G = typename std::conditional<kGlass == GLASS_F64, double, float>::type;
-        GT* const mypool = gpool[warp];
-        float4* const rec0 = reinterpret_cast<float4*>(tree) + (size_t)(blockIdx.x * (kFastBlock / 32) + warp) * 32 * kTreeNodes;
-        const bool own = lane < take;
-        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-        int x = 0, y = 0;
-        float t1 = 0.f;
-        GT task, priv[kTreeDepth + 1];
-        int n_priv = 0;
-        bool have = false;
-        if (own) {
-            e = src[lane];
-            const unsigned xy = __float_as_uint(e.w);
-            x = (int)(xy & 0xffffu);
-            y = (int)(xy >> 16);
-            const float X = pixel_X(fp, x), Y = pixel_Y(fp, y);
-            const float len2 = fmaf(X, X, fmaf(Y, Y, 1.f));
-            t1 = e.x * (len2 * fast_rsqrt(len2));               // stage A reports t in units of |D|
-            glass_primary_ray<G>(fp, x, y, task.o, task.d);
-            task.w = 1.f;
-            task.pix = lane;
-            task.node = 1;
-            task.level = 1;
-            have = true;
-        }
-        int avail = 0;                                          // tasks in the pool (warp-uniform)
-        for (int it = 0; it < 32 * kTreeNodes + 8; it++) {     // (every iteration retires at least one node: a bound, not a schedule)
-            if (!have && n_priv > 0) {
-                task = priv[--n_priv];
-                have = true;
-            }
-            const unsigned need = __ballot_sync(0xffffffffu, !have);
-            if (avail > 0 && need) {
-                const int r = __popc(need & lane_lt);
-                if (!have && r < avail) {
-                    task = mypool[avail - 1 - r];
-                    have = true;
-                }
-                avail = max(avail - __popc(need), 0);
-            }
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, have)) break;
-            int spawned = 0;
-            GT a, b;
-            if (have) {
-                Vec3<float> c;
-                spawned = glass_node<G>(fv, fp, task, t1, __float_as_int(e.y), __float_as_int(e.z), c, a, b);
-                __stcg(rec0 + task.pix * kTreeNodes + task.node, make_float4(c.x, c.y, c.z, 0.f));
-                atomicOr(&gmask[warp][task.pix][task.node >> 5], 1u << (task.node & 31));
-            }
-            const bool push = spawned == 3;
-            const unsigned pm = __ballot_sync(0xffffffffu, push);
-            if (push) {
-                const int r = avail + __popc(pm & lane_lt);
-                if (r < kGlassPool) mypool[r] = b;
-                else priv[n_priv++] = b;
-            }
-            avail = min(avail + __popc(pm), kGlassPool);
-            have = spawned != 0;
-            if (spawned & 1) task = a;
-            else if (spawned & 2) task = b;
-            __syncwarp();
-        }
-        if (own) {
-            Vec3<float> c = {0.f, 0.f, 0.f};
-            const float4* mine = rec0 + lane * kTreeNodes;
-            const int n_words = max((1 << fp.max_depth) >> 5, 1);
-            for (int wd = 0; wd < n_words; wd++) {
-                unsigned bits = gmask[warp][lane][wd];
-                gmask[warp][lane][wd] = 0u;
-                while (bits) {                                  // four contributions per trip: their loads are in flight together
-                    int idx[4];
-                    float4 v[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        idx[k] = bits ? wd * 32 + __ffs(bits) - 1 : -1;
-                        bits &= bits - 1;                       // (0 & anything stays 0)
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; k++) v[k] = idx[k] >= 0 ? __ldcg(mine + idx[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (idx[k] >= 0) c = c + Vec3<float>{v[k].x, v[k].y, v[k].z};
-                }
-            }
-            float* dst = rgb + 3 * ((size_t)(y - fp.buf_row0) * fp.width + x);
-            dst[0] = c.x;
-            dst[1] = c.y;
-            dst[2] = c.z;
-            m = fmaxf(m, fmaxf(fmaxf(c.x, c.y), c.z));
-        }
     };
 
     // Zero-fill (renderer.rs:300-306: a primary miss is black) of a 32-pixel wide strip of kStripRows rows by one warp,
@@ -698,11 +587,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                 src = wq + qn;
                 take = 32;
             }
-            if constexpr (kGlass != GLASS_NONE) {
-                shade_round_pooled(src, take);
-            } else {
-                if (lane < take) shade_entry(src[lane]);
-            }
+            if (lane < take) shade_entry(src[lane]);
             if (phase == 3) break;
         }
         if (phase == 3) break;
@@ -1075,21 +960,14 @@ cudaError_t launch_fast(const DeviceScene<float>& ds, const FrameParams<float>& 
     int occ = 1;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kFastBlock, cfg.dynamicSmemBytes)) != cudaSuccess) return e;
     cfg.gridDim = dim3(std::min(n_tiles, sm_count * std::max(occ, 1)));
-    // scratch of the pooled recursion: 32 pixels x kTreeNodes records per warp of the grid, every slot invalid between rounds
-    float4* tree = nullptr;
-    if (glass != GLASS_NONE) {
-        if (!ex || !ex->tree || ex->tree_bytes < (size_t)cfg.gridDim.x * (kFastBlock / 32) * 32 * kTreeNodes * sizeof(float4))
-            return cudaErrorInvalidValue;                       // (rm_api.cu provides it for every scene that can need it)
-        tree = static_cast<float4*>(ex->tree);
-    }
     e = cudaLaunchKernelEx(&cfg, k, ds, fp, cull_i, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order2, rgb8,
-                           link, rgb8_out, normalise, rgb8_next, stage_mat, tree);
+                           link, rgb8_out, normalise, rgb8_next, stage_mat);
     if (e != cudaSuccess && want_coop) {                        // not available in this combination: the plain persistent launch
         cudaGetLastError();
         coop = 0;
         cfg.numAttrs = 1;
         e = cudaLaunchKernelEx(&cfg, k, ds, fp, cull_i, tiles_x, n_tiles, inv_tiles_x, rgb, prim_id, dmax, ds.ctr, order, order2, rgb8,
-                               link, rgb8_out, normalise, rgb8_next, stage_mat, tree);
+                               link, rgb8_out, normalise, rgb8_next, stage_mat);
     }
     if (e != cudaSuccess) return e;
     if (launches) (*launches)++;

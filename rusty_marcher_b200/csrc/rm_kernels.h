@@ -74,10 +74,6 @@ struct RenderExtras {
     bool scheduled = false;
     // out: GlassMode of the production kernel that was launched (rm_fast.cuh)
     int glass_mode = 0;
-    // in: device scratch of the pooled recursion of the glass modes (rm_kernels.cu, shade_round_pooled): at least
-    // grid warps x 32 x kTreeNodes float4 (a node's contribution to its pixel); required for scenes with a glass mode
-    void* tree = nullptr;
-    size_t tree_bytes = 0;
 };
 
 // K0 + K1.  With counters == null and R = float this is the production path: prepare_raster_kernel

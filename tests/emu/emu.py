@@ -37,12 +37,11 @@ def lib():
 
 
 def render(scene, width, height, precision="f32", fov=1.5, max_depth=3, cull=True, threads=8, patch_rows=(0, -1), strip_bound=True, accel=False, glass_index=None,
-           glass_mode=None, depth_first=False):
+           glass_mode=None):
     """glass_mode (fast path): None = as the device decides per scene and camera (rm::glass_mode), 1 = FP32 ray geometry on
     glass paths, 2 = f64 ray geometry."""
     lib().emu_set_strip_bound(int(strip_bound))
     lib().emu_set_glass_mode(-1 if glass_mode is None else int(glass_mode))
-    lib().emu_set_glass_depth_first(int(depth_first))     # the recursion depth-first per pixel instead of node by node
     flat = scene.flatten()
     if glass_index is not None:
         flat.set_glass_index(float(glass_index))     # one pass of the per-channel dispersion (extension mode)

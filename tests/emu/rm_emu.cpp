@@ -231,7 +231,6 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
 extern "C" {
 void emu_set_strip_bound(int on) { g_strip_bound.store(on); }
 void emu_set_glass_mode(int mode) { g_glass_mode.store(mode); }
-void emu_set_glass_depth_first(int on) { rm::glass_force_depth_first() = on != 0; }
 int emu_last_glass_mode(void) { return g_last_glass_mode.load(); }
 void emu_set_cost_buffer(float* hw2) { g_cost.store(hw2); }
 // {walks, node visits, primitive tests} of the hierarchy walks since the last call (accel renders only)

@@ -215,24 +215,3 @@ def test_full_stress_scene_kernel_code_against_the_golden_frame():
     a, b = fp32["rgb"].astype(np.float64), ref["rgb"]
     rel = (np.abs(a - b) / np.maximum(np.abs(b), 1e-12)).max(axis=2)
     assert (rel <= parity.REL_TOL).mean() < parity.GOOD_FRACTION      # documents why the f64 geometry exists
-
-
-@pytest.mark.parametrize("name,kw,w,h,depth,mode", [("demo", {}, 256, 160, 3, None), ("demo", {}, 256, 160, 6, 2),
-                                                    ("stress", dict(n_spheres=256, grid=16), 320, 192, 6, None),
-                                                    ("ngons", {}, 320, 192, 4, 1), ("stress", dict(n_spheres=64, grid=7), 160, 128, 2, None)])
-def test_node_form_of_the_recursion_against_the_depth_first_form(name, kw, w, h, depth, mode):
-    """The production kernel processes a round's recursion trees node by node, pooled over the warp, and sums each pixel's
-    node contributions in heap order (glass_node, rm_fast.cuh): the terms of renderer.rs:254-309 with the nested sums
-    multiplied out.  Against the depth-first routine (cast_glass_impl: the recursion as a per-lane stack, additions in the
-    reference's own association): same primary ids, colours equal up to the re-association (a few 1e-7 relative)."""
-    scene = workloads.scene(name, **kw)
-    for accel in (False, True):
-        a = emu.render(scene, w, h, "fast", max_depth=depth, accel=accel, glass_mode=mode)
-        b = emu.render(scene, w, h, "fast", max_depth=depth, accel=accel, glass_mode=mode, depth_first=True)
-        assert (a["prim_id"] >= 0).any()
-        assert np.array_equal(a["prim_id"], b["prim_id"])
-        err = np.abs(a["rgb"].astype(np.float64) - b["rgb"]) / np.maximum(np.abs(b["rgb"]), 1e-6)
-        assert err.max() < 2e-6, err.max()
-    c = emu.render(scene, w, h, "fast", max_depth=8, glass_mode=mode)
-    d = emu.render(scene, w, h, "fast", max_depth=8, glass_mode=mode, depth_first=True)
-    assert np.abs(c["rgb"].astype(np.float64) - d["rgb"]).max() < 1e-5
