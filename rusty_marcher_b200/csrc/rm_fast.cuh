@@ -18,6 +18,7 @@
 //  * Spheres and n-gons (n > 3) reuse the routines of rm_trace.cuh.
 #pragma once
 
+#include <cassert>
 #include <type_traits>
 
 #include "rm_bvh.cuh"
@@ -642,6 +643,12 @@ template <int kPx, bool kCount> RM_HD void primary_bvh(PrimaryState<kPx>& ps, co
 // Which of the two a frame gets is decided per launch from the scene and the camera (glass_mode below).
 enum GlassMode { GLASS_NONE = 0, GLASS_F32 = 1, GLASS_F64 = 2 };
 
+#if defined(RM_CHECKED) && defined(__CUDA_ARCH__)
+#define RM_FAST_CHECK(cond) assert(cond)
+#else
+#define RM_FAST_CHECK(cond) ((void)0)
+#endif
+
 // f64 ray geometry when some sphere is small against the coordinates rays travel through: S > 64 r_min, with S the
 // largest coordinate magnitude of the scene's primitives and the camera.  (FP32 positions carry 2^-24 S; against a
 // radius of S / 64 that is a normal error of 4e-6, which the recursion's magnification keeps below the tolerance; the demo
@@ -734,6 +741,7 @@ RM_HD Vec3<float> cast_glass_impl(const FV& fv, const FrameParams<float>& fp, co
                     const bool has_refl = reflect_ray<G, N>(d, p, n, (G)mb.w, ro1, rd1);  // renderer.rs:203-207
                     const bool has_refr = refract_ray<G, N>(d, p, n, (G)mb.w, ro2, rd2);  // renderer.rs:235-239
                     if (has_refl || has_refr) {
+                        RM_FAST_CHECK(sp < kMaxDepth);
                         Frame& f = fr[sp];
                         f.c = c;
                         f.k = mb.z;

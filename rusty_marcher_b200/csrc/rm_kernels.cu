@@ -19,7 +19,17 @@
 #include "rm_kernels.h"
 
 #include <algorithm>
+#include <cassert>
 #include <cstdlib>
+
+// -DRM_CHECKED: bounds and protocol checks inside the kernels (device assert: file, line, block and thread on stderr, then
+// the kernel traps and the next CUDA call fails).  compute-sanitizer is closed on this project's GPU pool, so this is the
+// memory-safety pass that can be run there: tools/gpu_checked.sh builds the variant and runs the GPU suite with it.
+#ifdef RM_CHECKED
+#define RM_CHECK(cond) assert(cond)
+#else
+#define RM_CHECK(cond) ((void)0)
+#endif
 
 namespace rm {
 
@@ -99,6 +109,7 @@ __device__ __noinline__ unsigned long long wait_word(const unsigned long long* p
 }
 // Render kernel, last CTA out: this rank's channel maximum of frame link.seq to every rank's mailbox (its own included).
 __device__ __forceinline__ void publish_max(const PeerLink& link, const float m) {
+    RM_CHECK(link.world >= 1 && link.world <= kMaxRanks && link.rank >= 0 && link.rank < link.world && link.seq != 0u && m >= 0.f);
     const unsigned long long w = ((unsigned long long)link.seq << 32) | (unsigned long long)__float_as_uint(m);
     for (int r = 0; r < link.world; r++) st_sys(link.box[r] + (link.seq & 1u) * 16 + link.rank, w);
 }
@@ -440,6 +451,8 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         const unsigned xy = __float_as_uint(e.w);
         const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
         const Vec3<float> c = fast_shade<kGlass>(fv, fp, x, y, e.x, __float_as_int(e.y), __float_as_int(e.z));
+        RM_CHECK(x >= 0 && x < fp.width && y >= fp.row_begin && y < fp.row_begin + (fp.n_bands - 1) * fp.row_step + 32 &&
+                 (y - fp.row_begin) % fp.row_step < 32);
         float* dst = rgb + 3 * ((size_t)(y - fp.buf_row0) * fp.width + x);
         dst[0] = c.x;
         dst[1] = c.y;
@@ -464,6 +477,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
     auto fill_empty_tile = [&](const int tile) {                // always in pieces of four rows, whatever the strip height
         const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);
         const int tx = tile - ty * tiles_x;
+        RM_CHECK(tile >= 0 && tile < n_tiles && ty == tile / tiles_x && tx >= 0 && tx < tiles_x && ty < fp.n_bands);
         const size_t p0 = (size_t)(fp.row_begin + ty * fp.row_step - fp.buf_row0) * fp.width + tx * kFastTile;
 #pragma unroll
         for (int r = 0; r < 8; r++) {
@@ -508,6 +522,8 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                 const int tile = !order ? k : k < n_full ? __ldg(order + k) : __ldg(order2 + (k - n_full));
                 const int ty = (int)(((float)tile + 0.5f) * inv_tiles_x);          // exact for tile < 2^22
                 const int tx = tile - ty * tiles_x;
+                RM_CHECK(tile >= 0 && tile < n_tiles && ty == tile / tiles_x && tx >= 0 && tx < tiles_x && ty < fp.n_bands);
+                RM_CHECK(n_full >= 0 && n_busy >= n_full && n_busy <= n_tiles);
                 const int x0 = tx * kFastTile, ys = fp.row_begin + ty * fp.row_step + strip * kStripRows;
                 const size_t px = (size_t)(ys + ly - fp.buf_row0) * fp.width + x0 + lx;
                 fill_rows((size_t)(ys - fp.buf_row0) * fp.width + x0, kStripRows);         // misses stay black; stage B overwrites the hits
@@ -542,6 +558,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
 #pragma unroll
                 for (int c = 0; c < kPx; c++) {
                     const unsigned mc = __ballot_sync(0xffffffffu, ps.slot[c] >= 0);
+                    RM_CHECK(qn + __popc(mc) <= kWarpQueue);
                     if (ps.slot[c] >= 0) wq[qn + __popc(mc & lane_lt)] = make_float4(ps.t[c], __int_as_float(ps.slot[c]), __int_as_float(ps.id[c]), __uint_as_float(xy + c));
                     qn += __popc(mc);
                 }
@@ -569,6 +586,7 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
                 if (w < warp) before += c;
                 total += c;
             }
+            RM_CHECK(qn < 32 && total < kFastBlock && before + qn <= kFastBlock);
             if (lane < qn) pool[before + lane] = wq[lane];
             __syncthreads();
             final_take = min(max(total - warp * 32, 0), 32);    // total < 256: at most one round, warp w takes entries [32 w, 32 w + 32)
@@ -656,38 +674,51 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         if (blockIdx.x == 0 && threadIdx.x == 0) link.box[link.rank][58] = now_ns();                // stamp: maxima gathered
     }
     __threadfence();
-    // Work unit: a 32x4 strip of a busy tile = 96 float4 in, 96 words out, three per lane; a warp takes four units per
-    // round and issues their twelve loads before the first conversion (the phase is bound by L2 latency, not by bytes).
+    // Work unit: a 32x4 strip of a busy tile = 96 float4 in, 24 x 16 bytes out (a row of the strip is 96 bytes of RGB8: six
+    // 128-bit stores).  A warp takes four units per round = 96 output vectors, three per lane; a lane's vector is 16
+    // consecutive channel values = four consecutive float4, so all twelve of its loads are issued before the first
+    // conversion (the phase is bound by L2 latency, not by bytes) and every store -- into rank 0's frame over NVLink on
+    // ranks > 0 -- is a full 16-byte one.
     {
         constexpr int kToneRows = 4, kTonePerTile = kFastTile / kToneRows;
         const int n_units = n_busy * kTonePerTile;
         const int gw = blockIdx.x * (kFastBlock / 32) + warp;
         for (int u0 = gw; u0 < n_units; u0 += 4 * n_warps) {
-            float4 q[4][3];
             size_t base_v[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int u = u0 + k * n_warps;
-                base_v[k] = 0;
+                base_v[k] = ~(size_t)0;
                 if (u < n_units) {
                     const int t = u / kTonePerTile, strip = u - t * kTonePerTile;
                     const int tile = !order ? t : t < n_full ? __ldg(order + t) : __ldg(order2 + (t - n_full));
                     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                    RM_CHECK(tile >= 0 && tile < n_tiles && ty < fp.n_bands);
                     base_v[k] = 3 * ((size_t)(fp.row_begin + ty * fp.row_step + strip * kToneRows - fp.buf_row0) * fp.width + tx * 32);
+                }
+            }
+            float4 q[3][4];
+            size_t off[3];
 #pragma unroll
-                    for (int i = 0; i < 3; i++) q[k][i] = __ldcg(reinterpret_cast<const float4*>(rgb + base_v[k] + fill_off[lane + 32 * i]));
+            for (int i = 0; i < 3; i++) {
+                const int j = lane + 32 * i, k = j / 24, o = j - k * 24, row = o / 6, c6 = o - row * 6;
+                const size_t b = k == 0 ? base_v[0] : k == 1 ? base_v[1] : k == 2 ? base_v[2] : base_v[3];
+                off[i] = b == ~(size_t)0 ? b : b + (size_t)row * fp.width * 3 + c6 * 16;
+                if (off[i] != ~(size_t)0) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) q[i][v] = __ldcg(reinterpret_cast<const float4*>(rgb + off[i]) + v);
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (u0 + k * n_warps < n_units) {
+            for (int i = 0; i < 3; i++) {
+                if (off[i] == ~(size_t)0) continue;
+                unsigned w[4];
 #pragma unroll
-                    for (int i = 0; i < 3; i++) {
-                        const float4 f = q[k][i];
-                        const unsigned w = Tone<float>::q(f.x, inv) | (Tone<float>::q(f.y, inv) << 8) | (Tone<float>::q(f.z, inv) << 16) | (Tone<float>::q(f.w, inv) << 24);
-                        *reinterpret_cast<unsigned*>(rgb8_out + base_v[k] + fill_off[lane + 32 * i]) = w;
-                    }
+                for (int v = 0; v < 4; v++) {
+                    const float4 f = q[i][v];
+                    w[v] = Tone<float>::q(f.x, inv) | (Tone<float>::q(f.y, inv) << 8) | (Tone<float>::q(f.z, inv) << 16) | (Tone<float>::q(f.w, inv) << 24);
                 }
+                *reinterpret_cast<uint4*>(rgb8_out + off[i]) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
     }
@@ -797,6 +828,7 @@ sort_busy_kernel(const int* __restrict__ order, const int* __restrict__ order2, 
     __syncthreads();
     for (int t = tid; t < n_busy; t += 1024) {
         const int tile = t < n_full ? order[t] : order2[t - n_full];
+        RM_CHECK(tile >= 0 && tile < kSortMaxWords * 32);
         atomicOr(&bm[tile >> 5], 1u << (tile & 31));
     }
     __syncthreads();
@@ -834,6 +866,7 @@ pack_busy_kernel(const float* __restrict__ rgb, const FrameParams<float> fp, con
     for (int t = blockIdx.x; t < n_busy; t += gridDim.x) {
         const int tile = sorted[1 + t];
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        RM_CHECK(tile >= 0 && ty < fp.n_bands && (t == 0 || sorted[t] < tile));
         const size_t p0 = (size_t)(fp.row_begin + ty * fp.row_step - fp.buf_row0) * fp.width + tx * 32;
         float4* dst = reinterpret_cast<float4*>(packed + (size_t)t * 3072);
 #pragma unroll

@@ -2,7 +2,10 @@
 #include "rm_scene.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace rm {
@@ -239,10 +242,16 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
     int rc = validate_scene(fs, err);
     if (rc != RM_OK) return rc;
     out = PackedScene<R>();
+    // RM_B200_PACK_TRACE=1: phase times of the packing on stderr
+    static const bool trace = getenv("RM_B200_PACK_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_collect = 0, t_sort = 0, t_blob = 0, t_fast = 0;
 
     struct SphTmp { const RmSphere* s; int id, shape; };
     std::vector<SphTmp> sph;
     std::vector<PlaneTmp> pln;
+    pln.reserve((size_t)fs.n_polygons + (size_t)fs.n_triangles);
     int id = 0;
     for (int s = 0; s < fs.n_shapes; s++) {
         const RmShapeRef& ref = fs.shapes[s];
@@ -286,6 +295,7 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
         }
     }
     out.n_prims = id;
+    t_collect = ms_now();
     for (int f : out.mat_f) out.lay.any_glass |= f & 1;
     {
         double cm = 0., rmin = INFINITY;
@@ -305,6 +315,7 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
     // hittable planes first, then back-facing, then degenerate (stable: scene order inside each class)
     std::stable_sort(pln.begin(), pln.end(), [](const PlaneTmp& a, const PlaneTmp& b) { return a.cls < b.cls; });
 
+    t_sort = ms_now();
     BlobLayout& L = out.lay;
     L.n_sph = (int)sph.size();
     L.n_pln = (int)pln.size();
@@ -366,7 +377,9 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
         v0 += nv;
         b_pid[i] = p.id;
     }
+    t_blob = ms_now();
     write_fast<R>(pln, L, b, out);
+    t_fast = ms_now();
     if (sizeof(R) == 4) {
         // f64 sources for the refinement of winning hits on glass paths (cast_glass, rm_fast.cuh): spheres {c, r^2}
         // (sphere.rs:6-11) and planes by slot {n, n.C} (triangle.rs:33-47 / polygon.rs:16-42: precomputed normal, plane point)
@@ -405,6 +418,9 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
             out.order_shape[1].push_back(e.second.second);
         }
     }
+    if (trace)
+        std::fprintf(stderr, "rm pack (%s, %d primitives): collected %.1f ms, classes sorted %.1f, blob written %.1f, fast records + hierarchy %.1f, done %.1f\n",
+                     sizeof(R) == 4 ? "f32" : "f64", out.n_prims, t_collect, t_sort, t_blob, t_fast, ms_now());
     return RM_OK;
 }
 
