@@ -19,7 +19,7 @@ L = _abi.load()
 dev = torch.device("cuda:0")
 scene = workloads.scene(scene_name, **kw)
 r = rm.create_renderer(1.5, h, w)
-r.max_depth = depth
+r.max_depth = int(os.environ.get("BANDS_DEPTH", depth))
 r.accel = accel
 be = tiled.CudaBackend(scene, r, w, h, dev)
 rgb = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
