@@ -386,6 +386,7 @@ def heavy_leg(name, world, rank, dev, flush, steps=3, warmup=3):
         return {"workload": name, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms,
                 "segments_per_frame": segs, "value": segs / (ms * 1e-3) if segs else None, "unit": UNIT,
                 "n_prims": workloads.n_prims(desc), "frame_matches_n1": ok, "frame_sha256": sha, "frame_check": detail,
+                "dtype": "f32 (scene queries, shadow rays, lighting) with f64 ray geometry on the reflect / refract paths",
                 "timing": "CUDA events around each frame, L2 flushed before each, max over ranks"}
     finally:
         tr.close()
