@@ -571,7 +571,17 @@ def run_ours(args):
     else:
         name = [None]
         if rank == 0:
-            name[0] = "/dev/shm/rm_b200_bench_%d" % os.getpid()
+            # shared memory when it has room for the frame (a mapping of a file the tmpfs cannot back dies with SIGBUS on
+            # first touch), else a file in the temporary directory: page-cache backed, the same thing to the ranks
+            import tempfile
+            base = "/dev/shm"
+            try:
+                st_shm = os.statvfs(base)
+                if st_shm.f_bavail * st_shm.f_frsize < nbytes + (64 << 20):
+                    base = tempfile.gettempdir()
+            except OSError:
+                base = tempfile.gettempdir()
+            name[0] = os.path.join(base, "rm_b200_bench_%d" % os.getpid())
             with open(name[0], "wb") as f:
                 f.truncate(nbytes)
         dist.broadcast_object_list(name, src=0)
@@ -722,7 +732,7 @@ def run_ours(args):
                              "busy tiles packed on the device, one device-to-host copy, host threads clear the black tiles and scatter"
                              if world == 1 else
                              "every rank: Renderer.render(frame, scene, patch_rows = its bands) -> rm_scene_upload + rm_render into ONE float32 "
-                             "frame in host memory shared by the ranks (/dev/shm); timed barrier to barrier, max over ranks"),
+                             "frame in host memory shared by the ranks (a mapped file in /dev/shm); timed barrier to barrier, max over ranks"),
                     "frame_matches_n1": e2e_ok,
                     "pcie_gbs": d2h / (e2e_ms * 1e-3) / 1e9,
                     "host_threads_per_rank": int(os.environ.get("RM_B200_HOST_THREADS", "0")) or os.cpu_count(),
