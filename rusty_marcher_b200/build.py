@@ -55,5 +55,24 @@ def build(force=False, verbose=False):
     return LIB
 
 
+EXAMPLE_SRC = os.path.join(os.path.dirname(HERE), "examples", "rm_headless.cpp")
+EXAMPLE_BIN = os.path.join(os.path.dirname(HERE), "examples", "rm_headless")
+
+
+def build_examples(force=False):
+    """examples/rm_headless: the headless C++ stand-in for the reference's GTK front end, over the C ABI only."""
+    build()
+    if (not force and os.path.exists(EXAMPLE_BIN)
+            and os.path.getmtime(EXAMPLE_BIN) >= max(os.path.getmtime(EXAMPLE_SRC), os.path.getmtime(LIB))):
+        return EXAMPLE_BIN
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(os.path.dirname(HERE), "include"), EXAMPLE_SRC, "-o", EXAMPLE_BIN,
+           "-L", HERE, "-lrm_b200", "-Wl,-rpath," + HERE]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building examples/rm_headless")
+    return EXAMPLE_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

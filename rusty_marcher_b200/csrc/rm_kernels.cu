@@ -673,6 +673,10 @@ render_fast_kernel(const DeviceScene<float> ds, const FrameParams<float> fp, con
         if (normalise && mx > 0.f) inv = 1.f / mx;              // framebuffer.rs:71-76: scale(1. / max_val)
         if (blockIdx.x == 0 && threadIdx.x == 0) link.box[link.rank][58] = now_ns();                // stamp: maxima gathered
     }
+    // A wait that gave up (a rank -- or, on a shared device, CTAs of this very grid -- did not answer within 2 s): the float
+    // rows behind the barrier are not known to be complete.  Nothing is converted, the sticky flag (rm_peer_status) says why
+    // the 8-bit frame is stale; whoever waits for this rank's signal gives up the same way.
+    if (ld_sys(link.box[link.rank] + 48) != 0ull) return;
     __threadfence();
     // Work unit: a 32x4 strip of a busy tile = 96 float4 in, 24 x 16 bytes out (a row of the strip is 96 bytes of RGB8: six
     // 128-bit stores).  A warp takes four units per round and issues their twelve fully coalesced loads (lane l reads chunks

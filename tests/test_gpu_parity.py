@@ -686,3 +686,39 @@ def test_peer_exchange_across_gpus_equals_single_gpu_frame(rm_gpu, tmp_path, nam
     assert len(frames) == 7
     for i, f in enumerate(frames):
         assert np.array_equal(f, whole[i % len(CAMERAS)]), "frame %d differs from the single-GPU frame" % i
+
+
+def test_headless_cpp_harness_writes_the_golden_ppm(rm_gpu, tmp_path):
+    """examples/rm_headless -- the C++ stand-in for `cargo run` + its buttons, over the C ABI only: default scene at the golden
+    file's size, "Save to file".  With the f64 kernels the P6 stream is the reference's engine/out.ppm (up to a pow ulp at a
+    quantisation boundary); the FP32 production kernels and the f64-rows delivery are within 1 LSB."""
+    import json
+    import os
+    import subprocess
+    from rusty_marcher_b200 import build as b
+    exe = b.build_examples()
+    meta = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "out_ppm.json")))
+    ref = O.render(O.Scene.create_default(), 800, 600, want_ids=False, want_fragile=False, want_counters=False)
+    want = parity.oracle_rgb8(ref["rgb"]).ravel().astype(np.int16)
+    for flags in (["--f64"], [], ["--rows-f64", "--frames", "3"]):
+        out = str(tmp_path / ("out_%d.ppm" % len(flags)))
+        r = subprocess.run([exe, "--width", "800", "--height", "600", "--out", out] + flags, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "Rendering using patches of size 32, using 450 patches overall" in r.stdout and "Scene rendered in " in r.stdout
+        data = open(out, "rb").read()
+        assert len(data) == meta["size"] and data[:15].decode("latin1") == meta["header"]
+        got = np.frombuffer(data[15:], dtype=np.uint8).astype(np.int16)
+        d = np.abs(got - want)
+        assert d.max() <= 1 and (d > 0).mean() < (1e-5 if flags == ["--f64"] else 2e-3), (flags, d.max(), (d > 0).mean())
+        if flags == ["--f64"] and d.max() == 0:
+            assert hashlib.sha256(data).hexdigest() == meta["sha256"]
+    # "Open file": a two-triangle OBJ, moved by (0, 0, -500) like main.rs:278-288
+    objp = tmp_path / "quad.obj"
+    objp.write_text("o quad\nv -200 -150 0\nv 200 -150 0\nv 200 150 0\nv -200 150 0\nf 1 2 3 4\n")
+    out = str(tmp_path / "quad.ppm")
+    r = subprocess.run([exe, "--obj", str(objp), "--width", "256", "--height", "160", "--out", out], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "2 primitives resident" in r.stdout, r.stdout + r.stderr
+    scene = rm_gpu.Scene.from_obj(str(objp))
+    py = gpu_render(rm_gpu, scene, 256, 160, "f32")
+    assert np.array_equal(np.frombuffer(open(out, "rb").read()[15:], dtype=np.uint8).reshape(160, 256, 3), py["rgb8"])
+    assert (py["prim_id"] >= 0).any()
