@@ -153,13 +153,15 @@ struct Context {
     // again -- the reference's render() borrows &Scene for every frame -- gets its pack (sorted primitive classes, raster
     // sources, the hierarchy: 0.1 to 0.2 s for 10^5 primitives) from here and only pays the hash and the upload.
     struct PackEntry {
-        uint64_t hash = 0;
+        uint64_t hash = 0, hash2 = 0;   // two independent 64-bit hashes of the content: a 128-bit key
         size_t bytes = 0;
         std::shared_ptr<rm::PackedScene<float>> pack;
     };
     std::vector<PackEntry> pack_cache;
     Pinned h_upload;                  // pinned staging of a scene upload
     Pinned h_stage, h_order;          // host delivery: pinned staging of the packed tiles / of the tile schedule + counters
+    static constexpr int kChunks = 4; // ... the tiles cross PCIe in this many copies, each followed by an event
+    cudaEvent_t chunk_ev[kChunks] = {nullptr, nullptr, nullptr, nullptr};
     std::unique_ptr<rm::HostPool> pool;
     std::vector<Delivered> delivered; // a handful of frames (RM_ROWS_RETAINED)
     std::mutex mu;
@@ -261,8 +263,8 @@ uint64_t hash_bytes(const void* data, size_t n, uint64_t seed) {
     r ^= r >> 32;
     return r * 0x9FB21C651E98DF25ull;
 }
-uint64_t hash_scene(const rm::OwnedFlatScene& f, size_t& bytes) {
-    uint64_t h = 0x243F6A8885A308D3ull;
+uint64_t hash_scene(const rm::OwnedFlatScene& f, size_t& bytes, const uint64_t seed = 0x243F6A8885A308D3ull) {
+    uint64_t h = seed;
     bytes = 0;
     auto add = [&](const auto& v) {
         const size_t n = v.size() * sizeof(v[0]);
@@ -284,9 +286,9 @@ template <> int pack_for<double>(SceneEntry& se, std::shared_ptr<rm::PackedScene
 }
 template <> int pack_for<float>(SceneEntry& se, std::shared_ptr<rm::PackedScene<float>>& out) {
     size_t bytes = 0;
-    const uint64_t h = hash_scene(se.flat, bytes);
+    const uint64_t h = hash_scene(se.flat, bytes), h2 = hash_scene(se.flat, bytes, 0x13198A2E03707344ull);
     for (size_t i = 0; i < g.pack_cache.size(); i++)
-        if (g.pack_cache[i].hash == h && g.pack_cache[i].bytes == bytes) {
+        if (g.pack_cache[i].hash == h && g.pack_cache[i].hash2 == h2 && g.pack_cache[i].bytes == bytes) {
             out = g.pack_cache[i].pack;
             std::rotate(g.pack_cache.begin() + i, g.pack_cache.begin() + i + 1, g.pack_cache.end());   // most recent last
             return RM_OK;
@@ -297,7 +299,7 @@ template <> int pack_for<float>(SceneEntry& se, std::shared_ptr<rm::PackedScene<
     const int rc = rm::pack_scene<float>(fs, *out, err);
     if (rc != RM_OK) return fail(rc, err);
     if (g.pack_cache.size() >= 4) g.pack_cache.erase(g.pack_cache.begin());
-    g.pack_cache.push_back({h, bytes, out});
+    g.pack_cache.push_back({h, h2, bytes, out});
     return RM_OK;
 }
 
@@ -700,8 +702,8 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
         if ((rc = g.h_stage.ensure(std::max<size_t>((size_t)n_busy * 12288, 64))) != RM_OK) return rc;
         // the busy tiles cross PCIe in a few chunks, each followed by an event: the host scatters chunk k while chunk
         // k + 1 is still on its way (one cudaMemcpyAsync per chunk)
-        constexpr int kChunks = 4;
-        static cudaEvent_t chunk_ev[kChunks] = {};
+        constexpr int kChunks = Context::kChunks;
+        cudaEvent_t* const chunk_ev = g.chunk_ev;
         int chunk_end[kChunks];
         int n_chunks = 0;
         for (int k = 0; k < kChunks && n_busy > 0; k++) {
@@ -871,6 +873,7 @@ void rm_shutdown(void) {
     g.h_stage.release(); g.h_order.release(); g.h_upload.release();
     g.pool.reset();
     g.delivered.clear();
+    for (auto& ev : g.chunk_ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ev : g.ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
     for (auto& ps : g.prof)
         for (auto& ev : ps.e) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
