@@ -720,6 +720,7 @@ def run_ours(args):
                          + ("" if world == 1 else ", the exchange inside K1 over NVLink peer memory: max of one float per rank, RGB8 tiles stored straight into rank 0's frame"))
                         if tr.exchange == "peer" else "K0, K1 render + fused max, max all-reduce (NCCL), K4 normalise+quantise RGB8, RGB8 gather to rank 0 (NCCL)",
                 "exchange": tr.exchange,
+                "frames_as_one_graph_launch": int(L.rm_graph_launch_count()),
                 "parallelism": "32-row bands dealt round-robin to %d rank%s" % (world, "" if world == 1 else "s"),
                 "l2": "flushed between steps (256 MiB fill, outside each step's CUDA events)"}),
             "ms_per_frame": ms_per_step,

@@ -220,6 +220,7 @@ extern "C" {
                            d_max: *mut c_void, exchange: *const RmExchange, seq: u32, normalise: c_int,
                            stream: *mut c_void) -> c_int;
     pub fn rm_peer_status(exchange: *const RmExchange) -> c_int;
+    pub fn rm_graph_launch_count() -> i64;
     pub fn rm_peer_stamps(exchange: *const RmExchange, out_ns: *mut u64) -> c_int;
     // ---- measurement
     pub fn rm_set_profiling(on: c_int) -> c_int;

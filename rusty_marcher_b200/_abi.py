@@ -122,6 +122,7 @@ SYMBOLS = {
     "rm_peer_free": (C.c_int, [C.c_void_p]),
     "rm_render_frame": (C.c_int, [C.c_int64, _P(RmParams), C.c_void_p, C.c_void_p, C.c_void_p, _P(RmExchange), C.c_uint32, C.c_int, C.c_void_p]),
     "rm_peer_status": (C.c_int, [_P(RmExchange)]),
+    "rm_graph_launch_count": (C.c_longlong, []),
     "rm_peer_stamps": (C.c_int, [_P(RmExchange), _P(C.c_uint64)]),
     "rm_host_alloc": (C.c_void_p, [C.c_size_t]),
     "rm_host_free": (None, [C.c_void_p]),

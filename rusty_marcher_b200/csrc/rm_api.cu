@@ -137,6 +137,8 @@ struct Context {
     int device = -1;
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
+    cudaStream_t cap_stream = nullptr;   // frames are captured into their graph here (rm_render_frame)
+    long long graph_launches = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // rm_set_profiling: events around K0 / K1 / K4 of every device render, a ring of kProfRing frames
     bool profiling = false;
@@ -458,10 +460,14 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
         cudaEvent_t ev_begin = ex.ev_begin, ev_rendered = ex.ev_rendered;
         ex.ev_begin = ex.ev_prepared = ex.ev_rendered = nullptr;
         cudaGraph_t graph = nullptr;
-        cudaError_t e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed);
+        // captured on a stream of the library's own (the caller's may be the legacy default stream, which cannot capture);
+        // the graph is launched on the caller's
+        cudaError_t e = cudaSuccess;
+        if (!g.cap_stream) e = cudaStreamCreateWithFlags(&g.cap_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamBeginCapture(g.cap_stream, cudaStreamCaptureModeRelaxed);
         if (e == cudaSuccess) {
-            const cudaError_t el = rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, stream, params->camera, launches, &ex);
-            e = cudaStreamEndCapture(stream, &graph);
+            const cudaError_t el = rm::launch_render<R>(dp.ds, fp, cull, d_rgb, d_prim, d_max, d_counters, g.cap_stream, params->camera, launches, &ex);
+            e = cudaStreamEndCapture(g.cap_stream, &graph);
             if (el != cudaSuccess) e = el;
         }
         if (e == cudaSuccess && se.graph_exec) {
@@ -481,6 +487,7 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
         if (graph) cudaGraphDestroy(graph);
         if (e == cudaSuccess) {
             launched = true;
+            g.graph_launches++;
         } else {                                                // not on this driver: plain launches from now on
             cudaGetLastError();
             graph_mode = 0;
@@ -883,6 +890,9 @@ void rm_shutdown(void) {
     g.prof_frames = 0;
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
+    if (g.cap_stream) cudaStreamDestroy(g.cap_stream);
+    g.cap_stream = nullptr;
+    g.graph_launches = 0;
     g.ready = false;
     g.device = -1;
 }
@@ -1261,6 +1271,8 @@ int rm_render_frame(RmScene scene, const RmParams* params, void* d_rgb, int32_t*
     }
     return RM_OK;
 }
+
+long long rm_graph_launch_count(void) { return g.graph_launches; }
 
 int rm_peer_stamps(const RmExchange* x, uint64_t out_ns[7]) {
     if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed)");

@@ -577,6 +577,7 @@ def test_frame_level_call_equals_the_two_step_path(rm_gpu, name, w, h):
     be = tiled.CudaBackend(scene, rm_gpu.create_renderer(1.5, h, w), w, h, dev)
     tr = tiled.TiledRenderer(be, w, h, dev)
     assert tr.exchange == "peer" and tr.world == 1
+    graphs_before = _abi.load().rm_graph_launch_count()
     try:
         frames, ptrs = [], []
         for _ in range(3):
@@ -590,6 +591,11 @@ def test_frame_level_call_equals_the_two_step_path(rm_gpu, name, w, h):
         assert ptrs[0] != ptrs[1] and ptrs[0] == ptrs[2]
         for f in frames:
             assert np.array_equal(f, whole["rgb8"])
+        # from a scene's second frame on a frame is ONE graph launch (on torch's legacy default stream here: captured on
+        # a stream of the library's own, launched on the caller's)
+        import os
+        if os.environ.get("RM_B200_GRAPH", "1") != "0":
+            assert _abi.load().rm_graph_launch_count() - graphs_before == 2
     finally:
         tr.close()
 

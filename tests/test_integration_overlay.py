@@ -17,7 +17,7 @@ PATCHES = os.path.join(ROOT, "integration", "engine", "patches")
 
 C_TO_RUST = {"double": "f64", "float": "f32", "int32_t": "i32", "uint32_t": "u32", "int64_t": "i64", "uint64_t": "u64",
              "uint8_t": "u8", "int": "c_int", "size_t": "usize", "char": "c_char", "void": "c_void", "unsigned char": "u8",
-             "RmScene": "RmScene"}
+             "long long": "i64", "RmScene": "RmScene"}
 
 
 def strip_comments(src):
