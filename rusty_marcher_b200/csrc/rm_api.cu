@@ -448,13 +448,14 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
         ex.ev_rendered = ps.e[2];
     }
     SceneEntry& se = it->second;
-    // RM_B200_GRAPH (default on): frame-level calls go to the GPU as ONE graph launch from the scene's second frame on
-    // (the first one runs the launchers' one-time set-up).  A driver that cannot capture the launch pair switches it off.
-    static int graph_mode = -1;
-    if (graph_mode < 0) {
-        const char* env = getenv("RM_B200_GRAPH");
-        graph_mode = (env && env[0] == '0') ? 0 : 1;
-    }
+    // RM_B200_GRAPH=1: frame-level calls go to the GPU as ONE graph launch from the scene's second frame on (the first one
+    // runs the launchers' one-time set-up).  Off by default: measured on the 4K cornell frame the graph is 0.4 us per frame
+    // SLOWER than the two plain launches (69.66 vs 69.28 us, profiles/r5j_graph_ab.txt) -- the programmatic launch edge
+    // already hides K1's launch behind K0, and the capture + update cost host time on top.  Read per call, so a caller can
+    // switch between frames; a driver that cannot capture the pair switches it off for the process.
+    static int graph_broken = 0;
+    const char* genv = getenv("RM_B200_GRAPH");
+    const int graph_mode = (!graph_broken && genv && genv[0] == '1') ? 1 : 0;
     bool launched = false;
     if (as_graph && graph_mode == 1 && se.frames > 0 && fp.n_bands > 0) {
         cudaEvent_t ev_begin = ex.ev_begin, ev_rendered = ex.ev_rendered;
@@ -490,7 +491,7 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
             g.graph_launches++;
         } else {                                                // not on this driver: plain launches from now on
             cudaGetLastError();
-            graph_mode = 0;
+            graph_broken = 1;
             if (se.graph_exec) cudaGraphExecDestroy(se.graph_exec);
             se.graph_exec = nullptr;
             ex.ev_begin = ev_begin;

@@ -577,10 +577,14 @@ def test_frame_level_call_equals_the_two_step_path(rm_gpu, name, w, h):
     be = tiled.CudaBackend(scene, rm_gpu.create_renderer(1.5, h, w), w, h, dev)
     tr = tiled.TiledRenderer(be, w, h, dev)
     assert tr.exchange == "peer" and tr.world == 1
+    import os
     graphs_before = _abi.load().rm_graph_launch_count()
     try:
         frames, ptrs = [], []
-        for _ in range(3):
+        for i in range(5):
+            # frames 3..5 as ONE CUDA graph launch each (RM_B200_GRAPH is read per call; torch's legacy default stream here:
+            # captured on a stream of the library's own, launched on the caller's), camera parameters pushed by graph update
+            os.environ["RM_B200_GRAPH"] = "1" if i >= 2 else "0"
             f = tr.render()
             torch.cuda.synchronize()
             tr.peer.status()
@@ -591,12 +595,9 @@ def test_frame_level_call_equals_the_two_step_path(rm_gpu, name, w, h):
         assert ptrs[0] != ptrs[1] and ptrs[0] == ptrs[2]
         for f in frames:
             assert np.array_equal(f, whole["rgb8"])
-        # from a scene's second frame on a frame is ONE graph launch (on torch's legacy default stream here: captured on
-        # a stream of the library's own, launched on the caller's)
-        import os
-        if os.environ.get("RM_B200_GRAPH", "1") != "0":
-            assert _abi.load().rm_graph_launch_count() - graphs_before == 2
+        assert _abi.load().rm_graph_launch_count() - graphs_before == 3
     finally:
+        os.environ.pop("RM_B200_GRAPH", None)
         tr.close()
 
 
