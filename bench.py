@@ -507,24 +507,16 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # per-kernel CUDA events on the launching stream (K0 | K1 | K4), kept by the library for the last 256 frames
-    _abi.check(L.rm_set_profiling(1))
-    for _ in range(max(args.warmup, 3)):
-        flush.fill_(1)
-        tr.render()
-    barrier()
+    # ---- the timed region: K frames, each bracketed by CUDA events on the launching stream (a frame is the K0 -> K1 pair and
+    # nothing else), L2 flushed before each, barrier + synchronize on both sides, max over ranks
+    ms_per_step = timed_frames(tr, flush, args.steps, max(args.warmup, 3), world, dev)
+    value = segs / (ms_per_step * 1e-3)
 
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for a, b in ev:
-        flush.fill_(0)                       # L2 flush between timed iterations, outside the step's events
-        a.record()
-        tr.render()                          # one frame: K0 + K1 + K4 incl. the exchange (rm_render_frame)
-        b.record()
-    barrier()
-    if tr.peer is not None:
-        tr.peer.status()                     # raises if a wait on a peer timed out
-    step_ms = [a.elapsed_time(b) for a, b in ev]
+    # ---- the same K frames once more with the library's per-kernel events on (K0 | K1 | K4, kept for the last 256 frames):
+    # the split of a frame between the kernels.  Not the headline pass: the extra event records between the two launches
+    # cost ~5 us per frame (0.0697 against 0.0645 ms on the 4K cornell frame, profiles/r5l_*).
+    _abi.check(L.rm_set_profiling(1))
+    profiled_ms_per_step = timed_frames(tr, flush, args.steps, 3, world, dev)
     k0_ms, k1_ms, k4_ms = [], [], []
     if tr.exchange == "peer":
         t0, t1, t4 = C.c_double(0), C.c_double(0), C.c_double(0)
@@ -539,26 +531,29 @@ def run_ours(args):
         k0_ms, k1_ms, k4_ms = [t0.value], [t1.value], [0.0]
     _abi.check(L.rm_set_profiling(0))
     n_k = len(k1_ms)
-    total = torch.tensor([sum(step_ms), sum(k1_ms) / n_k, sum(k0_ms) / n_k, sum(k4_ms) / n_k], dtype=torch.float64, device=dev)
+    total = torch.tensor([sum(k1_ms) / n_k, sum(k0_ms) / n_k, sum(k4_ms) / n_k], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total, op=dist.ReduceOp.MAX)
-    total_ms, k1_ms_avg, k0_ms_avg, k4_ms_avg = (float(x) for x in total)
-    ms_per_step = total_ms / args.steps
-    value = segs / (ms_per_step * 1e-3)
+    k1_profiled_ms, k0_ms_avg, k4_ms_avg = (float(x) for x in total)
+    # the roofline's kernel duration: the timed region's own events (they bracket the kernel pair of a frame; on the peer
+    # path K1 contains the exchange wait and the fused K4)
+    k1_ms_avg = ms_per_step if tr.exchange == "peer" else k1_profiled_ms
 
     # ---- the same frames as ONE CUDA graph launch each (RM_B200_GRAPH=1, read per call): reported next
-    # to the headline, which uses the two plain launches because they measure faster
+    # to the headline, in alternating blocks so that clock drift hits both arms alike
     graph_ab = None
     graphs_headline = int(L.rm_graph_launch_count())          # of the headline's frames (0 unless RM_B200_GRAPH=1 is set)
     if os.environ.get("RM_B200_GRAPH") is None:
         n_g = min(args.steps, 100)
         before = int(L.rm_graph_launch_count())
-        os.environ["RM_B200_GRAPH"] = "1"
-        ms_graph = timed_frames(tr, flush, n_g, 5, world, dev)
-        os.environ["RM_B200_GRAPH"] = "0"
-        ms_plain = timed_frames(tr, flush, n_g, 5, world, dev)
+        arms = {"1": [], "0": []}
+        for _block in range(3):
+            for arm in ("1", "0"):
+                os.environ["RM_B200_GRAPH"] = arm
+                arms[arm].append(timed_frames(tr, flush, n_g, 3, world, dev))
         del os.environ["RM_B200_GRAPH"]
-        graph_ab = {"one_graph_launch_ms_per_frame": ms_graph, "two_launches_ms_per_frame": ms_plain, "frames": n_g,
+        graph_ab = {"one_graph_launch_ms_per_frame": sum(arms["1"]) / 3, "two_launches_ms_per_frame": sum(arms["0"]) / 3,
+                    "blocks": {"graph": arms["1"], "two_launches": arms["0"]}, "frames_per_block": n_g,
                     "graph_launches": int(L.rm_graph_launch_count()) - before}
 
     # ---- the frame the ranks assemble against the single-GPU frame: three consecutive frames, the camera moving
@@ -758,6 +753,9 @@ def run_ours(args):
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": peak_t.value, "unit": "TFLOP/s",
                          "frac": ach_tflops / peak_t.value if ach_tflops is not None else None, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": "render_fast_kernel<false, 1, *> (hierarchy walk)" if accel else "render_fast_kernel<true, 0, *>", "kernel_ms": k1_ms_avg,
+                         "kernel_ms_source": "the timed region's CUDA events (each step is the K0 -> K1 pair and nothing else)" if tr.exchange == "peer" else "the library's events around K1",
+                         "profiled_pass": {"ms_per_step": profiled_ms_per_step, "k0_plus_k1_ms": k1_profiled_ms,
+                                           "note": "second pass of the same frames with the library's per-kernel events on; they cost the difference to ms_per_step"},
                          "work_definition": (walk["definition"] if walk is not None else "reference traversal, resident primitives (SURVEY.md 8d)"),
                          "walk": walk, "brute_force_equivalent_frac": brute_frac if accel else None,
                          "brute_force_ms_same_frame": brute_ms,

@@ -250,6 +250,11 @@ int rm_render_device_stats(RmScene scene, const RmParams* params, void* d_rgb, i
 int rm_tonemap_device(const RmParams* params, const void* d_rgb, const void* d_max, int normalise,
                       uint8_t* d_rgb8, void* stream);
 
+/* 64-bit content hash of a byte range, at memory speed: the function the library keys its cache of packed scenes with
+ * (a scene uploaded again with the same content is not packed again).  Exported for bindings that keep caches of their own
+ * keyed by content -- the Python mirror's scene fingerprint.  Needs no GPU. */
+uint64_t rm_content_hash(const void* data, size_t bytes, uint64_t seed);
+
 /* ---- pinned host memory helpers ---------------------------------------------------------------- */
 void* rm_host_alloc(size_t bytes);
 void  rm_host_free(void* p);

@@ -207,6 +207,7 @@ extern "C" {
     pub fn rm_tonemap_device(params: *const RmParams, d_rgb: *const c_void, d_max: *const c_void, normalise: c_int,
                              d_rgb8: *mut u8, stream: *mut c_void) -> c_int;
     // ---- pinned host memory
+    pub fn rm_content_hash(data: *const c_void, bytes: usize, seed: u64) -> u64;
     pub fn rm_host_alloc(bytes: usize) -> *mut c_void;
     pub fn rm_host_free(p: *mut c_void);
     pub fn rm_host_register(p: *mut c_void, bytes: usize) -> c_int;

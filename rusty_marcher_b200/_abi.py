@@ -124,6 +124,7 @@ SYMBOLS = {
     "rm_peer_status": (C.c_int, [_P(RmExchange)]),
     "rm_graph_launch_count": (C.c_longlong, []),
     "rm_peer_stamps": (C.c_int, [_P(RmExchange), _P(C.c_uint64)]),
+    "rm_content_hash": (C.c_uint64, [C.c_void_p, C.c_size_t, C.c_uint64]),
     "rm_host_alloc": (C.c_void_p, [C.c_size_t]),
     "rm_host_free": (None, [C.c_void_p]),
     "rm_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),

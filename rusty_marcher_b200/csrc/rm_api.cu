@@ -265,17 +265,35 @@ uint64_t hash_bytes(const void* data, size_t n, uint64_t seed) {
     r ^= r >> 32;
     return r * 0x9FB21C651E98DF25ull;
 }
-uint64_t hash_scene(const rm::OwnedFlatScene& f, size_t& bytes, const uint64_t seed = 0x243F6A8885A308D3ull) {
-    uint64_t h = seed;
+// Two independent 64-bit content hashes of a flat scene (the key of the pack cache).  Large arrays are hashed in 256 KB
+// blocks on the host pool and the block hashes are chained in order: the key does not depend on the number of threads.
+rm::HostPool& host_pool();
+void hash_scene(const rm::OwnedFlatScene& f, size_t& bytes, uint64_t& h1, uint64_t& h2) {
+    constexpr uint64_t kSeed1 = 0x243F6A8885A308D3ull, kSeed2 = 0x13198A2E03707344ull;
+    constexpr size_t kBlock = 256 << 10;
+    h1 = kSeed1;
+    h2 = kSeed2;
     bytes = 0;
     auto add = [&](const auto& v) {
         const size_t n = v.size() * sizeof(v[0]);
-        h = hash_bytes(v.data(), n, h + v.size());
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(v.data());
+        const size_t n_blocks = std::max<size_t>(1, (n + kBlock - 1) / kBlock);
+        std::vector<uint64_t> part(2 * n_blocks);
+        auto one = [&](int k) {
+            const size_t at = (size_t)k * kBlock, len = std::min(kBlock, n - std::min(n, at));
+            part[2 * k] = hash_bytes(p + at, len, kSeed1);
+            part[2 * k + 1] = hash_bytes(p + at, len, kSeed2);
+        };
+        if (n_blocks >= 4) host_pool().run((int)n_blocks, one);
+        else for (size_t k = 0; k < n_blocks; k++) one((int)k);
+        for (size_t k = 0; k < n_blocks; k++) {
+            h1 = hash_bytes(&part[2 * k], 8, h1 + v.size());
+            h2 = hash_bytes(&part[2 * k + 1], 8, h2 + v.size());
+        }
         bytes += n;
     };
     add(f.shapes); add(f.spheres); add(f.polygons); add(f.polygon_vertices); add(f.objs); add(f.triangles);
     add(f.triangle_reflectances); add(f.lights);
-    return h;
 }
 
 template <typename R> int pack_for(SceneEntry& se, std::shared_ptr<rm::PackedScene<R>>& out);
@@ -283,12 +301,13 @@ template <> int pack_for<double>(SceneEntry& se, std::shared_ptr<rm::PackedScene
     out = std::make_shared<rm::PackedScene<double>>();
     std::string err;
     RmFlatScene fs = se.flat.view();
-    const int rc = rm::pack_scene<double>(fs, *out, err);
+    const int rc = rm::pack_scene<double>(fs, *out, err, &host_pool());
     return rc == RM_OK ? RM_OK : fail(rc, err);
 }
 template <> int pack_for<float>(SceneEntry& se, std::shared_ptr<rm::PackedScene<float>>& out) {
     size_t bytes = 0;
-    const uint64_t h = hash_scene(se.flat, bytes), h2 = hash_scene(se.flat, bytes, 0x13198A2E03707344ull);
+    uint64_t h = 0, h2 = 0;
+    hash_scene(se.flat, bytes, h, h2);
     for (size_t i = 0; i < g.pack_cache.size(); i++)
         if (g.pack_cache[i].hash == h && g.pack_cache[i].hash2 == h2 && g.pack_cache[i].bytes == bytes) {
             out = g.pack_cache[i].pack;
@@ -298,7 +317,7 @@ template <> int pack_for<float>(SceneEntry& se, std::shared_ptr<rm::PackedScene<
     out = std::make_shared<rm::PackedScene<float>>();
     std::string err;
     RmFlatScene fs = se.flat.view();
-    const int rc = rm::pack_scene<float>(fs, *out, err);
+    const int rc = rm::pack_scene<float>(fs, *out, err, &host_pool());
     if (rc != RM_OK) return fail(rc, err);
     if (g.pack_cache.size() >= 4) g.pack_cache.erase(g.pack_cache.begin());
     g.pack_cache.push_back({h, h2, bytes, out});
@@ -623,9 +642,7 @@ inline void put_values(char* dst, const float* src, int n, int elem) {
 
 rm::HostPool& host_pool() {
     if (!g.pool) {
-        int n = (int)std::thread::hardware_concurrency();
-        if (const char* env = getenv("RM_B200_HOST_THREADS")) n = atoi(env);
-        g.pool.reset(new rm::HostPool(std::max(1, std::min(n, 64))));
+        g.pool.reset(new rm::HostPool(rm::host_thread_count(64)));
     }
     return *g.pool;
 }
@@ -1338,6 +1355,8 @@ int rm_tonemap_device(const RmParams* params, const void* d_rgb, const void* d_m
     }
     return RM_OK;
 }
+
+uint64_t rm_content_hash(const void* data, size_t bytes, uint64_t seed) { return data || !bytes ? hash_bytes(data, bytes, seed) : 0; }
 
 void* rm_host_alloc(size_t bytes) {
     void* p = nullptr;

@@ -1,14 +1,16 @@
 // rm_bvh.cpp -- host-side builder of the hierarchy in rm_bvh.cuh: binned surface-area heuristic (16 bins, three
 // axes), leaves of at most kBvhLeafMax primitives, median splits when the heuristic cannot separate a range or
 // the tree gets deeper than 40 levels (so the traversal stack of kBvhStack entries always suffices).
-// Pure C++: runs once per scene at upload (~0.1 s for 10^5 primitives on one core; scenes of 8192 primitives and more
-// build their subtrees on a thread pool), shared with the host emulation.
+// Pure C++: runs once per scene at upload (~70 ms for 10^5 primitives on one core; scenes of 8192 primitives and more
+// sweep the top of the tree and build its subtrees on a thread pool -- the tree is the same for any number of threads),
+// shared with the host emulation.
 #include <algorithm>
 #include <atomic>
 #include <climits>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <thread>
 
 #include "rm_scene.h"
@@ -68,6 +70,7 @@ struct Builder {
     int max_depth = 0;
     std::vector<Task>* defer = nullptr;   // when set: ranges of at most `grain` items become tasks instead of subtrees
     int grain = 0;
+    HostPool* pool = nullptr;             // when set: large ranges are swept on its threads
 
     Builder(std::vector<Item>& i, std::vector<R4<float>>& n, std::vector<int>& p) : items(i), nodes(n), prims(p) {}
 
@@ -80,17 +83,38 @@ struct Builder {
     // returns the child code of the subtree over items [begin, end) and its box
     int build(int begin, int end, int depth, Box& box) {
         max_depth = std::max(max_depth, depth);
+        const int n = end - begin;
+        // ranges of the top of a large tree are swept in blocks on the pool's threads; min / max and counts combine
+        // exactly, so the splits are those of the sequential sweep
+        constexpr int kBlock = 4096;
+        const bool wide = pool != nullptr && n >= 4 * kBlock;
+        const int n_blocks = (n + kBlock - 1) / kBlock;
         box.clear();
         Box cb;
         cb.clear();
-        for (int i = begin; i < end; i++) {
-            box.grow(items[i].box);
-            for (int a = 0; a < 3; a++) {
-                cb.lo[a] = std::min(cb.lo[a], items[i].c[a]);
-                cb.hi[a] = std::max(cb.hi[a], items[i].c[a]);
+        auto bounds_of = [&](int b0, int b1, Box& bx, Box& cx) {
+            for (int i = b0; i < b1; i++) {
+                bx.grow(items[i].box);
+                for (int a = 0; a < 3; a++) {
+                    cx.lo[a] = std::min(cx.lo[a], items[i].c[a]);
+                    cx.hi[a] = std::max(cx.hi[a], items[i].c[a]);
+                }
             }
+        };
+        if (wide) {
+            std::vector<Box> part(2 * (size_t)n_blocks);
+            pool->run(n_blocks, [&](int k) {
+                part[2 * k].clear();
+                part[2 * k + 1].clear();
+                bounds_of(begin + k * kBlock, std::min(end, begin + (k + 1) * kBlock), part[2 * k], part[2 * k + 1]);
+            });
+            for (int k = 0; k < n_blocks; k++) {
+                box.grow(part[2 * k]);
+                cb.grow(part[2 * k + 1]);
+            }
+        } else {
+            bounds_of(begin, end, box, cb);
         }
-        const int n = end - begin;
         if (n <= kBvhLeafMax) return make_leaf(begin, end);
         if (defer && n <= grain) {
             defer->push_back({begin, end, depth});
@@ -100,21 +124,57 @@ struct Builder {
         int mid = -1;
         if (depth < 40) {
             constexpr int kBins = 16;
+            struct Bins {
+                Box bb[3][kBins];
+                int cnt[3][kBins];
+            };
+            double scale[3];
+            bool use[3];
+            for (int a = 0; a < 3; a++) {
+                const double ext = (double)cb.hi[a] - cb.lo[a];
+                use[a] = ext > 0. && std::isfinite(ext);
+                scale[a] = use[a] ? kBins / ext : 0.;
+            }
+            auto clear_bins = [](Bins& B) {
+                for (int a = 0; a < 3; a++)
+                    for (int k = 0; k < kBins; k++) {
+                        B.bb[a][k].clear();
+                        B.cnt[a][k] = 0;
+                    }
+            };
+            auto bin_range = [&](int b0, int b1, Bins& B) {
+                for (int i = b0; i < b1; i++)
+                    for (int a = 0; a < 3; a++) {
+                        if (!use[a]) continue;
+                        int k = (int)(((double)items[i].c[a] - cb.lo[a]) * scale[a]);
+                        k = std::min(std::max(k, 0), kBins - 1);
+                        B.bb[a][k].grow(items[i].box);
+                        B.cnt[a][k]++;
+                    }
+            };
+            Bins all;
+            clear_bins(all);
+            if (wide) {
+                std::vector<Bins> part((size_t)n_blocks);
+                pool->run(n_blocks, [&](int k) {
+                    clear_bins(part[k]);
+                    bin_range(begin + k * kBlock, std::min(end, begin + (k + 1) * kBlock), part[k]);
+                });
+                for (int k = 0; k < n_blocks; k++)
+                    for (int a = 0; a < 3; a++)
+                        for (int j = 0; j < kBins; j++) {
+                            all.bb[a][j].grow(part[k].bb[a][j]);
+                            all.cnt[a][j] += part[k].cnt[a][j];
+                        }
+            } else {
+                bin_range(begin, end, all);
+            }
             double best = std::numeric_limits<double>::infinity();
             int best_axis = -1, best_bin = -1;
             for (int a = 0; a < 3; a++) {
-                const double ext = (double)cb.hi[a] - cb.lo[a];
-                if (!(ext > 0.) || !std::isfinite(ext)) continue;
-                Box bb[kBins];
-                int cnt[kBins] = {};
-                for (auto& b : bb) b.clear();
-                const double scale = kBins / ext;
-                for (int i = begin; i < end; i++) {
-                    int k = (int)(((double)items[i].c[a] - cb.lo[a]) * scale);
-                    k = std::min(std::max(k, 0), kBins - 1);
-                    bb[k].grow(items[i].box);
-                    cnt[k]++;
-                }
+                if (!use[a]) continue;
+                const Box* bb = all.bb[a];
+                const int* cnt = all.cnt[a];
                 double right_area[kBins];
                 Box acc;
                 acc.clear();
@@ -183,10 +243,21 @@ struct Builder {
 
 }  // namespace
 
-int build_bvh(const std::vector<BvhPrimBox>& in, std::vector<R4<float>>& nodes, std::vector<int>& prims) {
+int build_bvh(const std::vector<BvhPrimBox>& in, std::vector<R4<float>>& nodes, std::vector<int>& prims, HostPool* shared_pool) {
     nodes.clear();
     prims.clear();
     if (in.empty()) return 0;
+    const int n = (int)in.size();
+    // large scenes: the caller's threads or, without any, some of this call's own
+    std::unique_ptr<HostPool> own_pool;
+    HostPool* pool = nullptr;
+    if (n >= 8192) {
+        pool = shared_pool;
+        if (!pool) {
+            own_pool.reset(new HostPool(host_thread_count(16)));
+            pool = own_pool.get();
+        }
+    }
     // S: largest finite coordinate magnitude; every box grows by 2^-14 S on each side (see rm_bvh.cuh)
     double S = 0.;
     for (const BvhPrimBox& p : in)
@@ -196,24 +267,30 @@ int build_bvh(const std::vector<BvhPrimBox>& in, std::vector<R4<float>>& nodes, 
         }
     const double pad = std::max(S, 1e-30) * (1.0 / 16384.0);
     const double big = 1e30;
-    std::vector<Item> items;
-    items.reserve(in.size());
-    for (const BvhPrimBox& p : in) {
-        Item it;
-        for (int a = 0; a < 3; a++) {
-            double lo = p.lo[a], hi = p.hi[a];
-            if (!(lo >= -big)) lo = -big;      // also catches NaN: an unbounded box is conservative
-            if (!(hi <= big)) hi = big;
-            if (!(lo <= hi)) { lo = -big; hi = big; }
-            it.box.lo[a] = round_down(lo - pad);
-            it.box.hi[a] = round_up(hi + pad);
-            it.c[a] = (float)(0.5 * (lo + hi));
+    std::vector<Item> items((size_t)n);
+    auto make_items = [&](int b0, int b1) {
+        for (int i = b0; i < b1; i++) {
+            const BvhPrimBox& p = in[i];
+            Item& it = items[i];
+            for (int a = 0; a < 3; a++) {
+                double lo = p.lo[a], hi = p.hi[a];
+                if (!(lo >= -big)) lo = -big;      // also catches NaN: an unbounded box is conservative
+                if (!(hi <= big)) hi = big;
+                if (!(lo <= hi)) { lo = -big; hi = big; }
+                it.box.lo[a] = round_down(lo - pad);
+                it.box.hi[a] = round_up(hi + pad);
+                it.c[a] = (float)(0.5 * (lo + hi));
+            }
+            it.code = p.code;
         }
-        it.code = p.code;
-        items.push_back(it);
+    };
+    if (pool) {
+        constexpr int kBlock = 4096;
+        pool->run((n + kBlock - 1) / kBlock, [&](int k) { make_items(k * kBlock, std::min(n, (k + 1) * kBlock)); });
+    } else {
+        make_items(0, n);
     }
     Builder b(items, nodes, prims);
-    const int n = (int)items.size();
     if (n <= kBvhLeafMax) {
         // the root is always an inner node: one real leaf and one empty one behind the same box
         Box box;
@@ -225,9 +302,7 @@ int build_bvh(const std::vector<BvhPrimBox>& in, std::vector<R4<float>>& nodes, 
         return 1;
     }
     Box root;
-    const unsigned hw = std::thread::hardware_concurrency();
-    const int n_threads = (int)std::min(16u, hw ? hw : 1u);
-    if (n < 8192 || n_threads < 2) {
+    if (!pool) {
         b.build(0, n, 1, root);
         return b.max_depth;
     }
@@ -237,6 +312,7 @@ int build_bvh(const std::vector<BvhPrimBox>& in, std::vector<R4<float>>& nodes, 
     std::vector<Task> tasks;
     b.defer = &tasks;
     b.grain = std::max(n / 64, 1024);
+    b.pool = pool;
     b.build(0, n, 1, root);
     struct Sub {
         std::vector<R4<float>> nodes;
@@ -244,27 +320,18 @@ int build_bvh(const std::vector<BvhPrimBox>& in, std::vector<R4<float>>& nodes, 
         int root = 0, depth = 0;
     };
     std::vector<Sub> subs(tasks.size());
-    std::atomic<int> next{0};
-    auto work = [&] {
-        for (;;) {
-            const int k = next.fetch_add(1);
-            if (k >= (int)tasks.size()) break;
-            // arrays local to the worker while they grow (neighbouring Sub records share cache lines)
-            std::vector<R4<float>> ln;
-            std::vector<int> lp;
-            Builder sb(items, ln, lp);
-            Box box;
-            const int root = sb.build(tasks[k].begin, tasks[k].end, tasks[k].depth, box);
-            subs[k].nodes = std::move(ln);
-            subs[k].prims = std::move(lp);
-            subs[k].root = root;
-            subs[k].depth = sb.max_depth;
-        }
-    };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < n_threads; t++) pool.emplace_back(work);
-    work();
-    for (auto& th : pool) th.join();
+    pool->run((int)tasks.size(), [&](int k) {
+        // arrays local to the worker while they grow (neighbouring Sub records share cache lines)
+        std::vector<R4<float>> ln;
+        std::vector<int> lp;
+        Builder sb(items, ln, lp);
+        Box box;
+        const int root_code = sb.build(tasks[k].begin, tasks[k].end, tasks[k].depth, box);
+        subs[k].nodes = std::move(ln);
+        subs[k].prims = std::move(lp);
+        subs[k].root = root_code;
+        subs[k].depth = sb.max_depth;
+    });
     int depth = b.max_depth;
     const size_t n_top = nodes.size() / 4;
     std::vector<int> mapped(tasks.size());

@@ -10,12 +10,20 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
 
 namespace rm {
+
+// Threads for a piece of host work: RM_B200_HOST_THREADS when set, else the hardware's, at most `cap`.
+inline int host_thread_count(int cap) {
+    int n = (int)std::thread::hardware_concurrency();
+    if (const char* env = std::getenv("RM_B200_HOST_THREADS")) n = std::atoi(env);
+    return n < 1 ? 1 : (n > cap ? cap : n);
+}
 
 class HostPool {
 public:

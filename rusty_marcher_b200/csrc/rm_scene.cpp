@@ -6,7 +6,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
+#include <memory>
+#include <thread>
 
 namespace rm {
 
@@ -88,12 +91,19 @@ template <> float pred_1e6<float>() { return std::nextafterf(1e-6f, 0.f); }
 
 int align32(int x) { return (x + 31) & ~31; }
 
+// A planar primitive while it is being packed: views of the caller's f64 arrays (nothing is copied or allocated per
+// primitive -- a scene of 10^5 triangles is packed in the time its first frame takes).
 struct PlaneTmp {
-    double n[3], c[3];
-    double thr_is_triangle;
-    std::vector<double> vxy;   // x,y pairs
+    const double* n;    // plane normal (triangle.rs:33-47 / polygon.rs:16-42: precomputed by the caller)
+    const double* c;    // plane point
+    const double* v;    // vertices, x y z each; only x and y are ever read (triangle.rs:13-15)
+    int nv;
     int id, shape;
-    int cls;   // 0 hittable, 1 back-facing (projected winding clockwise), 2 degenerate projection
+    int src;            // index of the RmPolygon / RmTriangle it views
+    int cls;            // 0 hittable, 1 back-facing (projected winding clockwise), 2 degenerate projection
+    bool is_triangle;   // an Obj's triangle: threshold 1e-6 on d.n (triangle.rs:61); a polygon tests == 0 (polygon.rs:67)
+    double x(size_t i) const { return v[3 * i]; }
+    double y(size_t i) const { return v[3 * i + 1]; }
 };
 
 // A planar primitive is hit only if every edge term ((v_i-p) x (v_i+1-p)).z is > 0
@@ -109,14 +119,14 @@ struct PlaneTmp {
 // their squared perimeter (e.g. the dodecahedron faces whose normal.z is 5e-9 because tobj rounds
 // vertices to f32): their edge terms are smaller than FP32 rounding noise, and no pixel ray of any
 // test scene passes through such a sliver in the reference either.
-int classify_plane(const std::vector<double>& vxy, bool single_precision) {
-    size_t n = vxy.size() / 2;
+int classify_plane(const PlaneTmp& p, bool single_precision) {
+    const size_t n = (size_t)p.nv;
     double area2 = 0., scale = 0., perimeter = 0.;
     for (size_t i = 0; i < n; i++) {
-        size_t j = (i + 1) % n;
-        area2 += vxy[2 * i] * vxy[2 * j + 1] - vxy[2 * i + 1] * vxy[2 * j];
-        scale = std::fmax(scale, std::fmax(std::fabs(vxy[2 * i]), std::fabs(vxy[2 * i + 1])));
-        perimeter += std::hypot(vxy[2 * j] - vxy[2 * i], vxy[2 * j + 1] - vxy[2 * i + 1]);
+        const size_t j = (i + 1) % n;
+        area2 += p.x(i) * p.y(j) - p.y(i) * p.x(j);
+        scale = std::fmax(scale, std::fmax(std::fabs(p.x(i)), std::fabs(p.y(i))));
+        perimeter += std::hypot(p.x(j) - p.x(i), p.y(j) - p.y(i));
     }
     double tol = 1e-9 * scale * scale;
     if (single_precision) tol = std::fmax(tol, 1e-6 * perimeter * perimeter);
@@ -129,16 +139,16 @@ template <typename R> R4<R> mk4(double x, double y, double z, double w) { return
 // f64 layout: the reference's own operands -- plane point and the x,y of every vertex.
 void write_plane(const PlaneTmp& p, R4<double>& c4, R2<double>* vert) {
     c4 = {p.c[0], p.c[1], p.c[2], 0.};
-    for (size_t v = 0; v < p.vxy.size() / 2; v++) vert[v] = {p.vxy[2 * v], p.vxy[2 * v + 1]};
+    for (size_t v = 0; v < (size_t)p.nv; v++) vert[v] = {p.x(v), p.y(v)};
 }
 // f32 layout: n.C and the affine edge functions about vertex 0, all folded in f64 and then rounded
 // once (see plane_intersect<float> in rm_trace.cuh).
 // edge function i of a plane about its vertex 0, in f64: e_i(q) = A*q.x + B*q.y + C, q = p - v0
 void edge_about_v0(const PlaneTmp& p, size_t i, double& A, double& B, double& C) {
-    const size_t nv = p.vxy.size() / 2, j = (i + 1) % nv;
-    const double x0 = p.vxy[0], y0 = p.vxy[1];
-    const double ax = p.vxy[2 * i] - x0, ay = p.vxy[2 * i + 1] - y0;
-    const double bx = p.vxy[2 * j] - x0, by = p.vxy[2 * j + 1] - y0;
+    const size_t nv = (size_t)p.nv, j = (i + 1) % nv;
+    const double x0 = p.x(0), y0 = p.y(0);
+    const double ax = p.x(i) - x0, ay = p.y(i) - y0;
+    const double bx = p.x(j) - x0, by = p.y(j) - y0;
     A = ay - by;
     B = bx - ax;
     C = ax * by - ay * bx;
@@ -146,8 +156,8 @@ void edge_about_v0(const PlaneTmp& p, size_t i, double& A, double& B, double& C)
 double plane_dn(const PlaneTmp& p) { return p.c[0] * p.n[0] + p.c[1] * p.n[1] + p.c[2] * p.n[2]; }
 
 void write_plane(const PlaneTmp& p, R4<float>& k4, R4<float>* edge) {
-    k4 = {(float)plane_dn(p), (float)p.vxy[0], (float)p.vxy[1], 0.f};
-    for (size_t i = 0; i < p.vxy.size() / 2; i++) {
+    k4 = {(float)plane_dn(p), (float)p.x(0), (float)p.y(0), 0.f};
+    for (size_t i = 0; i < (size_t)p.nv; i++) {
         double A, B, C;
         edge_about_v0(p, i, A, B, C);
         edge[i] = {(float)A, (float)B, (float)C, 0.f};
@@ -159,14 +169,14 @@ void write_triangle(const PlaneTmp& p, double* src, R4<float>* g) {
     double A[3], B[3], C[3];
     for (size_t i = 0; i < 3; i++) edge_about_v0(p, i, A[i], B[i], C[i]);   // C[0] == C[2] == 0: both edges touch vertex 0
     const double dn = plane_dn(p);
-    const float thr = (p.thr_is_triangle != 0.) ? std::nextafterf(1e-6f, 0.f) : 0.f;
-    const double s[kTriSrcDoubles] = {p.n[0], p.n[1], p.n[2], dn, p.vxy[0], p.vxy[1], A[0], B[0], A[1], B[1], C[1],
+    const float thr = p.is_triangle ? std::nextafterf(1e-6f, 0.f) : 0.f;
+    const double s[kTriSrcDoubles] = {p.n[0], p.n[1], p.n[2], dn, p.x(0), p.y(0), A[0], B[0], A[1], B[1], C[1],
                                       A[2], B[2], (double)thr, (double)p.id, 0.};
     std::memcpy(src, s, sizeof s);
     float idf;
     std::memcpy(&idf, &p.id, 4);
     g[0] = {(float)p.n[0], (float)p.n[1], (float)p.n[2], (float)dn};
-    g[1] = {(float)p.vxy[0], (float)p.vxy[1], (float)A[0], (float)B[0]};
+    g[1] = {(float)p.x(0), (float)p.y(0), (float)A[0], (float)B[0]};
     g[2] = {(float)A[1], (float)B[1], (float)C[1], (float)A[2]};
     g[3] = {(float)B[2], thr, idf, 0.f};
 }
@@ -181,8 +191,8 @@ BvhPrimBox plane_bounds(const PlaneTmp& p, int code) {
         b.lo[a] = INFINITY;
         b.hi[a] = -INFINITY;
     }
-    for (size_t v = 0; v < p.vxy.size() / 2; v++) {
-        const double x = p.vxy[2 * v], y = p.vxy[2 * v + 1];
+    for (size_t v = 0; v < (size_t)p.nv; v++) {
+        const double x = p.x(v), y = p.y(v);
         const double z = p.c[2] - (p.n[0] * (x - p.c[0]) + p.n[1] * (y - p.c[1])) / p.n[2];   // non-finite for n.z == 0: unbounded box
         const double q[3] = {x, y, z};
         for (int a = 0; a < 3; a++) {
@@ -197,48 +207,58 @@ BvhPrimBox plane_bounds(const PlaneTmp& p, int code) {
     return b;
 }
 
-template <typename R> void write_fast(const std::vector<PlaneTmp>&, BlobLayout&, unsigned char*, PackedScene<R>&) {}
-template <> void write_fast<float>(const std::vector<PlaneTmp>& pln, BlobLayout& L, unsigned char* b, PackedScene<float>& out) {
+// items [0, n) in blocks of 2048 on the pool's threads (in place when the pool has none)
+template <typename F> void for_blocks(HostPool& pool, size_t n, const F& body) {
+    constexpr size_t kBlock = 2048;
+    const int n_blocks = (int)((n + kBlock - 1) / kBlock);
+    pool.run(n_blocks, [&](int b) { body((size_t)b * kBlock, std::min(n, (size_t)(b + 1) * kBlock)); });
+}
+
+template <typename R> void write_fast(const std::vector<PlaneTmp>&, BlobLayout&, unsigned char*, PackedScene<R>&, HostPool&) {}
+template <> void write_fast<float>(const std::vector<PlaneTmp>& pln, BlobLayout& L, unsigned char* b, PackedScene<float>& out, HostPool& pool) {
     auto* g = reinterpret_cast<R4<float>*>(b + L.off_tri_g);
     auto* slot = reinterpret_cast<int*>(b + L.off_poly_slot);
     out.tri_src.assign((size_t)L.n_tri * kTriSrcDoubles + kTriSrcDoubles, 0.);
-    int t = 0, k = 0;
-    std::vector<BvhPrimBox> boxes;
+    // planes are sorted hittable | back-facing | degenerate: the hittable ones, in slot order, are the boxes after the spheres
+    std::vector<BvhPrimBox> boxes((size_t)L.n_sph + (size_t)L.n_pln_live);
     const auto* sph = reinterpret_cast<const R4<float>*>(b + L.off_sph);
     for (int i = 0; i < L.n_sph; i++) {
         // the sphere as the kernels see it: centre and r^2 already rounded to f32 (sphere.rs:6-11)
         const double r = std::sqrt((double)sph[i].w), c[3] = {sph[i].x, sph[i].y, sph[i].z};
-        BvhPrimBox bx;
+        BvhPrimBox& bx = boxes[i];
         for (int a = 0; a < 3; a++) {
             bx.lo[a] = c[a] - r;
             bx.hi[a] = c[a] + r;
         }
         bx.code = (BVH_SPHERE << 30) | i;
-        boxes.push_back(bx);
     }
+    // index of every non-degenerate plane in its list: triangle records / polygon slots
+    std::vector<int> index(pln.size());
+    int t = 0, k = 0;
     for (size_t i = 0; i < pln.size(); i++) {
         if (pln[i].cls == 2) continue;
-        if (pln[i].vxy.size() == 6) {
-            write_triangle(pln[i], out.tri_src.data() + (size_t)t * kTriSrcDoubles, g + 4 * t);
-            if (pln[i].cls == 0) boxes.push_back(plane_bounds(pln[i], (BVH_TRI << 30) | t));
-            t++;
-        } else {
-            if (pln[i].cls == 0) boxes.push_back(plane_bounds(pln[i], (int)((unsigned)BVH_POLY << 30 | (unsigned)i)));
-            slot[k++] = (int)i;
-        }
+        index[i] = pln[i].nv == 3 ? t++ : k++;
     }
-    out.bvh_depth = build_bvh(boxes, out.bvh_nodes, out.bvh_prims);
-}
-
-template <typename R> void push_material(PackedScene<R>& out, const RmReflectance& r) {
-    out.mat_a.push_back(mk4<R>(r.diffuse_color[0], r.diffuse_color[1], r.diffuse_color[2], r.diffusion));
-    out.mat_b.push_back(mk4<R>(r.specular, r.specular_exponent, r.reflection, r.refractive_index));
-    out.mat_f.push_back(r.is_glass_like ? 1 : 0);
+    for_blocks(pool, pln.size(), [&](size_t begin, size_t end) {
+        for (size_t i = begin; i < end; i++) {
+            if (pln[i].cls == 2) continue;
+            if (pln[i].nv == 3) {
+                write_triangle(pln[i], out.tri_src.data() + (size_t)index[i] * kTriSrcDoubles, g + 4 * index[i]);
+                if (pln[i].cls == 0) boxes[L.n_sph + i] = plane_bounds(pln[i], (BVH_TRI << 30) | index[i]);
+            } else {
+                if (pln[i].cls == 0) boxes[L.n_sph + i] = plane_bounds(pln[i], (int)((unsigned)BVH_POLY << 30 | (unsigned)i));
+                slot[index[i]] = (int)i;
+            }
+        }
+    });
+    const auto t0 = std::chrono::steady_clock::now();
+    out.bvh_depth = build_bvh(boxes, out.bvh_nodes, out.bvh_prims, &pool);
+    out.hierarchy_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
 }  // namespace
 
-template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out, std::string& err) {
+template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out, std::string& err, HostPool* shared_pool) {
     int rc = validate_scene(fs, err);
     if (rc != RM_OK) return rc;
     out = PackedScene<R>();
@@ -248,53 +268,62 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
     auto ms_now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     double t_collect = 0, t_sort = 0, t_blob = 0, t_fast = 0;
 
+    // Large scenes are packed on several threads: the caller's pool, or one of this call's own.  Every primitive's
+    // records depend on that primitive alone and land at indices fixed beforehand, so the result does not depend on the
+    // number of threads.
+    const size_t n_planar = (size_t)fs.n_polygons + (size_t)fs.n_triangles;
+    std::unique_ptr<HostPool> own_pool;
+    if (!shared_pool || n_planar < 8192) {
+        own_pool.reset(new HostPool(n_planar < 8192 ? 1 : host_thread_count(16)));
+    }
+    HostPool& pool = own_pool ? *own_pool : *shared_pool;
+
     struct SphTmp { const RmSphere* s; int id, shape; };
     std::vector<SphTmp> sph;
-    std::vector<PlaneTmp> pln;
-    pln.reserve((size_t)fs.n_polygons + (size_t)fs.n_triangles);
+    std::vector<PlaneTmp> found;      // planar primitives in scene order
+    found.reserve(n_planar);
     int id = 0;
     for (int s = 0; s < fs.n_shapes; s++) {
         const RmShapeRef& ref = fs.shapes[s];
         if (ref.kind == RM_SHAPE_SPHERE) {
-            const RmSphere& sp = fs.spheres[ref.index];
-            sph.push_back({&sp, id++, s});
-            push_material(out, sp.reflectance);
+            sph.push_back({&fs.spheres[ref.index], id++, s});
         } else if (ref.kind == RM_SHAPE_POLYGON) {
             const RmPolygon& p = fs.polygons[ref.index];
-            PlaneTmp t;
-            std::memcpy(t.n, p.plane_normal, sizeof t.n);
-            std::memcpy(t.c, p.plane_point, sizeof t.c);
-            t.thr_is_triangle = 0.;
-            for (int v = 0; v < p.n_vertices; v++) {
-                t.vxy.push_back(fs.polygon_vertices[3 * (p.first_vertex + v)]);
-                t.vxy.push_back(fs.polygon_vertices[3 * (p.first_vertex + v) + 1]);
-            }
-            t.id = id++;
-            t.shape = s;
-            t.cls = classify_plane(t.vxy, sizeof(R) == 4);
-            pln.push_back(std::move(t));
-            push_material(out, p.reflectance);
+            found.push_back({p.plane_normal, p.plane_point, fs.polygon_vertices + 3 * (size_t)p.first_vertex, p.n_vertices, id++, s, ref.index, 0, false});
         } else {
             const RmObj& o = fs.objs[ref.index];
             for (int k = 0; k < o.n_triangles; k++) {
                 const RmTriangle& tr = fs.triangles[o.first_triangle + k];
-                PlaneTmp t;
-                std::memcpy(t.n, tr.normal, sizeof t.n);
-                std::memcpy(t.c, tr.center, sizeof t.c);
-                t.thr_is_triangle = 1.;
-                for (int v = 0; v < 3; v++) {
-                    t.vxy.push_back(tr.vertices[3 * v]);
-                    t.vxy.push_back(tr.vertices[3 * v + 1]);
-                }
-                t.id = id++;
-                t.shape = s | (1 << 30);
-                t.cls = classify_plane(t.vxy, sizeof(R) == 4);
-                pln.push_back(std::move(t));
-                push_material(out, fs.triangle_reflectances[o.first_triangle + k]);
+                found.push_back({tr.normal, tr.center, tr.vertices, 3, id++, s | (1 << 30), o.first_triangle + k, 0, true});
             }
         }
     }
     out.n_prims = id;
+    // materials by primitive id
+    out.mat_a.resize((size_t)id);
+    out.mat_b.resize((size_t)id);
+    out.mat_f.resize((size_t)id);
+    auto put_material = [&](int at, const RmReflectance& r) {
+        out.mat_a[at] = mk4<R>(r.diffuse_color[0], r.diffuse_color[1], r.diffuse_color[2], r.diffusion);
+        out.mat_b[at] = mk4<R>(r.specular, r.specular_exponent, r.reflection, r.refractive_index);
+        out.mat_f[at] = r.is_glass_like ? 1 : 0;
+    };
+    for (auto& sp : sph) put_material(sp.id, sp.s->reflectance);
+    // per block: class of every plane, largest coordinate magnitude, any glass
+    const size_t n_found = found.size();
+    const size_t n_blocks = (n_found + 2047) / 2048;
+    std::vector<double> block_cm(n_blocks + 1, 0.);
+    for_blocks(pool, n_found, [&](size_t begin, size_t end) {
+        double cm = 0.;
+        for (size_t i = begin; i < end; i++) {
+            PlaneTmp& t = found[i];
+            t.cls = classify_plane(t, sizeof(R) == 4);
+            for (int v = 0; v < t.nv; v++) cm = std::fmax(cm, std::fmax(std::fabs(t.x(v)), std::fabs(t.y(v))));
+            cm = std::fmax(cm, std::fabs(t.c[2]));
+            put_material(t.id, t.is_triangle ? fs.triangle_reflectances[t.src] : fs.polygons[t.src].reflectance);
+        }
+        block_cm[begin / 2048] = cm;
+    });
     t_collect = ms_now();
     for (int f : out.mat_f) out.lay.any_glass |= f & 1;
     {
@@ -304,16 +333,22 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
             for (int a = 0; a < 3; a++) cm = std::fmax(cm, std::fabs(sp.s->center[a]) + r);
             rmin = std::fmin(rmin, r);
         }
-        for (auto& pl : pln) {
-            for (double v : pl.vxy) cm = std::fmax(cm, std::fabs(v));
-            cm = std::fmax(cm, std::fabs(pl.c[2]));
-        }
+        for (double v : block_cm) cm = std::fmax(cm, v);
         out.lay.coord_max = cm;
         out.lay.r_min = sph.empty() ? 0. : rmin;
     }
 
     // hittable planes first, then back-facing, then degenerate (stable: scene order inside each class)
-    std::stable_sort(pln.begin(), pln.end(), [](const PlaneTmp& a, const PlaneTmp& b) { return a.cls < b.cls; });
+    std::vector<PlaneTmp> pln(n_found);
+    {
+        size_t at[3] = {0, 0, 0};
+        for (const PlaneTmp& t : found) at[t.cls]++;
+        at[2] = at[0] + at[1];
+        at[1] = at[0];
+        at[0] = 0;
+        for (const PlaneTmp& t : found) pln[at[t.cls]++] = t;
+    }
+    found = std::vector<PlaneTmp>();
 
     t_sort = ms_now();
     BlobLayout& L = out.lay;
@@ -325,13 +360,13 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
     for (auto& p : pln) {
         L.n_pln_live += p.cls == 0 ? 1 : 0;
         L.n_pln_nondegenerate += p.cls != 2 ? 1 : 0;
-        L.n_vert += (int)p.vxy.size() / 2;
+        L.n_vert += p.nv;
     }
     L.n_lgt = fs.n_lights;
     if (sizeof(R) == 4) {
         for (auto& p : pln) {
             if (p.cls == 2) continue;
-            const bool tri = p.vxy.size() == 6;
+            const bool tri = p.nv == 3;
             (tri ? L.n_tri : L.n_poly)++;
             if (p.cls == 0) (tri ? L.n_tri_live : L.n_poly_live)++;
         }
@@ -366,19 +401,24 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
         b_sph[i] = mk4<R>(s.center[0], s.center[1], s.center[2], s.radius_square);
         b_sid[i] = sph[i].id;
     }
-    int v0 = 0;
-    for (int i = 0; i < L.n_pln; i++) {
-        const PlaneTmp& p = pln[i];
-        R thr = (p.thr_is_triangle != 0.) ? pred_1e6<R>() : R(0);
-        b_pn[i] = {(R)p.n[0], (R)p.n[1], (R)p.n[2], thr};
-        int nv = (int)p.vxy.size() / 2;
-        b_pv[i] = {v0, nv};
-        write_plane(p, b_pc[i], b_v + v0);
-        v0 += nv;
-        b_pid[i] = p.id;
+    {
+        int v0 = 0;
+        for (int i = 0; i < L.n_pln; i++) {
+            b_pv[i] = {v0, pln[i].nv};
+            v0 += pln[i].nv;
+        }
     }
+    for_blocks(pool, (size_t)L.n_pln, [&](size_t begin, size_t end) {
+        for (size_t i = begin; i < end; i++) {
+            const PlaneTmp& p = pln[i];
+            const R thr = p.is_triangle ? pred_1e6<R>() : R(0);
+            b_pn[i] = {(R)p.n[0], (R)p.n[1], (R)p.n[2], thr};
+            write_plane(p, b_pc[i], b_v + b_pv[i].x);
+            b_pid[i] = p.id;
+        }
+    });
     t_blob = ms_now();
-    write_fast<R>(pln, L, b, out);
+    write_fast<R>(pln, L, b, out, pool);
     t_fast = ms_now();
     if (sizeof(R) == 4) {
         // f64 sources for the refinement of winning hits on glass paths (cast_glass, rm_fast.cuh): spheres {c, r^2}
@@ -401,31 +441,40 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
         b_lc[l] = mk4<R>(lg.color[0], lg.color[1], lg.color[2], 0.);
     }
 
-    // scene-order lists for the instrumented kernel: sort slots by primitive id
-    std::vector<std::pair<int, std::pair<int, int>>> all;   // id -> (slot, shape)
-    for (int i = 0; i < L.n_sph; i++) all.push_back({sph[i].id, {i, sph[i].shape}});
-    for (int i = 0; i < L.n_pln; i++) all.push_back({pln[i].id, {L.n_sph + i, pln[i].shape}});
-    std::sort(all.begin(), all.end());
+    // scene-order lists for the instrumented kernel: slots by primitive id (ids are 0 .. n_prims-1, each once)
+    std::vector<int> slot_of((size_t)out.n_prims), shape_of((size_t)out.n_prims);
+    for (int i = 0; i < L.n_sph; i++) {
+        slot_of[sph[i].id] = i;
+        shape_of[sph[i].id] = sph[i].shape;
+    }
+    for (int i = 0; i < L.n_pln; i++) {
+        slot_of[pln[i].id] = L.n_sph + i;
+        shape_of[pln[i].id] = pln[i].shape;
+    }
     const int keep0 = plane_count<R>(L, false), keep1 = plane_count<R>(L, true);
-    for (auto& e : all) {
-        int slot = e.second.first;
+    out.order[0].reserve((size_t)L.n_sph + keep0);
+    out.order_shape[0].reserve((size_t)L.n_sph + keep0);
+    out.order[1].reserve((size_t)L.n_sph + keep1);
+    out.order_shape[1].reserve((size_t)L.n_sph + keep1);
+    for (int e = 0; e < out.n_prims; e++) {
+        const int slot = slot_of[e];
         if (slot < L.n_sph || (slot - L.n_sph) < keep0) {
             out.order[0].push_back(slot);
-            out.order_shape[0].push_back(e.second.second);
+            out.order_shape[0].push_back(shape_of[e]);
         }
         if (slot < L.n_sph || (slot - L.n_sph) < keep1) {
             out.order[1].push_back(slot);
-            out.order_shape[1].push_back(e.second.second);
+            out.order_shape[1].push_back(shape_of[e]);
         }
     }
     if (trace)
-        std::fprintf(stderr, "rm pack (%s, %d primitives): collected %.1f ms, classes sorted %.1f, blob written %.1f, fast records + hierarchy %.1f, done %.1f\n",
-                     sizeof(R) == 4 ? "f32" : "f64", out.n_prims, t_collect, t_sort, t_blob, t_fast, ms_now());
+        std::fprintf(stderr, "rm pack (%s, %d primitives): collected %.1f ms, classes sorted %.1f, blob written %.1f, fast records + hierarchy %.1f (hierarchy alone %.1f), done %.1f\n",
+                     sizeof(R) == 4 ? "f32" : "f64", out.n_prims, t_collect, t_sort, t_blob, t_fast, out.hierarchy_build_ms, ms_now());
     return RM_OK;
 }
 
-template int pack_scene<float>(const RmFlatScene&, PackedScene<float>&, std::string&);
-template int pack_scene<double>(const RmFlatScene&, PackedScene<double>&, std::string&);
+template int pack_scene<float>(const RmFlatScene&, PackedScene<float>&, std::string&, HostPool*);
+template int pack_scene<double>(const RmFlatScene&, PackedScene<double>&, std::string&, HostPool*);
 
 template <typename R> FrameParams<R> make_frame_params(const RmParams& p) {
     FrameParams<R> fp{};

@@ -17,6 +17,7 @@
 
 #include "../../include/rm_b200.h"
 #include "rm_fast.cuh"
+#include "rm_pool.h"
 
 namespace rm {
 
@@ -61,6 +62,7 @@ template <typename R> struct PackedScene {
     std::vector<R4<float>> bvh_nodes;
     std::vector<int> bvh_prims;
     int bvh_depth = 0;
+    double hierarchy_build_ms = 0.;
 };
 
 // Bounds of one hittable primitive (f64, unpadded) and its entry code kind << 30 | index for the hierarchy's leaves.
@@ -69,10 +71,13 @@ struct BvhPrimBox {
     int code;
 };
 // Builds the hierarchy of rm_bvh.cuh (nodes: 4 x R4<float> each; prims: leaf entries).  Returns its depth.
-int build_bvh(const std::vector<BvhPrimBox>& boxes, std::vector<R4<float>>& nodes, std::vector<int>& prims);
+// `pool`: threads to build on (large scenes); none = threads of the call's own.
+int build_bvh(const std::vector<BvhPrimBox>& boxes, std::vector<R4<float>>& nodes, std::vector<int>& prims, HostPool* pool = nullptr);
 
 // Validates `fs` and packs it.  Returns RM_OK or RM_ERR_SCENE / RM_ERR_INVALID_ARGUMENT with `err` set.
-template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out, std::string& err);
+// Scenes of 8192 planar primitives and more are packed on `pool`'s threads (none = threads of the call's own); the result
+// does not depend on the number of threads.
+template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out, std::string& err, HostPool* pool = nullptr);
 
 // Deep copy of a flat scene (the caller's arrays may go away after rm_scene_upload).
 struct OwnedFlatScene {

@@ -1,7 +1,6 @@
 """Scene (engine/src/scene.rs:9-211): lights, shapes and the camera position, plus the flattening
 of the shape list into the RmFlatScene PODs the C ABI consumes."""
 import ctypes as C
-import zlib
 
 import numpy as np
 
@@ -15,7 +14,7 @@ class _Flat:
     """Accumulates the arrays of an RmFlatScene and keeps them alive."""
 
     def __init__(self):
-        self.shapes, self.spheres, self.polygons, self.polygon_vertices, self.objs = [], [], [], [], []
+        self.shapes, self.sphere_rows, self.polygons, self.polygon_vertices, self.objs = [], [], [], [], []
         self.triangle_chunks, self.reflectance_chunks = [], []
         self.n_triangles = 0
         self.n_prims = 0
@@ -28,18 +27,32 @@ class _Flat:
                 a[i] = it
             return a
 
-        self._shapes = arr(_abi.RmShapeRef, [_abi.RmShapeRef(k, i) for k, i in self.shapes])
-        self._spheres = arr(_abi.RmSphere, self.spheres)
+        self._shapes_np = np.ascontiguousarray(self.shapes if self.shapes else [(0, 0)], dtype=np.int32)     # RmShapeRef {kind, index}
+        self._shapes = C.cast(self._shapes_np.ctypes.data, C.POINTER(_abi.RmShapeRef))
+        # RmSphere = 13 doubles, the 11th an int32 flag (+ padding)
+        assert C.sizeof(_abi.RmSphere) == 104 and _abi.RmSphere.reflectance.offset + _abi.RmReflectance.is_glass_like.offset == 80
+        rows = np.array(self.sphere_rows if self.sphere_rows else [(0.,) * 13], dtype=np.float64).reshape(-1, 13)
+        flags = rows[:, 10] != 0.
+        rows[:, 10] = 0.
+        rows.view(np.int32)[:, 20] = flags
+        self._spheres_np = rows
+        self._spheres = (_abi.RmSphere * rows.shape[0]).from_buffer(rows)
         self._polygons = arr(_abi.RmPolygon, self.polygons)
         self._pv = np.ascontiguousarray(self.polygon_vertices if self.polygon_vertices else [0.], dtype=np.float64)
         self._objs = arr(_abi.RmObj, [_abi.RmObj(f, n) for f, n in self.objs])
-        self._tris = np.ascontiguousarray(np.concatenate(self.triangle_chunks) if self.triangle_chunks else np.zeros((1, 15)))
-        self._refl = np.ascontiguousarray(np.concatenate(self.reflectance_chunks) if self.reflectance_chunks
-                                          else np.zeros(1, dtype=REFL_DTYPE))
+        # a scene with ONE mesh hands its arrays over as they are (rm_scene_upload copies what it keeps): no 20 MB
+        # concatenation for a 10^5-triangle mesh; set_glass_index() copies before it writes
+        def joined(chunks, empty):
+            if not chunks:
+                return empty
+            return np.ascontiguousarray(chunks[0] if len(chunks) == 1 else np.concatenate(chunks))
+        self._tris = joined(self.triangle_chunks, np.zeros((1, 15)))
+        self._refl = joined(self.reflectance_chunks, np.zeros(1, dtype=REFL_DTYPE))
+        self._refl_shared = len(self.reflectance_chunks) == 1
         self._lights = arr(_abi.RmLight, self.lights)
         fs = _abi.RmFlatScene()
         fs.n_shapes, fs.shapes = len(self.shapes), self._shapes
-        fs.n_spheres, fs.spheres = len(self.spheres), self._spheres
+        fs.n_spheres, fs.spheres = len(self.sphere_rows), self._spheres
         fs.n_polygons, fs.polygons = len(self.polygons), self._polygons
         fs.n_polygon_vertices = len(self.polygon_vertices) // 3
         fs.polygon_vertices = self._pv.ctypes.data_as(C.POINTER(C.c_double))
@@ -64,6 +77,9 @@ class _Flat:
                 self._polygons[i].reflectance.refractive_index = refractive_index
                 n += 1
         if self.n_triangles:
+            if self._refl_shared:                      # still the mesh's own array
+                self._refl, self._refl_shared = self._refl.copy(), False
+                self.c.triangle_reflectances = C.cast(self._refl.ctypes.data, C.POINTER(_abi.RmReflectance))
             glass = self._refl["is_glass_like"] != 0
             self._refl["refractive_index"][glass] = refractive_index
             n += int(glass.sum())
@@ -155,12 +171,12 @@ class Scene:
 
     @staticmethod
     def _checksum(a):
-        """Content key of an array: CRC-32 of its raw bytes, whatever its size (zlib runs at several GB/s: a mesh of 10^5
-        triangles, 12 MB, costs about 2 ms).  Every bit and every position counts -- a float sum misses an int field seen
-        as a denormal, a permutation of the triangles (order sets the colour gradient and the tie-breaks, obj.rs:125-138,
-        198) and any sum-preserving edit."""
-        b = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
-        return (a.shape, zlib.crc32(b))
+        """Content key of an array: the library's 64-bit content hash of its raw bytes (rm_content_hash, memory speed: a mesh
+        of 10^5 triangles, 12 MB, costs about 2 ms; zlib's CRC-32 took five times that).  Every bit and every position
+        counts -- a float sum misses an int field seen as a denormal, a permutation of the triangles (order sets the colour
+        gradient and the tie-breaks, obj.rs:125-138, 198) and any sum-preserving edit."""
+        b = np.ascontiguousarray(a)
+        return (a.shape, _abi.load().rm_content_hash(b.ctypes.data, b.nbytes, 0))
 
     def _fp(self):
         def key(s):

@@ -1,5 +1,4 @@
 """Sphere (engine/src/sphere.rs:6-25)."""
-from . import _abi
 from .geometry import Vec3f
 from .shapes import Reflectance, Shape
 
@@ -11,12 +10,13 @@ class Sphere(Shape):
         self.reflectance = reflectance.copy()
 
     def flatten(self, flat):
-        s = _abi.RmSphere()
-        s.center[:] = list(self.center)
-        s.radius_square = self.radius_square
-        s.reflectance = self.reflectance.to_c()
-        flat.spheres.append(s)
-        flat.shapes.append((0, len(flat.spheres) - 1))
+        # one row of 13 doubles = the RmSphere POD (center, radius_square, reflectance; the int flag is patched in by
+        # finish()): a scene of thousands of spheres is marshalled as ONE array, not one ctypes object per sphere
+        c, r = self.center, self.reflectance
+        dr, dg, db = r.diffuse_color
+        flat.sphere_rows.append((c.x, c.y, c.z, self.radius_square, r.diffusion, dr, dg, db, r.specular, r.specular_exponent,
+                                 1. if r.is_glass_like else 0., r.reflection, r.refractive_index))
+        flat.shapes.append((0, len(flat.sphere_rows) - 1))
         flat.n_prims += 1
 
 
