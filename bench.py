@@ -509,8 +509,10 @@ def run_ours(args):
         sampler.start()
     # ---- the timed region: K frames, each bracketed by CUDA events on the launching stream (a frame is the K0 -> K1 pair and
     # nothing else), L2 flushed before each, barrier + synchronize on both sides, max over ranks
+    graphs_before = int(L.rm_graph_launch_count())
     ms_per_step = timed_frames(tr, flush, args.steps, max(args.warmup, 3), world, dev)
     value = segs / (ms_per_step * 1e-3)
+    graphs_headline = int(L.rm_graph_launch_count()) - graphs_before      # frames (warm-up included) issued as one graph launch
 
     # ---- the same K frames once more with the library's per-kernel events on (K0 | K1 | K4, kept for the last 256 frames):
     # the split of a frame between the kernels.  Not the headline pass: the extra event records between the two launches
@@ -539,10 +541,9 @@ def run_ours(args):
     # path K1 contains the exchange wait and the fused K4)
     k1_ms_avg = ms_per_step if tr.exchange == "peer" else k1_profiled_ms
 
-    # ---- the same frames as ONE CUDA graph launch each (RM_B200_GRAPH=1, read per call): reported next
-    # to the headline, in alternating blocks so that clock drift hits both arms alike
+    # ---- one CUDA graph launch per frame (the default) against the two plain launches (RM_B200_GRAPH=0,
+    # read per call), in alternating blocks so that clock drift hits both arms alike
     graph_ab = None
-    graphs_headline = int(L.rm_graph_launch_count())          # of the headline's frames (0 unless RM_B200_GRAPH=1 is set)
     if os.environ.get("RM_B200_GRAPH") is None:
         n_g = min(args.steps, 100)
         before = int(L.rm_graph_launch_count())

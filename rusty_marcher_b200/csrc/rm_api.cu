@@ -467,14 +467,15 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
         ex.ev_rendered = ps.e[2];
     }
     SceneEntry& se = it->second;
-    // RM_B200_GRAPH=1: frame-level calls go to the GPU as ONE graph launch from the scene's second frame on (the first one
-    // runs the launchers' one-time set-up).  Off by default: measured on the 4K cornell frame the graph is 0.4 us per frame
-    // SLOWER than the two plain launches (69.66 vs 69.28 us, profiles/r5j_graph_ab.txt) -- the programmatic launch edge
-    // already hides K1's launch behind K0, and the capture + update cost host time on top.  Read per call, so a caller can
-    // switch between frames; a driver that cannot capture the pair switches it off for the process.
+    // Frame-level calls go to the GPU as ONE graph launch from the scene's second frame on (the first one runs the launchers'
+    // one-time set-up); RM_B200_GRAPH=0 keeps the two plain launches.  Measured on the 4K cornell frame in alternating blocks
+    // of 100 frames: 64.30 us per frame as a graph, 64.57 as two launches joined by a programmatic edge (bench.py's
+    // graph_ab, profiles/r5m_*) -- the edge already hides K1's launch behind K0, the graph saves the second submission.
+    // Read per call, so a caller can switch between frames; a driver that cannot capture the pair switches it off for the
+    // process.
     static int graph_broken = 0;
     const char* genv = getenv("RM_B200_GRAPH");
-    const int graph_mode = (!graph_broken && genv && genv[0] == '1') ? 1 : 0;
+    const int graph_mode = (!graph_broken && !(genv && genv[0] == '0')) ? 1 : 0;
     bool launched = false;
     if (as_graph && graph_mode == 1 && se.frames > 0 && fp.n_bands > 0) {
         cudaEvent_t ev_begin = ex.ev_begin, ev_rendered = ex.ev_rendered;
@@ -952,7 +953,7 @@ int rm_scene_upload(const RmFlatScene* scene, RmScene* out_handle) {
     int rc = rm::validate_scene(*scene, err);
     if (rc != RM_OK) return fail(rc, err);
     SceneEntry se;
-    se.flat.assign(*scene);
+    se.flat.assign(*scene, &host_pool());
     if ((rc = ensure_pack<float>(se, se.f32)) != RM_OK) { destroy_scene(se); return rc; }
     RmScene h = g.next_handle++;
     g.scenes.emplace(h, std::move(se));

@@ -64,7 +64,7 @@ struct Task {
 constexpr int kDeferred = INT_MIN;
 
 struct Builder {
-    std::vector<Item>& items;          // shared; a builder only touches the ranges it is given
+    Buf<Item>& items;                  // shared; a builder only touches the ranges it is given
     std::vector<R4<float>>& nodes;
     std::vector<int>& prims;
     int max_depth = 0;
@@ -72,7 +72,7 @@ struct Builder {
     int grain = 0;
     HostPool* pool = nullptr;             // when set: large ranges are swept on its threads
 
-    Builder(std::vector<Item>& i, std::vector<R4<float>>& n, std::vector<int>& p) : items(i), nodes(n), prims(p) {}
+    Builder(Buf<Item>& i, std::vector<R4<float>>& n, std::vector<int>& p) : items(i), nodes(n), prims(p) {}
 
     int make_leaf(int begin, int end) {
         const int first = (int)prims.size();
@@ -243,7 +243,7 @@ struct Builder {
 
 }  // namespace
 
-int build_bvh(const std::vector<BvhPrimBox>& in, std::vector<R4<float>>& nodes, std::vector<int>& prims, HostPool* shared_pool) {
+int build_bvh(const Buf<BvhPrimBox>& in, std::vector<R4<float>>& nodes, std::vector<int>& prims, HostPool* shared_pool) {
     nodes.clear();
     prims.clear();
     if (in.empty()) return 0;
@@ -267,7 +267,7 @@ int build_bvh(const std::vector<BvhPrimBox>& in, std::vector<R4<float>>& nodes, 
         }
     const double pad = std::max(S, 1e-30) * (1.0 / 16384.0);
     const double big = 1e30;
-    std::vector<Item> items((size_t)n);
+    Buf<Item> items((size_t)n);
     auto make_items = [&](int b0, int b1) {
         for (int i = b0; i < b1; i++) {
             const BvhPrimBox& p = in[i];

@@ -33,14 +33,25 @@ RmFlatScene OwnedFlatScene::view() const {
     return fs;
 }
 
-void OwnedFlatScene::assign(const RmFlatScene& fs) {
+void OwnedFlatScene::assign(const RmFlatScene& fs, HostPool* pool) {
+    auto copy_large = [&](auto& dst, const auto* src, size_t n) {
+        dst.resize(n);
+        const size_t bytes = n * sizeof(dst[0]), kBlock = 1 << 20;
+        const int n_blocks = (int)((bytes + kBlock - 1) / kBlock);
+        auto one = [&](int k) {
+            const size_t at = (size_t)k * kBlock;
+            std::memcpy(reinterpret_cast<char*>(dst.data()) + at, reinterpret_cast<const char*>(src) + at, std::min(kBlock, bytes - at));
+        };
+        if (pool && n_blocks >= 4) pool->run(n_blocks, one);
+        else for (int k = 0; k < n_blocks; k++) one(k);
+    };
     shapes.assign(fs.shapes, fs.shapes + fs.n_shapes);
     spheres.assign(fs.spheres, fs.spheres + fs.n_spheres);
     polygons.assign(fs.polygons, fs.polygons + fs.n_polygons);
     polygon_vertices.assign(fs.polygon_vertices, fs.polygon_vertices + 3 * (size_t)fs.n_polygon_vertices);
     objs.assign(fs.objs, fs.objs + fs.n_objs);
-    triangles.assign(fs.triangles, fs.triangles + fs.n_triangles);
-    triangle_reflectances.assign(fs.triangle_reflectances, fs.triangle_reflectances + fs.n_triangles);
+    copy_large(triangles, fs.triangles, (size_t)fs.n_triangles);
+    copy_large(triangle_reflectances, fs.triangle_reflectances, (size_t)fs.n_triangles);
     lights.assign(fs.lights, fs.lights + fs.n_lights);
 }
 
@@ -214,13 +225,14 @@ template <typename F> void for_blocks(HostPool& pool, size_t n, const F& body) {
     pool.run(n_blocks, [&](int b) { body((size_t)b * kBlock, std::min(n, (size_t)(b + 1) * kBlock)); });
 }
 
-template <typename R> void write_fast(const std::vector<PlaneTmp>&, BlobLayout&, unsigned char*, PackedScene<R>&, HostPool&) {}
-template <> void write_fast<float>(const std::vector<PlaneTmp>& pln, BlobLayout& L, unsigned char* b, PackedScene<float>& out, HostPool& pool) {
+template <typename R> void write_fast(const Buf<PlaneTmp>&, BlobLayout&, unsigned char*, PackedScene<R>&, HostPool&) {}
+template <> void write_fast<float>(const Buf<PlaneTmp>& pln, BlobLayout& L, unsigned char* b, PackedScene<float>& out, HostPool& pool) {
     auto* g = reinterpret_cast<R4<float>*>(b + L.off_tri_g);
     auto* slot = reinterpret_cast<int*>(b + L.off_poly_slot);
-    out.tri_src.assign((size_t)L.n_tri * kTriSrcDoubles + kTriSrcDoubles, 0.);
+    out.tri_src.resize((size_t)L.n_tri * kTriSrcDoubles + kTriSrcDoubles);      // every record is written in full below
+    std::fill(out.tri_src.end() - kTriSrcDoubles, out.tri_src.end(), 0.);       // one record of padding
     // planes are sorted hittable | back-facing | degenerate: the hittable ones, in slot order, are the boxes after the spheres
-    std::vector<BvhPrimBox> boxes((size_t)L.n_sph + (size_t)L.n_pln_live);
+    Buf<BvhPrimBox> boxes((size_t)L.n_sph + (size_t)L.n_pln_live);
     const auto* sph = reinterpret_cast<const R4<float>*>(b + L.off_sph);
     for (int i = 0; i < L.n_sph; i++) {
         // the sphere as the kernels see it: centre and r^2 already rounded to f32 (sphere.rs:6-11)
@@ -233,7 +245,7 @@ template <> void write_fast<float>(const std::vector<PlaneTmp>& pln, BlobLayout&
         bx.code = (BVH_SPHERE << 30) | i;
     }
     // index of every non-degenerate plane in its list: triangle records / polygon slots
-    std::vector<int> index(pln.size());
+    Buf<int> index(pln.size());
     int t = 0, k = 0;
     for (size_t i = 0; i < pln.size(); i++) {
         if (pln[i].cls == 2) continue;
@@ -339,7 +351,7 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
     }
 
     // hittable planes first, then back-facing, then degenerate (stable: scene order inside each class)
-    std::vector<PlaneTmp> pln(n_found);
+    Buf<PlaneTmp> pln(n_found);
     {
         size_t at[3] = {0, 0, 0};
         for (const PlaneTmp& t : found) at[t.cls]++;
@@ -384,8 +396,9 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
     L.off_tri_g = off;  off = align32(off + L.n_tri * 4 * (int)sizeof(R4<float>));
     L.off_poly_slot = off; off = align32(off + L.n_poly * (int)sizeof(int));
     L.bytes = std::max(off, 32);
-    out.blob.assign(L.bytes / 32, BlobChunk{});
+    out.blob.resize((size_t)L.bytes / 32);
     unsigned char* b = reinterpret_cast<unsigned char*>(out.blob.data());
+    for_blocks(pool, (size_t)L.bytes / 32, [&](size_t begin, size_t end) { std::memset(b + 32 * begin, 0, 32 * (end - begin)); });   // padding included
     auto* b_sph = reinterpret_cast<R4<R>*>(b + L.off_sph);
     auto* b_pn = reinterpret_cast<R4<R>*>(b + L.off_pln_n);
     auto* b_pc = reinterpret_cast<R4<R>*>(b + L.off_pln_c);
@@ -423,17 +436,21 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
     if (sizeof(R) == 4) {
         // f64 sources for the refinement of winning hits on glass paths (cast_glass, rm_fast.cuh): spheres {c, r^2}
         // (sphere.rs:6-11) and planes by slot {n, n.C} (triangle.rs:33-47 / polygon.rs:16-42: precomputed normal, plane point)
-        out.sph64.resize((size_t)L.n_sph * 4 + 4, 0.);
+        out.sph64.resize((size_t)L.n_sph * 4 + 4);
+        std::fill(out.sph64.end() - 4, out.sph64.end(), 0.);
         for (int i = 0; i < L.n_sph; i++) {
             const RmSphere& sp = *sph[i].s;
             const double q[4] = {sp.center[0], sp.center[1], sp.center[2], sp.radius_square};
             std::memcpy(out.sph64.data() + 4 * (size_t)i, q, sizeof q);
         }
-        out.pln64.resize((size_t)L.n_pln * 4 + 4, 0.);
-        for (int i = 0; i < L.n_pln; i++) {
-            const double q[4] = {pln[i].n[0], pln[i].n[1], pln[i].n[2], plane_dn(pln[i])};
-            std::memcpy(out.pln64.data() + 4 * (size_t)i, q, sizeof q);
-        }
+        out.pln64.resize((size_t)L.n_pln * 4 + 4);
+        std::fill(out.pln64.end() - 4, out.pln64.end(), 0.);
+        for_blocks(pool, (size_t)L.n_pln, [&](size_t begin, size_t end) {
+            for (size_t i = begin; i < end; i++) {
+                const double q[4] = {pln[i].n[0], pln[i].n[1], pln[i].n[2], plane_dn(pln[i])};
+                std::memcpy(out.pln64.data() + 4 * i, q, sizeof q);
+            }
+        });
     }
     for (int l = 0; l < L.n_lgt; l++) {
         const RmLight& lg = fs.lights[l];

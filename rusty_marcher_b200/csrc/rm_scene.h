@@ -12,7 +12,10 @@
 // the scene-order lists of the instrumented kernel stay in plain global arrays.
 #pragma once
 
+#include <memory>
+#include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/rm_b200.h"
@@ -36,6 +39,23 @@ struct BlobLayout {
 
 struct alignas(32) BlobChunk { unsigned char b[32]; };
 
+// std::vector whose resize() / sized constructor leave trivially constructible elements uninitialised: the packer's large
+// arrays are written once, in parallel, by the threads that first touch their pages -- not zero-filled by one thread first
+// (for 10^5 primitives the arrays are ~60 MB of fresh pages; faulting and zeroing them on one thread cost as much as the
+// arithmetic).
+template <typename T> struct NoInit {
+    using value_type = T;
+    NoInit() = default;
+    template <typename U> NoInit(const NoInit<U>&) {}
+    T* allocate(size_t n) { return std::allocator<T>().allocate(n); }
+    void deallocate(T* p, size_t n) { std::allocator<T>().deallocate(p, n); }
+    template <typename U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+    template <typename U, typename... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+    template <typename U> bool operator==(const NoInit<U>&) const { return true; }
+    template <typename U> bool operator!=(const NoInit<U>&) const { return false; }
+};
+template <typename T> using Buf = std::vector<T, NoInit<T>>;
+
 // Planar primitives traced: culling keeps the hittable class only.  Without culling the f64 kernels
 // trace everything like the reference; the f32 kernels still skip the degenerate-projection class,
 // whose edge terms are rounding noise that single precision cannot reproduce.
@@ -48,13 +68,13 @@ RM_HD int poly_count(const BlobLayout& L, bool cull) { return cull ? L.n_poly_li
 
 template <typename R> struct PackedScene {
     BlobLayout lay;
-    std::vector<BlobChunk> blob;      // lay.bytes bytes, 32-byte aligned
+    Buf<BlobChunk> blob;              // lay.bytes bytes, 32-byte aligned
     const unsigned char* blob_data() const { return reinterpret_cast<const unsigned char*>(blob.data()); }
     size_t blob_bytes() const { return blob.size() * sizeof(BlobChunk); }
-    std::vector<double> tri_src;      // FP32 pack only: kTriSrcDoubles per fast-path triangle (prepare_raster input)
-    std::vector<double> sph64, pln64; // FP32 pack only: f64 {c, r^2} per sphere and {n, n.C} per plane slot (cast_glass)
-    std::vector<R4<R>> mat_a, mat_b;
-    std::vector<int> mat_f;
+    Buf<double> tri_src;              // FP32 pack only: kTriSrcDoubles per fast-path triangle (prepare_raster input)
+    Buf<double> sph64, pln64;         // FP32 pack only: f64 {c, r^2} per sphere and {n, n.C} per plane slot (cast_glass)
+    Buf<R4<R>> mat_a, mat_b;
+    Buf<int> mat_f;
     // scene-order traversal lists: [0] = every primitive, [1] = after culling
     std::vector<int> order[2], order_shape[2];
     int n_prims = 0;
@@ -72,7 +92,7 @@ struct BvhPrimBox {
 };
 // Builds the hierarchy of rm_bvh.cuh (nodes: 4 x R4<float> each; prims: leaf entries).  Returns its depth.
 // `pool`: threads to build on (large scenes); none = threads of the call's own.
-int build_bvh(const std::vector<BvhPrimBox>& boxes, std::vector<R4<float>>& nodes, std::vector<int>& prims, HostPool* pool = nullptr);
+int build_bvh(const Buf<BvhPrimBox>& boxes, std::vector<R4<float>>& nodes, std::vector<int>& prims, HostPool* pool = nullptr);
 
 // Validates `fs` and packs it.  Returns RM_OK or RM_ERR_SCENE / RM_ERR_INVALID_ARGUMENT with `err` set.
 // Scenes of 8192 planar primitives and more are packed on `pool`'s threads (none = threads of the call's own); the result
@@ -86,11 +106,11 @@ struct OwnedFlatScene {
     std::vector<RmPolygon> polygons;
     std::vector<double> polygon_vertices;
     std::vector<RmObj> objs;
-    std::vector<RmTriangle> triangles;
-    std::vector<RmReflectance> triangle_reflectances;
+    Buf<RmTriangle> triangles;                        // the two large arrays: copied block by block on the pool's threads
+    Buf<RmReflectance> triangle_reflectances;
     std::vector<RmLight> lights;
     RmFlatScene view() const;
-    void assign(const RmFlatScene& fs);
+    void assign(const RmFlatScene& fs, HostPool* pool = nullptr);
 };
 
 int validate_scene(const RmFlatScene& fs, std::string& err);
