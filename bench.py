@@ -541,8 +541,8 @@ def run_ours(args):
     # path K1 contains the exchange wait and the fused K4)
     k1_ms_avg = ms_per_step if tr.exchange == "peer" else k1_profiled_ms
 
-    # ---- one CUDA graph launch per frame (the default) against the two plain launches (RM_B200_GRAPH=0,
-    # read per call), in alternating blocks so that clock drift hits both arms alike
+    # ---- one CUDA graph launch per frame (RM_B200_GRAPH=1, read per call) against the two plain launches
+    # of the headline, in alternating blocks so that clock drift hits both arms alike
     graph_ab = None
     if os.environ.get("RM_B200_GRAPH") is None:
         n_g = min(args.steps, 100)

@@ -467,15 +467,16 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
         ex.ev_rendered = ps.e[2];
     }
     SceneEntry& se = it->second;
-    // Frame-level calls go to the GPU as ONE graph launch from the scene's second frame on (the first one runs the launchers'
-    // one-time set-up); RM_B200_GRAPH=0 keeps the two plain launches.  Measured on the 4K cornell frame in alternating blocks
-    // of 100 frames: 64.30 us per frame as a graph, 64.57 as two launches joined by a programmatic edge (bench.py's
-    // graph_ab, profiles/r5m_*) -- the edge already hides K1's launch behind K0, the graph saves the second submission.
-    // Read per call, so a caller can switch between frames; a driver that cannot capture the pair switches it off for the
-    // process.
+    // RM_B200_GRAPH=1 (read per call): frame-level calls go to the GPU as ONE graph launch from the scene's second frame on
+    // (the first one runs the launchers' one-time set-up).  Opt-in, because on the device it is a wash: 4K cornell frame,
+    // alternating blocks of 100 frames, graph against the two launches joined by a programmatic edge: 64.30 / 64.57 us on
+    // one box, 64.88 / 64.61 on another, 57.82 / 57.22 at two GPUs (bench.py's graph_ab; profiles/r5m-r5o) -- the edge
+    // already hides K1's launch behind K0.  What the graph does save is host time: 40 us instead of 51 us to issue a frame
+    // (tools/frame_rate.py), which matters to a caller whose loop is bound by its own thread, not by the GPU.
+    // A driver that cannot capture the pair switches it off for the process.
     static int graph_broken = 0;
     const char* genv = getenv("RM_B200_GRAPH");
-    const int graph_mode = (!graph_broken && !(genv && genv[0] == '0')) ? 1 : 0;
+    const int graph_mode = (!graph_broken && genv && genv[0] == '1') ? 1 : 0;
     bool launched = false;
     if (as_graph && graph_mode == 1 && se.frames > 0 && fp.n_bands > 0) {
         cudaEvent_t ev_begin = ex.ev_begin, ev_rendered = ex.ev_rendered;

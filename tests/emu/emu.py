@@ -81,6 +81,20 @@ def bvh(scene):
     return nodes[:n_nodes.value], prims[:n_prims.value], depth.value
 
 
+def pack_digest(scene):
+    """(FP32, FP64) digests of everything the library's packer produces for the scene (blob, records, materials, lists,
+    hierarchy)."""
+    L = lib()
+    flat = scene.flatten()
+    out = (C.c_ulonglong * 2)()
+    L.emu_pack_digest.restype = C.c_int
+    L.emu_pack_digest.argtypes = [C.POINTER(_abi.RmFlatScene), C.POINTER(C.c_ulonglong)]
+    rc = L.emu_pack_digest(C.byref(flat.c), out)
+    if rc != 0:
+        raise RuntimeError("emu_pack_digest rc %d" % rc)
+    return int(out[0]), int(out[1])
+
+
 def walk_stats():
     """(walks, node visits, primitive tests) of the hierarchy walks of the accel renders since the last call."""
     out = (C.c_ulonglong * 3)()

@@ -228,6 +228,44 @@ int emu_render_fast_impl(const RmFlatScene* fs, const RmParams* p, float* out_rg
     return RM_OK;
 }
 
+// FNV-1a digests of everything the packer produces for a scene (layout, hot blob, records, materials, scene-order lists,
+// hierarchy): out[0] the FP32 pack, out[1] the FP64 pack.  The packer runs on several threads for large scenes; its output
+// must not depend on how many.
+namespace {
+unsigned long long fnv(const void* p, size_t n, unsigned long long h) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; i++) {
+        h ^= b[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+template <typename R> unsigned long long pack_digest(const rm::PackedScene<R>& ps) {
+    unsigned long long h = 1469598103934665603ull;
+    const rm::BlobLayout L = ps.lay;
+    h = fnv(&L.n_sph, sizeof(int) * 6, h);
+    h = fnv(&L.off_sph, sizeof(int) * 9, h);
+    h = fnv(&L.n_tri, sizeof(int) * 7, h);
+    h = fnv(&L.any_glass, 4, h);
+    h = fnv(&L.coord_max, 16, h);
+    h = fnv(ps.blob.data(), ps.blob_bytes(), h);
+    h = fnv(ps.tri_src.data(), ps.tri_src.size() * 8, h);
+    h = fnv(ps.sph64.data(), ps.sph64.size() * 8, h);
+    h = fnv(ps.pln64.data(), ps.pln64.size() * 8, h);
+    h = fnv(ps.mat_a.data(), ps.mat_a.size() * sizeof(ps.mat_a[0]), h);
+    h = fnv(ps.mat_b.data(), ps.mat_b.size() * sizeof(ps.mat_b[0]), h);
+    h = fnv(ps.mat_f.data(), ps.mat_f.size() * 4, h);
+    for (int k = 0; k < 2; k++) {
+        h = fnv(ps.order[k].data(), ps.order[k].size() * 4, h);
+        h = fnv(ps.order_shape[k].data(), ps.order_shape[k].size() * 4, h);
+    }
+    h = fnv(&ps.n_prims, 4, h);
+    h = fnv(ps.bvh_nodes.data(), ps.bvh_nodes.size() * 16, h);
+    h = fnv(ps.bvh_prims.data(), ps.bvh_prims.size() * 4, h);
+    h = fnv(&ps.bvh_depth, 4, h);
+    return h;
+}
+}  // namespace
 extern "C" {
 void emu_set_strip_bound(int on) { g_strip_bound.store(on); }
 void emu_set_glass_mode(int mode) { g_glass_mode.store(mode); }
@@ -254,6 +292,18 @@ int emu_bvh(const RmFlatScene* fs, float* nodes, int nodes_cap, int* prims, int 
     if (*n_nodes > nodes_cap || *n_prims > prims_cap) return RM_ERR_INVALID_ARGUMENT;
     std::memcpy(nodes, ps.bvh_nodes.data(), ps.bvh_nodes.size() * sizeof(rm::R4<float>));
     std::memcpy(prims, ps.bvh_prims.data(), ps.bvh_prims.size() * sizeof(int));
+    return RM_OK;
+}
+int emu_pack_digest(const RmFlatScene* fs, unsigned long long out[2]) {
+    std::string err;
+    rm::PackedScene<float> pf;
+    int rc = rm::pack_scene<float>(*fs, pf, err);
+    if (rc != RM_OK) return rc;
+    rm::PackedScene<double> pd;
+    rc = rm::pack_scene<double>(*fs, pd, err);
+    if (rc != RM_OK) return rc;
+    out[0] = pack_digest(pf);
+    out[1] = pack_digest(pd);
     return RM_OK;
 }
 int emu_render_f32(const RmFlatScene* fs, const RmParams* p, float* out_rgb, int32_t* prim, RmStats* stats, int n_threads) {
