@@ -264,7 +264,7 @@ def verify_frames(tr, backend, cameras, world, rank, dev):
     import hashlib
     import torch
     import torch.distributed as dist
-    from rusty_marcher_b200 import _abi
+    from rusty_marcher_b200 import _abi, tiled
     L = backend.L
     h, w, n_patch = tr.height, tr.width, tr.n_patch_rows
     rows = n_patch * 32
@@ -275,19 +275,20 @@ def verify_frames(tr, backend, cameras, world, rank, dev):
         f = tr.render()
         if rank == 0:
             frames8.append(f.clone())                        # stream-ordered: valid until the next frame is issued
-        mine = tr.rgb[:rows].view(n_patch, 32, w, 3)[rank::world].contiguous()
+        first = [tiled.bands_of(n_patch, r, world)[0] for r in range(world)]      # first band of every rank
+        mine = tr.rgb[:rows].view(n_patch, 32, w, 3)[first[rank]::world].contiguous()
         if world == 1:
             floats.append(tr.rgb.clone())
         elif rank == 0:
             full = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
             fv = full[:rows].view(n_patch, 32, w, 3)
-            fv[0::world] = mine
+            fv[first[0]::world] = mine
             for r in range(1, world):
-                n = len(range(r, n_patch, world))
+                n = len(range(first[r], n_patch, world))
                 if n:
                     buf = torch.empty((n, 32, w, 3), dtype=torch.float32, device=dev)
                     dist.recv(buf, src=r)
-                    fv[r::world] = buf
+                    fv[first[r]::world] = buf
             floats.append(full)
         elif mine.shape[0]:
             dist.send(mine, dst=0)

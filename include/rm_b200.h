@@ -263,7 +263,7 @@ int   rm_host_unregister(void* p);
 
 /* ---- one frame on the GPUs of one box: render + the path's single exchange step, in two launches ---------- *
  * The reference's Rayon loop splits the frame into independent 32x32 patches (renderer.rs:46-89); across GPUs the
- * frame is split into 32-row bands (RmParams.patch_row_begin/end/stride; rank k of G renders bands k, k+G, ...), one
+ * frame is split into 32-row bands (RmParams.patch_row_begin/end/stride; a rank renders every G-th band, from a first band of its own), one
  * process per GPU.  The only data the ranks must exchange is what FrameBuffer::normalize (framebuffer.rs:58-76) needs
  * -- ONE float, the global channel maximum -- and the finished 8-bit rows, which go to rank 0.  Both travel over
  * NVLink peer memory from inside the render kernel (no NCCL call on the path, two launches per frame and rank):

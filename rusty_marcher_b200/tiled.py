@@ -1,7 +1,7 @@
 """Row-tiled multi-GPU rendering: one process per GPU (torch.distributed), SURVEY.md 8(e).
 
 The frame's floor(H/32) patch rows (32-row bands) are dealt round-robin to the ranks, rank k of G renders bands
-k, k + G, ... with the same kernels as the single-GPU path.  The path has exactly one exchange step:
+G-1-k, 2G-1-k, ... (bands_of) with the same kernels as the single-GPU path.  The path has exactly one exchange step:
 (1) the maximum of ONE float per rank (FrameBuffer::normalize is a global maximum, framebuffer.rs:58-69) and
 (2) the normalised RGB8 rows go to rank 0.
 
@@ -31,10 +31,12 @@ def tile_of(n_patch_rows, rank, world):
 
 
 def bands_of(n_patch_rows, rank, world):
-    """Interleaved row tiles: rank k renders patch rows k, k + world, ... as (begin, end, stride).  Scenes keep their
-    work in one part of the frame (the cornell box's visible block sits in the top half), so contiguous tiles leave
-    most ranks idle; dealing the 32-row bands round-robin balances them without any knowledge of the scene."""
-    return rank, n_patch_rows, world
+    """Interleaved row tiles: a rank renders every world-th patch row, as (begin, end, stride).  Scenes keep their work
+    in one part of the frame (the cornell box's visible block sits in the top half), so contiguous tiles leave most
+    ranks idle; dealing the 32-row bands round-robin balances them without any knowledge of the scene.  Rank k starts at
+    band world-1-k: when the bands do not divide evenly the classes that start first get one band more, and rank 0 --
+    which also receives every other rank's tiles and waits for the last of them -- should be among those with one less."""
+    return world - 1 - rank, n_patch_rows, world
 
 
 class _DeviceBytes:
@@ -212,9 +214,10 @@ class TiledRenderer:
     def _setup_collective(self):
         height, width, device = self.height, self.width, self.device
         self.rgb8 = torch.zeros((height, width, 3), dtype=torch.uint8, device=device)
-        # [patch row, 32, W, 3] view of the rendered part: rank r owns [r::world]
+        # [patch row, 32, W, 3] view of the rendered part: rank r owns [firsts[r]::world]
         self.bands8 = self.rgb8[:self.n_patch_rows * 32].view(self.n_patch_rows, 32, width, 3)
-        self.counts = [len(range(r, self.n_patch_rows, self.world)) for r in range(self.world)]
+        self.firsts = [bands_of(self.n_patch_rows, r, self.world)[0] for r in range(self.world)]
+        self.counts = [len(range(f, self.n_patch_rows, self.world)) for f in self.firsts]
         # equal-size gather slots: ranks with one band less pad
         self.slot = torch.zeros((max(self.counts + [1]), 32, width, 3), dtype=torch.uint8, device=device)
         self.gathered = ([torch.zeros_like(self.slot) for _ in range(self.world)] if self.rank == 0 and self.world > 1 else None)
@@ -236,13 +239,13 @@ class TiledRenderer:
         self.backend.tonemap_rows(self.rows, self.rgb, self.dmax, self.rgb8)
         n = self.counts[self.rank]
         if n:
-            self.slot[:n].copy_(self.bands8[self.rank::self.world])
+            self.slot[:n].copy_(self.bands8[self.firsts[self.rank]::self.world])
         dist.gather(self.slot, self.gathered, dst=0, group=self.group)
         if self.rank != 0:
             return None
         for r in range(1, self.world):
             if self.counts[r]:
-                self.bands8[r::self.world].copy_(self.gathered[r][:self.counts[r]])
+                self.bands8[self.firsts[r]::self.world].copy_(self.gathered[r][:self.counts[r]])
         return self.rgb8
 
     def set_camera(self, camera):
