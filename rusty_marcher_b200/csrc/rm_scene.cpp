@@ -218,11 +218,11 @@ BvhPrimBox plane_bounds(const PlaneTmp& p, int code) {
     return b;
 }
 
-// items [0, n) in blocks of 2048 on the pool's threads (in place when the pool has none)
+// items [0, n) in blocks of kPackBlock on the pool's threads (in place when the pool has none)
+constexpr size_t kPackBlock = 2048;
 template <typename F> void for_blocks(HostPool& pool, size_t n, const F& body) {
-    constexpr size_t kBlock = 2048;
-    const int n_blocks = (int)((n + kBlock - 1) / kBlock);
-    pool.run(n_blocks, [&](int b) { body((size_t)b * kBlock, std::min(n, (size_t)(b + 1) * kBlock)); });
+    const int n_blocks = (int)((n + kPackBlock - 1) / kPackBlock);
+    pool.run(n_blocks, [&](int b) { body((size_t)b * kPackBlock, std::min(n, (size_t)(b + 1) * kPackBlock)); });
 }
 
 template <typename R> void write_fast(const Buf<PlaneTmp>&, BlobLayout&, unsigned char*, PackedScene<R>&, HostPool&) {}
@@ -323,8 +323,7 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
     for (auto& sp : sph) put_material(sp.id, sp.s->reflectance);
     // per block: class of every plane, largest coordinate magnitude, any glass
     const size_t n_found = found.size();
-    const size_t n_blocks = (n_found + 2047) / 2048;
-    std::vector<double> block_cm(n_blocks + 1, 0.);
+    std::vector<double> block_cm((n_found + kPackBlock - 1) / kPackBlock + 1, 0.);
     for_blocks(pool, n_found, [&](size_t begin, size_t end) {
         double cm = 0.;
         for (size_t i = begin; i < end; i++) {
@@ -334,7 +333,7 @@ template <typename R> int pack_scene(const RmFlatScene& fs, PackedScene<R>& out,
             cm = std::fmax(cm, std::fabs(t.c[2]));
             put_material(t.id, t.is_triangle ? fs.triangle_reflectances[t.src] : fs.polygons[t.src].reflectance);
         }
-        block_cm[begin / 2048] = cm;
+        block_cm[begin / kPackBlock] = cm;
     });
     t_collect = ms_now();
     for (int f : out.mat_f) out.lay.any_glass |= f & 1;
