@@ -561,6 +561,15 @@ def run_ours(args):
     # ---- the frame the ranks assemble against the single-GPU frame: three consecutive frames, the camera moving
     cams = VERIFY_CAMERAS["stress" if scene_name == "stress" else "default"]
     frame_ok, frame_sha, frame_detail = verify_frames(tr, backend, cams, world, rank, dev)
+    # the same check with every frame issued as one CUDA graph launch (the first frames of a scene went out as plain
+    # launches long ago: all three are graph launches)
+    if graph_ab is not None:
+        before = int(L.rm_graph_launch_count())
+        os.environ["RM_B200_GRAPH"] = "1"
+        g_ok, g_sha, _g_detail = verify_frames(tr, backend, cams, world, rank, dev)
+        del os.environ["RM_B200_GRAPH"]
+        graph_ab["frames_match_n1"] = bool(g_ok and g_sha == frame_sha and int(L.rm_graph_launch_count()) - before == len(cams))
+        frame_ok = frame_ok and graph_ab["frames_match_n1"]
 
     # ---- the workload that can scale, at the same N (extra key; the headline is unchanged)
     heavy = None
