@@ -164,6 +164,11 @@ struct Context {
     Pinned h_stage, h_order;          // host delivery: pinned staging of the packed tiles / of the tile schedule + counters
     static constexpr int kChunks = 4; // ... the tiles cross PCIe in this many copies, each followed by an event
     cudaEvent_t chunk_ev[kChunks] = {nullptr, nullptr, nullptr, nullptr};
+    // ... and the tile schedule is read off the device as soon as K0 has written it, on a stream of its own, so that the
+    // host clears the black tiles while K1 renders
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_early = nullptr, ev_list = nullptr;
+    Pinned h_early;
     std::unique_ptr<rm::HostPool> pool;
     std::vector<Delivered> delivered; // a handful of frames (RM_ROWS_RETAINED)
     std::mutex mu;
@@ -433,7 +438,7 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
                        int buf_row0_is_tile, unsigned long long* d_counters, rm::FrameParams<R>* out_fp, int* resident,
                        int* launches = nullptr, unsigned char* d_rgb8_zero = nullptr, bool* scheduled = nullptr,
                        const rm::PeerLink* link = nullptr, unsigned char* d_rgb8_out = nullptr, bool normalise = true,
-                       unsigned char* d_rgb8_next = nullptr, bool as_graph = false) {
+                       unsigned char* d_rgb8_next = nullptr, bool as_graph = false, cudaEvent_t ev_after_k0 = nullptr) {
     if (!g.ready) return fail(RM_ERR_NOT_INITIALISED, "rm_init() has not been called (or failed): no CUDA device bound");
     int rc = check_params(params);
     if (rc != RM_OK) return rc;
@@ -466,6 +471,7 @@ int render_device_impl(RmScene scene, const RmParams* params, R* d_rgb, int* d_p
         ex.ev_prepared = ps.split ? ps.e[1] : nullptr;
         ex.ev_rendered = ps.e[2];
     }
+    if (ev_after_k0 && !ex.ev_prepared) ex.ev_prepared = ev_after_k0;      // recorded between K0 and K1 (host delivery reads the schedule early)
     SceneEntry& se = it->second;
     // RM_B200_GRAPH=1 (read per call): frame-level calls go to the GPU as ONE graph launch from the scene's second frame on
     // (the first one runs the launchers' one-time set-up).  Opt-in, because on the device it is a wash: 4K cornell frame,
@@ -675,7 +681,17 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
     CK(cudaMemsetAsync(g.small.p, 0, 64, s));
     CK(cudaEventRecord(g.ev[1], s));
     int resident = 0, launches = 0;
-    rc = render_device_impl<float>(scene, params, static_cast<float*>(g.rgb.p), nullptr, d_max, s, 1, nullptr, &fp, &resident, &launches);
+    // (the tile schedule is read off the device right after K0, below: an event between the two launches)
+    static const bool early_env = !(getenv("RM_B200_EARLY_SCHEDULE") && getenv("RM_B200_EARLY_SCHEDULE")[0] == '0');
+    const bool early_wanted = !g.profiling && early_env;
+    if (early_wanted && !g.side_stream) {
+        CK(cudaStreamCreateWithFlags(&g.side_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&g.ev_k0, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.ev_early, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.ev_list, cudaEventDisableTiming));
+    }
+    rc = render_device_impl<float>(scene, params, static_cast<float*>(g.rgb.p), nullptr, d_max, s, 1, nullptr, &fp, &resident, &launches,
+                                   nullptr, nullptr, nullptr, nullptr, true, nullptr, false, early_wanted ? g.ev_k0 : nullptr);
     if (rc != RM_OK) return rc;
     CK(cudaEventRecord(g.ev[2], s));
     SceneEntry& se = g.scenes.find(scene)->second;
@@ -720,12 +736,38 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
         float* h_maxp = reinterpret_cast<float*>(static_cast<char*>(g.h_order.p) + list_bytes);
         CK(cudaMemcpyAsync(h_sorted, d_sorted, (size_t)(n_tiles + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(h_maxp, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        const int n_busy = h_sorted[0];
+        // The schedule as K0 left it -- counters and the two unsorted lists, contiguous in the scene's arena -- crosses on a
+        // stream of its own as soon as K0 is done, while K1 renders: the host then knows the busy tiles ~70 us before the
+        // sorted list arrives, sizes and issues the tile copies without a synchronisation in the middle of the frame and
+        // clears the black tiles while the GPU is still rendering.  The snapshot is only used when it is consistent (K1's last
+        // block resets the counters: a snapshot taken after that says so by not adding up) and is checked against the
+        // sorted list afterwards.
+        const rm::DeviceScene<float>& ds = se.f32.ds;
+        const int cap_half = ds.tile_order_cap / 2;
+        int early_busy = -1;
+        const int* early = nullptr;
+        if (early_wanted) {
+            CK(cudaEventRecord(g.ev_list, s));
+            const size_t early_ints = 16 + (size_t)cap_half + (size_t)n_tiles;
+            if ((rc = g.h_early.ensure(early_ints * sizeof(int))) != RM_OK) return rc;
+            CK(cudaStreamWaitEvent(g.side_stream, g.ev_k0, 0));
+            CK(cudaMemcpyAsync(g.h_early.p, ds.ctr, early_ints * sizeof(int), cudaMemcpyDeviceToHost, g.side_stream));
+            CK(cudaEventRecord(g.ev_early, g.side_stream));
+            CK(cudaEventSynchronize(g.ev_early));
+            early = static_cast<const int*>(g.h_early.p);
+            const int n_full = early[1], n_part = early[5], n_none = early[2];
+            if (n_full >= 0 && n_part >= 0 && n_none >= 0 && n_full <= n_tiles && n_part <= n_tiles && n_full + n_part + n_none == n_tiles)
+                early_busy = n_full + n_part;
+        }
+        int n_busy = early_busy;
         const int* tiles = h_sorted + 1;
-        h_max = *h_maxp;
+        if (n_busy < 0) {                                        // no snapshot: wait for the sorted list
+            CK(cudaStreamSynchronize(s));
+            n_busy = h_sorted[0];
+            h_max = *h_maxp;
+            if (n_busy < 0 || n_busy > n_tiles) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
+        }
         t_sched = us_now();
-        if (n_busy < 0 || n_busy > n_tiles) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
         if ((rc = g.h_stage.ensure(std::max<size_t>((size_t)n_busy * 12288, 64))) != RM_OK) return rc;
         // the busy tiles cross PCIe in a few chunks, each followed by an event: the host scatters chunk k while chunk
         // k + 1 is still on its way (one cudaMemcpyAsync per chunk)
@@ -746,9 +788,19 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
         d2h = (uint64_t)n_busy * 12288 + (uint64_t)(n_tiles + 1) * sizeof(int) + 4;
         // while they travel: which tiles are busy now, and the black ones cleared
         std::vector<unsigned char> now((size_t)n_tiles, 0);
-        for (int t = 0; t < n_busy; t++) {
-            if (tiles[t] < 0 || tiles[t] >= n_tiles || (t && tiles[t] <= tiles[t - 1])) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
-            now[tiles[t]] = 1;
+        if (early_busy >= 0) {
+            d2h += (uint64_t)(16 + cap_half + n_tiles) * sizeof(int);
+            const int n_full = early[1];
+            for (int t = 0; t < n_busy; t++) {
+                const int tile = t < n_full ? early[16 + t] : early[16 + cap_half + (t - n_full)];
+                if (tile < 0 || tile >= n_tiles || now[tile]) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
+                now[tile] = 1;
+            }
+        } else {
+            for (int t = 0; t < n_busy; t++) {
+                if (tiles[t] < 0 || tiles[t] >= n_tiles || (t && tiles[t] <= tiles[t - 1])) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
+                now[tiles[t]] = 1;
+            }
         }
         const int band0 = fp.row_begin / 32, band_step = fp.row_step / 32;
         unsigned char* pb = prev->busy.data();
@@ -782,6 +834,14 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
         for (int b = 0; b < fp.n_bands; b++) {
             prev->known[band0 + b * band_step] = 1;
             std::memcpy(pb + (size_t)(band0 + b * band_step) * tiles_x, now.data() + (size_t)b * tiles_x, tiles_x);
+        }
+        if (early_busy >= 0) {
+            // the sorted list (the order the tiles were packed in) and the maximum have arrived long since: same tiles?
+            CK(cudaEventSynchronize(g.ev_list));
+            h_max = *h_maxp;
+            bool same = h_sorted[0] == n_busy;
+            for (int t = 0; t < n_busy && same; t++) same = tiles[t] >= 0 && tiles[t] < n_tiles && now[tiles[t]] && (!t || tiles[t] > tiles[t - 1]);
+            if (!same) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
         }
         t_zero = us_now();
         // scatter, chunk by chunk; an item is a run of up to 8 tiles in frame order -- neighbours in a band share the pages
@@ -897,7 +957,10 @@ void rm_shutdown(void) {
     g.arena_cache.clear();
     g.pack_cache.clear();
     g.rgb.release(); g.prim.release(); g.rgb8.release(); g.small.release(); g.mix.release(); g.pack.release();
-    g.h_stage.release(); g.h_order.release(); g.h_upload.release();
+    g.h_stage.release(); g.h_order.release(); g.h_upload.release(); g.h_early.release();
+    if (g.side_stream) cudaStreamDestroy(g.side_stream);
+    g.side_stream = nullptr;
+    for (cudaEvent_t* ev : {&g.ev_k0, &g.ev_early, &g.ev_list}) { if (*ev) cudaEventDestroy(*ev); *ev = nullptr; }
     g.pool.reset();
     g.delivered.clear();
     for (auto& ev : g.chunk_ev) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
