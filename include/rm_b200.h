@@ -204,8 +204,9 @@ int rm_render_f64(RmScene scene, const RmParams* params, double* out_rgb, int32_
  * channels.  rows[y] (y < params->height) points to row y: width * 3 doubles (rm_render_rows_f64; the FP32 results widened,
  * exactly) or floats (rm_render_rows_f32).  Only rows of the call's bands are touched, like renderer.rs:92-108.
  * Delivery: when the frame has a tile schedule (triangle-only scenes) the busy tiles are packed on the device and cross
- * PCIe in one copy; the library's host threads (RM_B200_HOST_THREADS, default: all) zero-fill the provably black tiles
- * while it runs and then scatter / widen the busy ones.
+ * PCIe in a few chunked copies; the library's host threads (RM_B200_HOST_THREADS, default: all) zero-fill the provably
+ * black tiles meanwhile -- from the moment the prepare kernel's schedule is on the host, while the frame is still being
+ * rendered (RM_B200_EARLY_SCHEDULE=0: only once the render kernel is done) -- and then scatter / widen the busy ones.
  * flags: RM_ROWS_RETAINED -- the caller has not touched the frame since the library's previous delivery into it (the
  * re-render loop of engine/src/main.rs:329-351 keeps one FrameBuffer): only tiles that held something then and are black
  * now are cleared.  The first delivery into a frame clears every black tile regardless.  stats: timings, max_value.
