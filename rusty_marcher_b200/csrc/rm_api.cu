@@ -724,18 +724,6 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
     }
 
     if (classified) {
-        // device: [sorted list: n_tiles + 1 ints][packed tiles]; host (pinned): the same list, then the tiles
-        const size_t list_bytes = align256((size_t)(n_tiles + 1) * sizeof(int));
-        if ((rc = g.pack.ensure(list_bytes + (size_t)n_tiles * 12288)) != RM_OK) return rc;
-        if ((rc = g.h_order.ensure(list_bytes + 64)) != RM_OK) return rc;
-        int* d_sorted = static_cast<int*>(g.pack.p);
-        float* d_packed = reinterpret_cast<float*>(static_cast<char*>(g.pack.p) + list_bytes);
-        CK(rm::launch_pack_busy(se.f32.ds, fp, static_cast<const float*>(g.rgb.p), d_sorted, d_packed, s));
-        launches += 2;
-        int* h_sorted = static_cast<int*>(g.h_order.p);
-        float* h_maxp = reinterpret_cast<float*>(static_cast<char*>(g.h_order.p) + list_bytes);
-        CK(cudaMemcpyAsync(h_sorted, d_sorted, (size_t)(n_tiles + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(h_maxp, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
         // The schedule as K0 left it -- counters and the two unsorted lists, contiguous in the scene's arena -- crosses on a
         // stream of its own as soon as K0 is done, while K1 renders: the host then knows the busy tiles ~70 us before the
         // sorted list arrives, sizes and issues the tile copies without a synchronisation in the middle of the frame and
@@ -747,7 +735,6 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
         int early_busy = -1;
         const int* early = nullptr;
         if (early_wanted) {
-            CK(cudaEventRecord(g.ev_list, s));
             const size_t early_ints = 16 + (size_t)cap_half + (size_t)n_tiles;
             if ((rc = g.h_early.ensure(early_ints * sizeof(int))) != RM_OK) return rc;
             CK(cudaStreamWaitEvent(g.side_stream, g.ev_k0, 0));
@@ -759,6 +746,43 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
             if (n_full >= 0 && n_part >= 0 && n_none >= 0 && n_full <= n_tiles && n_part <= n_tiles && n_full + n_part + n_none == n_tiles)
                 early_busy = n_full + n_part;
         }
+        // A contiguous float32 frame in pinned host memory the device can address is written by the device itself, tile by
+        // tile (deliver_busy_kernel): no staging buffer, no scatter.  RM_B200_DIRECT_DELIVERY=0 keeps the staged path.
+        float* direct_frame = nullptr;
+        static const bool direct_env = !(getenv("RM_B200_DIRECT_DELIVERY") && getenv("RM_B200_DIRECT_DELIVERY")[0] == '0');
+        if (direct_env && early_busy >= 0 && elem == 4 && !sink.rows && sink.row_bytes % 16 == 0) {
+            char* first = sink.row(fp.row_begin);
+            char* last = sink.row(fp.row_begin + (int)span_rows - 1) + (size_t)W * 12 - 1;
+            cudaPointerAttributes pa0, pa1;
+            if (cudaPointerGetAttributes(&pa0, first) == cudaSuccess && cudaPointerGetAttributes(&pa1, last) == cudaSuccess &&
+                pa0.type == cudaMemoryTypeHost && pa1.type == cudaMemoryTypeHost && pa0.devicePointer && pa1.devicePointer &&
+                static_cast<char*>(pa1.devicePointer) - static_cast<char*>(pa0.devicePointer) == last - first &&
+                (reinterpret_cast<uintptr_t>(pa0.devicePointer) & 15) == 0)
+                direct_frame = reinterpret_cast<float*>(static_cast<char*>(pa0.devicePointer) - (size_t)fp.row_begin * sink.row_bytes);
+            else
+                cudaGetLastError();                             // (pageable memory: not an error, the staged path takes it)
+        }
+        // device: [sorted list: n_tiles + 1 ints][packed tiles]; host (pinned): the same list, then the tiles
+        const size_t list_bytes = align256((size_t)(n_tiles + 1) * sizeof(int));
+        if ((rc = g.h_order.ensure(list_bytes + 64)) != RM_OK) return rc;
+        int* h_sorted = static_cast<int*>(g.h_order.p);
+        float* h_maxp = reinterpret_cast<float*>(static_cast<char*>(g.h_order.p) + list_bytes);
+        int* d_sorted = nullptr;
+        float* d_packed = nullptr;
+        if (direct_frame) {
+            CK(rm::launch_deliver_busy(ds, fp, static_cast<const float*>(g.rgb.p), early[1], early_busy, direct_frame, sink.row_bytes / 4, s));
+            launches += 1;
+            CK(cudaMemcpyAsync(h_maxp, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
+        } else {
+            if ((rc = g.pack.ensure(list_bytes + (size_t)n_tiles * 12288)) != RM_OK) return rc;
+            d_sorted = static_cast<int*>(g.pack.p);
+            d_packed = reinterpret_cast<float*>(static_cast<char*>(g.pack.p) + list_bytes);
+            CK(rm::launch_pack_busy(ds, fp, static_cast<const float*>(g.rgb.p), d_sorted, d_packed, s));
+            launches += 2;
+            CK(cudaMemcpyAsync(h_sorted, d_sorted, (size_t)(n_tiles + 1) * sizeof(int), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(h_maxp, d_max, sizeof(float), cudaMemcpyDeviceToHost, s));
+            if (early_wanted) CK(cudaEventRecord(g.ev_list, s));
+        }
         int n_busy = early_busy;
         const int* tiles = h_sorted + 1;
         if (n_busy < 0) {                                        // no snapshot: wait for the sorted list
@@ -768,14 +792,14 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
             if (n_busy < 0 || n_busy > n_tiles) return fail(RM_ERR_CUDA, "tile schedule of the frame is inconsistent");
         }
         t_sched = us_now();
-        if ((rc = g.h_stage.ensure(std::max<size_t>((size_t)n_busy * 12288, 64))) != RM_OK) return rc;
+        if (!direct_frame && (rc = g.h_stage.ensure(std::max<size_t>((size_t)n_busy * 12288, 64))) != RM_OK) return rc;
         // the busy tiles cross PCIe in a few chunks, each followed by an event: the host scatters chunk k while chunk
         // k + 1 is still on its way (one cudaMemcpyAsync per chunk)
         constexpr int kChunks = Context::kChunks;
         cudaEvent_t* const chunk_ev = g.chunk_ev;
         int chunk_end[kChunks];
         int n_chunks = 0;
-        for (int k = 0; k < kChunks && n_busy > 0; k++) {
+        for (int k = 0; k < kChunks && n_busy > 0 && !direct_frame; k++) {
             const int a0 = (int)((long long)n_busy * k / kChunks), a1 = (int)((long long)n_busy * (k + 1) / kChunks);
             if (a1 <= a0) continue;
             if (!chunk_ev[n_chunks]) CK(cudaEventCreateWithFlags(&chunk_ev[n_chunks], cudaEventDisableTiming));
@@ -785,7 +809,7 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
             chunk_end[n_chunks++] = a1;
         }
         CK(cudaEventRecord(g.ev[3], s));
-        d2h = (uint64_t)n_busy * 12288 + (uint64_t)(n_tiles + 1) * sizeof(int) + 4;
+        d2h = (uint64_t)n_busy * 12288 + (direct_frame ? 0 : (uint64_t)(n_tiles + 1) * sizeof(int)) + 4;
         // while they travel: which tiles are busy now, and the black ones cleared
         std::vector<unsigned char> now((size_t)n_tiles, 0);
         if (early_busy >= 0) {
@@ -835,7 +859,11 @@ int render_rows_impl(RmScene scene, const RmParams* params, const RowSink& sink,
             prev->known[band0 + b * band_step] = 1;
             std::memcpy(pb + (size_t)(band0 + b * band_step) * tiles_x, now.data() + (size_t)b * tiles_x, tiles_x);
         }
-        if (early_busy >= 0) {
+        if (direct_frame) {
+            CK(cudaStreamSynchronize(s));                       // the device has written the busy tiles into the caller's frame
+            h_max = *h_maxp;
+            t_copy = us_now();
+        } else if (early_busy >= 0) {
             // the sorted list (the order the tiles were packed in) and the maximum have arrived long since: same tiles?
             CK(cudaEventSynchronize(g.ev_list));
             h_max = *h_maxp;

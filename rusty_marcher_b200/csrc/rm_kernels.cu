@@ -876,6 +876,30 @@ pack_busy_kernel(const float* __restrict__ rgb, const FrameParams<float> fp, con
     }
 }
 
+// (3) ... or, when the caller's float32 frame is pinned host memory the device can address, written straight into it:
+// tile k of K0's schedule (unsorted: every tile is written exactly once, the order does not matter) goes row by row --
+// 384 contiguous bytes each, 24 lanes x 16 bytes -- over PCIe to its place in the frame.  No staging buffer, no scatter on
+// the host, whose memory system is what bounds a fresh frame: the tiles cross it once instead of three times.
+__global__ void __launch_bounds__(256)
+deliver_busy_kernel(const float* __restrict__ rgb, const FrameParams<float> fp, const int tiles_x, const int* __restrict__ order,
+                    const int* __restrict__ order2, const int n_full, const int n_busy, float* __restrict__ host_frame,
+                    const size_t host_row_floats) {
+    for (int t = blockIdx.x; t < n_busy; t += gridDim.x) {
+        const int tile = t < n_full ? order[t] : order2[t - n_full];
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        RM_CHECK(tile >= 0 && ty < fp.n_bands);
+        const int y0 = fp.row_begin + ty * fp.row_step;
+        const size_t p0 = (size_t)(y0 - fp.buf_row0) * fp.width + tx * 32;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int c = threadIdx.x + 256 * i;                // 768 float4 per tile: 32 rows x 24
+            const int row = c / 24, col = c - row * 24;
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(rgb + 3 * (p0 + (size_t)row * fp.width) + 4 * col));
+            *reinterpret_cast<float4*>(host_frame + (size_t)(y0 + row) * host_row_floats + (size_t)tx * 96 + 4 * col) = v;
+        }
+    }
+}
+
 __global__ void publish_zero_kernel(const PeerLink link, float* __restrict__ dmax) {
     *dmax = 0.f;
     publish_max(link, 0.f);
@@ -1061,6 +1085,15 @@ cudaError_t launch_pack_busy(const DeviceScene<float>& ds, const FrameParams<flo
     if (n_tiles > kSortMaxWords * 32) return cudaErrorInvalidValue;
     sort_busy_kernel<<<1, 1024, 0, stream>>>(ds.tile_order, ds.tile_order + ds.tile_order_cap / 2, ds.ctr, sorted);
     pack_busy_kernel<<<std::min(n_tiles, 148 * 8), 256, 0, stream>>>(rgb, fp, tiles_x, sorted, packed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_deliver_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, int n_full, int n_busy,
+                                float* host_frame, size_t host_row_floats, cudaStream_t stream) {
+    const int tiles_x = fp.width / kFastTile;
+    if (n_busy <= 0) return cudaSuccess;
+    deliver_busy_kernel<<<std::min(n_busy, 148 * 8), 256, 0, stream>>>(rgb, fp, tiles_x, ds.tile_order, ds.tile_order + ds.tile_order_cap / 2,
+                                                                       n_full, n_busy, host_frame, host_row_floats);
     return cudaGetLastError();
 }
 

@@ -97,6 +97,10 @@ cudaError_t launch_tonemap_busy(const DeviceScene<float>& ds, const FrameParams<
 // k-th in frame order (n_tiles + 1 ints), packed[3072 k ...] = its 32 x 32 x 3 floats.  Two launches.
 cudaError_t launch_pack_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, int* sorted, float* packed,
                              cudaStream_t stream);
+// ... or written straight into a float32 frame in pinned host memory (device pointer `host_frame`, rows of `host_row_floats`
+// floats), tiles [0, n_full) of the schedule's first list and [0, n_busy - n_full) of its second
+cudaError_t launch_deliver_busy(const DeviceScene<float>& ds, const FrameParams<float>& fp, const float* rgb, int n_full, int n_busy,
+                                float* host_frame, size_t host_row_floats, cudaStream_t stream);
 // launch_tonemap<float> that takes the frame maximum from this rank's mailbox (waiting for every rank's word of frame
 // link.seq) and signals rank 0 when its bytes are stored -- the exchange of a rank that has no rows to render (its render
 // kernel, which normally does both, is not launched).

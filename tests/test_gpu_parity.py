@@ -528,6 +528,38 @@ def test_host_delivery_of_rows(rm_gpu, name, w, h, depth):
     fb32.buffer[:] = 3.
     r.render(fb32, scene)
     assert np.array_equal(fb32.buffer[:rows], want[-1][:rows])
+    # a float32 frame in PINNED host memory (rm_host_alloc): the device writes the busy tiles straight into it (no staging,
+    # no scatter; three launches instead of four) -- fresh, retained, and as interleaved bands of three 'ranks'
+    pin = L.rm_host_alloc(h * w * 12)
+    assert pin
+    try:
+        fbp = rm.create_frame_buffer(32, 32)
+        fbp.width, fbp.height = w, h
+        fbp.buffer = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_float)), shape=(h, w, 3))
+        r.render(fb, scene)
+        staged_launches = r.last_stats.kernel_launches
+        for retained in (False, True):                           # (retained: the frame as the previous delivery left it)
+            r.retained = retained
+            for cam, ref in zip(cams, want):
+                scene.camera = type(scene.camera)(*cam)
+                if not retained:
+                    fbp.buffer[:] = 7.
+                r.render(fbp, scene)
+                assert np.array_equal(fbp.buffer[:rows], ref[:rows]) and np.all(fbp.buffer[rows:] == 7.)
+                assert r.last_stats.max_value == float(ref.max())
+                if name == "cornell_box":
+                    assert r.last_stats.kernel_launches == staged_launches - 1 == 3
+        r.retained = False
+        fbp.buffer[:] = 7.
+        scene.camera = type(scene.camera)(*cams[2])
+        for k in range(3):
+            p = r.params(fbp, scene, (k, -1, 3))
+            st = _abi.RmStats()
+            _abi.check(L.rm_render(scene.device_handle(), C.byref(p), fbp.buffer.ctypes.data, None, None, C.byref(st)))
+        assert np.array_equal(fbp.buffer[:rows], want[2][:rows]) and np.all(fbp.buffer[rows:] == 7.)
+        fbp.buffer = None
+    finally:
+        L.rm_host_free(pin)
     # one allocation per row (Vec<Vec<Vec3f>>), bands of three 'ranks' into the same frame
     row_arrays = [np.full((w, 3), 7., dtype=np.float64) for _ in range(h)]
     ptrs = (C.c_void_p * h)(*[a.ctypes.data for a in row_arrays])
