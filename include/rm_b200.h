@@ -203,10 +203,13 @@ int rm_render_f64(RmScene scene, const RmParams* params, double* out_rgb, int32_
  * FrameBuffer.buffer is a Vec<Vec<Vec3f>> (engine/src/framebuffer.rs:6-10): one heap allocation per pixel row, f64
  * channels.  rows[y] (y < params->height) points to row y: width * 3 doubles (rm_render_rows_f64; the FP32 results widened,
  * exactly) or floats (rm_render_rows_f32).  Only rows of the call's bands are touched, like renderer.rs:92-108.
- * Delivery: when the frame has a tile schedule (triangle-only scenes) the busy tiles are packed on the device and cross
- * PCIe in a few chunked copies; the library's host threads (RM_B200_HOST_THREADS, default: all) zero-fill the provably
+ * Delivery: when the frame has a tile schedule (triangle-only scenes) only the busy tiles cross PCIe.  Into a contiguous
+ * float32 frame in pinned host memory (rm_host_alloc / rm_host_register; rm_render with out_rgb only, rm_render_rows_f32
+ * with rows that follow each other) the device writes them itself, tile row by tile row (RM_B200_DIRECT_DELIVERY=0: never);
+ * otherwise they are packed on the device, cross in a few chunked copies into a staging buffer and are scattered / widened
+ * by the library's host threads (RM_B200_HOST_THREADS, default: all).  Either way those threads zero-fill the provably
  * black tiles meanwhile -- from the moment the prepare kernel's schedule is on the host, while the frame is still being
- * rendered (RM_B200_EARLY_SCHEDULE=0: only once the render kernel is done) -- and then scatter / widen the busy ones.
+ * rendered (RM_B200_EARLY_SCHEDULE=0: only once the render kernel is done).
  * flags: RM_ROWS_RETAINED -- the caller has not touched the frame since the library's previous delivery into it (the
  * re-render loop of engine/src/main.rs:329-351 keeps one FrameBuffer): only tiles that held something then and are black
  * now are cleared.  The first delivery into a frame clears every black tile regardless.  stats: timings, max_value.
