@@ -35,6 +35,8 @@ int fail(int code, const std::string& msg) {
 }
 int fail_cuda(cudaError_t e, const char* what) {
     g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    cudaGetLastError();         // reported here: a recoverable failure (a refused cudaHostRegister, say) must not surface again
+                                // from the next launcher's cudaGetLastError(); a sticky one stays whatever is read
     return (e == cudaErrorMemoryAllocation) ? RM_ERR_OUT_OF_MEMORY : RM_ERR_CUDA;
 }
 #define CK(call)                                                   \

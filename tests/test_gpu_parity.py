@@ -573,6 +573,22 @@ def test_host_delivery_of_rows(rm_gpu, name, w, h, depth):
     assert L.rm_render_rows_f64(scene.device_handle(), C.byref(p), None, 0, None) == -3
 
 
+def test_refused_host_register_does_not_poison_later_calls(rm_gpu):
+    """A recoverable CUDA failure reported through the ABI (registering the same range twice) is not reported again by
+    the next call that checks for launch errors."""
+    L = _abi.load()
+    buf = np.zeros(1 << 20, dtype=np.uint8)
+    assert L.rm_host_register(buf.ctypes.data, buf.nbytes) == 0
+    try:
+        assert L.rm_host_register(buf.ctypes.data, buf.nbytes) != 0
+        assert b"cudaHostRegister" in L.rm_last_error()
+        scene = workloads.scene("cornell_box")
+        got = gpu_render(rm_gpu, scene, 256, 160, "f32")
+        assert (got["prim_id"] >= 0).any()
+    finally:
+        assert L.rm_host_unregister(buf.ctypes.data) == 0
+
+
 def test_kernel_profiling_events(rm_gpu):
     import torch
     from rusty_marcher_b200 import tiled
