@@ -481,8 +481,9 @@ def test_host_api_interleaved_bands(rm_gpu):
 
 @pytest.mark.parametrize("name,w,h,depth", [("cornell_box", 1920, 1080, 3), ("dodecahedron", 640, 480, 3), ("demo", 800, 600, 3)])
 def test_host_delivery_of_rows(rm_gpu, name, w, h, depth):
-    """What Renderer::render hands back (renderer.rs:92-108): the float frame in HOST memory.  The packed delivery (busy
-    tiles in one copy, host threads clear the black tiles and scatter) against the plain copy of every row: float32 frame,
+    """What Renderer::render hands back (renderer.rs:92-108): the float frame in HOST memory.  The delivery of busy tiles
+    only (staged: packed on the device, chunked copies, host threads scatter; pinned frames: written by the device itself;
+    host threads clear the black tiles either way) against the plain copy of every row: float32 frame,
     the reference's f64 rows (contiguous and one allocation per row, framebuffer.rs:6-10), the retained mode over a moving
     camera, interleaved bands of several 'ranks' into one frame -- all bit-identical, on poisoned buffers."""
     rm = rm_gpu
